@@ -1,0 +1,71 @@
+"""In-tree nvcc build of ``libseeme_b200.so`` (sm_100a only; cross-compiles without a GPU).
+
+``python -m seeme_b200.build`` or ``seeme_b200.build.build()``.  Objects land in
+``seeme_b200/csrc/_build/`` and the library in ``seeme_b200/lib/`` (both git-ignored, NOT
+gpurun-ignored, so the built library travels to the GPU box with the snapshot).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_build")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libseeme_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-O2",
+         "-Xptxas", "-v"]
+
+
+def sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _headers_mtime() -> float:
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(HERE, "..", "include", "seeme_b200.h"))
+    return max(os.path.getmtime(h) for h in hs)
+
+
+def _compile(src: str, force: bool, verbose: bool) -> str:
+    obj = os.path.join(OBJ, src[:-3] + ".o")
+    spath = os.path.join(CSRC, src)
+    if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(spath)
+            and os.path.getmtime(obj) > _headers_mtime()):
+        return obj
+    cmd = [NVCC, *ARCH, *FLAGS, "-c", spath, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log = os.path.join(OBJ, src[:-3] + ".log")
+    with open(log, "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        print(f"[seeme_b200.build] compiled {src}", file=sys.stderr)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = True) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(LIBDIR, exist_ok=True)
+    srcs = sources()
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(lambda s: _compile(s, force, verbose), srcs))
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(f"[seeme_b200.build] linked {LIB}", file=sys.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)
+    print(LIB)

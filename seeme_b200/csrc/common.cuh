@@ -1,0 +1,153 @@
+// Shared helpers for the seeme_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include "../../include/seeme_b200.h"
+
+namespace seeme {
+
+// ---- error plumbing (thread-local message behind seeme_last_error) --------------------------
+void set_error(const char* fmt, ...);
+extern unsigned long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
+
+#define SEEME_CUDA(expr)                                                                          \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      seeme::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return SEEME_ECUDA;                                                                         \
+    }                                                                                             \
+  } while (0)
+
+#define SEEME_REQUIRE(cond, code, ...)   \
+  do {                                   \
+    if (!(cond)) {                       \
+      seeme::set_error(__VA_ARGS__);     \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+#define SEEME_TRY(expr)          \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != SEEME_OK) return _r; \
+  } while (0)
+
+#define SEEME_LAUNCH_CHECK()                                                                 \
+  do {                                                                                       \
+    cudaError_t _e = cudaPeekAtLastError();                                                  \
+    if (_e != cudaSuccess) {                                                                 \
+      seeme::set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__,                 \
+                       cudaGetErrorString(_e));                                              \
+      return SEEME_ECUDA;                                                                    \
+    }                                                                                        \
+    seeme::count_launch();                                                                   \
+  } while (0)
+
+// ---- a tiny bump allocator over one cudaMalloc'd slab (everything allocated at create) -------
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+  int init(size_t bytes) {
+    cap = bytes;
+    used = 0;
+    cudaError_t e = cudaMalloc((void**)&base, bytes);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+      base = nullptr;
+      return SEEME_ENOMEM;
+    }
+    return SEEME_OK;
+  }
+  template <typename T>
+  T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    if (used + bytes > cap) return nullptr;
+    T* p = reinterpret_cast<T*>(base + used);
+    used += bytes;
+    return p;
+  }
+  void release() {
+    if (base) cudaFree(base);
+    base = nullptr;
+  }
+};
+inline size_t pad256(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+
+constexpr int D_MODEL = 256;
+constexpr int NUM_SMS = 148;
+
+// ---- device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+
+// order-preserving float <-> uint mapping (for atomicMax / redux on floats)
+__device__ __forceinline__ unsigned f2ord(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3 };
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(v, 0.f);
+    case ACT_GELU: return gelu_erf(v);
+    case ACT_SILU: return silu(v);
+    default: return v;
+  }
+}
+
+// ---- generic fp32 linear: Y = act(pre(X) W^T + bias) (+R) ------------------------------------
+struct GemmP {
+  const float* X; int ldx;      // [M,K]
+  const float* W; int ldw;      // [N,K] (nn.Linear weight layout)
+  const float* bias;            // [N] or [G,N] (per row-group); nullable
+  int bias_group_rows;          // 0: one bias; else bias row = m / bias_group_rows
+  const float* R; int ldr;      // residual added after the activation; nullable
+  float* Y; int ldy;
+  int M, N, K;
+  int pre_act;                  // Act applied to X on load (ACT_NONE/ACT_RELU/ACT_SILU)
+  int act;                      // Act applied to (acc + bias)
+  int accumulate;               // Y += instead of Y =
+};
+inline GemmP gemm_params(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y,
+                         int ldy, int M, int N, int K) {
+  GemmP p;
+  memset(&p, 0, sizeof(p));
+  p.X = X; p.ldx = ldx; p.W = W; p.ldw = ldw; p.bias = bias; p.Y = Y; p.ldy = ldy;
+  p.M = M; p.N = N; p.K = K;
+  return p;
+}
+int gemm_f32(const GemmP& p, cudaStream_t s);
+
+// ---- row-wise ops on [rows,256] (one warp per row) -------------------------------------------
+// y = LN(x (+ r)) * g + b      (r nullable; r_group_rows > 0: r row = row / r_group_rows, i.e. a
+// per-sample vector broadcast over frames)
+int layernorm256(const float* x, const float* r, int r_group_rows, const float* g, const float* b,
+                 float* y, int rows, cudaStream_t s);
+
+// p[i] *= s on the default stream (create-time weight folding)
+void scale_kernel_launch(float* p, size_t n, float s);
+
+}  // namespace seeme

@@ -1,0 +1,293 @@
+// Motion VAE: MldVae.encode / MldVae.decode (mld/models/architectures/mld_vae.py:128-256) over the
+// skip-connected DETR stacks of mld/models/operator/cross_attention.py (post-norm, 1 head, d=256,
+// ff=128, GELU(erf), learned PE added once).
+//
+// Internal layout is sample-major [B, S, 256] (the reference is [S, B, 256]; per-token math is
+// layout independent).  Algebra used: the decoder's cross-attention has ONE key
+// (memory = z[1,B,256]) so its softmax is identically 1 and its output is
+// out_proj(v_proj(z_b)) for every frame of sample b -- a per-sample vector computed up-front for
+// all five layers; the q/k projections of that attention never influence the result.
+#include "common.cuh"
+#include "rowops.cuh"
+
+namespace seeme {
+
+// Single-head attention over <= 64 tokens per sample.  One CTA per sample, K and V of the sample
+// staged in shared memory (2 x S x 1 KB), one warp per query row, fp32 softmax.
+// qkv [B*S, 768] = (q * 1/16 | k | v);  key j is valid iff j < n_prefix + lengths[b].
+__global__ void __launch_bounds__(256) mha1_kernel(const float* __restrict__ qkv, const int* __restrict__ lengths,
+                                                   int n_prefix, int S, float* __restrict__ out) {
+  extern __shared__ __align__(16) float sm[];
+  float* Ks = sm;
+  float* Vs = sm + (size_t)S * 256;
+  const int b = blockIdx.x;
+  const float* base = qkv + (size_t)b * S * 768;
+  for (int i = threadIdx.x; i < S * 64; i += blockDim.x) {
+    int row = i >> 6, c4 = i & 63;
+    reinterpret_cast<float4*>(Ks)[row * 64 + c4] = reinterpret_cast<const float4*>(base + (size_t)row * 768 + 256)[c4];
+    reinterpret_cast<float4*>(Vs)[row * 64 + c4] = reinterpret_cast<const float4*>(base + (size_t)row * 768 + 512)[c4];
+  }
+  __syncthreads();
+  int nvalid = n_prefix + lengths[b];
+  nvalid = nvalid < S ? nvalid : S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int qi = warp; qi < S; qi += (blockDim.x >> 5)) {
+    const Row8 q = row_load(base + (size_t)qi * 768, lane);
+    // lane j holds the score of key j and key j+32
+    float s0 = -INFINITY, s1 = -INFINITY;
+    for (int j = 0; j < nvalid; ++j) {
+      const Row8 k = row_load(Ks + (size_t)j * 256, lane);
+      const float d = row_dot(q, k);
+      if (j < 32) { if (lane == j) s0 = d; } else { if (lane == j - 32) s1 = d; }
+    }
+    const float m = warp_max(fmaxf(s0, s1));
+    const float e0 = (s0 == -INFINITY) ? 0.f : expf(s0 - m);
+    const float e1 = (s1 == -INFINITY) ? 0.f : expf(s1 - m);
+    const float inv = 1.0f / warp_sum(e0 + e1);
+    Row8 acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+    for (int j = 0; j < nvalid; ++j) {
+      const float p = __shfl_sync(0xffffffffu, j < 32 ? e0 : e1, j & 31) * inv;
+      const Row8 v = row_load(Vs + (size_t)j * 256, lane);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(p, v.v[i], acc.v[i]);
+    }
+    row_store(out + ((size_t)b * S + qi) * 256, lane, acc);
+  }
+}
+
+// xseq[b, s] = (s < 2 ? global_motion_token[s] : emb[b, s-2]) + pe[s]     (mld_vae.py:147-164)
+__global__ void vae_enc_assemble_kernel(const float* __restrict__ emb, const float* __restrict__ token,
+                                        const float* __restrict__ pe, float* __restrict__ x, int B, int T) {
+  const int S = T + 2;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * S) return;
+  const int b = row / S, s = row % S;
+  Row8 v = (s < 2) ? row_load(token + (size_t)s * 256, lane) : row_load(emb + ((size_t)b * T + (s - 2)) * 256, lane);
+  const Row8 p = row_load(pe + (size_t)s * 256, lane);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v.v[i] += p.v[i];
+  row_store(x + (size_t)row * 256, lane, v);
+}
+
+// queries[b, t] = 0 + pe[t]                                                (mld_vae.py:198,230)
+__global__ void vae_dec_queries_kernel(const float* __restrict__ pe, float* __restrict__ x, int B, int T) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * T) return;
+  row_store(x + (size_t)row * 256, lane, row_load(pe + (size_t)(row % T) * 256, lane));
+}
+
+// final encoder LayerNorm on tokens 0/1 of each sample, then mu/logvar -> std = exp(logvar)^0.5,
+// z = mu + std * eps                                                        (mld_vae.py:181-192)
+__global__ void vae_sample_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ bta,
+                                  const float* __restrict__ eps, float* __restrict__ z, float* __restrict__ mu_out,
+                                  float* __restrict__ std_out, int B, int S) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const Row8 mu = row_layernorm(row_load(x + ((size_t)b * S + 0) * 256, lane), g, bta, lane);
+  const Row8 lv = row_layernorm(row_load(x + ((size_t)b * S + 1) * 256, lane), g, bta, lane);
+  const Row8 e = row_load(eps + (size_t)b * 256, lane);
+  Row8 sd, zz;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sd.v[i] = sqrtf(expf(lv.v[i]));
+    zz.v[i] = mu.v[i] + sd.v[i] * e.v[i];
+  }
+  row_store(z + (size_t)b * 256, lane, zz);
+  if (mu_out) row_store(mu_out + (size_t)b * 256, lane, mu);
+  if (std_out) row_store(std_out + (size_t)b * 256, lane, sd);
+}
+
+}  // namespace seeme
+
+using namespace seeme;
+
+namespace {
+enum { V_TOKEN = 0, V_PE_ENC = 1, V_PE_DEC = 2, V_SKEL_W = 3, V_SKEL_B = 4, V_FINAL_W = 5, V_FINAL_B = 6,
+       V_ENC = 7, V_ENC_BLK = 13, V_DEC = 73, V_DEC_BLK = 79 };
+// per-stack header: norm.w, norm.b, lb0.w, lb0.b, lb1.w, lb1.b
+// encoder block (12): in_w in_b out_w out_b l1w l1b l2w l2b n1w n1b n2w n2b
+// decoder block (18): sa(in_w in_b out_w out_b) ca(in_w in_b out_w out_b) l1w l1b l2w l2b n1 n2 n3 (w,b)
+}  // namespace
+
+struct seeme_vae {
+  int device = 0, nfeats = 0, max_batch = 0, max_frames = 0;
+  Arena arena;
+  float* w[SEEME_VAE_NUM_TENSORS];
+  float *emb, *x, *L[5], *qkv, *att, *t0, *x1, *x2, *ff, *ca[5], *vtmp;
+};
+
+static size_t vae_tensor_elems(int i, int nfeats) {
+  if (i == V_TOKEN) return 2 * 256;
+  if (i == V_PE_ENC || i == V_PE_DEC) return 500 * 256;
+  if (i == V_SKEL_W) return (size_t)256 * nfeats;
+  if (i == V_SKEL_B) return 256;
+  if (i == V_FINAL_W) return (size_t)nfeats * 256;
+  if (i == V_FINAL_B) return nfeats;
+  auto header = [](int k) -> size_t { return k < 2 ? 256 : (k % 2 == 0 ? 256 * 512 : 256); };
+  if (i < V_ENC_BLK) return header(i - V_ENC);
+  if (i < V_DEC) {
+    static const size_t e[12] = {768 * 256, 768, 256 * 256, 256, 128 * 256, 128, 256 * 128, 256, 256, 256, 256, 256};
+    return e[(i - V_ENC_BLK) % 12];
+  }
+  if (i < V_DEC_BLK) return header(i - V_DEC);
+  static const size_t d[18] = {768 * 256, 768, 256 * 256, 256, 768 * 256, 768, 256 * 256, 256,
+                               128 * 256, 128, 256 * 128, 256, 256, 256, 256, 256, 256, 256};
+  return d[(i - V_DEC_BLK) % 18];
+}
+
+extern "C" int seeme_vae_create(seeme_vae_t* out, const float* const* w, int n_w, int nfeats, int max_batch,
+                                int max_frames) {
+  SEEME_REQUIRE(out && w, SEEME_EINVAL, "seeme_vae_create: null argument");
+  SEEME_REQUIRE(n_w == SEEME_VAE_NUM_TENSORS, SEEME_EINVAL, "seeme_vae_create: expected %d tensors, got %d",
+                SEEME_VAE_NUM_TENSORS, n_w);
+  SEEME_REQUIRE(nfeats > 0 && nfeats <= 512 && max_batch > 0 && max_frames > 0 && max_frames + 2 <= 64, SEEME_EINVAL,
+                "seeme_vae_create: unsupported sizes (nfeats=%d, max_batch=%d, max_frames=%d; frames+2 must be <= 64)",
+                nfeats, max_batch, max_frames);
+  seeme_vae* h = new seeme_vae();
+  SEEME_CUDA(cudaGetDevice(&h->device));
+  h->nfeats = nfeats; h->max_batch = max_batch; h->max_frames = max_frames;
+  size_t wbytes = 0;
+  for (int i = 0; i < n_w; ++i) wbytes += pad256(vae_tensor_elems(i, nfeats) * 4);
+  const size_t rows = (size_t)max_batch * (max_frames + 2);
+  size_t ws = pad256(rows * 256 * 4) * (1 + 1 + 5 + 1 + 1 + 1 + 1) + pad256(rows * 768 * 4) + pad256(rows * 128 * 4) +
+              6 * pad256((size_t)max_batch * 256 * 4);
+  int rc = h->arena.init(wbytes + ws + 4096);
+  if (rc) { delete h; return rc; }
+  for (int i = 0; i < n_w; ++i) {
+    size_t n = vae_tensor_elems(i, nfeats);
+    h->w[i] = h->arena.take<float>(n);
+    if (!h->w[i] || !w[i]) { set_error("seeme_vae_create: tensor %d null or arena exhausted", i); h->arena.release(); delete h; return SEEME_EINVAL; }
+    cudaError_t e = cudaMemcpy(h->w[i], w[i], n * 4, cudaMemcpyDeviceToDevice);
+    if (e != cudaSuccess) { set_error("seeme_vae_create: copy of tensor %d failed: %s", i, cudaGetErrorString(e)); h->arena.release(); delete h; return SEEME_ECUDA; }
+  }
+  // fold the 1/sqrt(256) attention scale into the q rows of every self-attention in_proj
+  auto scale_q = [&](int wi, int bi) {
+    scale_kernel_launch(h->w[wi], 256 * 256, 0.0625f);
+    scale_kernel_launch(h->w[bi], 256, 0.0625f);
+  };
+  for (int l = 0; l < 5; ++l) {
+    scale_q(V_ENC_BLK + 12 * l, V_ENC_BLK + 12 * l + 1);
+    scale_q(V_DEC_BLK + 18 * l, V_DEC_BLK + 18 * l + 1);
+  }
+  SEEME_CUDA(cudaDeviceSynchronize());
+  h->emb = h->arena.take<float>(rows * 256);
+  h->x = h->arena.take<float>(rows * 256);
+  for (int l = 0; l < 5; ++l) h->L[l] = h->arena.take<float>(rows * 256);
+  h->att = h->arena.take<float>(rows * 256);
+  h->t0 = h->arena.take<float>(rows * 256);
+  h->x1 = h->arena.take<float>(rows * 256);
+  h->x2 = h->arena.take<float>(rows * 256);
+  h->qkv = h->arena.take<float>(rows * 768);
+  h->ff = h->arena.take<float>(rows * 128);
+  for (int l = 0; l < 5; ++l) h->ca[l] = h->arena.take<float>((size_t)max_batch * 256);
+  h->vtmp = h->arena.take<float>((size_t)max_batch * 256);
+  if (!h->vtmp) { set_error("seeme_vae_create: arena exhausted (workspace)"); h->arena.release(); delete h; return SEEME_ENOMEM; }
+  SEEME_CUDA(cudaFuncSetAttribute(mha1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 256 * 4));
+  *out = h;
+  return SEEME_OK;
+}
+
+// self-attention + (optional single-key cross-attention vector) + FFN, post-norm.
+// wb points at the block's first tensor; dec selects the 18-tensor decoder layout.
+static int vae_layer(seeme_vae* h, float* const* wb, bool dec, const float* xin, float* xout, const int* lengths,
+                     int n_prefix, int B, int S, const float* ca_vec, cudaStream_t s) {
+  const int rows = B * S;
+  SEEME_TRY(gemm_f32(gemm_params(xin, 256, wb[0], 256, wb[1], h->qkv, 768, rows, 768, 256), s));
+  mha1_kernel<<<B, 256, (size_t)2 * S * 256 * 4, s>>>(h->qkv, lengths, n_prefix, S, h->att);
+  SEEME_LAUNCH_CHECK();
+  GemmP go = gemm_params(h->att, 256, wb[2], 256, wb[3], h->t0, 256, rows, 256, 256);
+  go.R = xin; go.ldr = 256;
+  SEEME_TRY(gemm_f32(go, s));
+  float* const* f = wb + (dec ? 8 : 4);     // l1w l1b l2w l2b n1w n1b n2w n2b (n3w n3b)
+  SEEME_TRY(layernorm256(h->t0, nullptr, 0, f[4], f[5], h->x1, rows, s));
+  const float* xa = h->x1;
+  if (dec) {   // tgt = norm2(tgt + ca[b])
+    SEEME_TRY(layernorm256(h->x1, ca_vec, S, f[6], f[7], h->x2, rows, s));
+    xa = h->x2;
+  }
+  GemmP g1 = gemm_params(xa, 256, f[0], 256, f[1], h->ff, 128, rows, 128, 256);
+  g1.act = ACT_GELU;
+  SEEME_TRY(gemm_f32(g1, s));
+  GemmP g2 = gemm_params(h->ff, 128, f[2], 128, f[3], h->t0, 256, rows, 256, 128);
+  g2.R = xa; g2.ldr = 256;
+  SEEME_TRY(gemm_f32(g2, s));
+  const float* gn = dec ? f[8] : f[6];
+  const float* bn = dec ? f[9] : f[7];
+  SEEME_TRY(layernorm256(h->t0, nullptr, 0, gn, bn, xout, rows, s));
+  return SEEME_OK;
+}
+
+// the 2-1-2 skip topology of SkipTransformerEncoder/Decoder (cross_attention.py:42-65, 108-147)
+static int vae_stack(seeme_vae* h, int hdr, int blk, int blk_stride, bool dec, const float* x0, const int* lengths,
+                     int n_prefix, int B, int S, cudaStream_t s) {
+  const int rows = B * S;
+  const float* x = x0;
+  for (int l = 0; l < 5; ++l) {
+    if (l >= 3) {   // x = Linear(cat[x, skip]);  skip = L[1] for l == 3, L[0] for l == 4
+      const int i = l - 3;
+      const float* skip = h->L[l == 3 ? 1 : 0];
+      const float* W = h->w[hdr + 2 + 2 * i];
+      SEEME_TRY(gemm_f32(gemm_params(x, 256, W, 512, h->w[hdr + 3 + 2 * i], h->x, 256, rows, 256, 256), s));
+      GemmP ga = gemm_params(skip, 256, W + 256, 512, nullptr, h->x, 256, rows, 256, 256);
+      ga.accumulate = 1;
+      SEEME_TRY(gemm_f32(ga, s));
+      x = h->x;
+    }
+    SEEME_TRY(vae_layer(h, h->w + blk + blk_stride * l, dec, x, h->L[l], lengths, n_prefix, B, S, dec ? h->ca[l] : nullptr, s));
+    x = h->L[l];
+  }
+  return SEEME_OK;
+}
+
+extern "C" int seeme_vae_encode(seeme_vae_t h, const float* features, const int32_t* lengths, const float* eps, int B,
+                                int T, float* z, float* mu, float* std, void* stream) {
+  SEEME_REQUIRE(h && features && lengths && eps && z, SEEME_EINVAL, "seeme_vae_encode: null argument");
+  SEEME_REQUIRE(B > 0 && T > 0, SEEME_EINVAL, "seeme_vae_encode: empty input (B=%d, T=%d)", B, T);
+  SEEME_REQUIRE(B <= h->max_batch && T <= h->max_frames, SEEME_ECAP, "seeme_vae_encode: B=%d T=%d exceeds capacity (%d, %d)",
+                B, T, h->max_batch, h->max_frames);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int S = T + 2, rows = B * S;
+  SEEME_TRY(gemm_f32(gemm_params(features, h->nfeats, h->w[V_SKEL_W], h->nfeats, h->w[V_SKEL_B], h->emb, 256, B * T, 256,
+                                 h->nfeats), s));
+  // x2 is not a scratch buffer of the encoder layers, so it can hold the stack input
+  vae_enc_assemble_kernel<<<(rows + 7) / 8, 256, 0, s>>>(h->emb, h->w[V_TOKEN], h->w[V_PE_ENC], h->x2, B, T);
+  SEEME_LAUNCH_CHECK();
+  SEEME_TRY(vae_stack(h, V_ENC, V_ENC_BLK, 12, false, h->x2, lengths, 2, B, S, s));
+  vae_sample_kernel<<<(B + 7) / 8, 256, 0, s>>>(h->L[4], h->w[V_ENC], h->w[V_ENC + 1], eps, z, mu, std, B, S);
+  SEEME_LAUNCH_CHECK();
+  return SEEME_OK;
+}
+
+extern "C" int seeme_vae_decode(seeme_vae_t h, const float* z, const int32_t* lengths, int B, int T, float* feats,
+                                void* stream) {
+  SEEME_REQUIRE(h && z && lengths && feats, SEEME_EINVAL, "seeme_vae_decode: null argument");
+  SEEME_REQUIRE(B > 0 && T > 0, SEEME_EINVAL, "seeme_vae_decode: empty input (B=%d, T=%d)", B, T);
+  SEEME_REQUIRE(B <= h->max_batch && T <= h->max_frames, SEEME_ECAP, "seeme_vae_decode: B=%d T=%d exceeds capacity (%d, %d)",
+                B, T, h->max_batch, h->max_frames);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int rows = B * T;
+  // single-key cross-attention vectors for all five layers: ca_l[b] = out_proj(v_proj(z_b))
+  for (int l = 0; l < 5; ++l) {
+    float* const* wb = h->w + V_DEC_BLK + 18 * l;
+    SEEME_TRY(gemm_f32(gemm_params(z, 256, wb[4] + 512 * 256, 256, wb[5] + 512, h->vtmp, 256, B, 256, 256), s));
+    SEEME_TRY(gemm_f32(gemm_params(h->vtmp, 256, wb[6], 256, wb[7], h->ca[l], 256, B, 256, 256), s));
+  }
+  vae_dec_queries_kernel<<<(rows + 7) / 8, 256, 0, s>>>(h->w[V_PE_DEC], h->emb, B, T);
+  SEEME_LAUNCH_CHECK();
+  SEEME_TRY(vae_stack(h, V_DEC, V_DEC_BLK, 18, true, h->emb, lengths, 0, B, T, s));
+  SEEME_TRY(layernorm256(h->L[4], nullptr, 0, h->w[V_DEC], h->w[V_DEC + 1], h->t0, rows, s));
+  SEEME_TRY(gemm_f32(gemm_params(h->t0, 256, h->w[V_FINAL_W], 256, h->w[V_FINAL_B], feats, h->nfeats, rows, h->nfeats, 256), s));
+  return SEEME_OK;
+}
+
+extern "C" int seeme_vae_destroy(seeme_vae_t h) {
+  if (!h) return SEEME_OK;
+  h->arena.release();
+  delete h;
+  return SEEME_OK;
+}

@@ -1,0 +1,125 @@
+"""Batched, device-side EgoMetric with the same state sums as the reference's ``ComputeMetrics``
+(``mld/models/metrics/compute.py:349-580`` update, ``:184-232`` compute).
+
+The reference loops over sequences and frames in Python/numpy (6.6 ms per sequence); here every
+sequence of the batch is reduced at once with masked tensor ops on the GPU and one small D2H copy
+per ``update``.  Semantics kept: start alignment on joint 15 of frame 0, per-frame root alignment,
+MPJPE / root error in mm, acceleration error (x1000), head-orientation error
+``mean_t ||I - R_gt R_pred^-1||_F`` with ``quaternion_matrix`` normalisation, and the test-split
+gating ``head_err < 0.9 and root_err < 300 and accl > 0`` (``:545-562``).  States are plain sums
+(``dist_reduce_fx="sum"`` in the reference) so ranks combine with one all-reduce
+(``seeme_b200.dist.reduce_metric_state``).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+STATE_KEYS = ["count", "n_batch", "count_seq", "count_seq_root", "count_seq_accl", "count_seq_head_orientation",
+              "count_seq_int", "MPJPE", "mpjpe_interactee", "ROOT_ERROR", "ACCL", "HEAD_ORIENTATION_ERROR"]
+
+
+def quaternion_rotmat(q: torch.Tensor) -> torch.Tensor:
+    """``quaternion_matrix`` (compute.py:34-56) batched: [N,4] (w,x,y,z) float64 -> [N,3,3]; identity when |q|^2 < 1e-4."""
+    n = (q * q).sum(-1, keepdim=True)
+    small = n < 1e-4
+    qs = q * torch.sqrt(2.0 / torch.where(small, torch.ones_like(n), n))
+    o = qs[:, :, None] * qs[:, None, :]
+    R = torch.stack([
+        1.0 - o[:, 2, 2] - o[:, 3, 3], o[:, 1, 2] - o[:, 3, 0], o[:, 1, 3] + o[:, 2, 0],
+        o[:, 1, 2] + o[:, 3, 0], 1.0 - o[:, 1, 1] - o[:, 3, 3], o[:, 2, 3] - o[:, 1, 0],
+        o[:, 1, 3] - o[:, 2, 0], o[:, 2, 3] + o[:, 1, 0], 1.0 - o[:, 1, 1] - o[:, 2, 2]], dim=-1).view(-1, 3, 3)
+    eye = torch.eye(3, dtype=q.dtype, device=q.device).expand_as(R)
+    return torch.where(small[:, :, None], eye, R)
+
+
+def per_sequence_errors(jts_text, jts_ref, ori_quat_text, ori_quat_ref, lengths: List[int]) -> Dict[str, torch.Tensor]:
+    """[B] vectors: mpjpe (mm), root_err (mm), accl (x1000), head_err."""
+    B, T, NJ, _ = jts_text.shape
+    dev = jts_text.device
+    ln = torch.as_tensor(lengths, device=dev)
+    mask = (torch.arange(T, device=dev)[None, :] < ln[:, None])               # [B,T]
+    fm = mask.double()
+    jr = jts_ref.double() - jts_ref[:, 0:1, 15:16, :].double()                 # align_start (compute.py:367-372)
+    jp = jts_text.double() - jts_text[:, 0:1, 15:16, :].double()
+    pelvis_gt, pelvis_pred = jr[:, :, 0], jp[:, :, 0]
+    root_err = ((pelvis_gt - pelvis_pred).norm(dim=-1) * fm).sum(1) / ln * 1000.0
+    jr = jr - jr[:, :, [0]]                                                    # align_root
+    jp = jp - jp[:, :, [0]]
+    mpjpe = ((jp - jr).norm(dim=-1).mean(-1) * fm).sum(1) / ln * 1000.0
+    # acceleration error over the valid prefix (compute.py:254-279): frames 0..len-3
+    acc_gt = jr[:, :-2] - 2 * jr[:, 1:-1] + jr[:, 2:]
+    acc_pr = jp[:, :-2] - 2 * jp[:, 1:-1] + jp[:, 2:]
+    am = (torch.arange(T - 2, device=dev)[None, :] < (ln[:, None] - 2)).double()
+    accl = ((acc_pr - acc_gt).norm(dim=-1).mean(-1) * am).sum(1) / (ln - 2).clamp(min=1) * 1000.0
+    accl = torch.where(ln > 2, accl, torch.full_like(accl, float("nan")))     # np.mean of an empty array
+    # head orientation (compute.py:335-346, 527)
+    Rg = quaternion_rotmat(ori_quat_ref.double()).view(B, T, 3, 3)
+    Rp = quaternion_rotmat(ori_quat_text.double()).view(B, T, 3, 3)
+    err = torch.eye(3, dtype=torch.float64, device=dev) - Rg @ torch.linalg.inv(Rp)
+    head = (err.flatten(-2).norm(dim=-1) * fm).sum(1) / ln
+    return {"mpjpe": mpjpe, "root_err": root_err, "accl": accl, "head_err": head}
+
+
+class EgoMetric:
+    """Same call surface as the reference's ``ComputeMetrics``: ``update(split, ...)``, ``compute(sanity_flag)``, ``reset()``."""
+
+    def __init__(self, njoints: int = 23, jointstype: str = "humanml3d", force_in_meter: bool = True,
+                 dist_sync_on_step: bool = True, **kwargs):
+        self.name = "APE and AVE"
+        self.dist_sync_on_step = dist_sync_on_step
+        self.reset()
+        self.last_per_sequence: Optional[Dict[str, torch.Tensor]] = None
+
+    def reset(self):
+        self.state = {k: 0.0 for k in STATE_KEYS}
+
+    def state_vector(self) -> torch.Tensor:
+        return torch.tensor([self.state[k] for k in STATE_KEYS], dtype=torch.float64)
+
+    def load_state_vector(self, v: torch.Tensor):
+        for k, x in zip(STATE_KEYS, v.tolist()):
+            self.state[k] = x
+
+    @torch.no_grad()
+    def update(self, split, jts_text, jts_ref, ori_quat_text, ori_quat_ref, root_interactee, joints_interactee,
+               orientation_quat_int, joints_interactee_gt, lengths: Optional[List[int]] = None, list_names=None):
+        if lengths is None:
+            lengths = [jts_text.shape[1]] * jts_text.shape[0]
+        s = self.state
+        s["count"] += float(sum(lengths))
+        s["n_batch"] += 1
+        e = per_sequence_errors(jts_text, jts_ref, ori_quat_text, ori_quat_ref, lengths)
+        self.last_per_sequence = e
+        if joints_interactee_gt is not None:
+            ji = joints_interactee.double() - joints_interactee[:, :, [0]].double()
+            jg = joints_interactee_gt.double() - joints_interactee_gt[:, :, [0]].double()
+            ln = torch.as_tensor(lengths, device=ji.device)
+            fm = (torch.arange(ji.shape[1], device=ji.device)[None, :] < ln[:, None]).double()
+            mi = ((ji - jg).norm(dim=-1).mean(-1) * fm).sum(1) / ln * 1000.0
+            s["mpjpe_interactee"] += float(mi.sum())
+            s["count_seq_int"] += len(lengths)
+        ok = e["accl"] > 0
+        if split == "test":
+            ok = ok & (e["head_err"] < 0.9) & (e["root_err"] < 300)
+        packed = torch.stack([ok.double(), torch.where(ok, e["mpjpe"], 0.0), torch.where(ok, e["root_err"], 0.0),
+                              torch.where(ok, e["accl"], 0.0), torch.where(ok, e["head_err"], 0.0)]).sum(1).cpu()
+        n, mp, rt, ac, hd = packed.tolist()
+        s["MPJPE"] += mp
+        s["count_seq"] += n
+        s["ROOT_ERROR"] += rt
+        s["count_seq_root"] += n
+        if split == "test":                                                   # compute.py:553-561
+            s["HEAD_ORIENTATION_ERROR"] += hd
+            s["count_seq_head_orientation"] += n
+            s["ACCL"] += ac
+            s["count_seq_accl"] += n
+
+    def compute(self, sanity_flag=False) -> Dict[str, float]:
+        s = self.state
+        div = lambda a, b: (a / b) if b else float("nan")
+        return {"MPJPE": div(s["MPJPE"], s["count_seq"]), "ROOT_ERROR": div(s["ROOT_ERROR"], s["count_seq_root"]),
+                "ACCL": div(s["ACCL"], s["count_seq_accl"]),
+                "HEAD_ORIENTATION_ERROR": div(s["HEAD_ORIENTATION_ERROR"], s["count_seq_head_orientation"]),
+                "mpjpe_interactee": div(s["mpjpe_interactee"], s["count_seq_int"])}

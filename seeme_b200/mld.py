@@ -1,0 +1,301 @@
+"""``MLD`` -- the reference's LightningModule surface (``mld/models/modeltype/mld.py``,
+``mld/models/modeltype/base.py``) for the inference hot path, running on sm_100a kernels.
+
+Kept from the reference: constructor ``MLD(cfg, datamodule, **kw)``, attribute names, ``state_dict``
+prefixes (``denoiser.*``, ``vae.*``, ``proscene.scene_enc.*``, ``output_scene.1.*``, ``smpl_model.*``),
+``forward(batch)``, ``test_step`` / ``allsplit_step`` / ``ego_eval(batch) -> rs_set`` and
+``_diffusion_reverse(encoder_hidden_states, lengths)``, including the quirks that are part of the
+contract: CFG half ordering (scene: cond first, interactee: uncond first),
+GT betas for the predicted mesh, ``TEST.GLOBAL_ORIENT_PRED`` switch, GIMO's 63-d body pose with two
+zeroed hand joints, un-masked padded frames, float64 ``m_ref``/``m_rst``.  Deviations: ``save_for_edo``
+is off (App. D1), ``rs_set`` always carries ``list_names`` (App. D2), training paths are not built.
+
+It is a plain ``nn.Module`` (pytorch_lightning is not required); when Lightning is installed it can be
+wrapped or used as the ``LightningModule`` base by passing ``base=`` to ``make_lightning_class``.
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .config import instantiate_from_config
+from .modules import MldDenoiser, MldVae, ProHMRScene, SMPL, time_sinusoid
+
+
+class MLD(nn.Module):
+    def __init__(self, cfg, datamodule, smpl_buffers: Optional[Dict[str, torch.Tensor]] = None, **kwargs):
+        super().__init__()
+        self.cfg = cfg
+        self.times: List[float] = []                                     # base.py:26
+        self.stage = cfg.TRAIN.STAGE
+        self.condition = list(cfg.model.condition)
+        self.is_vae = cfg.model.vae
+        self.predict_epsilon = cfg.TRAIN.ABLATION.get("PREDICT_EPSILON", True)
+        self.name_dataset = cfg.DATASET_NAME
+        self.njoints = cfg.model.njoints
+        self.latent_dim = list(cfg.model.latent_dim)
+        self.guidance_scale = float(cfg.model.guidance_scale)
+        self.guidance_uncodp = cfg.model.guidance_uncondp
+        self.datamodule = datamodule
+        self.estimate = cfg.ESTIMATE
+        self.pred_global_orient = cfg.TEST.GLOBAL_ORIENT_PRED
+        self.pred_betas = cfg.TEST.BETAS_PRED
+        self.global_orient_egoego = cfg.TEST.GLOBAL_ORIENT_EGOEGO
+        self.transl_egoego = cfg.TEST.TRANSL_EGOEGO
+        self.pose_estimation_task = cfg.TEST.POSE_ESTIMATION_TASK
+        self.see_future = cfg.TEST.SEE_FUTURE
+        self.predict_transl = cfg.TRAIN.ABLATION.PREDICT_TRANSL
+        if self.name_dataset == "egobody":
+            self.nfeats = 75 if self.predict_transl else 72              # mld.py:119-123
+        elif self.name_dataset == "gimo":
+            self.nfeats = 69 if self.predict_transl else 66
+        else:
+            raise NotImplementedError(f"dataset {self.name_dataset!r}: only egobody and gimo are on the SEE-ME path")
+        self.data_type = cfg.DATA_TYPE
+        self.save_for_edo = False                                        # App. D1
+        unsupported = []
+        if self.data_type != "angle":
+            unsupported.append("DATA_TYPE must be 'angle'")
+        if self.stage != "diffusion":
+            unsupported.append("only TRAIN.STAGE=diffusion (stage-2 inference) is built")
+        if not self.predict_transl:
+            unsupported.append("PREDICT_TRANSL must be True")
+        if self.pred_betas or self.global_orient_egoego or self.transl_egoego or self.pose_estimation_task or self.see_future:
+            unsupported.append("BETAS_PRED / *_EGOEGO / POSE_ESTIMATION_TASK / SEE_FUTURE variants are not built")
+        if "image" in self.condition:
+            unsupported.append("image conditioning is a 'next' row (SURVEY 8f-4)")
+        if unsupported:
+            raise NotImplementedError("MLD (sm_100a): " + "; ".join(unsupported))
+
+        max_batch = int(kwargs.get("max_batch", max(int(cfg.TEST.BATCH_SIZE), 1)))
+        n_points = int(kwargs.get("max_points", 20000))
+        max_frames = int(cfg.get("MOTION_LENGTH", 60))
+        # body model: smplx.SMPL(model_path=cfg.model.smpl_path, ...) in the reference (mld.py:151-153)
+        self.smpl_model = SMPL(smpl_buffers if smpl_buffers is not None else cfg.model.smpl_path,
+                               batch_size=cfg.TRAIN.BATCH_SIZE, gender="neutral", max_frames=max_batch * max_frames)
+        try:
+            self.vae_type = cfg.model.vae_type
+        except AttributeError:
+            self.vae_type = cfg.model.motion_vae.target.split(".")[-1].lower().replace("vae", "")   # -> "mld"
+        if "scene" in self.condition:
+            self.proscene = ProHMRScene(cfg.get("PROSCENE"), max_batch=max_batch, max_points=n_points)
+            self.output_scene = nn.Sequential(nn.ReLU(), nn.Linear(512, 256))                        # mld.py:257-261
+        mv = cfg.model.motion_vae
+        mv_params = dict(mv.get("params", {}))
+        mv_params.setdefault("max_batch", max_batch)
+        mv_params.setdefault("max_frames", max_frames)
+        self.vae = instantiate_from_config({"target": mv["target"], "params": mv_params})
+        dn = cfg.model.denoiser
+        dn_params = dict(dn.get("params", {}))
+        dn_params.setdefault("max_rows", 2 * max_batch)
+        self.denoiser = instantiate_from_config({"target": dn["target"], "params": dn_params})
+        self.scheduler = instantiate_from_config(cfg.model.scheduler)
+        self.noise_scheduler = instantiate_from_config(cfg.model.noise_scheduler) if "noise_scheduler" in cfg.model else None
+        for p in self.parameters():
+            p.requires_grad = False
+        self.metrics_dict = list(cfg.METRIC.TYPE)
+        self.configure_metrics(kwargs.get("metrics"))
+        self.do_classifier_free_guidance = self.guidance_scale > 1.0       # mld.py:331
+        self.renorm = datamodule.renorm                                     # mld.py:333
+        # which bodies get the 6890-vertex skinning: "rst" (predicted, default), "all", or "none";
+        # the reference skins all three and discards the vertices (only joints reach rs_set)
+        self.compute_vertices = kwargs.get("compute_vertices", "rst")
+        self.last_vertices: Dict[str, torch.Tensor] = {}
+        self._uncond_scene = None
+        self.eval()
+
+    # ------------------------------------------------------------------------------------------
+    def configure_metrics(self, metrics=None):
+        """base.py:160-173.  ``metrics`` may carry ready metric objects ({"EgoMetric": obj}); otherwise the
+        in-repo batched EgoMetric is used (same state sums as mld/models/metrics/compute.py)."""
+        from .metrics import EgoMetric
+        for m in self.metrics_dict:
+            if metrics and m in metrics:
+                obj = metrics[m]
+            elif m == "EgoMetric":
+                obj = EgoMetric(njoints=self.njoints, dist_sync_on_step=self.cfg.METRIC.get("DIST_SYNC_ON_STEP", True))
+            else:
+                raise NotImplementedError(f"Do not support Metric Type {m}")
+            object.__setattr__(self, m, obj)     # metrics hold no persistent state
+
+    def _stats(self, device):
+        cache = self.__dict__.setdefault("_stats_cache", {})
+        if device not in cache:
+            mean, std = np.asarray(self.datamodule.mean), np.asarray(self.datamodule.std)
+            mean = mean[0] if mean.ndim == 2 else mean               # renorm reads row 0 (EgoBody.py:152-154)
+            std = std[0] if std.ndim == 2 else std
+            cache[device] = (torch.as_tensor(mean, dtype=torch.float64).to(device), torch.as_tensor(std, dtype=torch.float64).to(device))
+        return cache[device]
+
+    # ------------------------------------------------------------------------------------------
+    def _diffusion_reverse(self, encoder_hidden_states, lengths=None, latents=None):
+        """mld.py:432-511.  encoder_hidden_states [B',Nc,256] (B' = 2B under CFG) -> [1,B,256].
+        ``latents`` ([B,1,256]) injects the initial noise; when None it is drawn with ``torch.randn``
+        exactly where the reference draws it (:449-453)."""
+        bsz = encoder_hidden_states.shape[0]
+        if self.do_classifier_free_guidance:
+            bsz = bsz // 2
+        dev = encoder_hidden_states.device
+        if latents is None:
+            latents = torch.randn((bsz, self.latent_dim[0], self.latent_dim[-1]), device=dev, dtype=torch.float)
+        latents = latents * self.scheduler.init_noise_sigma
+        n_steps = self.cfg.model.scheduler.num_inference_timesteps
+        if self.scheduler.num_inference_steps != n_steps:
+            self.scheduler.set_timesteps(n_steps)
+            self.__dict__["_coef"] = None
+        ts = [int(t) for t in self.scheduler.timesteps]
+        if self.__dict__.get("_coef") is None:
+            self.__dict__["_coef"] = self.scheduler.step_coefficients()
+            self.__dict__["_sinus"] = time_sinusoid(self.scheduler.timesteps)
+        op = self.denoiser.op
+        key = (id(op), tuple(ts))
+        if self.__dict__.get("_table_key") != key:
+            op.set_time_table(ts, self.__dict__["_sinus"])
+            self.__dict__["_table_key"] = key
+        cond = encoder_hidden_states.permute(1, 0, 2).contiguous()         # [Nc,B',256] as the denoiser receives it
+        z = op.sample(latents.reshape(bsz, 256), cond, self.guidance_scale, ts, self.__dict__["_coef"])
+        return z.view(bsz, 1, 256).permute(1, 0, 2)
+
+    # ------------------------------------------------------------------------------------------
+    def _encode_scene(self, scene):
+        op = self.proscene.scene_enc.op(self.output_scene)
+        emb = op(scene.float())                                           # output_scene(encode_scene(.)) fused
+        if not self.do_classifier_free_guidance:
+            return emb[None]
+        # encode_scene(zeros) is input independent (every point identical -> the max-pool is that point,
+        # SURVEY App. H8): computed once on a tiny all-zero cloud and cached per packed-weights handle
+        if self._uncond_scene is None or self._uncond_scene[0] is not op:
+            self._uncond_scene = (op, op(torch.zeros(1, 8, 3, device=scene.device)))
+        unc = self._uncond_scene[1].expand(emb.shape[0], -1)
+        return torch.cat([emb, unc], dim=0)[None]                          # mld.py:1157-1158 (COND first)
+
+    def ego_eval(self, batch, noise: Optional[Dict[str, torch.Tensor]] = None):
+        """mld.py:1076-1905 (scene / scene+interactee / interactee-only branches).
+        ``noise`` = {"eps_int", "eps_unc" [1,B,256], "x_T" [B,1,256]} injects the three draws; missing
+        entries are drawn with torch.randn in the reference's order."""
+        noise = noise or {}
+        if "scene" in self.condition:
+            feats_ref, transl, beta, utils_, scene, length, dict_images = batch
+            scene_emb = self._encode_scene(scene)                          # [1,B or 2B,256]
+        else:
+            feats_ref, transl, beta, utils_, length = batch[:5]
+            scene_emb = None
+        feats_ref, transl, beta = feats_ref.float(), transl.float(), beta.float()
+        dev = feats_ref.device
+        lengths = length.long().reshape(-1).tolist()                       # mld.py:1264
+        len_dev = length.reshape(-1).to(torch.int32)
+        start = time.time()
+        f_ref_int = None
+        if "interactee" in self.condition:
+            f_ref_int = torch.cat([feats_ref[:, :, 1, :], transl[:, 1, :, :]], dim=-1).contiguous()
+            B, T, _ = f_ref_int.shape
+            text_emb, _ = self.vae.encode(f_ref_int, None, lengths, eps=noise.get("eps_int"))
+            if self.do_classifier_free_guidance:
+                unc, _ = self.vae.encode(torch.zeros_like(f_ref_int), None, lengths, eps=noise.get("eps_unc"))
+                text_emb = torch.cat([unc, text_emb], dim=1)               # mld.py:1290 (UNCOND first)
+            cond_emb = torch.cat([text_emb, scene_emb], dim=0) if scene_emb is not None else text_emb
+        else:
+            cond_emb = scene_emb
+        if cond_emb is None:
+            raise NotImplementedError("MLD (sm_100a): at least one of scene / interactee conditioning is required")
+        z = self._diffusion_reverse(cond_emb.permute(1, 0, 2), lengths, latents=noise.get("x_T"))
+        feats_rst = self.vae.decode(z, lengths)                            # [B,max(lengths),nfeats_net]
+        self.times.append(time.time() - start)                             # mld.py:1367-1368 (no device sync, like the reference)
+
+        min_len = min(feats_ref.shape[1], feats_rst.shape[1])
+        idx_ref = 0 if self.estimate == "wearer" else 1
+        mean, std = self._stats(dev)
+        Bsz = feats_ref.shape[0]
+        n_body = 69 if self.name_dataset == "egobody" else 63             # gimo: 21 joints + 2 zeroed hands (mld.py:1659-1665)
+        want_all = self.compute_vertices == "all"
+        # ground-truth body: cat(feats_ref, transl) -> renorm -> SMPL (mld.py:1451-1488 / 1656-1690)
+        f_ref = torch.cat([feats_ref[:, :min_len, idx_ref, :], transl[:, idx_ref, :min_len, :]], dim=-1).contiguous()
+        betas_w = beta[:, idx_ref, :min_len, :].contiguous()
+        m_ref, v_ref, joints_ref, quat_ref = self._body(f_ref, betas_w, mean, std, n_body, want_all)
+        # predicted body, GT betas (mld.py:1490-1534 / 1692-1741)
+        fr = feats_rst[:, :min_len]
+        if self.name_dataset == "gimo":
+            fr = torch.cat([fr[:, :, :66], fr[:, :, -3:]], dim=-1)          # mld.py:1692-1694
+        if not self.pred_global_orient:
+            fr = torch.cat([f_ref[:, :, :3], fr[:, :, 3:]], dim=-1)         # mld.py:1501-1505 (same stats on both sides)
+        m_rst, v_rst, joints_rst, quat_rst = self._body(fr.contiguous(), betas_w, mean, std, n_body,
+                                                        self.compute_vertices in ("rst", "all"))
+        rs_set = {
+            "m_ref": m_ref, "m_rst": m_rst, "joints_ref": joints_ref, "joints_rst": joints_rst,
+            "orientation_quat_rst": quat_rst, "orientation_quat_ref": quat_ref,
+            "joints_interactee_gt": None, "lengths": lengths, "list_names": {},
+        }
+        v_int = None
+        if f_ref_int is not None:
+            # the interactee is always a 75-d row with a 69-d body pose (mld.py:1542-1570 / 1744-1766)
+            _, v_int, joints_int, quat_int = self._body(f_ref_int[:, :min_len].contiguous(), beta[:, 1, :min_len, :].contiguous(),
+                                                        mean, std, 69, want_all, want_m=False)
+            rs_set["joints_interactee"] = joints_int
+            rs_set["root_interactee"] = joints_int[:, :, [0], :]
+            rs_set["orientation_quat_int"] = quat_int
+        else:
+            joints_int = torch.rand_like(joints_rst)                        # mld.py:1572-1574 (RNG side effect kept)
+            rs_set["joints_interactee"] = joints_int
+            rs_set["root_interactee"] = joints_int[:, :, [0], :]
+            rs_set["orientation_quat_int"] = torch.rand_like(quat_rst)
+        self.last_vertices = {k: (None if v is None else v.view(Bsz, min_len, 6890, 3))
+                              for k, v in (("rst", v_rst), ("ref", v_ref), ("int", v_int))}
+        self.last_latent = z
+        return rs_set
+
+    def _body(self, feats, betas, mean, std, n_body, want_v, want_m=True):
+        """renorm (float64) + slicing + SMPL forward + aa_to_quat for a [B,T,Dn] normalised feature tensor."""
+        B, T, Dn = feats.shape
+        if mean.numel() < Dn:
+            raise ValueError(f"dataset statistics have {mean.numel()} dims, features have {Dn}")
+        m, v, j, q = self.smpl_model.op.forward_feats(feats.reshape(B * T, Dn), mean[:Dn], std[:Dn], n_body,
+                                                      betas.reshape(B * T, 10), want_vertices=want_v, want_m=want_m)
+        return (None if m is None else m.view(B, T, Dn)), v, j.view(B, T, 24, 3), q
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, batch):
+        """The reference's ``forward`` is dead code calling a removed text encoder (App. D3); here tuple
+        batches are routed to ``ego_eval`` and the un-padded predicted joints are returned."""
+        rs_set = self.ego_eval(batch)
+        return [j[:n] for j, n in zip(rs_set["joints_rst"], rs_set["lengths"])]
+
+    def test_step(self, batch, batch_idx):                                  # base.py:44-53
+        return self.allsplit_step("test", batch, batch_idx)
+
+    def validation_step(self, batch, batch_idx):
+        return self.allsplit_step("val", batch, batch_idx)
+
+    def training_step(self, batch, batch_idx):
+        raise NotImplementedError("training is out of scope for the B200 inference path")
+
+    def allsplit_step(self, split: str, batch, batch_idx):                  # mld.py:2037-2130
+        if split not in ("val", "test"):
+            raise NotImplementedError("training is out of scope for the B200 inference path")
+        rs_set = self.ego_eval(batch)
+        for metric in self.metrics_dict:
+            if metric == "EgoMetric":
+                getattr(self, metric).update(
+                    split, rs_set["joints_rst"], rs_set["joints_ref"], rs_set["orientation_quat_rst"],
+                    rs_set["orientation_quat_ref"], rs_set["root_interactee"], rs_set["joints_interactee"],
+                    rs_set["orientation_quat_int"], rs_set["joints_interactee_gt"], rs_set["lengths"], rs_set["list_names"])
+            else:
+                raise TypeError(f"Not support this metric {metric}")
+        if split == "test":
+            return rs_set["joints_rst"]
+        return None
+
+    def allsplit_epoch_end(self, split: str, outputs=None):                 # base.py:58-99
+        dico = {}
+        for metric in self.metrics_dict:
+            metrics_dict = getattr(self, metric).compute(sanity_flag=False)
+            getattr(self, metric).reset()
+            dico.update({f"Metrics/{m}": float(v) for m, v in metrics_dict.items()})
+        return dico
+
+    def on_test_epoch_end(self, outputs=None):
+        self.cfg.TEST.REP_I = self.cfg.TEST.get("REP_I", 0) + 1
+        return self.allsplit_epoch_end("test", outputs)

@@ -288,7 +288,8 @@ def make_batch(B: int, seed: int = 1234, n_points: int = N_POINTS, T: int = T_MA
     (feats_ref[B,T,2,72], transl[B,2,T,3], beta[B,2,T,10], utils_[B,T,6], scene[B,N,3],
     length[B,1] int32, dict_images: T tuples of B strings)."""
     g = torch.Generator().manual_seed(seed)
-    feats_ref = torch.randn(B, T, 2, 72, generator=g)
+    # GIMO rows carry 21 body joints: 3 + 63 = 66 pose dims (mld.py:1656, Gimo.py numdims 69 with transl)
+    feats_ref = torch.randn(B, T, 2, 72 if dataset == "egobody" else 66, generator=g)
     transl = torch.randn(B, 2, T, 3, generator=g)
     beta = (0.5 * torch.randn(B, 2, 1, 10, generator=g)).expand(B, 2, T, 10).contiguous()
     utils_ = torch.rand(B, T, 6, generator=g)

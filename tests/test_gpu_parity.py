@@ -1,0 +1,304 @@
+"""GPU parity tests (pytest -m gpu, on a B200): the CUDA path, called through the C ABI, against
+(1) the committed golden vectors produced by the UNMODIFIED reference modules and (2) the CPU oracle
+(oracle/restate.py) on fresh seeded inputs, plus size-independent properties at full size.
+
+Tolerances (fp32 accumulation everywhere unless a test says otherwise): per-stage activations 1e-4
+absolute on O(1..10) values; joints / vertices <= 1e-3 m (north_star), expected ~1e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+T = lambda a: torch.from_numpy(np.asarray(a))
+DEV = "cuda:0"
+
+
+def cu(sd):
+    return {k: v.to(DEV) for k, v in sd.items()}
+
+
+@pytest.fixture(scope="module")
+def den_op(weights):
+    from seeme_b200 import ops
+    return ops.DenoiserOp(cu(weights["denoiser"]), max_rows=64)
+
+
+@pytest.fixture(scope="module")
+def vae_op(weights):
+    from seeme_b200 import ops
+    return ops.VaeOp(cu(weights["vae"]), 75, max_batch=16, max_frames=60)
+
+
+@pytest.fixture(scope="module")
+def pn_op(weights):
+    from seeme_b200 import ops
+    return ops.PointNetOp(cu(weights["pointnet"]), cu(weights["output_scene"]), max_batch=4, max_points=20000)
+
+
+@pytest.fixture(scope="module")
+def smpl_op(smpl_buffers):
+    from seeme_b200 import ops
+    return ops.SmplOp(cu(smpl_buffers), max_frames=4096)
+
+
+# ---- denoiser ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key,t,enc", [("den_out_t481_nc2", 481, "den_enc2"), ("den_out_t1_nc2", 1, "den_enc2"),
+                                       ("den_out_t981_nc1", 981, "den_enc1")])
+def test_denoiser_vs_reference_golden(den_op, golden_stages, key, t, enc):
+    from seeme_b200.modules import time_sinusoid
+    g = golden_stages
+    den_op.set_time_table([t], time_sinusoid(torch.tensor([t])))
+    out = den_op.forward(T(g["den_x"]).reshape(-1, 256).to(DEV), t, T(g[enc]).to(DEV)).cpu()
+    ref = T(g[key]).reshape(-1, 256)
+    assert (out - ref).abs().max() < 1e-4, float((out - ref).abs().max())
+
+
+def test_denoiser_internal_sinusoid_and_module_surface(weights, golden_stages):
+    """MldDenoiser.forward mirror (tuple output, [B,1,256]) and the internally computed time table"""
+    from seeme_b200.modules import MldDenoiser
+    g = golden_stages
+    abl = {"SKIP_CONNECT": True, "MD_TRANS": True, "DIFF_PE_TYPE": "mld", "VAE_TYPE": "actor"}
+    m = MldDenoiser(abl, nfeats=75, condition=["text", "scene", "interactee"], latent_dim=[1, 256], ff_size=128, num_layers=5,
+                    num_heads=1, text_encoded_dim=256, max_rows=16)
+    m.load_state_dict(weights["denoiser"])
+    m.to(DEV)
+    out = m(sample=T(g["den_x"]).to(DEV), timestep=torch.tensor(481), encoder_hidden_states=T(g["den_enc2"]).to(DEV), lengths=[60] * 6)
+    assert isinstance(out, tuple) and out[0].shape == (6, 1, 256)
+    assert (out[0].cpu() - T(g["den_out_t481_nc2"])).abs().max() < 1e-4
+    op = m.op
+    op.set_time_table([481], None)            # sinusoid computed inside the library
+    out2 = op.forward(T(g["den_x"]).reshape(-1, 256).to(DEV), 481, T(g["den_enc2"]).to(DEV)).cpu()
+    assert (out2 - T(g["den_out_t481_nc2"]).reshape(-1, 256)).abs().max() < 2e-4
+
+
+@pytest.mark.parametrize("gs,B", [(7.5, 5), (1.0, 3)])
+def test_sampler_vs_oracle(den_op, weights, gs, B):
+    """50-step DDIM (+CFG) chain vs the restated _diffusion_reverse, with the per-step trajectory"""
+    from oracle import restate as O
+    from seeme_b200.modules import time_sinusoid
+    from seeme_b200.scheduler import DDIMScheduler
+    g = torch.Generator().manual_seed(21)
+    R = 2 * B if gs > 1 else B
+    enc = torch.randn(R, 2, 256, generator=g)
+    xT = torch.randn(B, 1, 256, generator=g)
+    with torch.no_grad():
+        ref = O.diffusion_reverse(weights["denoiser"], enc, xT, gs, 50)[0]
+    s = DDIMScheduler(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                      clip_sample=False, set_alpha_to_one=False, steps_offset=1)
+    s.set_timesteps(50)
+    ts = s.timesteps.tolist()
+    den_op.set_time_table(ts, time_sinusoid(s.timesteps))
+    cond = enc.permute(1, 0, 2).contiguous().to(DEV)
+    z = den_op.sample(xT.reshape(B, 256).to(DEV), cond, gs, ts, s.step_coefficients()).cpu()
+    scale = float(ref.abs().max())
+    err = float((z - ref).abs().max())
+    assert err < 2e-4 * max(scale, 1.0), (err, scale)
+    z2 = den_op.sample(xT.reshape(B, 256).to(DEV), cond, gs, ts, s.step_coefficients()).cpu()   # graph replay is deterministic
+    assert torch.equal(z, z2)
+
+
+def test_scheduler_step_kernel_vs_oracle():
+    from oracle import restate as O
+    from seeme_b200.scheduler import DDIMScheduler
+    s = DDIMScheduler(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                      clip_sample=False, set_alpha_to_one=False, steps_offset=1)
+    s.set_timesteps(50)
+    o = O.DDIMRef()
+    o.set_timesteps(50)
+    x, e = torch.randn(7, 1, 256), torch.randn(7, 1, 256)
+    for t in (981, 501, 1):
+        out = s.step(e.to(DEV), torch.tensor(t), x.to(DEV), eta=0.0).prev_sample.cpu()
+        assert torch.allclose(out, o.step(e, t, x).prev_sample, atol=1e-6, rtol=1e-6)
+
+
+# ---- VAE -------------------------------------------------------------------------------------------------
+def test_vae_vs_reference_golden(vae_op, golden_stages):
+    g = golden_stages
+    lens = T(g["vae_lens"])
+    z, mu, std = vae_op.encode(T(g["vae_f"]).to(DEV), lens, T(g["vae_eps"]).to(DEV))
+    assert (z.cpu() - T(g["vae_z"])[0]).abs().max() < 1e-4
+    assert (mu.cpu() - T(g["vae_mu"])[0]).abs().max() < 1e-4
+    assert (std.cpu() - T(g["vae_std"])[0]).abs().max() < 1e-4
+    dec = vae_op.decode(T(g["vae_z"]).to(DEV), lens, 60).cpu()
+    assert dec.shape == (4, 60, 75)
+    assert (dec - T(g["vae_dec"])).abs().max() < 1e-4      # includes the un-masked padded frames (mld_vae.py:253)
+
+
+def test_vae_short_and_single_frame_vs_oracle(vae_op, weights):
+    """T = 1 (config_mld_interactee MOTION_LENGTH 1) and a short ragged batch"""
+    from oracle import restate as O
+    g = torch.Generator().manual_seed(5)
+    for T_, lens in ((1, [1, 1, 1]), (7, [7, 3, 1])):
+        f = torch.randn(len(lens), T_, 75, generator=g)
+        eps = torch.randn(1, len(lens), 256, generator=g)
+        with torch.no_grad():
+            zr, mur, stdr = O.vae_encode(weights["vae"], f, lens, eps)
+            dr = O.vae_decode(weights["vae"], zr, lens)
+        z, mu, std = vae_op.encode(f.to(DEV), torch.tensor(lens), eps.to(DEV))
+        assert (z.cpu() - zr[0]).abs().max() < 1e-4
+        d = vae_op.decode(zr.to(DEV), torch.tensor(lens), T_).cpu()
+        assert (d - dr).abs().max() < 1e-4
+
+
+# ---- scene encoder ----------------------------------------------------------------------------------------
+def test_pointnet_vs_reference_golden(pn_op, golden_stages, weights):
+    g = golden_stages
+    emb, feat = pn_op(T(g["pn_p"]).to(DEV), want_feat=True)
+    assert (feat.cpu() - T(g["pn_out"])).abs().max() < 1e-4
+    w = weights["output_scene"]
+    ref_emb = torch.nn.functional.linear(torch.relu(T(g["pn_out"])), w["1.weight"], w["1.bias"])
+    assert (emb.cpu() - ref_emb).abs().max() < 1e-4
+    _, fz = pn_op(torch.zeros(1, 16, 3, device=DEV), want_feat=True)
+    assert (fz.cpu() - T(g["pn_out_zero"])).abs().max() < 1e-5
+
+
+def test_pointnet_full_size_properties(pn_op, weights):
+    """N = 20000: permutation invariance (max-pool) and duplicate-point invariance; ragged N vs oracle"""
+    from oracle import restate as O
+    from seeme_b200 import synthetic as S
+    p = S.egobody_scene(2, 20000, torch.Generator().manual_seed(3)).to(DEV)
+    e0 = pn_op(p)
+    perm = torch.randperm(20000, generator=torch.Generator().manual_seed(4)).to(DEV)
+    e1 = pn_op(p[:, perm])
+    assert (e0 - e1).abs().max() < 1e-5
+    p2 = p.clone()
+    p2[:, 10000:] = p2[:, :10000]
+    e2 = pn_op(p2)
+    e3 = pn_op(p2[:, :10000].contiguous())
+    assert (e2 - e3).abs().max() < 1e-5
+    pr = S.egobody_scene(3, 777, torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        ref = O.scene_embed(weights["pointnet"], weights["output_scene"], pr)
+    assert (pn_op(pr.to(DEV)).cpu() - ref).abs().max() < 1e-4
+
+
+# ---- SMPL -------------------------------------------------------------------------------------------------------
+def test_smpl_vs_oracle(smpl_op, smpl_buffers):
+    from oracle import restate as O
+    g = torch.Generator().manual_seed(8)
+    F = 37          # ragged vs the 16-frame tile
+    betas = 0.5 * torch.randn(F, 10, generator=g)
+    pose = 0.3 * torch.randn(F, 69, generator=g)
+    go = 0.5 * torch.randn(F, 3, generator=g)
+    tr = torch.randn(F, 3, generator=g)
+    vr, jr = O.smpl_forward(smpl_buffers, betas, pose, go, tr)
+    v, j, q = smpl_op.forward(betas.to(DEV), pose.to(DEV), go.to(DEV), tr.to(DEV))
+    assert (j.cpu() - jr).abs().max() < 1e-5, float((j.cpu() - jr).abs().max())
+    assert (v.cpu() - vr).abs().max() < 1e-5, float((v.cpu() - vr).abs().max())
+    assert (q.cpu() - O.aa_to_quat(go)).abs().max() < 1e-6
+    # no translation / zero pose edge cases
+    v0, j0, _ = smpl_op.forward(betas.to(DEV), torch.zeros(F, 69, device=DEV), torch.zeros(F, 3, device=DEV), None)
+    vr0, jr0 = O.smpl_forward(smpl_buffers, betas, torch.zeros(F, 69), torch.zeros(F, 3), None)
+    assert (v0.cpu() - vr0).abs().max() < 1e-5 and (j0.cpu() - jr0).abs().max() < 1e-5
+
+
+def test_smpl_dense_weights_fallback():
+    """a body model whose skinning weights have > 4 non-zeros per vertex takes the dense-24 layout"""
+    from oracle import restate as O
+    from seeme_b200 import ops, synthetic as S
+    buf = S.smpl_buffers(seed=2, sparse_lbs=False)
+    op = ops.SmplOp(cu(buf), max_frames=64)
+    g = torch.Generator().manual_seed(9)
+    F = 5
+    betas, pose, go = 0.5 * torch.randn(F, 10, generator=g), 0.3 * torch.randn(F, 69, generator=g), 0.5 * torch.randn(F, 3, generator=g)
+    vr, jr = O.smpl_forward(buf, betas, pose, go, None)
+    v, j, _ = op.forward(betas.to(DEV), pose.to(DEV), go.to(DEV), None)
+    assert (v.cpu() - vr).abs().max() < 1e-5 and (j.cpu() - jr).abs().max() < 1e-5
+
+
+def test_smpl_feats_prologue_and_module_surface(smpl_op, smpl_buffers):
+    """fused float64 renorm + slicing (egobody 75-d / gimo 69-d) and the smplx-style SMPL module (45 joints)"""
+    from oracle import restate as O
+    from seeme_b200 import synthetic as S
+    from seeme_b200.modules import SMPL, SMPL_EXTRA_VERTEX_IDS
+    mean, std = S.norm_stats()
+    g = torch.Generator().manual_seed(10)
+    F = 9
+    betas = 0.5 * torch.randn(F, 10, generator=g)
+    for Dn, nb in ((75, 69), (69, 63)):
+        feats = torch.randn(F, Dn, generator=g)
+        m_ref = O.renorm(feats, mean, std)
+        bp = m_ref[:, 3:3 + nb].float()
+        if nb == 63:
+            bp = torch.cat([bp, torch.zeros(F, 6)], dim=-1)
+        vr, jr = O.smpl_forward(smpl_buffers, betas, bp, m_ref[:, :3].float(), m_ref[:, -3:].float())
+        m, v, j, q = smpl_op.forward_feats(feats.to(DEV), mean[0, :Dn].to(DEV), std[0, :Dn].to(DEV), nb, betas.to(DEV))
+        assert m.dtype == torch.float64 and torch.equal(m.cpu(), m_ref)
+        assert (v.cpu() - vr).abs().max() < 1e-5 and (j.cpu() - jr).abs().max() < 1e-5
+        assert (q.cpu() - O.aa_to_quat(m_ref[:, :3].float())).abs().max() < 1e-6
+    mod = SMPL(smpl_buffers).to(DEV)
+    pose, go = 0.3 * torch.randn(F, 69, generator=g), 0.3 * torch.randn(F, 3, generator=g)
+    out = mod(betas=betas.to(DEV), body_pose=pose.to(DEV), global_orient=go.to(DEV), transl=None, pose2rot=True)
+    vr, jr = O.smpl_forward(smpl_buffers, betas, pose, go, None)
+    assert out.joints.shape == (F, 45, 3) and out.vertices.shape == (F, 6890, 3)
+    assert (out.joints[:, :24].cpu() - jr).abs().max() < 1e-5
+    assert torch.equal(out.joints[:, 24:], out.vertices[:, SMPL_EXTRA_VERTEX_IDS])
+
+
+def test_smpl_full_size_properties(smpl_buffers):
+    """C5-sized batch (16k frames): translation equivariance and zero-pose identity, checked on device"""
+    from seeme_b200 import ops
+    op = ops.SmplOp(cu(smpl_buffers), max_frames=16384)
+    g = torch.Generator().manual_seed(12)
+    F = 16384
+    betas = (0.5 * torch.randn(F, 10, generator=g)).to(DEV)
+    pose = (0.3 * torch.randn(F, 69, generator=g)).to(DEV)
+    go = (0.5 * torch.randn(F, 3, generator=g)).to(DEV)
+    tr = torch.randn(F, 3, generator=g).to(DEV)
+    v0, j0, _ = op.forward(betas, pose, go, None)
+    v1, j1, _ = op.forward(betas, pose, go, tr)
+    assert (v1 - (v0 + tr[:, None])).abs().max() < 1e-5
+    assert (j1 - (j0 + tr[:, None])).abs().max() < 1e-5
+    vz, _, _ = op.forward(betas, torch.zeros_like(pose), torch.zeros_like(go), None)
+    b = cu(smpl_buffers)
+    v_shaped = b["v_template"][None] + torch.einsum("bl,mkl->bmk", betas[:64], b["shapedirs"])
+    assert (vz[:64] - v_shaped).abs().max() < 1e-5
+
+
+# ---- the whole path through the reference-facing MLD surface ---------------------------------------------------------------
+@pytest.mark.parametrize("name,config,gs", [("egobody_cfg", "config_mld_egobody.yaml", 7.5),
+                                            ("egobody_nocfg", "config_mld_egobody.yaml", 1.0),
+                                            ("gimo_cfg", "config_mld_gimo.yaml", 7.5)])
+def test_ego_eval_vs_unmodified_reference_golden(name, config, gs):
+    """MLD.ego_eval (CUDA) vs the rs_set the UNMODIFIED reference ego_eval produced on the same weights,
+    batch and noise (tests/golden/ego_eval_*.npz).  Joint tolerance 1e-3 m (north_star); observed ~1e-5."""
+    import seeme_b200
+    from seeme_b200 import synthetic as S
+    g = dict(np.load(os.path.join(GOLDEN, f"ego_eval_{name}.npz")))
+    B = g["joints_rst"].shape[0]
+    model = seeme_b200.build_model(config, device=DEV, guidance_scale=gs, max_batch=B, n_points=1000)
+    batch = S.make_batch(B, n_points=1000, ragged=True, dataset=model.name_dataset)
+    batch = tuple(x.to(DEV) if torch.is_tensor(x) else x for x in batch)
+    noise = {k[6:]: T(v).to(DEV) for k, v in g.items() if k.startswith("noise_")}
+    rs = model.ego_eval(batch, noise)
+    assert rs["lengths"] == g["lengths"].tolist() and rs["list_names"] == {}
+    assert rs["m_rst"].dtype == torch.float64 and rs["m_ref"].dtype == torch.float64
+    assert torch.equal(rs["m_ref"].cpu(), T(g["m_ref"]))
+    errs = {k: float((rs[k].double().cpu() - T(g[k]).double()).abs().max())
+            for k in ("m_rst", "joints_ref", "joints_rst", "orientation_quat_rst", "orientation_quat_ref")}
+    assert errs["joints_ref"] < 1e-5 and errs["orientation_quat_ref"] < 1e-6, errs
+    assert errs["joints_rst"] < 1e-3 and errs["m_rst"] < 1e-3 and errs["orientation_quat_rst"] < 1e-3, errs
+    assert errs["joints_rst"] < 1e-4, errs          # what fp32 accumulation actually delivers
+    if "interactee" in model.condition:
+        for k in ("joints_interactee", "root_interactee", "orientation_quat_int"):
+            assert (rs[k].cpu() - T(g[k])).abs().max() < 1e-5, k
+    v = model.last_vertices["rst"]
+    assert v is not None and v.shape == (B, 60, 6890, 3) and bool(torch.isfinite(v).all())
+    # test_step / metric surface
+    out = model.test_step(batch, 0)
+    assert out.shape == (B, 60, 24, 3)
+    m = model.on_test_epoch_end()
+    assert "Metrics/MPJPE" in m
+
+
+def test_error_conventions(den_op, vae_op):
+    with pytest.raises(RuntimeError, match="capacity"):
+        den_op.forward(torch.zeros(65, 256, device=DEV), 1, torch.zeros(1, 65, 256, device=DEV))
+    with pytest.raises(RuntimeError, match="Nc"):
+        den_op.forward(torch.zeros(4, 256, device=DEV), 1, torch.zeros(5, 4, 256, device=DEV))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        vae_op.decode(torch.zeros(1, 256), torch.tensor([4]), 4)
