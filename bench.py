@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""Headline benchmark: sampled SMPL sequences / second through the SEE-ME inference hot path
+(scene + interactee conditioning -> 50-step DDIM with CFG -> VAE decode -> SMPL LBS, 6890 verts).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port)
+
+A "step" is one pass of the hot path (``MLD.ego_eval``) over one batch of synthetic sequences:
+BASELINE.json configs[1] = config_mld_egobody.yaml, batch 256, guidance 7.5, 50 DDIM steps, 20 000
+scene points, 60 frames.  ``value`` is measured with the batch resident in HBM; ``e2e`` goes through
+the same public call with HOST (pinned) buffers, the H2D copies of the batch and the D2H read of the
+predicted joints inside the timed region.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SMPL sequences/sec (50-step DDIM+VAE+LBS)"
+UNIT = "sequences/s"
+GUIDANCE = 7.5
+N_POINTS = 20000
+# algorithmic (essential) work per unit, SURVEY 8(d) / App. E
+POINTNET_FLOP_PER_POINT = 2 * 919_040          # fc_pos + 4 blocks with the pooled half hoisted
+SMPL_BYTES_PER_FRAME = 82_680 + 340
+
+
+def workload(batch):
+    return {"workload": f"config_mld_egobody.yaml (BASELINE configs[1]): scene+interactee cond, batch {batch}/GPU, "
+                        f"CFG {GUIDANCE}, 50 DDIM steps, {N_POINTS} scene points, 60 frames, VAE decode + SMPL LBS (6890 verts) "
+                        "of the predicted body, joints for GT and interactee bodies",
+            "batch_per_gpu": batch, "ddim_steps": 50, "guidance_scale": GUIDANCE, "scene_points": N_POINTS, "frames": 60,
+            "l2_policy": "per-step inputs+activations (>= 3 GB per 32-sample chunk) exceed the 126 MB L2; no flush needed"}
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_weights():
+    from seeme_b200 import synthetic as S
+    return {"denoiser": S.denoiser_state(0), "vae": S.vae_state(0), "pointnet": S.pointnet_state(0),
+            "output_scene": S.output_scene_state(0)}
+
+
+def cpu_reference_step(W, smpl, stats, batch, noise):
+    """the reference's CPU algorithm for the same path (oracle/restate.py: as-written math, fp32, all host threads)"""
+    import torch
+    from oracle import restate as O
+    with torch.no_grad():
+        return O.ego_eval(W, smpl, stats, batch, noise, guidance_scale=GUIDANCE, want_vertices=True)
+
+
+def make_noise(B, seed=7):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return {"eps_int": torch.randn(1, B, 256, generator=g), "eps_unc": torch.randn(1, B, 256, generator=g),
+            "x_T": torch.randn(B, 1, 256, generator=g)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  /root/reference cannot travel to
+    the GPU box and is pure Python on uninstallable deps, so this arm times the oracle port of its algorithm
+    (pinned against the unmodified reference modules in tests/) on the box's host cores."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from seeme_b200 import synthetic as S
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = args.ref_batch
+    W, smpl, stats = oracle_weights(), S.smpl_buffers(), S.norm_stats()
+    batch = S.make_batch(B, n_points=N_POINTS)
+    noise = make_noise(B)
+    for _ in range(args.warmup):
+        cpu_reference_step(W, smpl, stats, batch, noise)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(W, smpl, stats, batch, noise)
+    dt = time.perf_counter() - t0
+    v = B * args.steps / dt
+    sample = f"{args.steps} steps of a batch of {B} sequences (same per-sequence workload as configs[1]; configs[0] batch), fp32, as-written math"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(B),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="seeme_b200", choices=["seeme_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="sequences per GPU per step")
+    ap.add_argument("--ref-batch", type=int, default=8, help="batch of the CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import seeme_b200
+    from seeme_b200 import _lib, synthetic as S
+    from seeme_b200.metrics import STATE_KEYS
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    model = seeme_b200.build_model("config_mld_egobody.yaml", device=dev, guidance_scale=GUIDANCE, max_batch=B, n_points=N_POINTS)
+    # every rank owns its own sequences (weak scaling: the work list is sharded by sequence)
+    host_batch = S.make_batch(B, seed=1234 + rank, n_points=N_POINTS)
+    host_batch = tuple(x.pin_memory() if torch.is_tensor(x) else x for x in host_batch)
+    noise_h = {k: v.pin_memory() for k, v in make_noise(B, 7 + rank).items()}
+    dev_batch = tuple(x.to(dev) if torch.is_tensor(x) else x for x in host_batch)
+    noise_d = {k: v.to(dev) for k, v in noise_h.items()}
+    h2d = sum(x.numel() * x.element_size() for x in host_batch if torch.is_tensor(x)) + sum(v.numel() * 4 for v in noise_h.values())
+
+    def step_resident():
+        return model.ego_eval(dev_batch, noise_d)
+
+    joints_host = torch.empty(B, 60, 24, 3).pin_memory()
+
+    def step_e2e():
+        b = tuple(x.to(dev, non_blocking=True) if torch.is_tensor(x) else x for x in host_batch)
+        n = {k: v.to(dev, non_blocking=True) for k, v in noise_h.items()}
+        rs = model.ego_eval(b, n)
+        joints_host.copy_(rs["joints_rst"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller reads the result on the host
+        return rs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, prof=False):
+        barrier()
+        if prof:
+            for i in range(6):
+                _lib.prof_read(i)
+            _lib.prof_enable(True)
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            rs = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        launches = _lib.launch_count() - n0
+        if prof:
+            _lib.prof_enable(False)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms) / 1e3, launches, rs
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    clocks = ClockSampler(local) if rank == 0 else None
+    t_res, launches, rs = timed(step_resident, args.steps, prof=True)
+    clk = clocks.stop() if clocks else None
+    prof = {name: _lib.prof_read(i) for i, name in enumerate(["pointnet_gemm", "smpl_skin", "smpl_pose", "sampler_graph"])}
+    value = world * B * args.steps / t_res
+
+    # the per-epoch metric gather (the path's only collective): all-reduce(sum) of the EgoMetric state vector
+    model.EgoMetric.update("test", rs["joints_rst"], rs["joints_ref"], rs["orientation_quat_rst"], rs["orientation_quat_ref"],
+                           rs["root_interactee"], rs["joints_interactee"], rs["orientation_quat_int"], None, rs["lengths"], {})
+    state = model.EgoMetric.state_vector().to(dev)
+    if world > 1:
+        dist.all_reduce(state)
+    n_seq_metric = float(state[STATE_KEYS.index("count")]) / 60.0
+
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            step_e2e()
+        t_e2e, _, _ = timed(step_e2e, args.steps)
+        e2e = {"value": world * B * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(joints_host.numel() * 4)}
+
+    if rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        # dominant kernel class: the scene-encoder GEMMs (tensor-bound class)
+        pn_ms, pn_n = prof["pointnet_gemm"]
+        flops = POINTNET_FLOP_PER_POINT * N_POINTS * B * args.steps - 2 * 3 * 512 * N_POINTS * B * args.steps  # fc_pos (K=3) is not in this class
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        ach = flops / (pn_ms / 1e3) / 1e12 if pn_ms > 0 else None
+        roofline = {"kernel": "scene-encoder GEMM launches (gemm_f32_kernel<128,128,8,8>)", "bound": "tensor", "achieved": ach,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": (ach / peak_tf) if ach else None, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
+                    "launches": pn_n, "avg_launch_ms": pn_ms / pn_n if pn_n else None,
+                    "share_of_step": (pn_ms / 1e3) / t_res if t_res else None}
+        sk_ms, sk_n = prof["smpl_skin"]
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        sk_ach = SMPL_BYTES_PER_FRAME * 60 * B * args.steps / (sk_ms / 1e3) / 1e9 if sk_ms > 0 else None
+        other = {"smpl_skin": {"bound": "hbm", "achieved": sk_ach, "peak": hbm, "unit": "GB/s", "frac": (sk_ach / hbm) if sk_ach else None,
+                               "launches": sk_n, "avg_launch_ms": sk_ms / sk_n if sk_n else None},
+                 "sampler_graph_ms_per_step": prof["sampler_graph"][0] / max(prof["sampler_graph"][1], 1),
+                 "smpl_pose_ms_per_launch": prof["smpl_pose"][0] / max(prof["smpl_pose"][1], 1)}
+        cpu_baseline = None
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            Bc = args.ref_batch
+            W, smpl, stats = oracle_weights(), S.smpl_buffers(), S.norm_stats()
+            cb = S.make_batch(Bc, n_points=N_POINTS)
+            cn = make_noise(Bc)
+            t0 = time.perf_counter()
+            cpu_reference_step(W, smpl, stats, cb, cn)
+            dt = time.perf_counter() - t0
+            cpu_baseline = {"value": Bc / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                            "sample": f"1 pass over a batch of {Bc} sequences of the same per-sequence workload ({dt:.1f} s), oracle/restate.py fp32"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload(B), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "kernels": other, "cpu_baseline": cpu_baseline,
+                "metric_gather": {"collective": "all_reduce(sum) of the EgoMetric state vector", "sequences": n_seq_metric}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,13 @@ const char* seeme_last_error(void);
  * `gpu_launches`); graph replays count the kernels inside the graph. */
 unsigned long long seeme_launch_count(void);
 
+/* Per-kernel-class device timing for bench.py's live roofline measurement: with profiling enabled,
+ * every launch of an instrumented kernel class is bracketed by a cudaEvent pair on its stream.
+ * ids: 0 scene-encoder GEMMs, 1 SMPL blend+skinning kernel, 2 SMPL pose kernel, 3 sampler graph,
+ * 4 VAE attention, 5 tcgen05 GEMM.  seeme_prof_read synchronises, returns and clears the sums. */
+int seeme_prof_enable(int on);
+int seeme_prof_read(int id, double* total_ms, long long* count);
+
 /* ------------------------------------------------------------------------------------------------
  * Scene encoder.  Replaces `ProHMRScene.encode_scene` -> `ResnetPointnet.forward`
  * (EgoHMR/models/prohmr/prohmr_scene.py:102-104, EgoHMR/models/respointnet.py:33-59) and

@@ -21,6 +21,8 @@ SIGNATURES = {
     "seeme_abi_version": (C.c_int, []),
     "seeme_last_error": (C.c_char_p, []),
     "seeme_launch_count": (C.c_ulonglong, []),
+    "seeme_prof_enable": (C.c_int, [C.c_int]),
+    "seeme_prof_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "seeme_pointnet_create": (C.c_int, [C.POINTER(c_handle), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]),
     "seeme_pointnet_forward": (C.c_int, [c_handle, c_float_p, C.c_int, C.c_int, c_float_p, c_float_p, C.c_void_p]),
     "seeme_pointnet_destroy": (C.c_int, [c_handle]),
@@ -69,6 +71,16 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = lib().seeme_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed with code {rc}: {msg}")
+
+
+def prof_enable(on: bool) -> None:
+    check(lib().seeme_prof_enable(1 if on else 0), "seeme_prof_enable")
+
+
+def prof_read(prof_id: int):
+    ms, n = C.c_double(), C.c_longlong()
+    check(lib().seeme_prof_read(prof_id, C.byref(ms), C.byref(n)), "seeme_prof_read")
+    return ms.value, n.value
 
 
 def launch_count() -> int:

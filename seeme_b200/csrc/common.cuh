@@ -52,6 +52,20 @@ inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
     seeme::count_launch();                                                                   \
   } while (0)
 
+// ---- optional per-kernel-class device timing (bench.py's live roofline measurement) ----------
+// When enabled with seeme_prof_enable(1), each instrumented launch is bracketed by a cudaEvent pair on
+// its own stream; seeme_prof_read() synchronises and returns the summed duration and launch count.
+enum ProfId { PROF_POINTNET_GEMM = 0, PROF_SMPL_SKIN = 1, PROF_SMPL_POSE = 2, PROF_SAMPLER_GRAPH = 3, PROF_VAE_ATTN = 4,
+              PROF_UMMA_GEMM = 5, PROF_COUNT = 8 };
+extern bool g_prof_on;
+void prof_begin(int id, cudaStream_t s);
+void prof_end(int id, cudaStream_t s);
+struct ProfScope {
+  int id; cudaStream_t s; bool on;
+  ProfScope(int id_, cudaStream_t s_) : id(id_), s(s_), on(g_prof_on && id_ >= 0) { if (on) prof_begin(id, s); }
+  ~ProfScope() { if (on) prof_end(id, s); }
+};
+
 // ---- a tiny bump allocator over one cudaMalloc'd slab (everything allocated at create) -------
 struct Arena {
   char* base = nullptr;
@@ -130,6 +144,7 @@ struct GemmP {
   int pre_act;                  // Act applied to X on load (ACT_NONE/ACT_RELU/ACT_SILU)
   int act;                      // Act applied to (acc + bias)
   int accumulate;               // Y += instead of Y =
+  int prof_id;                  // ProfId + 1 to time this launch, 0 = not timed
 };
 inline GemmP gemm_params(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y,
                          int ldy, int M, int N, int K) {

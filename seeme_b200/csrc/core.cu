@@ -13,6 +13,27 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool g_prof_on = false;
+namespace {
+struct ProfPair { cudaEvent_t a, b; };
+std::vector<ProfPair> g_prof_pairs[PROF_COUNT];
+cudaEvent_t g_prof_open[PROF_COUNT];
+double g_prof_ms[PROF_COUNT];
+long long g_prof_n[PROF_COUNT];
+}  // namespace
+void prof_begin(int id, cudaStream_t s) {
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, s);
+  g_prof_open[id] = e;
+}
+void prof_end(int id, cudaStream_t s) {
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, s);
+  g_prof_pairs[id].push_back({g_prof_open[id], e});
+}
+
 // ------------------------------------------------------------------------------------------------
 // gemm_f32: register-tiled CUDA-core SGEMM for the "TN" case both operands K-contiguous
 // (activations [M,K] row-major, nn.Linear weight [N,K] row-major).  Used where a contraction must
@@ -163,6 +184,7 @@ gemm_f32_kernel(const GemmP p) {
 
 int gemm_f32(const GemmP& p, cudaStream_t s) {
   if (p.M <= 0 || p.N <= 0) return SEEME_OK;
+  ProfScope prof(p.prof_id - 1, s);
   if (p.M >= 2048 && p.N >= 128) {
     dim3 grid((p.N + 127) / 128, (p.M + 127) / 128);
     gemm_f32_kernel<128, 128, 8, 8><<<grid, 256, 0, s>>>(p);
@@ -242,6 +264,30 @@ extern "C" {
 int seeme_abi_version(void) { return SEEME_ABI_VERSION; }
 const char* seeme_last_error(void) { return seeme::g_err; }
 unsigned long long seeme_launch_count(void) { return seeme::g_launch_count; }
+
+int seeme_prof_enable(int on) {
+  seeme::g_prof_on = on != 0;
+  return SEEME_OK;
+}
+int seeme_prof_read(int id, double* total_ms, long long* count) {
+  using namespace seeme;
+  SEEME_REQUIRE(id >= 0 && id < PROF_COUNT && total_ms && count, SEEME_EINVAL, "seeme_prof_read: bad argument");
+  for (auto& pr : g_prof_pairs[id]) {
+    SEEME_CUDA(cudaEventSynchronize(pr.b));
+    float ms = 0.f;
+    SEEME_CUDA(cudaEventElapsedTime(&ms, pr.a, pr.b));
+    g_prof_ms[id] += ms;
+    g_prof_n[id] += 1;
+    cudaEventDestroy(pr.a);
+    cudaEventDestroy(pr.b);
+  }
+  g_prof_pairs[id].clear();
+  *total_ms = g_prof_ms[id];
+  *count = g_prof_n[id];
+  g_prof_ms[id] = 0.0;
+  g_prof_n[id] = 0;
+  return SEEME_OK;
+}
 
 int seeme_ddim_step(const float* eps, const float* sample, float* prev, size_t n, float c0, float c1, float c2,
                     float c3, void* stream) {

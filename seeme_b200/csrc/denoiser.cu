@@ -460,7 +460,10 @@ extern "C" int seeme_sampler_run(seeme_denoiser_t h, const float* x_T, const flo
       if (e != cudaSuccess) { h->gexec = nullptr; set_error("seeme_sampler_run: graph instantiate failed: %s", cudaGetErrorString(e)); return SEEME_ECUDA; }
       h->g_Nc = Nc; h->g_B = B; h->g_cfg = cfg; h->g_steps = n_steps;
     }
-    SEEME_CUDA(cudaGraphLaunch(h->gexec, s));
+    {
+      ProfScope prof(PROF_SAMPLER_GRAPH, s);
+      SEEME_CUDA(cudaGraphLaunch(h->gexec, s));
+    }
     count_launch(h->g_kernels);
   } else {
     SEEME_TRY(sampler_enqueue(h, Nc, B, R, cfg, n_steps, s));

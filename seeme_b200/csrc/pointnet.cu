@@ -135,11 +135,13 @@ extern "C" int seeme_pointnet_forward(seeme_pointnet_t h, const float* pcd, int 
     float* nxt = h->net[1];
     {  // block_0 (K = 512, no pooled half)
       GemmP g = gemm_params(h->x0, 512, h->w0[0], 512, h->b0[0], h->h, 256, rows, 256, 512);
-      g.pre_act = ACT_RELU;
+      g.pre_act = ACT_RELU; g.prof_id = PROF_POINTNET_GEMM + 1;
       SEEME_TRY(gemm_f32(g, s));
-      SEEME_TRY(gemm_f32(gemm_params(h->x0, 512, h->ws[0], 512, h->b1[0], net, 256, rows, 256, 512), s));
+      GemmP gs0 = gemm_params(h->x0, 512, h->ws[0], 512, h->b1[0], net, 256, rows, 256, 512);
+      gs0.prof_id = PROF_POINTNET_GEMM + 1;
+      SEEME_TRY(gemm_f32(gs0, s));
       GemmP g1 = gemm_params(h->h, 256, h->w1[0], 256, nullptr, net, 256, rows, 256, 256);
-      g1.pre_act = ACT_RELU; g1.accumulate = 1;
+      g1.pre_act = ACT_RELU; g1.accumulate = 1; g1.prof_id = PROF_POINTNET_GEMM + 1;
       SEEME_TRY(gemm_f32(g1, s));
     }
     for (int i = 1; i < 4; ++i) {
@@ -149,13 +151,13 @@ extern "C" int seeme_pointnet_forward(seeme_pointnet_t h, const float* pcd, int 
       SEEME_TRY(gemm_f32(gc0, s));
       SEEME_TRY(gemm_f32(gemm_params(h->pool, 256, h->ws[i] + 256, 512, h->b1[i], h->cs, 256, C, 256, 256), s));
       GemmP g0 = gemm_params(net, 256, h->w0[i], 512, h->c0, h->h, 256, rows, 256, 256);
-      g0.pre_act = ACT_RELU; g0.bias_group_rows = N;
+      g0.pre_act = ACT_RELU; g0.bias_group_rows = N; g0.prof_id = PROF_POINTNET_GEMM + 1;
       SEEME_TRY(gemm_f32(g0, s));
       GemmP gs = gemm_params(net, 256, h->ws[i], 512, h->cs, nxt, 256, rows, 256, 256);
-      gs.bias_group_rows = N;
+      gs.bias_group_rows = N; gs.prof_id = PROF_POINTNET_GEMM + 1;
       SEEME_TRY(gemm_f32(gs, s));
       GemmP g1 = gemm_params(h->h, 256, h->w1[i], 256, nullptr, nxt, 256, rows, 256, 256);
-      g1.pre_act = ACT_RELU; g1.accumulate = 1;
+      g1.pre_act = ACT_RELU; g1.accumulate = 1; g1.prof_id = PROF_POINTNET_GEMM + 1;
       SEEME_TRY(gemm_f32(g1, s));
       float* t = net; net = nxt; nxt = t;
     }

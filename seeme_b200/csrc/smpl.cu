@@ -351,10 +351,14 @@ static int smpl_run(seeme_smpl* h, const float* betas, const float* body_pose, c
                     double* m_out, int F, float* vertices, float* joints, float* quat, cudaStream_t s) {
   SEEME_REQUIRE(F > 0, SEEME_EINVAL, "seeme_smpl: empty batch");
   SEEME_REQUIRE(F <= h->max_frames, SEEME_ECAP, "seeme_smpl: %d frames exceed capacity %d", F, h->max_frames);
-  smpl_pose_kernel<<<(F + 7) / 8, 256, 0, s>>>(betas, body_pose, global_orient, transl, feats, Dn, mean, stdv, n_body, m_out,
-                                               h->Jt, h->Jd, h->topo, F, h->A, h->coef, joints, quat);
+  {
+    ProfScope prof(PROF_SMPL_POSE, s);
+    smpl_pose_kernel<<<(F + 7) / 8, 256, 0, s>>>(betas, body_pose, global_orient, transl, feats, Dn, mean, stdv, n_body, m_out,
+                                                 h->Jt, h->Jd, h->topo, F, h->A, h->coef, joints, quat);
+  }
   SEEME_LAUNCH_CHECK();
   if (vertices) {
+    ProfScope prof(PROF_SMPL_SKIN, s);
     dim3 grid(SVP / 128, (F + FT - 1) / FT);
     if (h->max_nnz <= 4)
       smpl_skin_kernel<4><<<grid, 128, 0, s>>>(h->basis, h->vtp, h->w4, h->i4, h->A, h->coef, F, vertices);
