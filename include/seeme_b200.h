@@ -53,6 +53,15 @@ unsigned long long seeme_launch_count(void);
 int seeme_prof_enable(int on);
 int seeme_prof_read(int id, double* total_ms, long long* count);
 
+/* Self-test hook for the tcgen05/TMA linear used by every dense contraction on the path:
+ * Y[M,N] = act(A[M,K] W[N,K]^T + bias[N]) (+ R[M,N]); fp32 device inputs are converted to (split) bf16
+ * internally.  K multiple of 64, N multiple of 128; npass 1 = bf16, 3 = split-bf16 (hi.hi+lo.hi+hi.lo).
+ * colmax (nullable): [ceil(M/group), N] order-preserving-uint column max per group of rows (zeroed by
+ * the caller).  Synchronises the stream. */
+int seeme_test_umma_linear(const float* A, const float* W, const float* bias, const float* R, float* Y,
+                           int M, int N, int K, int act, int npass, unsigned* colmax,
+                           int colmax_group_rows, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Scene encoder.  Replaces `ProHMRScene.encode_scene` -> `ResnetPointnet.forward`
  * (EgoHMR/models/prohmr/prohmr_scene.py:102-104, EgoHMR/models/respointnet.py:33-59) and
