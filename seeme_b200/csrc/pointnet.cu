@@ -1,16 +1,26 @@
 // Scene encoder: ResnetPointnet (EgoHMR/models/respointnet.py:33-59,88-97) + output_scene
 // (mld/models/modeltype/mld.py:257-261).
 //
-// Dataflow (per chunk of samples, all per-point tensors [rows = C*N, channels]):
-//   x0  = fc_pos_0(p)                                     [rows,512]
-//   blk0: h = fc_0(relu(x0)); net = shortcut(x0) + b1 + fc_1(relu(h))
-//   blk i>=1: the reference concatenates the per-sample max-pool to every point
-//     ([net, pooled], respointnet.py:37-46).  The pooled half of each contraction is constant over the
-//     points of a sample, so it is folded into per-sample bias vectors:
-//       c0[b] = W0[:,256:] relu(pool_b) + b0 ;  cs[b] = Ws[:,256:] pool_b + b1
-//       h = W0[:,:256] relu(net) + c0[b] ;  net' = Ws[:,:256] net + cs[b] + fc_1(relu(h))
-//   pooling: per-(sample,channel) max via order-preserving atomicMax.
+// Algebra (exact up to fp32 re-association):
+//  * the reference concatenates the per-sample max-pool to every point ([net, pooled],
+//    respointnet.py:37-46).  The pooled half of each contraction is constant over the points of a
+//    sample, so it becomes a per-sample bias:
+//        c0[b] = W0[:,256:] relu(pool_b) + b0 ;  cs[b] = Ws[:,256:] pool_b + b1
+//        h = relu(W0[:,:256] relu(net) + c0[b]) ;  net' = [net | h] . [Ws[:,:256] | W1]^T + cs[b]
+//  * block 0's shortcut acts on x0 = fc_pos_0(p), an affine map of the 3 coordinates, so
+//        shortcut(x0) = (Ws Wp) p + Ws bp      -- a rank-3 term evaluated in the GEMM epilogue.
+//
+// Tensor path (default): per chunk of samples, rows = points
+//   prologue   xr0 = bf16(relu(Wp p + bp))                              [rows,512]  (CUDA cores, K = 3)
+//   G1_i       hr  = bf16(relu(W0 . xr + bias))                          tcgen05, K = 512 / 256
+//   G2_i       out = [x | hr] . Wcat^T + bias (+ rank-3 fold for i = 0)   tcgen05, K = 256 / 512
+//              epilogue writes bf16 x' and relu(x') for the next block and the fused per-sample column max
+//   tail       fc_c(relu(pool)) and output_scene on [B,256] rows (fp32 CUDA cores)
+// Precision: SEEME_POINTNET_PRECISION = 3 (split-bf16, default), 1 (plain bf16) or 0 (fp32 CUDA-core GEMMs,
+// the layer-by-layer path kept for accuracy studies).
 #include "common.cuh"
+#include "umma.cuh"
+#include <stdlib.h>
 
 namespace seeme {
 
@@ -35,19 +45,77 @@ __global__ void ord_decode_kernel(const unsigned* __restrict__ in, float* __rest
   if (i < n) out[i] = ord2f(in[i]);
 }
 
+// xr0[m, c] = bf16 split of relu(Wp[c,:] . p[m] + bp[c]); thread = 8 consecutive channels, grid-stride over points
+__global__ void __launch_bounds__(256) fcpos_relu_bf16_kernel(const float* __restrict__ p, const float* __restrict__ Wp,
+                                                              const float* __restrict__ bp, __nv_bfloat16* __restrict__ hi,
+                                                              __nv_bfloat16* __restrict__ lo, int rows) {
+  const int cg = threadIdx.x & 63;             // channel group: channels [8 cg, 8 cg + 8)
+  float w[8][3], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = cg * 8 + i;
+    w[i][0] = Wp[c * 3]; w[i][1] = Wp[c * 3 + 1]; w[i][2] = Wp[c * 3 + 2];
+    b[i] = bp[c];
+  }
+  const int ppb = blockDim.x >> 6;             // points per block per iteration
+  for (int m = blockIdx.x * ppb + (threadIdx.x >> 6); m < rows; m += gridDim.x * ppb) {
+    const float x = p[(size_t)m * 3], y = p[(size_t)m * 3 + 1], z = p[(size_t)m * 3 + 2];
+    __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float v = fmaxf(fmaf(w[i][2], z, fmaf(w[i][1], y, fmaf(w[i][0], x, b[i]))), 0.f);
+      h[i] = __float2bfloat16_rn(v);
+      l[i] = __float2bfloat16_rn(v - __bfloat162float(h[i]));
+    }
+    *reinterpret_cast<uint4*>(hi + (size_t)m * 512 + cg * 8) = *reinterpret_cast<const uint4*>(h);
+    if (lo) *reinterpret_cast<uint4*>(lo + (size_t)m * 512 + cg * 8) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+// p'[b, i] = p[b, i % N] for i < 128: duplicating points does not change a max-pooled encoding, and a
+// 128-row GEMM tile then never spans more than two samples
+__global__ void pad_cloud_kernel(const float* __restrict__ p, float* __restrict__ out, int B, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 128) return;
+  const int b = i / 128, j = (i % 128) % N;
+  out[(size_t)i * 3] = p[((size_t)b * N + j) * 3];
+  out[(size_t)i * 3 + 1] = p[((size_t)b * N + j) * 3 + 1];
+  out[(size_t)i * 3 + 2] = p[((size_t)b * N + j) * 3 + 2];
+}
+
+// pf[n][0..2] = sum_c Ws[n,c] Wp[c,:],  cst[n] = sum_c Ws[n,c] bp[c] + b1[n]       (create time)
+__global__ void pointnet_fold_kernel(const float* __restrict__ Ws, const float* __restrict__ Wp, const float* __restrict__ bp,
+                                     const float* __restrict__ b1, float* __restrict__ pf, float* __restrict__ cst) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= 256) return;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  for (int c = 0; c < 512; ++c) {
+    const double w = Ws[(size_t)n * 512 + c];
+    a0 += w * Wp[c * 3]; a1 += w * Wp[c * 3 + 1]; a2 += w * Wp[c * 3 + 2]; a3 += w * bp[c];
+  }
+  pf[n * 4] = (float)a0; pf[n * 4 + 1] = (float)a1; pf[n * 4 + 2] = (float)a2; pf[n * 4 + 3] = 0.f;
+  cst[n] = (float)(a3 + (double)b1[n]);
+}
+
 }  // namespace seeme
 
 using namespace seeme;
 
 struct seeme_pointnet {
-  int device = 0, max_batch = 0, max_points = 0, chunk = 0;
+  int device = 0, max_batch = 0, max_points = 0, chunk = 0, precision = 3;
   Arena arena;
-  // packed copies of the weights (contiguous fp32)
+  // fp32 copies of the weights
   float *fc_pos_w, *fc_pos_b;
   float *w0[4], *b0[4], *w1[4], *b1[4], *ws[4];
   float *wc, *bc, *wo, *bo;
-  // workspace
-  float *x0, *h, *net[2], *pool, *c0, *cs, *feat;
+  // tensor path: bf16 (hi, lo) packed weights; g1[i] = W0 (i = 0: [256,512], else [:, :256]); g2[i] = W1 (i = 0) or [Ws[:, :256] | W1]
+  __nv_bfloat16 *g1h[4], *g1l[4], *g2h[4], *g2l[4];
+  float *pfold, *cst0;
+  __nv_bfloat16 *xr0h, *xr0l, *hrh, *hrl, *xh[2], *xl[2], *xrh[2], *xrl[2];
+  // fp32 path workspace
+  float *x0, *h, *net[2];
+  // shared
+  float *pool, *c0, *cs, *feat, *padbuf;
   unsigned* pool_ord;
 };
 
@@ -56,6 +124,11 @@ static int copy_w(Arena& a, float*& dst, const float* src, size_t n) {
   SEEME_REQUIRE(dst != nullptr, SEEME_ENOMEM, "pointnet: arena exhausted");
   SEEME_CUDA(cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice));
   return SEEME_OK;
+}
+
+static void destroy(seeme_pointnet* h) {
+  h->arena.release();
+  delete h;
 }
 
 extern "C" int seeme_pointnet_create(seeme_pointnet_t* out, const float* const* w, int n_w, int max_batch,
@@ -69,14 +142,23 @@ extern "C" int seeme_pointnet_create(seeme_pointnet_t* out, const float* const* 
   SEEME_CUDA(cudaGetDevice(&h->device));
   h->max_batch = max_batch;
   h->max_points = max_points;
-  // samples per pass: bound the per-point workspace to ~3.3 GB
-  h->chunk = max_batch < 32 ? max_batch : 32;
-  const size_t rows = (size_t)h->chunk * max_points;
+  const char* pe = getenv("SEEME_POINTNET_PRECISION");
+  h->precision = pe ? atoi(pe) : 3;
+  if (h->precision != 0 && h->precision != 1 && h->precision != 3) {
+    set_error("SEEME_POINTNET_PRECISION must be 0, 1 or 3");
+    delete h;
+    return SEEME_EINVAL;
+  }
+  h->chunk = max_batch < 32 ? max_batch : 32;   // samples per pass: bounds the per-point workspace
+  const size_t rows = (size_t)h->chunk * (max_points < 128 ? 128 : max_points);
+  const bool split = h->precision == 3;
   size_t wbytes = pad256(512 * 3 * 4) + pad256(512 * 4) + 4 * (pad256(256 * 512 * 4) * 2 + pad256(256 * 256 * 4) + 2 * pad256(256 * 4)) +
-                  pad256(512 * 256 * 4) + pad256(512 * 4) + pad256(256 * 512 * 4) + pad256(256 * 4);
-  size_t ws = pad256(rows * 512 * 4) + 3 * pad256(rows * 256 * 4) + 4 * pad256((size_t)max_batch * 256 * 4) +
-              pad256((size_t)max_batch * 512 * 4);
-  int rc = h->arena.init(wbytes + ws + 4096);
+                  pad256(512 * 256 * 4) + pad256(512 * 4) + pad256(256 * 512 * 4) + pad256(256 * 4) +
+                  8 * 2 * pad256(256 * 512 * 2) + pad256(256 * 4 * 4) + pad256(256 * 4);
+  size_t ws = 4 * pad256((size_t)max_batch * 256 * 4) + pad256((size_t)max_batch * 512 * 4) + pad256((size_t)max_batch * 128 * 3 * 4);
+  if (h->precision == 0) ws += pad256(rows * 512 * 4) + 3 * pad256(rows * 256 * 4);
+  else ws += (split ? 2 : 1) * (pad256(rows * 512 * 2) + 5 * pad256(rows * 256 * 2));
+  int rc = h->arena.init(wbytes + ws + 65536);
   if (rc != SEEME_OK) { delete h; return rc; }
   int k = 0;
   rc = copy_w(h->arena, h->fc_pos_w, w[k++], 512 * 3);
@@ -92,18 +174,60 @@ extern "C" int seeme_pointnet_create(seeme_pointnet_t* out, const float* const* 
   if (!rc) rc = copy_w(h->arena, h->bc, w[k++], 512);
   if (!rc) rc = copy_w(h->arena, h->wo, w[k++], 256 * 512);
   if (!rc) rc = copy_w(h->arena, h->bo, w[k++], 256);
-  if (rc) { h->arena.release(); delete h; return rc; }
-  h->x0 = h->arena.take<float>(rows * 512);
-  h->h = h->arena.take<float>(rows * 256);
-  h->net[0] = h->arena.take<float>(rows * 256);
-  h->net[1] = h->arena.take<float>(rows * 256);
+  if (rc) { destroy(h); return rc; }
   h->pool = h->arena.take<float>((size_t)max_batch * 256);
   h->c0 = h->arena.take<float>((size_t)max_batch * 256);
   h->cs = h->arena.take<float>((size_t)max_batch * 256);
   h->pool_ord = h->arena.take<unsigned>((size_t)max_batch * 256);
   h->feat = h->arena.take<float>((size_t)max_batch * 512);
-  if (!h->feat) { set_error("pointnet: arena exhausted (workspace)"); h->arena.release(); delete h; return SEEME_ENOMEM; }
+  h->padbuf = h->arena.take<float>((size_t)max_batch * 128 * 3);
+  bool ok = h->feat != nullptr && h->padbuf != nullptr;
+  if (h->precision == 0) {
+    h->x0 = h->arena.take<float>(rows * 512);
+    h->h = h->arena.take<float>(rows * 256);
+    h->net[0] = h->arena.take<float>(rows * 256);
+    h->net[1] = h->arena.take<float>(rows * 256);
+    ok = ok && h->net[1];
+  } else {
+    for (int i = 0; i < 4; ++i) {
+      h->g1h[i] = h->arena.take<__nv_bfloat16>(256 * 512);
+      h->g1l[i] = h->arena.take<__nv_bfloat16>(256 * 512);
+      h->g2h[i] = h->arena.take<__nv_bfloat16>(256 * 512);
+      h->g2l[i] = h->arena.take<__nv_bfloat16>(256 * 512);
+    }
+    h->pfold = h->arena.take<float>(256 * 4);
+    h->cst0 = h->arena.take<float>(256);
+    auto take16 = [&](size_t n, bool need) -> __nv_bfloat16* { return need ? h->arena.take<__nv_bfloat16>(n) : nullptr; };
+    h->xr0h = take16(rows * 512, true); h->xr0l = take16(rows * 512, split);
+    h->hrh = take16(rows * 256, true); h->hrl = take16(rows * 256, split);
+    for (int i = 0; i < 2; ++i) {
+      h->xh[i] = take16(rows * 256, true); h->xl[i] = take16(rows * 256, split);
+      h->xrh[i] = take16(rows * 256, true); h->xrl[i] = take16(rows * 256, split);
+    }
+    ok = ok && h->xrh[1] && (!split || h->xrl[1]);
+    if (ok) {
+      // pack the tensor-path weights (default stream, create time)
+      rc = to_bf16_split(h->w0[0], 512, 256, 512, h->g1h[0], h->g1l[0], 512, 0, 0);
+      if (!rc) rc = to_bf16_split(h->w1[0], 256, 256, 256, h->g2h[0], h->g2l[0], 256, 0, 0);
+      for (int i = 1; i < 4 && !rc; ++i) {
+        rc = to_bf16_split(h->w0[i], 512, 256, 256, h->g1h[i], h->g1l[i], 256, 0, 0);
+        if (!rc) rc = to_bf16_split(h->ws[i], 512, 256, 256, h->g2h[i], h->g2l[i], 512, 0, 0);          // columns [0,256)
+        if (!rc) rc = to_bf16_split(h->w1[i], 256, 256, 256, h->g2h[i] + 256, h->g2l[i] + 256, 512, 0, 0);  // columns [256,512)
+      }
+      if (rc) { destroy(h); return rc; }
+      pointnet_fold_kernel<<<1, 256>>>(h->ws[0], h->fc_pos_w, h->fc_pos_b, h->b1[0], h->pfold, h->cst0);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { set_error("seeme_pointnet_create: weight packing failed: %s", cudaGetErrorString(e)); destroy(h); return SEEME_ECUDA; }
+    }
+  }
+  if (!ok) { set_error("pointnet: arena exhausted (workspace)"); destroy(h); return SEEME_ENOMEM; }
   *out = h;
+  return SEEME_OK;
+}
+
+static int decode_pool(seeme_pointnet* h, int C, cudaStream_t s) {
+  ord_decode_kernel<<<(C * 256 + 255) / 256, 256, 0, s>>>(h->pool_ord, h->pool, C * 256);
+  SEEME_LAUNCH_CHECK();
   return SEEME_OK;
 }
 
@@ -113,9 +237,109 @@ static int pool_stage(seeme_pointnet* h, const float* net, int C, int N, cudaStr
   dim3 grid((N + rows_per_cta - 1) / rows_per_cta, C);
   colmax_kernel<<<grid, 256, 0, s>>>(net, h->pool_ord, N, rows_per_cta);
   SEEME_LAUNCH_CHECK();
-  ord_decode_kernel<<<(C * 256 + 255) / 256, 256, 0, s>>>(h->pool_ord, h->pool, C * 256);
-  SEEME_LAUNCH_CHECK();
-  return SEEME_OK;
+  return decode_pool(h, C, s);
+}
+
+// per-sample bias vectors of block i >= 1 from the pooled features
+static int pooled_bias(seeme_pointnet* h, int i, int C, cudaStream_t s) {
+  GemmP gc0 = gemm_params(h->pool, 256, h->w0[i] + 256, 512, h->b0[i], h->c0, 256, C, 256, 256);
+  gc0.pre_act = ACT_RELU;
+  SEEME_TRY(gemm_f32(gc0, s));
+  return gemm_f32(gemm_params(h->pool, 256, h->ws[i] + 256, 512, h->b1[i], h->cs, 256, C, 256, 256), s);
+}
+
+// ---- layer-by-layer fp32 path (precision 0) ----------------------------------------------------------
+static int blocks_fp32(seeme_pointnet* h, const float* p, int C, int N, cudaStream_t s) {
+  const int rows = C * N;
+  SEEME_TRY(gemm_f32(gemm_params(p, 3, h->fc_pos_w, 3, h->fc_pos_b, h->x0, 512, rows, 512, 3), s));
+  float* net = h->net[0];
+  float* nxt = h->net[1];
+  {  // block_0 (K = 512, no pooled half)
+    GemmP g = gemm_params(h->x0, 512, h->w0[0], 512, h->b0[0], h->h, 256, rows, 256, 512);
+    g.pre_act = ACT_RELU; g.prof_id = PROF_POINTNET_GEMM + 1;
+    SEEME_TRY(gemm_f32(g, s));
+    GemmP gs0 = gemm_params(h->x0, 512, h->ws[0], 512, h->b1[0], net, 256, rows, 256, 512);
+    gs0.prof_id = PROF_POINTNET_GEMM + 1;
+    SEEME_TRY(gemm_f32(gs0, s));
+    GemmP g1 = gemm_params(h->h, 256, h->w1[0], 256, nullptr, net, 256, rows, 256, 256);
+    g1.pre_act = ACT_RELU; g1.accumulate = 1; g1.prof_id = PROF_POINTNET_GEMM + 1;
+    SEEME_TRY(gemm_f32(g1, s));
+  }
+  for (int i = 1; i < 4; ++i) {
+    SEEME_TRY(pool_stage(h, net, C, N, s));
+    SEEME_TRY(pooled_bias(h, i, C, s));
+    GemmP g0 = gemm_params(net, 256, h->w0[i], 512, h->c0, h->h, 256, rows, 256, 256);
+    g0.pre_act = ACT_RELU; g0.bias_group_rows = N; g0.prof_id = PROF_POINTNET_GEMM + 1;
+    SEEME_TRY(gemm_f32(g0, s));
+    GemmP gs = gemm_params(net, 256, h->ws[i], 512, h->cs, nxt, 256, rows, 256, 256);
+    gs.bias_group_rows = N; gs.prof_id = PROF_POINTNET_GEMM + 1;
+    SEEME_TRY(gemm_f32(gs, s));
+    GemmP g1 = gemm_params(h->h, 256, h->w1[i], 256, nullptr, nxt, 256, rows, 256, 256);
+    g1.pre_act = ACT_RELU; g1.accumulate = 1; g1.prof_id = PROF_POINTNET_GEMM + 1;
+    SEEME_TRY(gemm_f32(g1, s));
+    float* t = net; net = nxt; nxt = t;
+  }
+  return pool_stage(h, net, C, N, s);
+}
+
+// ---- tcgen05 path (precision 1 / 3) ---------------------------------------------------------------------
+static int blocks_tensor(seeme_pointnet* h, const float* p, int C, int N, cudaStream_t s) {
+  const int rows = C * N;
+  const int np = h->precision;
+  {
+    const int ppb = 4;
+    int grid = (rows + ppb - 1) / ppb;
+    if (grid > NUM_SMS * 16) grid = NUM_SMS * 16;
+    fcpos_relu_bf16_kernel<<<grid, 256, 0, s>>>(p, h->fc_pos_w, h->fc_pos_b, h->xr0h, h->xr0l, rows);
+    SEEME_LAUNCH_CHECK();
+  }
+  int cur = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (i > 0) {
+      SEEME_TRY(decode_pool(h, C, s));
+      SEEME_TRY(pooled_bias(h, i, C, s));
+    }
+    UmmaLinear g1;   // hr = relu(W0 . xr + bias)
+    g1.A1 = {i == 0 ? h->xr0h : h->xrh[cur], i == 0 ? h->xr0l : h->xrl[cur], i == 0 ? 512 : 256};
+    g1.W = {h->g1h[i], h->g1l[i], i == 0 ? 512 : 256};
+    g1.M = rows; g1.N = 256; g1.K1 = i == 0 ? 512 : 256;
+    g1.bias = i == 0 ? h->b0[0] : h->c0;
+    g1.bias_group_rows = i == 0 ? 0 : N;
+    g1.act = ACT_RELU;
+    g1.Yh = h->hrh; g1.Yl = h->hrl; g1.ldb = 256;
+    g1.prof_id = PROF_POINTNET_GEMM + 1;
+    SEEME_TRY(umma_linear(g1, np, s));
+
+    SEEME_CUDA(cudaMemsetAsync(h->pool_ord, 0, (size_t)C * 256 * sizeof(unsigned), s));
+    UmmaLinear g2;   // net' = [x | hr] . [Ws_a | W1]^T + bias  (block 0: W1 . hr + rank-3 fold of the shortcut)
+    if (i == 0) {
+      g2.A1 = {h->hrh, h->hrl, 256};
+      g2.K1 = 256;
+      g2.W = {h->g2h[0], h->g2l[0], 256};
+      g2.bias = h->cst0;
+      g2.pfold = h->pfold;
+      g2.xyz = p;
+    } else {
+      g2.A1 = {h->xh[cur], h->xl[cur], 256};
+      g2.A2 = {h->hrh, h->hrl, 256};
+      g2.K1 = 256; g2.K2 = 256;
+      g2.W = {h->g2h[i], h->g2l[i], 512};
+      g2.bias = h->cs;
+      g2.bias_group_rows = N;
+    }
+    g2.M = rows; g2.N = 256;
+    if (i < 3) {   // the last block only feeds the pooling
+      g2.Yh = h->xh[cur ^ 1]; g2.Yl = h->xl[cur ^ 1];
+      g2.Zh = h->xrh[cur ^ 1]; g2.Zl = h->xrl[cur ^ 1];
+      g2.ldb = 256;
+    }
+    g2.colmax = h->pool_ord;
+    g2.colmax_group_rows = N;
+    g2.prof_id = PROF_POINTNET_GEMM + 1;
+    SEEME_TRY(umma_linear(g2, np, s));
+    cur ^= 1;
+  }
+  return decode_pool(h, C, s);
 }
 
 extern "C" int seeme_pointnet_forward(seeme_pointnet_t h, const float* pcd, int B, int N, float* feat512,
@@ -125,43 +349,17 @@ extern "C" int seeme_pointnet_forward(seeme_pointnet_t h, const float* pcd, int 
   SEEME_REQUIRE(B <= h->max_batch && N <= h->max_points, SEEME_ECAP,
                 "seeme_pointnet_forward: B=%d N=%d exceeds capacity (%d, %d)", B, N, h->max_batch, h->max_points);
   cudaStream_t s = (cudaStream_t)stream;
+  if (N < 128 && h->precision != 0) {
+    pad_cloud_kernel<<<(B * 128 + 255) / 256, 256, 0, s>>>(pcd, h->padbuf, B, N);
+    SEEME_LAUNCH_CHECK();
+    pcd = h->padbuf;
+    N = 128;
+  }
   for (int b0 = 0; b0 < B; b0 += h->chunk) {
     const int C = (B - b0 < h->chunk) ? (B - b0) : h->chunk;
-    const int rows = C * N;
     const float* p = pcd + (size_t)b0 * N * 3;
-    // fc_pos_0
-    SEEME_TRY(gemm_f32(gemm_params(p, 3, h->fc_pos_w, 3, h->fc_pos_b, h->x0, 512, rows, 512, 3), s));
-    float* net = h->net[0];
-    float* nxt = h->net[1];
-    {  // block_0 (K = 512, no pooled half)
-      GemmP g = gemm_params(h->x0, 512, h->w0[0], 512, h->b0[0], h->h, 256, rows, 256, 512);
-      g.pre_act = ACT_RELU; g.prof_id = PROF_POINTNET_GEMM + 1;
-      SEEME_TRY(gemm_f32(g, s));
-      GemmP gs0 = gemm_params(h->x0, 512, h->ws[0], 512, h->b1[0], net, 256, rows, 256, 512);
-      gs0.prof_id = PROF_POINTNET_GEMM + 1;
-      SEEME_TRY(gemm_f32(gs0, s));
-      GemmP g1 = gemm_params(h->h, 256, h->w1[0], 256, nullptr, net, 256, rows, 256, 256);
-      g1.pre_act = ACT_RELU; g1.accumulate = 1; g1.prof_id = PROF_POINTNET_GEMM + 1;
-      SEEME_TRY(gemm_f32(g1, s));
-    }
-    for (int i = 1; i < 4; ++i) {
-      SEEME_TRY(pool_stage(h, net, C, N, s));
-      GemmP gc0 = gemm_params(h->pool, 256, h->w0[i] + 256, 512, h->b0[i], h->c0, 256, C, 256, 256);
-      gc0.pre_act = ACT_RELU;
-      SEEME_TRY(gemm_f32(gc0, s));
-      SEEME_TRY(gemm_f32(gemm_params(h->pool, 256, h->ws[i] + 256, 512, h->b1[i], h->cs, 256, C, 256, 256), s));
-      GemmP g0 = gemm_params(net, 256, h->w0[i], 512, h->c0, h->h, 256, rows, 256, 256);
-      g0.pre_act = ACT_RELU; g0.bias_group_rows = N; g0.prof_id = PROF_POINTNET_GEMM + 1;
-      SEEME_TRY(gemm_f32(g0, s));
-      GemmP gs = gemm_params(net, 256, h->ws[i], 512, h->cs, nxt, 256, rows, 256, 256);
-      gs.bias_group_rows = N; gs.prof_id = PROF_POINTNET_GEMM + 1;
-      SEEME_TRY(gemm_f32(gs, s));
-      GemmP g1 = gemm_params(h->h, 256, h->w1[i], 256, nullptr, nxt, 256, rows, 256, 256);
-      g1.pre_act = ACT_RELU; g1.accumulate = 1; g1.prof_id = PROF_POINTNET_GEMM + 1;
-      SEEME_TRY(gemm_f32(g1, s));
-      float* t = net; net = nxt; nxt = t;
-    }
-    SEEME_TRY(pool_stage(h, net, C, N, s));
+    if (h->precision == 0) SEEME_TRY(blocks_fp32(h, p, C, N, s));
+    else SEEME_TRY(blocks_tensor(h, p, C, N, s));
     // fc_c(relu(pool)) -> [C,512]; output_scene: Linear(relu(.)) -> [C,256]
     GemmP gc = gemm_params(h->pool, 256, h->wc, 256, h->bc, h->feat + (size_t)b0 * 512, 512, C, 512, 256);
     gc.pre_act = ACT_RELU;
@@ -180,7 +378,6 @@ extern "C" int seeme_pointnet_forward(seeme_pointnet_t h, const float* pcd, int 
 
 extern "C" int seeme_pointnet_destroy(seeme_pointnet_t h) {
   if (!h) return SEEME_OK;
-  h->arena.release();
-  delete h;
+  destroy(h);
   return SEEME_OK;
 }

@@ -128,8 +128,8 @@ struct UmmaLinear {
 // precision: 1 = single bf16 pass, 3 = split-bf16 (hi.hi + lo.hi + hi.lo)
 int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s);
 
-// fp32 -> bf16 hi (+ lo = bf16(x - hi)) conversion of a dense [rows, cols] matrix into a [rows, ld_out] one
-// (zero padding for cols..ld_out), optional relu on load
+// fp32 -> bf16 hi (+ lo = bf16(x - hi)) conversion of a [rows, cols] matrix (pitch ldx) into columns [0, cols)
+// of a destination with pitch ld_out (the other destination columns are not written), optional relu on load
 int to_bf16_split(const float* x, int ldx, int rows, int cols, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_out, int relu,
                   cudaStream_t s);
 

@@ -299,18 +299,19 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
 __global__ void to_bf16_split_kernel(const float* __restrict__ x, int ldx, int rows, int cols, __nv_bfloat16* __restrict__ hi,
                                      __nv_bfloat16* __restrict__ lo, int ld_out, int relu) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= (size_t)rows * ld_out) return;
-  const int r = (int)(i / ld_out), c = (int)(i % ld_out);
-  float v = c < cols ? x[(size_t)r * ldx + c] : 0.f;
+  if (i >= (size_t)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  float v = x[(size_t)r * ldx + c];
   if (relu) v = fmaxf(v, 0.f);
   const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  hi[i] = h;
-  if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  const size_t o = (size_t)r * ld_out + c;      // columns [cols, ld_out) of the destination are left untouched
+  hi[o] = h;
+  if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
 int to_bf16_split(const float* x, int ldx, int rows, int cols, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_out, int relu,
                   cudaStream_t s) {
-  const size_t n = (size_t)rows * ld_out;
+  const size_t n = (size_t)rows * cols;
   if (!n) return SEEME_OK;
   to_bf16_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, ldx, rows, cols, hi, lo, ld_out, relu);
   SEEME_LAUNCH_CHECK();
