@@ -242,7 +242,10 @@ def main():
         flops = POINTNET_FLOP_PER_POINT * N_POINTS * B * args.steps - 2 * 3 * 512 * N_POINTS * B * args.steps  # fc_pos (K=3) is not in this class
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         ach = flops / (pn_ms / 1e3) / 1e12 if pn_ms > 0 else None
-        roofline = {"kernel": "scene-encoder GEMM launches (gemm_f32_kernel<128,128,8,8>)", "bound": "tensor", "achieved": ach,
+        prec = os.environ.get("SEEME_POINTNET_PRECISION", "3")
+        kname = {"3": "umma_linear_kernel<256,3,2> (tcgen05, split-bf16: 3 MMAs per algorithmic MAC)",
+                 "1": "umma_linear_kernel<256,1,2> (tcgen05, bf16)", "0": "gemm_f32_kernel<128,128,8,8> (fp32 CUDA cores)"}[prec]
+        roofline = {"kernel": "scene-encoder GEMM launches: " + kname, "bound": "tensor", "achieved": ach,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": (ach / peak_tf) if ach else None, "traffic": None,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
                     "launches": pn_n, "avg_launch_ms": pn_ms / pn_n if pn_n else None,

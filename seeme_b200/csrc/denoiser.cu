@@ -14,13 +14,14 @@
 // update are fused into the kernel that applies the final LayerNorm.
 #include "common.cuh"
 #include "rowops.cuh"
+#include "umma.cuh"
 #include <stdlib.h>
 
 namespace seeme {
 
 // x[r] = lat[r % B] + pe[0]      (torch.cat([latents]*2), mld.py:469-473; query_pos, mld_denoiser.py:210)
 __global__ void den_prep_kernel(const float* __restrict__ lat, const float* __restrict__ pe0, float* __restrict__ x,
-                                int R, int B) {
+                                __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ xl, int R, int B) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -29,12 +30,14 @@ __global__ void den_prep_kernel(const float* __restrict__ lat, const float* __re
 #pragma unroll
   for (int i = 0; i < 8; ++i) v.v[i] += p.v[i];
   row_store(x + (size_t)row * 256, lane, v);
+  row_store_split(xh + (size_t)row * 256, xl + (size_t)row * 256, lane, v);
 }
 
 // token-0 self-attention over keys {x_r, cond_0..cond_{Nc-1}, time}; qkv [R,768] (q pre-scaled),
 // kvc [Nc*R,512] = (k|v) of the cond tokens (row n*R + r), tkv [512] = (k|v) of the time token.
 __global__ void den_sa_attn_kernel(const float* __restrict__ qkv, const float* __restrict__ kvc,
-                                   const float* __restrict__ tkv, int Nc, int R, float* __restrict__ out) {
+                                   const float* __restrict__ tkv, int Nc, int R, __nv_bfloat16* __restrict__ oh,
+                                   __nv_bfloat16* __restrict__ ol) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -68,7 +71,7 @@ __global__ void den_sa_attn_kernel(const float* __restrict__ qkv, const float* _
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(p, v.v[i], acc.v[i]);
   }
-  row_store(out + (size_t)row * 256, lane, acc);
+  row_store_split(oh + (size_t)row * 256, ol + (size_t)row * 256, lane, acc);
 }
 
 // FiLM tail of a StylizationBlock (mdiff_transformer.py:152-163) before its out Linear:
@@ -87,7 +90,7 @@ __device__ __forceinline__ Row8 film_silu(const Row8& y, const float* __restrict
 // followed by the FiLM tail.  q [R,256]; kv2 [Nc*R,512] = (key|value) rows n*R + r.
 __global__ void den_ca_kernel(const float* __restrict__ q, const float* __restrict__ kv2, int Nc, int R,
                               const float* __restrict__ film, const float* __restrict__ g, const float* __restrict__ b,
-                              float* __restrict__ out) {
+                              __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -122,15 +125,32 @@ __global__ void den_ca_kernel(const float* __restrict__ q, const float* __restri
 #pragma unroll
     for (int i = 0; i < 8; ++i) y.v[i] = fmaf(w, v.v[i], y.v[i]);
   }
-  row_store(out + (size_t)row * 256, lane, film_silu(y, film, g, b, lane));
+  row_store_split(oh + (size_t)row * 256, ol + (size_t)row * 256, lane, film_silu(y, film, g, b, lane));
 }
 
 __global__ void den_film_kernel(const float* __restrict__ y, const float* __restrict__ film, const float* __restrict__ g,
-                                const float* __restrict__ b, float* __restrict__ out, int R) {
+                                const float* __restrict__ b, __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol,
+                                int R) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
-  row_store(out + (size_t)row * 256, lane, film_silu(row_load(y + (size_t)row * 256, lane), film, g, b, lane));
+  row_store_split(oh + (size_t)row * 256, ol + (size_t)row * 256, lane,
+                  film_silu(row_load(y + (size_t)row * 256, lane), film, g, b, lane));
+}
+
+// y = LN(x) -> fp32 and bf16 (hi, lo);  optionally a second LayerNorm chained on the result:
+// y2 = LN2(y) -> bf16 only (norm2 of the self-attention block followed by the cross-attention's input norm)
+__global__ void den_ln_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                              float* __restrict__ y, __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl,
+                              const float* __restrict__ g2, const float* __restrict__ b2, __nv_bfloat16* __restrict__ y2h,
+                              __nv_bfloat16* __restrict__ y2l, int R) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const Row8 v = row_layernorm(row_load(x + (size_t)row * 256, lane), g, b, lane);
+  if (y) row_store(y + (size_t)row * 256, lane, v);
+  if (yh) row_store_split(yh + (size_t)row * 256, yl + (size_t)row * 256, lane, v);
+  if (g2) row_store_split(y2h + (size_t)row * 256, y2l + (size_t)row * 256, lane, row_layernorm(v, g2, b2, lane));
 }
 
 // eps = LN_final(x); [CFG] eps = eps_u + s (eps_c - eps_u) with u = rows [0,B), c = rows [B,2B)
@@ -195,7 +215,12 @@ struct seeme_denoiser {
   std::vector<int> table_ts;      // timesteps the tables currently hold
   // per-run cond projections (H3) and activations
   float *cond, *tn, *kvc[5], *kv2[5];
-  float *lat, *x, *L[5], *qkv, *att, *t0, *x1, *x2, *ff, *g1;
+  float *lat, *qkv, *t0, *caq, *y;
+  // tcgen05 path: packed (hi, lo) weights and activations carried as fp32 (residuals, row-wise ops) and/or
+  // split bf16 (GEMM A operands)
+  int npass = 3;
+  PackedLinear Wqkv[5], Wout[5], Wl1[5], Wl2[5], Wcaq[5], Wcaout[5], Wf1[5], Wf2[5], Wfout[5], Wskip[2];
+  ActBuf x, L[5], att, x1, x2, ln, hb, ff, g1;
   float *d_coef, *d_gscale;
   std::vector<float> coef_host;   // what d_coef / d_gscale currently hold
   float gscale_host = -1.f;
@@ -223,8 +248,10 @@ extern "C" int seeme_denoiser_create(seeme_denoiser_t* out, const float* const* 
   const size_t R = max_rows, NC = SEEME_MAX_COND_TOKENS;
   size_t tbytes = 3 * pad256((size_t)MAX_STEPS * 256 * 4) + 15 * pad256((size_t)MAX_STEPS * 512 * 4);
   size_t ws = 2 * pad256(NC * R * 256 * 4) + 10 * pad256(NC * R * 512 * 4) + 12 * pad256(R * 256 * 4) + pad256(R * 768 * 4) +
-              pad256(R * 1024 * 4) + pad256(R * 128 * 4) + pad256(MAX_STEPS * 4 * 4) + 256;
-  int rc = h->arena.init(wbytes + tbytes + ws + 8192);
+              22 * pad256(R * 256 * 2) + 2 * pad256(R * 1024 * 2) + 2 * pad256(R * 128 * 2) + pad256(MAX_STEPS * 4 * 4) + 256;
+  // bf16 (hi, lo) copies of the per-step weights: ~5.6 M parameters x 2 x 2 bytes
+  const size_t pbytes = 2 * 2 * (size_t)(5 * (768 * 256 + 256 * 256 + 2 * 1024 * 256 + 3 * 256 * 256 + 2 * 128 * 256) + 2 * 256 * 512) + 64 * 1024;
+  int rc = h->arena.init(wbytes + tbytes + ws + pbytes + 65536);
   if (rc) { delete h; return rc; }
   for (int i = 0; i < n_w; ++i) {
     size_t n = den_tensor_elems(i);
@@ -250,18 +277,47 @@ extern "C" int seeme_denoiser_create(seeme_denoiser_t* out, const float* const* 
   h->tn = h->arena.take<float>(NC * R * 256);
   for (int l = 0; l < 5; ++l) { h->kvc[l] = h->arena.take<float>(NC * R * 512); h->kv2[l] = h->arena.take<float>(NC * R * 512); }
   h->lat = h->arena.take<float>(R * 256);
-  h->x = h->arena.take<float>(R * 256);
-  for (int l = 0; l < 5; ++l) h->L[l] = h->arena.take<float>(R * 256);
-  h->att = h->arena.take<float>(R * 256);
   h->t0 = h->arena.take<float>(R * 256);
-  h->x1 = h->arena.take<float>(R * 256);
-  h->x2 = h->arena.take<float>(R * 256);
+  h->caq = h->arena.take<float>(R * 256);
+  h->y = h->arena.take<float>(R * 256);
   h->qkv = h->arena.take<float>(R * 768);
-  h->ff = h->arena.take<float>(R * 1024);
-  h->g1 = h->arena.take<float>(R * 128);
+  auto mk = [&](ActBuf& a, int ld, bool f32, bool b16) {
+    a.ld = ld;
+    a.f = f32 ? h->arena.take<float>(R * ld) : nullptr;
+    a.h = b16 ? h->arena.take<__nv_bfloat16>(R * ld) : nullptr;
+    a.l = b16 ? h->arena.take<__nv_bfloat16>(R * ld) : nullptr;
+  };
+  mk(h->x, 256, true, true);
+  for (int l = 0; l < 5; ++l) mk(h->L[l], 256, true, true);
+  mk(h->att, 256, false, true);
+  mk(h->x1, 256, true, true);
+  mk(h->x2, 256, true, false);
+  mk(h->ln, 256, false, true);
+  mk(h->hb, 256, false, true);
+  mk(h->ff, 1024, false, true);
+  mk(h->g1, 128, false, true);
   h->d_coef = h->arena.take<float>((size_t)MAX_STEPS * 4);
   h->d_gscale = h->arena.take<float>(1);
   if (!h->d_gscale) { set_error("seeme_denoiser_create: arena exhausted (workspace)"); h->arena.release(); delete h; return SEEME_ENOMEM; }
+  // pack the per-step weights for the tcgen05 linears (q rows already carry the 1/16 attention scale)
+  const char* pe = getenv("SEEME_DENOISER_PRECISION");
+  h->npass = (pe && atoi(pe) == 1) ? 1 : 3;
+  rc = SEEME_OK;
+  for (int l = 0; l < 5 && !rc; ++l) {
+    rc = pack_linear(h->arena, h->Wqkv[l], blkw(h, l, SA_IN_W), 256, 768, 256, blkw(h, l, SA_IN_B));
+    if (!rc) rc = pack_linear(h->arena, h->Wout[l], blkw(h, l, SA_OUT_W), 256, 256, 256, blkw(h, l, SA_OUT_B));
+    if (!rc) rc = pack_linear(h->arena, h->Wl1[l], blkw(h, l, SA_L1_W), 256, 1024, 256, blkw(h, l, SA_L1_B));
+    if (!rc) rc = pack_linear(h->arena, h->Wl2[l], blkw(h, l, SA_L2_W), 1024, 256, 1024, blkw(h, l, SA_L2_B));
+    if (!rc) rc = pack_linear(h->arena, h->Wcaq[l], blkw(h, l, CA_Q_W), 256, 256, 256, blkw(h, l, CA_Q_B));
+    if (!rc) rc = pack_linear(h->arena, h->Wcaout[l], blkw(h, l, CA_OUT_W), 256, 256, 256, blkw(h, l, CA_OUT_B));
+    if (!rc) rc = pack_linear(h->arena, h->Wf1[l], blkw(h, l, FF_L1_W), 256, 128, 256, blkw(h, l, FF_L1_B));
+    if (!rc) rc = pack_linear(h->arena, h->Wf2[l], blkw(h, l, FF_L2_W), 128, 256, 128, blkw(h, l, FF_L2_B));
+    if (!rc) rc = pack_linear(h->arena, h->Wfout[l], blkw(h, l, FF_OUT_W), 256, 256, 256, blkw(h, l, FF_OUT_B));
+  }
+  for (int i = 0; i < 2 && !rc; ++i)
+    rc = pack_linear(h->arena, h->Wskip[i], h->w[DN_LB0_W + 2 * i], 512, 256, 512, h->w[DN_LB0_B + 2 * i]);
+  if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_error("seeme_denoiser_create: weight packing failed"); rc = SEEME_ECUDA; }
+  if (rc) { h->arena.release(); delete h; return rc; }
   SEEME_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
   *out = h;
   return SEEME_OK;
@@ -319,61 +375,53 @@ static int den_cond_precompute(seeme_denoiser* h, int Nc, int R, cudaStream_t s)
   return SEEME_OK;
 }
 
-// one block (mdiff_transformer.py:286-304) for table row `ti`
-static int den_block(seeme_denoiser* h, int l, int ti, const float* xin, float* xout, int Nc, int R, cudaStream_t s) {
-  const int nb = (R + 7) / 8;
-  SEEME_TRY(gemm_f32(gemm_params(xin, 256, blkw(h, l, SA_IN_W), 256, blkw(h, l, SA_IN_B), h->qkv, 768, R, 768, 256), s));
-  den_sa_attn_kernel<<<nb, 256, 0, s>>>(h->qkv, h->kvc[l], h->tkv[l] + (size_t)ti * 512, Nc, R, h->att);
+// one block (mdiff_transformer.py:286-304) for table row `ti`: 9 tcgen05 linears + 5 row-wise kernels
+static int den_block(seeme_denoiser* h, int l, int ti, const ActBuf& xin, const ActBuf& xout, int Nc, int R, cudaStream_t s) {
+  const int nb = (R + 7) / 8, np = h->npass;
+  ActBuf qkv; qkv.f = h->qkv; qkv.ld = 768;
+  ActBuf t0; t0.f = h->t0; t0.ld = 256;
+  ActBuf caq; caq.f = h->caq; caq.ld = 256;
+  ActBuf y; y.f = h->y; y.ld = 256;
+  // self-attention over {x, cond tokens, time token}, token 0 only (H1)
+  SEEME_TRY(run_linear(h->Wqkv[l], xin, nullptr, R, ACT_NONE, nullptr, 0, qkv, np, s));
+  den_sa_attn_kernel<<<nb, 256, 0, s>>>(h->qkv, h->kvc[l], h->tkv[l] + (size_t)ti * 512, Nc, R, h->att.h, h->att.l);
   SEEME_LAUNCH_CHECK();
-  GemmP go = gemm_params(h->att, 256, blkw(h, l, SA_OUT_W), 256, blkw(h, l, SA_OUT_B), h->t0, 256, R, 256, 256);
-  go.R = xin; go.ldr = 256;
-  SEEME_TRY(gemm_f32(go, s));
-  SEEME_TRY(layernorm256(h->t0, nullptr, 0, blkw(h, l, SA_N1_W), blkw(h, l, SA_N1_B), h->x1, R, s));
-  GemmP g1 = gemm_params(h->x1, 256, blkw(h, l, SA_L1_W), 256, blkw(h, l, SA_L1_B), h->ff, 1024, R, 1024, 256);
-  g1.act = ACT_RELU;
-  SEEME_TRY(gemm_f32(g1, s));
-  GemmP g2 = gemm_params(h->ff, 1024, blkw(h, l, SA_L2_W), 1024, blkw(h, l, SA_L2_B), h->t0, 256, R, 256, 1024);
-  g2.R = h->x1; g2.ldr = 256;
-  SEEME_TRY(gemm_f32(g2, s));
-  SEEME_TRY(layernorm256(h->t0, nullptr, 0, blkw(h, l, SA_N2_W), blkw(h, l, SA_N2_B), h->x2, R, s));
-  // cross-attention to the cond tokens + FiLM
-  SEEME_TRY(layernorm256(h->x2, nullptr, 0, blkw(h, l, CA_N_W), blkw(h, l, CA_N_B), h->t0, R, s));
-  SEEME_TRY(gemm_f32(gemm_params(h->t0, 256, blkw(h, l, CA_Q_W), 256, blkw(h, l, CA_Q_B), h->att, 256, R, 256, 256), s));
-  den_ca_kernel<<<nb, 256, 0, s>>>(h->att, h->kv2[l], Nc, R, h->film_ca[l] + (size_t)ti * 512, blkw(h, l, CA_PN_W),
-                                   blkw(h, l, CA_PN_B), h->t0);
+  SEEME_TRY(run_linear(h->Wout[l], h->att, nullptr, R, ACT_NONE, xin.f, 256, t0, np, s));
+  den_ln_kernel<<<nb, 256, 0, s>>>(h->t0, blkw(h, l, SA_N1_W), blkw(h, l, SA_N1_B), h->x1.f, h->x1.h, h->x1.l, nullptr, nullptr,
+                                   nullptr, nullptr, R);
   SEEME_LAUNCH_CHECK();
-  GemmP gc = gemm_params(h->t0, 256, blkw(h, l, CA_OUT_W), 256, blkw(h, l, CA_OUT_B), h->x1, 256, R, 256, 256);
-  gc.R = h->x2; gc.ldr = 256;
-  SEEME_TRY(gemm_f32(gc, s));       // x3 in x1
+  SEEME_TRY(run_linear(h->Wl1[l], h->x1, nullptr, R, ACT_RELU, nullptr, 0, h->ff, np, s));
+  SEEME_TRY(run_linear(h->Wl2[l], h->ff, nullptr, R, ACT_NONE, h->x1.f, 256, t0, np, s));
+  // x2 = norm2(.) and the cross-attention's input norm chained in one kernel
+  den_ln_kernel<<<nb, 256, 0, s>>>(h->t0, blkw(h, l, SA_N2_W), blkw(h, l, SA_N2_B), h->x2.f, nullptr, nullptr, blkw(h, l, CA_N_W),
+                                   blkw(h, l, CA_N_B), h->ln.h, h->ln.l, R);
+  SEEME_LAUNCH_CHECK();
+  // linear cross-attention to the cond tokens (H2) + FiLM
+  SEEME_TRY(run_linear(h->Wcaq[l], h->ln, nullptr, R, ACT_NONE, nullptr, 0, caq, np, s));
+  den_ca_kernel<<<nb, 256, 0, s>>>(h->caq, h->kv2[l], Nc, R, h->film_ca[l] + (size_t)ti * 512, blkw(h, l, CA_PN_W),
+                                   blkw(h, l, CA_PN_B), h->hb.h, h->hb.l);
+  SEEME_LAUNCH_CHECK();
+  SEEME_TRY(run_linear(h->Wcaout[l], h->hb, nullptr, R, ACT_NONE, h->x2.f, 256, h->x1, np, s));    // x3 -> x1 (fp32 + bf16)
   // FFN + FiLM
-  GemmP gf1 = gemm_params(h->x1, 256, blkw(h, l, FF_L1_W), 256, blkw(h, l, FF_L1_B), h->g1, 128, R, 128, 256);
-  gf1.act = ACT_GELU;
-  SEEME_TRY(gemm_f32(gf1, s));
-  SEEME_TRY(gemm_f32(gemm_params(h->g1, 128, blkw(h, l, FF_L2_W), 128, blkw(h, l, FF_L2_B), h->att, 256, R, 256, 128), s));
-  den_film_kernel<<<nb, 256, 0, s>>>(h->att, h->film_ff[l] + (size_t)ti * 512, blkw(h, l, FF_PN_W), blkw(h, l, FF_PN_B), h->t0, R);
+  SEEME_TRY(run_linear(h->Wf1[l], h->x1, nullptr, R, ACT_GELU, nullptr, 0, h->g1, np, s));
+  SEEME_TRY(run_linear(h->Wf2[l], h->g1, nullptr, R, ACT_NONE, nullptr, 0, y, np, s));
+  den_film_kernel<<<nb, 256, 0, s>>>(h->y, h->film_ff[l] + (size_t)ti * 512, blkw(h, l, FF_PN_W), blkw(h, l, FF_PN_B), h->hb.h,
+                                     h->hb.l, R);
   SEEME_LAUNCH_CHECK();
-  GemmP gf = gemm_params(h->t0, 256, blkw(h, l, FF_OUT_W), 256, blkw(h, l, FF_OUT_B), xout, 256, R, 256, 256);
-  gf.R = h->x1; gf.ldr = 256;
-  SEEME_TRY(gemm_f32(gf, s));
+  SEEME_TRY(run_linear(h->Wfout[l], h->hb, nullptr, R, ACT_NONE, h->x1.f, 256, xout, np, s));
   return SEEME_OK;
 }
 
 // the skip stack (cross_attention.py:67-83) on h->x for table row ti; result (pre final norm) in h->L[4]
 static int den_stack(seeme_denoiser* h, int ti, int Nc, int R, cudaStream_t s) {
-  const float* x = h->x;
+  const ActBuf* x = &h->x;
   for (int l = 0; l < 5; ++l) {
-    if (l >= 3) {
-      const int i = l - 3;
-      const float* skip = h->L[l == 3 ? 1 : 0];
-      const float* W = h->w[DN_LB0_W + 2 * i];
-      SEEME_TRY(gemm_f32(gemm_params(x, 256, W, 512, h->w[DN_LB0_B + 2 * i], h->x, 256, R, 256, 256), s));
-      GemmP ga = gemm_params(skip, 256, W + 256, 512, nullptr, h->x, 256, R, 256, 256);
-      ga.accumulate = 1;
-      SEEME_TRY(gemm_f32(ga, s));
-      x = h->x;
+    if (l >= 3) {   // x = Linear(cat[x, skip]); skip = L[1] for l == 3, L[0] for l == 4
+      SEEME_TRY(run_linear(h->Wskip[l - 3], *x, &h->L[l == 3 ? 1 : 0], R, ACT_NONE, nullptr, 0, h->x, h->npass, s));
+      x = &h->x;
     }
-    SEEME_TRY(den_block(h, l, ti, x, h->L[l], Nc, R, s));
-    x = h->L[l];
+    SEEME_TRY(den_block(h, l, ti, *x, h->L[l], Nc, R, s));
+    x = &h->L[l];
   }
   return SEEME_OK;
 }
@@ -393,10 +441,10 @@ extern "C" int seeme_denoiser_forward(seeme_denoiser_t h, const float* sample, i
   if (!(h->table_ts.size() == 1 && h->table_ts[0] == timestep)) SEEME_TRY(den_build_tables(h, &timestep, 1, nullptr, s));
   SEEME_CUDA(cudaMemcpyAsync(h->cond, cond, (size_t)Nc * R * 256 * 4, cudaMemcpyDeviceToDevice, s));
   SEEME_TRY(den_cond_precompute(h, Nc, R, s));
-  den_prep_kernel<<<(R + 7) / 8, 256, 0, s>>>(sample, h->w[DN_PE], h->x, R, R);
+  den_prep_kernel<<<(R + 7) / 8, 256, 0, s>>>(sample, h->w[DN_PE], h->x.f, h->x.h, h->x.l, R, R);
   SEEME_LAUNCH_CHECK();
   SEEME_TRY(den_stack(h, 0, Nc, R, s));
-  SEEME_TRY(layernorm256(h->L[4], nullptr, 0, h->w[DN_NORM_W], h->w[DN_NORM_B], out, R, s));
+  SEEME_TRY(layernorm256(h->L[4].f, nullptr, 0, h->w[DN_NORM_W], h->w[DN_NORM_B], out, R, s));
   return SEEME_OK;
 }
 
@@ -409,10 +457,10 @@ extern "C" int seeme_denoiser_set_time_table(seeme_denoiser_t h, const int32_t* 
 static int sampler_enqueue(seeme_denoiser* h, int Nc, int B, int R, int cfg, int n_steps, cudaStream_t s) {
   SEEME_TRY(den_cond_precompute(h, Nc, R, s));
   for (int i = 0; i < n_steps; ++i) {
-    den_prep_kernel<<<(R + 7) / 8, 256, 0, s>>>(h->lat, h->w[DN_PE], h->x, R, B);
+    den_prep_kernel<<<(R + 7) / 8, 256, 0, s>>>(h->lat, h->w[DN_PE], h->x.f, h->x.h, h->x.l, R, B);
     SEEME_LAUNCH_CHECK();
     SEEME_TRY(den_stack(h, i, Nc, R, s));
-    den_final_ddim_kernel<<<(B + 7) / 8, 256, 0, s>>>(h->L[4], h->w[DN_NORM_W], h->w[DN_NORM_B], h->lat, B, cfg,
+    den_final_ddim_kernel<<<(B + 7) / 8, 256, 0, s>>>(h->L[4].f, h->w[DN_NORM_W], h->w[DN_NORM_B], h->lat, B, cfg,
                                                       h->d_coef + 4 * i, h->d_gscale);
     SEEME_LAUNCH_CHECK();
   }

@@ -21,6 +21,22 @@ __device__ __forceinline__ void row_store(float* __restrict__ p, int lane, const
   reinterpret_cast<float4*>(p)[lane] = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
   reinterpret_cast<float4*>(p)[lane + 32] = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
+// bf16 split store of a row: hi = bf16(x), lo = bf16(x - hi) (lo may be null)
+__device__ __forceinline__ void row_store_split(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int lane,
+                                                const Row8& r) {
+  __align__(8) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = __float2bfloat16_rn(r.v[i]);
+    l[i] = __float2bfloat16_rn(r.v[i] - __bfloat162float(h[i]));
+  }
+  reinterpret_cast<uint2*>(hi)[lane] = reinterpret_cast<const uint2*>(h)[0];
+  reinterpret_cast<uint2*>(hi)[lane + 32] = reinterpret_cast<const uint2*>(h)[1];
+  if (lo) {
+    reinterpret_cast<uint2*>(lo)[lane] = reinterpret_cast<const uint2*>(l)[0];
+    reinterpret_cast<uint2*>(lo)[lane + 32] = reinterpret_cast<const uint2*>(l)[1];
+  }
+}
 __device__ __forceinline__ float row_dot(const Row8& a, const Row8& b) {
   float s = 0.f;
 #pragma unroll

@@ -128,6 +128,23 @@ struct UmmaLinear {
 // precision: 1 = single bf16 pass, 3 = split-bf16 (hi.hi + lo.hi + hi.lo)
 int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s);
 
+// ---- convenience layer used by the transformer stacks ----------------------------------------------
+struct PackedLinear {           // nn.Linear weight [N,K] packed once as bf16 (hi, lo); bias stays fp32
+  __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+  const float* bias = nullptr;
+  int N = 0, K = 0;
+};
+struct ActBuf {                 // an activation tensor [rows, ld]: fp32 copy and/or bf16 (hi, lo) copy
+  float* f = nullptr;
+  __nv_bfloat16 *h = nullptr, *l = nullptr;
+  int ld = 0;
+};
+int pack_linear(Arena& arena, PackedLinear& out, const float* W, int ldw, int N, int K, const float* bias);
+// out = act(A W^T + bias) (+ R); A2 (nullable) supplies the second half of K (torch.cat([A, A2], -1));
+// the fp32 and bf16 members of `out` that are non-null are written
+int run_linear(const PackedLinear& W, const ActBuf& A, const ActBuf* A2, int M, int act, const float* R, int ldr,
+               const ActBuf& out, int npass, cudaStream_t s, int bias_group_rows = 0, const float* bias_override = nullptr);
+
 // fp32 -> bf16 hi (+ lo = bf16(x - hi)) conversion of a [rows, cols] matrix (pitch ldx) into columns [0, cols)
 // of a destination with pitch ld_out (the other destination columns are not written), optional relu on load
 int to_bf16_split(const float* x, int ldx, int rows, int cols, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_out, int relu,

@@ -275,8 +275,10 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
   SEEME_REQUIRE(npass == 1 || npass == 3, SEEME_EINVAL, "umma_linear: npass must be 1 or 3");
   SEEME_REQUIRE(npass == 1 || (g.A1.lo && g.W.lo && (g.K2 == 0 || g.A2.lo)), SEEME_EINVAL, "umma_linear: split-bf16 needs lo operands");
   SEEME_REQUIRE(!g.colmax || g.colmax_group_rows >= 128, SEEME_EINVAL, "umma_linear: colmax groups must have >= 128 rows");
-  const int BN = (g.N % 256 == 0) ? 256 : 128;
-  SEEME_REQUIRE(g.N % BN == 0, SEEME_EINVAL, "umma_linear: N=%d must be a multiple of 128", g.N);
+  // few rows (the latency-bound sampler / per-sample GEMMs): narrow tiles spread one GEMM over more SMs;
+  // many rows: the widest tile that divides N
+  const int BN = (g.M <= 2048 && !g.colmax) ? 64 : ((g.N % 256 == 0) ? 256 : 128);
+  SEEME_REQUIRE(g.N % BN == 0, SEEME_EINVAL, "umma_linear: N=%d must be a multiple of %d", g.N, BN);
   CUtensorMap maps[6];
   memset(maps, 0, sizeof(maps));
   SEEME_TRY(make_map(&maps[0], g.A1.hi, g.M, g.K1, g.A1.ld, 128));
@@ -293,6 +295,7 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
   e.R = g.R; e.ldr = g.ldr; e.Y = g.Y; e.ldy = g.ldy; e.Yh = g.Yh; e.Yl = g.Yl; e.Zh = g.Zh; e.Zl = g.Zl; e.ldb = g.ldb;
   e.colmax = g.colmax; e.colmax_group_rows = g.colmax_group_rows;
   if (BN == 256) return npass == 1 ? launch<256, 1, 2>(g, maps, e, s) : launch<256, 3, 2>(g, maps, e, s);
+  if (BN == 64) return npass == 1 ? launch<64, 1, 4>(g, maps, e, s) : launch<64, 3, 4>(g, maps, e, s);
   return npass == 1 ? launch<128, 1, 4>(g, maps, e, s) : launch<128, 3, 2>(g, maps, e, s);
 }
 
@@ -316,6 +319,35 @@ int to_bf16_split(const float* x, int ldx, int rows, int cols, __nv_bfloat16* hi
   to_bf16_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, ldx, rows, cols, hi, lo, ld_out, relu);
   SEEME_LAUNCH_CHECK();
   return SEEME_OK;
+}
+
+int pack_linear(Arena& arena, PackedLinear& out, const float* W, int ldw, int N, int K, const float* bias) {
+  out.hi = arena.take<__nv_bfloat16>((size_t)N * K);
+  out.lo = arena.take<__nv_bfloat16>((size_t)N * K);
+  SEEME_REQUIRE(out.hi && out.lo, SEEME_ENOMEM, "pack_linear: arena exhausted (N=%d K=%d)", N, K);
+  out.N = N; out.K = K; out.bias = bias;
+  return to_bf16_split(W, ldw, N, K, out.hi, out.lo, K, 0, 0);
+}
+
+int run_linear(const PackedLinear& W, const ActBuf& A, const ActBuf* A2, int M, int act, const float* R, int ldr,
+               const ActBuf& out, int npass, cudaStream_t s, int bias_group_rows, const float* bias_override) {
+  UmmaLinear g;
+  g.M = M; g.N = W.N;
+  g.A1 = {A.h, A.l, A.ld};
+  if (A2) {
+    g.A2 = {A2->h, A2->l, A2->ld};
+    g.K1 = W.K / 2; g.K2 = W.K / 2;
+  } else {
+    g.K1 = W.K;
+  }
+  g.W = {W.hi, W.lo, W.K};
+  g.bias = bias_override ? bias_override : W.bias;
+  g.bias_group_rows = bias_group_rows;
+  g.act = act;
+  g.R = R; g.ldr = ldr;
+  g.Y = out.f; g.ldy = out.ld;
+  g.Yh = out.h; g.Yl = out.l; g.ldb = out.ld;
+  return umma_linear(g, npass, s);
 }
 
 }  // namespace seeme

@@ -9,6 +9,8 @@
 // all five layers; the q/k projections of that attention never influence the result.
 #include "common.cuh"
 #include "rowops.cuh"
+#include "umma.cuh"
+#include <stdlib.h>
 
 namespace seeme {
 
@@ -16,7 +18,8 @@ namespace seeme {
 // staged in shared memory (2 x S x 1 KB), one warp per query row, fp32 softmax.
 // qkv [B*S, 768] = (q * 1/16 | k | v);  key j is valid iff j < n_prefix + lengths[b].
 __global__ void __launch_bounds__(256) mha1_kernel(const float* __restrict__ qkv, const int* __restrict__ lengths,
-                                                   int n_prefix, int S, float* __restrict__ out) {
+                                                   int n_prefix, int S, __nv_bfloat16* __restrict__ oh,
+                                                   __nv_bfloat16* __restrict__ ol) {
   extern __shared__ __align__(16) float sm[];
   float* Ks = sm;
   float* Vs = sm + (size_t)S * 256;
@@ -53,13 +56,14 @@ __global__ void __launch_bounds__(256) mha1_kernel(const float* __restrict__ qkv
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(p, v.v[i], acc.v[i]);
     }
-    row_store(out + ((size_t)b * S + qi) * 256, lane, acc);
+    row_store_split(oh + ((size_t)b * S + qi) * 256, ol + ((size_t)b * S + qi) * 256, lane, acc);
   }
 }
 
 // xseq[b, s] = (s < 2 ? global_motion_token[s] : emb[b, s-2]) + pe[s]     (mld_vae.py:147-164)
 __global__ void vae_enc_assemble_kernel(const float* __restrict__ emb, const float* __restrict__ token,
-                                        const float* __restrict__ pe, float* __restrict__ x, int B, int T) {
+                                        const float* __restrict__ pe, float* __restrict__ x,
+                                        __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ xl, int B, int T) {
   const int S = T + 2;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -70,14 +74,18 @@ __global__ void vae_enc_assemble_kernel(const float* __restrict__ emb, const flo
 #pragma unroll
   for (int i = 0; i < 8; ++i) v.v[i] += p.v[i];
   row_store(x + (size_t)row * 256, lane, v);
+  row_store_split(xh + (size_t)row * 256, xl + (size_t)row * 256, lane, v);
 }
 
 // queries[b, t] = 0 + pe[t]                                                (mld_vae.py:198,230)
-__global__ void vae_dec_queries_kernel(const float* __restrict__ pe, float* __restrict__ x, int B, int T) {
+__global__ void vae_dec_queries_kernel(const float* __restrict__ pe, float* __restrict__ x, __nv_bfloat16* __restrict__ xh,
+                                       __nv_bfloat16* __restrict__ xl, int B, int T) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B * T) return;
-  row_store(x + (size_t)row * 256, lane, row_load(pe + (size_t)(row % T) * 256, lane));
+  const Row8 v = row_load(pe + (size_t)(row % T) * 256, lane);
+  row_store(x + (size_t)row * 256, lane, v);
+  row_store_split(xh + (size_t)row * 256, xl + (size_t)row * 256, lane, v);
 }
 
 // final encoder LayerNorm on tokens 0/1 of each sample, then mu/logvar -> std = exp(logvar)^0.5,
@@ -102,6 +110,24 @@ __global__ void vae_sample_kernel(const float* __restrict__ x, const float* __re
   if (std_out) row_store(std_out + (size_t)b * 256, lane, sd);
 }
 
+// y = LN(x (+ r[row / r_group_rows])) -> fp32 and split bf16
+__global__ void vae_ln_kernel(const float* __restrict__ x, const float* __restrict__ r, int r_group_rows,
+                              const float* __restrict__ g, const float* __restrict__ b, float* __restrict__ y,
+                              __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int rows) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  Row8 v = row_load(x + (size_t)row * 256, lane);
+  if (r) {
+    const Row8 a = row_load(r + (size_t)(row / r_group_rows) * 256, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v.v[i] += a.v[i];
+  }
+  v = row_layernorm(v, g, b, lane);
+  if (y) row_store(y + (size_t)row * 256, lane, v);
+  if (yh) row_store_split(yh + (size_t)row * 256, yl + (size_t)row * 256, lane, v);
+}
+
 }  // namespace seeme
 
 using namespace seeme;
@@ -118,7 +144,11 @@ struct seeme_vae {
   int device = 0, nfeats = 0, max_batch = 0, max_frames = 0;
   Arena arena;
   float* w[SEEME_VAE_NUM_TENSORS];
-  float *emb, *x, *L[5], *qkv, *att, *t0, *x1, *x2, *ff, *ca[5], *vtmp;
+  float *emb, *qkv, *t0, *ca[5], *vtmp;
+  int npass = 3;
+  // per stack (0 encoder, 1 decoder) and block: packed (hi, lo) weights of the tcgen05 linears
+  PackedLinear Wqkv[2][5], Wout[2][5], Wl1[2][5], Wl2[2][5], Wskip[2][2];
+  ActBuf x0, x, L[5], att, x1, x2, ff;
 };
 
 static size_t vae_tensor_elems(int i, int nfeats) {
@@ -154,9 +184,11 @@ extern "C" int seeme_vae_create(seeme_vae_t* out, const float* const* w, int n_w
   size_t wbytes = 0;
   for (int i = 0; i < n_w; ++i) wbytes += pad256(vae_tensor_elems(i, nfeats) * 4);
   const size_t rows = (size_t)max_batch * (max_frames + 2);
-  size_t ws = pad256(rows * 256 * 4) * (1 + 1 + 5 + 1 + 1 + 1 + 1) + pad256(rows * 768 * 4) + pad256(rows * 128 * 4) +
+  // fp32: emb, t0, x0, x, L[5], x1, x2 (11 x 256) + qkv (768); bf16 pairs: x0, x, L[5], att, x1, x2 (10 x 256) + ff (128)
+  size_t ws = 11 * pad256(rows * 256 * 4) + pad256(rows * 768 * 4) + 20 * pad256(rows * 256 * 2) + 2 * pad256(rows * 128 * 2) +
               6 * pad256((size_t)max_batch * 256 * 4);
-  int rc = h->arena.init(wbytes + ws + 4096);
+  const size_t pbytes = 2 * 2 * 2 * (size_t)(5 * (768 * 256 + 256 * 256 + 2 * 128 * 256) + 2 * 256 * 512) + 64 * 1024;
+  int rc = h->arena.init(wbytes + ws + pbytes + 65536);
   if (rc) { delete h; return rc; }
   for (int i = 0; i < n_w; ++i) {
     size_t n = vae_tensor_elems(i, nfeats);
@@ -176,70 +208,87 @@ extern "C" int seeme_vae_create(seeme_vae_t* out, const float* const* w, int n_w
   }
   SEEME_CUDA(cudaDeviceSynchronize());
   h->emb = h->arena.take<float>(rows * 256);
-  h->x = h->arena.take<float>(rows * 256);
-  for (int l = 0; l < 5; ++l) h->L[l] = h->arena.take<float>(rows * 256);
-  h->att = h->arena.take<float>(rows * 256);
   h->t0 = h->arena.take<float>(rows * 256);
-  h->x1 = h->arena.take<float>(rows * 256);
-  h->x2 = h->arena.take<float>(rows * 256);
   h->qkv = h->arena.take<float>(rows * 768);
-  h->ff = h->arena.take<float>(rows * 128);
+  auto mk = [&](ActBuf& a, int ld, bool f32) {
+    a.ld = ld;
+    a.f = f32 ? h->arena.take<float>(rows * ld) : nullptr;
+    a.h = h->arena.take<__nv_bfloat16>(rows * ld);
+    a.l = h->arena.take<__nv_bfloat16>(rows * ld);
+  };
+  mk(h->x0, 256, true);
+  mk(h->x, 256, true);
+  for (int l = 0; l < 5; ++l) mk(h->L[l], 256, true);
+  mk(h->att, 256, false);
+  mk(h->x1, 256, true);
+  mk(h->x2, 256, true);
+  mk(h->ff, 128, false);
   for (int l = 0; l < 5; ++l) h->ca[l] = h->arena.take<float>((size_t)max_batch * 256);
   h->vtmp = h->arena.take<float>((size_t)max_batch * 256);
   if (!h->vtmp) { set_error("seeme_vae_create: arena exhausted (workspace)"); h->arena.release(); delete h; return SEEME_ENOMEM; }
+  const char* pe = getenv("SEEME_VAE_PRECISION");
+  h->npass = (pe && atoi(pe) == 1) ? 1 : 3;
+  rc = SEEME_OK;
+  for (int st = 0; st < 2 && !rc; ++st) {
+    const int hdr = st ? V_DEC : V_ENC, blk = st ? V_DEC_BLK : V_ENC_BLK, stride = st ? 18 : 12, fo = st ? 8 : 4;
+    for (int l = 0; l < 5 && !rc; ++l) {
+      float* const* wb = h->w + blk + stride * l;
+      rc = pack_linear(h->arena, h->Wqkv[st][l], wb[0], 256, 768, 256, wb[1]);
+      if (!rc) rc = pack_linear(h->arena, h->Wout[st][l], wb[2], 256, 256, 256, wb[3]);
+      if (!rc) rc = pack_linear(h->arena, h->Wl1[st][l], wb[fo + 0], 256, 128, 256, wb[fo + 1]);
+      if (!rc) rc = pack_linear(h->arena, h->Wl2[st][l], wb[fo + 2], 128, 256, 128, wb[fo + 3]);
+    }
+    for (int i = 0; i < 2 && !rc; ++i) rc = pack_linear(h->arena, h->Wskip[st][i], h->w[hdr + 2 + 2 * i], 512, 256, 512, h->w[hdr + 3 + 2 * i]);
+  }
+  if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_error("seeme_vae_create: weight packing failed"); rc = SEEME_ECUDA; }
+  if (rc) { h->arena.release(); delete h; return rc; }
   SEEME_CUDA(cudaFuncSetAttribute(mha1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 256 * 4));
   *out = h;
   return SEEME_OK;
 }
 
-// self-attention + (optional single-key cross-attention vector) + FFN, post-norm.
-// wb points at the block's first tensor; dec selects the 18-tensor decoder layout.
-static int vae_layer(seeme_vae* h, float* const* wb, bool dec, const float* xin, float* xout, const int* lengths,
-                     int n_prefix, int B, int S, const float* ca_vec, cudaStream_t s) {
-  const int rows = B * S;
-  SEEME_TRY(gemm_f32(gemm_params(xin, 256, wb[0], 256, wb[1], h->qkv, 768, rows, 768, 256), s));
-  mha1_kernel<<<B, 256, (size_t)2 * S * 256 * 4, s>>>(h->qkv, lengths, n_prefix, S, h->att);
-  SEEME_LAUNCH_CHECK();
-  GemmP go = gemm_params(h->att, 256, wb[2], 256, wb[3], h->t0, 256, rows, 256, 256);
-  go.R = xin; go.ldr = 256;
-  SEEME_TRY(gemm_f32(go, s));
+// self-attention + (optional single-key cross-attention vector) + FFN, post-norm; 4 tcgen05 linears,
+// the fused attention kernel and 2-3 LayerNorm kernels.  st = 0 encoder stack, 1 decoder stack.
+static int vae_layer(seeme_vae* h, int st, int l, const ActBuf& xin, const ActBuf& xout, const int* lengths, int n_prefix, int B,
+                     int S, cudaStream_t s) {
+  const int rows = B * S, nb = (rows + 7) / 8, np = h->npass;
+  const bool dec = st == 1;
+  float* const* wb = h->w + (dec ? V_DEC_BLK + 18 * l : V_ENC_BLK + 12 * l);
   float* const* f = wb + (dec ? 8 : 4);     // l1w l1b l2w l2b n1w n1b n2w n2b (n3w n3b)
-  SEEME_TRY(layernorm256(h->t0, nullptr, 0, f[4], f[5], h->x1, rows, s));
-  const float* xa = h->x1;
-  if (dec) {   // tgt = norm2(tgt + ca[b])
-    SEEME_TRY(layernorm256(h->x1, ca_vec, S, f[6], f[7], h->x2, rows, s));
-    xa = h->x2;
+  ActBuf qkv; qkv.f = h->qkv; qkv.ld = 768;
+  ActBuf t0; t0.f = h->t0; t0.ld = 256;
+  SEEME_TRY(run_linear(h->Wqkv[st][l], xin, nullptr, rows, ACT_NONE, nullptr, 0, qkv, np, s));
+  {
+    ProfScope prof(PROF_VAE_ATTN, s);
+    mha1_kernel<<<B, 256, (size_t)2 * S * 256 * 4, s>>>(h->qkv, lengths, n_prefix, S, h->att.h, h->att.l);
   }
-  GemmP g1 = gemm_params(xa, 256, f[0], 256, f[1], h->ff, 128, rows, 128, 256);
-  g1.act = ACT_GELU;
-  SEEME_TRY(gemm_f32(g1, s));
-  GemmP g2 = gemm_params(h->ff, 128, f[2], 128, f[3], h->t0, 256, rows, 256, 128);
-  g2.R = xa; g2.ldr = 256;
-  SEEME_TRY(gemm_f32(g2, s));
-  const float* gn = dec ? f[8] : f[6];
-  const float* bn = dec ? f[9] : f[7];
-  SEEME_TRY(layernorm256(h->t0, nullptr, 0, gn, bn, xout, rows, s));
+  SEEME_LAUNCH_CHECK();
+  SEEME_TRY(run_linear(h->Wout[st][l], h->att, nullptr, rows, ACT_NONE, xin.f, 256, t0, np, s));
+  vae_ln_kernel<<<nb, 256, 0, s>>>(h->t0, nullptr, 0, f[4], f[5], h->x1.f, h->x1.h, h->x1.l, rows);
+  SEEME_LAUNCH_CHECK();
+  const ActBuf* xa = &h->x1;
+  if (dec) {   // tgt = norm2(tgt + ca[b]): the one-key cross-attention adds a per-sample vector (H6)
+    vae_ln_kernel<<<nb, 256, 0, s>>>(h->x1.f, h->ca[l], S, f[6], f[7], h->x2.f, h->x2.h, h->x2.l, rows);
+    SEEME_LAUNCH_CHECK();
+    xa = &h->x2;
+  }
+  SEEME_TRY(run_linear(h->Wl1[st][l], *xa, nullptr, rows, ACT_GELU, nullptr, 0, h->ff, np, s));
+  SEEME_TRY(run_linear(h->Wl2[st][l], h->ff, nullptr, rows, ACT_NONE, xa->f, 256, t0, np, s));
+  vae_ln_kernel<<<nb, 256, 0, s>>>(h->t0, nullptr, 0, dec ? f[8] : f[6], dec ? f[9] : f[7], xout.f, xout.h, xout.l, rows);
+  SEEME_LAUNCH_CHECK();
   return SEEME_OK;
 }
 
-// the 2-1-2 skip topology of SkipTransformerEncoder/Decoder (cross_attention.py:42-65, 108-147)
-static int vae_stack(seeme_vae* h, int hdr, int blk, int blk_stride, bool dec, const float* x0, const int* lengths,
-                     int n_prefix, int B, int S, cudaStream_t s) {
-  const int rows = B * S;
-  const float* x = x0;
+// the 2-1-2 skip topology of SkipTransformerEncoder/Decoder (cross_attention.py:42-65, 108-147); input h->x0
+static int vae_stack(seeme_vae* h, int st, const int* lengths, int n_prefix, int B, int S, cudaStream_t s) {
+  const ActBuf* x = &h->x0;
   for (int l = 0; l < 5; ++l) {
     if (l >= 3) {   // x = Linear(cat[x, skip]);  skip = L[1] for l == 3, L[0] for l == 4
-      const int i = l - 3;
-      const float* skip = h->L[l == 3 ? 1 : 0];
-      const float* W = h->w[hdr + 2 + 2 * i];
-      SEEME_TRY(gemm_f32(gemm_params(x, 256, W, 512, h->w[hdr + 3 + 2 * i], h->x, 256, rows, 256, 256), s));
-      GemmP ga = gemm_params(skip, 256, W + 256, 512, nullptr, h->x, 256, rows, 256, 256);
-      ga.accumulate = 1;
-      SEEME_TRY(gemm_f32(ga, s));
-      x = h->x;
+      SEEME_TRY(run_linear(h->Wskip[st][l - 3], *x, &h->L[l == 3 ? 1 : 0], B * S, ACT_NONE, nullptr, 0, h->x, h->npass, s));
+      x = &h->x;
     }
-    SEEME_TRY(vae_layer(h, h->w + blk + blk_stride * l, dec, x, h->L[l], lengths, n_prefix, B, S, dec ? h->ca[l] : nullptr, s));
-    x = h->L[l];
+    SEEME_TRY(vae_layer(h, st, l, *x, h->L[l], lengths, n_prefix, B, S, s));
+    x = &h->L[l];
   }
   return SEEME_OK;
 }
@@ -252,13 +301,13 @@ extern "C" int seeme_vae_encode(seeme_vae_t h, const float* features, const int3
                 B, T, h->max_batch, h->max_frames);
   cudaStream_t s = (cudaStream_t)stream;
   const int S = T + 2, rows = B * S;
+  // skel_embedding: K = nfeats (75) is not a multiple of the tensor-core K granule -> fp32 CUDA-core GEMM
   SEEME_TRY(gemm_f32(gemm_params(features, h->nfeats, h->w[V_SKEL_W], h->nfeats, h->w[V_SKEL_B], h->emb, 256, B * T, 256,
                                  h->nfeats), s));
-  // x2 is not a scratch buffer of the encoder layers, so it can hold the stack input
-  vae_enc_assemble_kernel<<<(rows + 7) / 8, 256, 0, s>>>(h->emb, h->w[V_TOKEN], h->w[V_PE_ENC], h->x2, B, T);
+  vae_enc_assemble_kernel<<<(rows + 7) / 8, 256, 0, s>>>(h->emb, h->w[V_TOKEN], h->w[V_PE_ENC], h->x0.f, h->x0.h, h->x0.l, B, T);
   SEEME_LAUNCH_CHECK();
-  SEEME_TRY(vae_stack(h, V_ENC, V_ENC_BLK, 12, false, h->x2, lengths, 2, B, S, s));
-  vae_sample_kernel<<<(B + 7) / 8, 256, 0, s>>>(h->L[4], h->w[V_ENC], h->w[V_ENC + 1], eps, z, mu, std, B, S);
+  SEEME_TRY(vae_stack(h, 0, lengths, 2, B, S, s));
+  vae_sample_kernel<<<(B + 7) / 8, 256, 0, s>>>(h->L[4].f, h->w[V_ENC], h->w[V_ENC + 1], eps, z, mu, std, B, S);
   SEEME_LAUNCH_CHECK();
   return SEEME_OK;
 }
@@ -271,16 +320,17 @@ extern "C" int seeme_vae_decode(seeme_vae_t h, const float* z, const int32_t* le
                 B, T, h->max_batch, h->max_frames);
   cudaStream_t s = (cudaStream_t)stream;
   const int rows = B * T;
-  // single-key cross-attention vectors for all five layers: ca_l[b] = out_proj(v_proj(z_b))
+  // single-key cross-attention vectors for all five layers: ca_l[b] = out_proj(v_proj(z_b))   (B rows: fp32 GEMMs)
   for (int l = 0; l < 5; ++l) {
     float* const* wb = h->w + V_DEC_BLK + 18 * l;
     SEEME_TRY(gemm_f32(gemm_params(z, 256, wb[4] + 512 * 256, 256, wb[5] + 512, h->vtmp, 256, B, 256, 256), s));
     SEEME_TRY(gemm_f32(gemm_params(h->vtmp, 256, wb[6], 256, wb[7], h->ca[l], 256, B, 256, 256), s));
   }
-  vae_dec_queries_kernel<<<(rows + 7) / 8, 256, 0, s>>>(h->w[V_PE_DEC], h->emb, B, T);
+  vae_dec_queries_kernel<<<(rows + 7) / 8, 256, 0, s>>>(h->w[V_PE_DEC], h->x0.f, h->x0.h, h->x0.l, B, T);
   SEEME_LAUNCH_CHECK();
-  SEEME_TRY(vae_stack(h, V_DEC, V_DEC_BLK, 18, true, h->emb, lengths, 0, B, T, s));
-  SEEME_TRY(layernorm256(h->L[4], nullptr, 0, h->w[V_DEC], h->w[V_DEC + 1], h->t0, rows, s));
+  SEEME_TRY(vae_stack(h, 1, lengths, 0, B, T, s));
+  SEEME_TRY(layernorm256(h->L[4].f, nullptr, 0, h->w[V_DEC], h->w[V_DEC + 1], h->t0, rows, s));
+  // final_layer: N = nfeats (75) -> fp32 CUDA-core GEMM writing the [B,T,nfeats] output directly
   SEEME_TRY(gemm_f32(gemm_params(h->t0, 256, h->w[V_FINAL_W], 256, h->w[V_FINAL_B], feats, h->nfeats, rows, h->nfeats, 256), s));
   return SEEME_OK;
 }
