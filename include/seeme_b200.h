@@ -57,10 +57,12 @@ int seeme_prof_read(int id, double* total_ms, long long* count);
  * Y[M,N] = act(A[M,K] W[N,K]^T + bias[N]) (+ R[M,N]); fp32 device inputs are converted to (split) bf16
  * internally.  K multiple of 64, N multiple of 128; npass 1 = bf16, 3 = split-bf16 (hi.hi+lo.hi+hi.lo).
  * colmax (nullable): [ceil(M/group), N] order-preserving-uint column max per group of rows (zeroed by
- * the caller).  Synchronises the stream. */
+ * the caller).  Ysplit / Zsplit (nullable, fp32 [M,N]): hi+lo of the kernel's bf16 outputs of the result and
+ * of relu(result) (when Zsplit is given the fp32 output Y is not produced: they share staging).
+ * Synchronises the stream. */
 int seeme_test_umma_linear(const float* A, const float* W, const float* bias, const float* R, float* Y,
                            int M, int N, int K, int act, int npass, unsigned* colmax,
-                           int colmax_group_rows, void* stream);
+                           int colmax_group_rows, float* Ysplit, float* Zsplit, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Scene encoder.  Replaces `ProHMRScene.encode_scene` -> `ResnetPointnet.forward`

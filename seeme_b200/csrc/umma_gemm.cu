@@ -5,9 +5,16 @@
 //   warp 1      allocates TMEM, then one elected lane issues tcgen05.mma (M=128, N=BN, K=16 per
 //               instruction; fp32 accumulator in TMEM); tcgen05.commit releases ring slots ("empty"
 //               mbarriers) and finally signals the epilogue
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step, thread = output row),
-//               bias / per-sample bias / rank-3 xyz fold / activation / residual, then fp32 and/or bf16
-//               (hi, lo) stores and the fused per-sample column max (scene-encoder pooling)
+//   warps 2..5  epilogue, 64 output columns at a time: tcgen05.ld (thread = output row), bias /
+//               per-sample bias / rank-3 xyz fold / activation / fp32 residual (TMA-prefetched into
+//               shared memory while the main loop runs), then the results are written as 128-byte-
+//               swizzled tiles into a double-buffered shared-memory staging area (conflict-free 16-byte
+//               stores) and leave the SM as TMA tensor stores (fp32 and/or bf16 hi/lo, plus bf16 of
+//               relu(.)); the fused per-sample column max (scene-encoder pooling) is a warp redux on
+//               order-preserving integers followed by one atomicMax per (tile, column).
+//   Thread-per-row global loads/stores would touch 32 different 128-byte lines per instruction; the
+//   ncu capture of that first version (profiles/r1_umma_v1_*.md) showed the epilogue's LSU wavefronts
+//   bounding the kernel at 8-14 % tensor-pipe activity, hence the TMA staging.
 //
 // Precision: NPASS = 1 multiplies bf16(A) x bf16(W); NPASS = 3 adds the two first-order correction
 // terms lo(A).hi(W) + hi(A).lo(W) of the split x = hi + lo (|lo| <= 2^-9 |x|), which restores ~16 mantissa
@@ -17,36 +24,57 @@
 
 namespace seeme {
 
+struct UmmaMaps {
+  CUtensorMap a1h, a1l, a2h, a2l, wh, wl;   // operands
+  CUtensorMap yh, yl, zh, zl, yf, rf;       // bf16 outputs, fp32 output, fp32 residual
+};
+
 struct UmmaEpi {
   int M, N, nkb1, nkb;           // nkb1 k-blocks come from A1, the remaining from A2
   const float* bias; int bias_group_rows;
   const float* pfold; const float* xyz;
   int act;
-  const float* R; int ldr;
-  float* Y; int ldy;
-  __nv_bfloat16 *Yh, *Yl, *Zh, *Zl; int ldb;
+  int has_r, has_yf, has_yh, has_yl, has_zh, has_zl;
   unsigned* colmax; int colmax_group_rows;
 };
+
+constexpr int TILE_BYTES = 128 * 128;            // one 128-row x 128-byte swizzled staging tile
+constexpr int STORE_BUF_BYTES = 4 * TILE_BYTES;  // slots: Yh, Yl, Zh | Yf(cols 0-31), Zl | Yf(cols 32-63)
+constexpr int RES_BUF_BYTES = 2 * TILE_BYTES;    // residual: two 32-column fp32 tiles per 64-column group
 
 template <int BN, int NPASS>
 struct UmmaCfg {
   static constexpr int A_BYTES = 128 * 64 * 2;
   static constexpr int W_BYTES = BN * 64 * 2;
   static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES) * (NPASS == 3 ? 2 : 1);
+  static constexpr int NG = BN / 64;             // 64-column store groups
+  static constexpr int NBUF = NG > 1 ? 2 : 1;
 };
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// byte offset of logical 16-byte chunk j of row r inside a 128-byte-swizzled [128 x 128 B] tile
+__device__ __forceinline__ uint32_t sw128(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+
 template <int BN, int NPASS, int STAGES>
-__global__ void __launch_bounds__(192) umma_linear_kernel(const __grid_constant__ CUtensorMap tmA1h,
-                                                          const __grid_constant__ CUtensorMap tmA1l,
-                                                          const __grid_constant__ CUtensorMap tmA2h,
-                                                          const __grid_constant__ CUtensorMap tmA2l,
-                                                          const __grid_constant__ CUtensorMap tmWh,
-                                                          const __grid_constant__ CUtensorMap tmWl, const UmmaEpi e) {
+__global__ void __launch_bounds__(192) umma_linear_kernel(const __grid_constant__ UmmaMaps tm, const UmmaEpi e) {
   using Cfg = UmmaCfg<BN, NPASS>;
+  constexpr int RING_BYTES = Cfg::STAGE_BYTES * STAGES;
+  constexpr int STORE_BYTES = Cfg::NBUF * STORE_BUF_BYTES;
+  constexpr int MAIN_BYTES = RING_BYTES > STORE_BYTES ? RING_BYTES : STORE_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // SWIZZLE_128B operands need 1024-byte aligned tiles
+  // SWIZZLE_128B tiles need 1024-byte alignment.  Layout: [ring, reused as store staging after the last MMA | residual staging]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+  uint8_t* res_stage = smem + MAIN_BYTES;
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, res_bar[2];
   __shared__ uint32_t tmem_slot;
   __shared__ unsigned colmax_s[2][BN];
 
@@ -54,11 +82,13 @@ __global__ void __launch_bounds__(192) umma_linear_kernel(const __grid_constant_
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * 128;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA1h);
-    tma_prefetch_desc(&tmWh);
-    if (NPASS == 3) { tma_prefetch_desc(&tmA1l); tma_prefetch_desc(&tmWl); }
+    tma_prefetch_desc(&tm.a1h);
+    tma_prefetch_desc(&tm.wh);
+    if (NPASS == 3) { tma_prefetch_desc(&tm.a1l); tma_prefetch_desc(&tm.wl); }
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&tmem_full_bar, 1);
+    mbar_init(&res_bar[0], 1);
+    mbar_init(&res_bar[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_slot, BN < 32 ? 32 : BN);
@@ -78,10 +108,10 @@ __global__ void __launch_bounds__(192) umma_linear_kernel(const __grid_constant_
         uint8_t* sw = sa + Cfg::A_BYTES * (NPASS == 3 ? 2 : 1);
         const bool first = kb < e.nkb1;
         const int kc = (first ? kb : kb - e.nkb1) * 64;
-        tma_load_2d(sa, first ? &tmA1h : &tmA2h, &full_bar[st], kc, m0);
-        if (NPASS == 3) tma_load_2d(sa + Cfg::A_BYTES, first ? &tmA1l : &tmA2l, &full_bar[st], kc, m0);
-        tma_load_2d(sw, &tmWh, &full_bar[st], kb * 64, n0);
-        if (NPASS == 3) tma_load_2d(sw + Cfg::W_BYTES, &tmWl, &full_bar[st], kb * 64, n0);
+        tma_load_2d(sa, first ? &tm.a1h : &tm.a2h, &full_bar[st], kc, m0);
+        if (NPASS == 3) tma_load_2d(sa + Cfg::A_BYTES, first ? &tm.a1l : &tm.a2l, &full_bar[st], kc, m0);
+        tma_load_2d(sw, &tm.wh, &full_bar[st], kb * 64, n0);
+        if (NPASS == 3) tma_load_2d(sw + Cfg::W_BYTES, &tm.wl, &full_bar[st], kb * 64, n0);
       }
     }
   } else if (warp == 1) {
@@ -113,68 +143,87 @@ __global__ void __launch_bounds__(192) umma_linear_kernel(const __grid_constant_
     const int row = q * 32 + lane;
     const int m = m0 + row;
     const bool valid = m < e.M;
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after();
+    const bool elected = (warp == 2 && lane == 0);
+    // residual tiles of the first store groups travel while the main loop runs
+    if (e.has_r && elected) {
+      for (int g = 0; g < Cfg::NBUF; ++g) {
+        mbar_arrive_expect_tx(&res_bar[g], RES_BUF_BYTES);
+        tma_load_2d(res_stage + g * RES_BUF_BYTES, &tm.rf, &res_bar[g], n0 + g * 64, m0);
+        tma_load_2d(res_stage + g * RES_BUF_BYTES + TILE_BYTES, &tm.rf, &res_bar[g], n0 + g * 64 + 32, m0);
+      }
+    }
     const float* brow = nullptr;
     if (e.bias) brow = e.bias + (e.bias_group_rows ? (size_t)((valid ? m : e.M - 1) / e.bias_group_rows) * e.N : 0);
     float px = 0.f, py = 0.f, pz = 0.f;
     if (e.pfold && valid) { px = e.xyz[(size_t)m * 3]; py = e.xyz[(size_t)m * 3 + 1]; pz = e.xyz[(size_t)m * 3 + 2]; }
     int g0 = 0, gmine = 0;
     if (e.colmax) { g0 = m0 / e.colmax_group_rows; gmine = (valid ? m : m0) / e.colmax_group_rows - g0; }
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t raw[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
-      tmem_ld_wait();
-      const int n = n0 + c0;
-      float f[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(raw[i]);
-      if (brow) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(brow + n + i));
-          f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
-        }
+    mbar_wait(&tmem_full_bar, 0);       // all MMAs done: the accumulator is complete and the ring is free
+    tc_fence_after();
+#pragma unroll 1
+    for (int g = 0; g < Cfg::NG; ++g) {
+      const int buf = g & (Cfg::NBUF - 1);
+      uint8_t* sbuf = smem + buf * STORE_BUF_BYTES;
+      if (g >= 2) {                     // the stores of group g-2 must have drained this staging buffer
+        if (elected) tma_store_wait_read<1>();
+        epi_bar_sync();
       }
-      if (e.pfold) {
+      if (e.has_r) mbar_wait(&res_bar[buf], (g >> 1) & 1);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int c0 = g * 64 + half * 32;
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+        tmem_ld_wait();
+        const int n = n0 + c0;
+        float f[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float4 p = __ldg(reinterpret_cast<const float4*>(e.pfold) + n + i);
-          f[i] += p.x * px + p.y * py + p.z * pz;
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(raw[i]);
+        if (brow) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(brow + n + i));
+            f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+          }
         }
-      }
-      if (e.act != ACT_NONE) {
+        if (e.pfold) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = apply_act(f[i], e.act);
-      }
-      if (e.R && valid) {
-        const float4* rp = reinterpret_cast<const float4*>(e.R + (size_t)m * e.ldr + n);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 r = __ldg(rp + i);
-          f[4 * i] += r.x; f[4 * i + 1] += r.y; f[4 * i + 2] += r.z; f[4 * i + 3] += r.w;
+          for (int i = 0; i < 32; ++i) {
+            const float4 p = __ldg(reinterpret_cast<const float4*>(e.pfold) + n + i);
+            f[i] += p.x * px + p.y * py + p.z * pz;
+          }
         }
-      }
-      if (valid) {
-        if (e.Y) {
-          float4* yp = reinterpret_cast<float4*>(e.Y + (size_t)m * e.ldy + n);
+        if (e.act != ACT_NONE) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) yp[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          for (int i = 0; i < 32; ++i) f[i] = apply_act(f[i], e.act);
         }
-        if (e.Yh) {
+        if (e.has_r) {
+          const uint8_t* rt = res_stage + buf * RES_BUF_BYTES + half * TILE_BYTES;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 r = *reinterpret_cast<const float4*>(rt + sw128(row, j));
+            f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+          }
+        }
+        if (e.has_yf) {                 // fp32 tile of 32 columns: slot 2 (half 0) / slot 3 (half 1)
+          uint8_t* t = sbuf + (2 + half) * TILE_BYTES;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(t + sw128(row, j)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+        if (e.has_yh) {
           __align__(16) __nv_bfloat16 hb[32], lb[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) { hb[i] = __float2bfloat16_rn(f[i]); lb[i] = __float2bfloat16_rn(f[i] - __bfloat162float(hb[i])); }
-          uint4* hp = reinterpret_cast<uint4*>(e.Yh + (size_t)m * e.ldb + n);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) hp[i] = reinterpret_cast<const uint4*>(hb)[i];
-          if (e.Yl) {
-            uint4* lp = reinterpret_cast<uint4*>(e.Yl + (size_t)m * e.ldb + n);
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(sbuf + sw128(row, half * 4 + j)) = reinterpret_cast<const uint4*>(hb)[j];
+          if (e.has_yl) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) lp[i] = reinterpret_cast<const uint4*>(lb)[i];
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(sbuf + TILE_BYTES + sw128(row, half * 4 + j)) = reinterpret_cast<const uint4*>(lb)[j];
           }
         }
-        if (e.Zh) {
+        if (e.has_zh) {
           __align__(16) __nv_bfloat16 hb[32], lb[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -182,32 +231,52 @@ __global__ void __launch_bounds__(192) umma_linear_kernel(const __grid_constant_
             hb[i] = __float2bfloat16_rn(r);
             lb[i] = __float2bfloat16_rn(r - __bfloat162float(hb[i]));
           }
-          uint4* hp = reinterpret_cast<uint4*>(e.Zh + (size_t)m * e.ldb + n);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) hp[i] = reinterpret_cast<const uint4*>(hb)[i];
-          if (e.Zl) {
-            uint4* lp = reinterpret_cast<uint4*>(e.Zl + (size_t)m * e.ldb + n);
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(sbuf + 2 * TILE_BYTES + sw128(row, half * 4 + j)) = reinterpret_cast<const uint4*>(hb)[j];
+          if (e.has_zl) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) lp[i] = reinterpret_cast<const uint4*>(lb)[i];
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(sbuf + 3 * TILE_BYTES + sw128(row, half * 4 + j)) = reinterpret_cast<const uint4*>(lb)[j];
+          }
+        }
+        if (e.colmax) {
+          // per-sample max over the rows of this tile; a tile spans at most two samples (group >= 128 rows)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const unsigned o = f2ord(f[i]);
+            const unsigned a = __reduce_max_sync(0xffffffffu, (valid && gmine == 0) ? o : 0u);
+            const unsigned b = __reduce_max_sync(0xffffffffu, (valid && gmine == 1) ? o : 0u);
+            if (lane == 0) {
+              if (a) atomicMax(&colmax_s[0][c0 + i], a);
+              if (b) atomicMax(&colmax_s[1][c0 + i], b);
+            }
           }
         }
       }
-      if (e.colmax) {
-        // per-sample max over the rows of this tile; a tile spans at most two samples (group >= 128 rows)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const unsigned o = f2ord(f[i]);
-          const unsigned a = __reduce_max_sync(0xffffffffu, (valid && gmine == 0) ? o : 0u);
-          const unsigned b = __reduce_max_sync(0xffffffffu, (valid && gmine == 1) ? o : 0u);
-          if (lane == 0) {
-            if (a) atomicMax(&colmax_s[0][c0 + i], a);
-            if (b) atomicMax(&colmax_s[1][c0 + i], b);
-          }
+      fence_proxy_async();              // staging writes (generic proxy) -> visible to the TMA (async proxy)
+      epi_bar_sync();
+      if (elected) {
+        const int c = n0 + g * 64;
+        if (e.has_yh) tma_store_2d(&tm.yh, sbuf, c, m0);
+        if (e.has_yl) tma_store_2d(&tm.yl, sbuf + TILE_BYTES, c, m0);
+        if (e.has_zh) tma_store_2d(&tm.zh, sbuf + 2 * TILE_BYTES, c, m0);
+        if (e.has_zl) tma_store_2d(&tm.zl, sbuf + 3 * TILE_BYTES, c, m0);
+        if (e.has_yf) {
+          tma_store_2d(&tm.yf, sbuf + 2 * TILE_BYTES, c, m0);
+          tma_store_2d(&tm.yf, sbuf + 3 * TILE_BYTES, c + 32, m0);
+        }
+        tma_store_commit();
+        if (e.has_r && g + 2 < Cfg::NG) {   // everyone is past the reads of this residual buffer
+          mbar_arrive_expect_tx(&res_bar[buf], RES_BUF_BYTES);
+          tma_load_2d(res_stage + buf * RES_BUF_BYTES, &tm.rf, &res_bar[buf], n0 + (g + 2) * 64, m0);
+          tma_load_2d(res_stage + buf * RES_BUF_BYTES + TILE_BYTES, &tm.rf, &res_bar[buf], n0 + (g + 2) * 64 + 32, m0);
         }
       }
     }
+    if (elected) tma_store_wait_read<0>();   // shared memory must outlive the bulk stores reading it
     if (e.colmax) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
+      epi_bar_sync();
       const int G = (e.M + e.colmax_group_rows - 1) / e.colmax_group_rows;
       for (int i = threadIdx.x - 64; i < 2 * BN; i += 128) {
         const int which = i / BN, c = i % BN;
@@ -237,32 +306,40 @@ static int get_encoder() {
   return SEEME_OK;
 }
 
-// bf16 [rows, cols] with row pitch ld (elements), box = box_rows x 64, SWIZZLE_128B, OOB -> zeros
-static int make_map(CUtensorMap* map, const __nv_bfloat16* ptr, int rows, int cols, int ld, int box_rows) {
-  SEEME_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld % 8) == 0, SEEME_EINVAL,
-                "umma_linear: operand base must be 16-byte aligned and its pitch a multiple of 8 elements (ld=%d)", ld);
+// [rows, cols] matrix with row pitch ld (elements); box = box_rows x 128 bytes, SWIZZLE_128B, OOB reads -> zeros
+static int make_map(CUtensorMap* map, const void* ptr, bool f32, int rows, int cols, int ld, int box_rows) {
+  const int esz = f32 ? 4 : 2;
+  SEEME_REQUIRE(ptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ((size_t)ld * esz) % 16 == 0, SEEME_EINVAL,
+                "umma_linear: tensor base must be 16-byte aligned and its pitch a multiple of 16 bytes (ld=%d)", ld);
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = g_encode(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim,
+                        gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SEEME_REQUIRE(r == CUDA_SUCCESS, SEEME_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%d cols=%d ld=%d)", (int)r, rows, cols, ld);
   return SEEME_OK;
 }
 
 template <int BN, int NPASS, int STAGES>
-static int launch(const UmmaLinear& g, const CUtensorMap* maps, const UmmaEpi& e, cudaStream_t s) {
-  constexpr int smem = UmmaCfg<BN, NPASS>::STAGE_BYTES * STAGES + 1024;
+static int launch(const UmmaLinear& g, const UmmaMaps& maps, const UmmaEpi& e, cudaStream_t s) {
+  using Cfg = UmmaCfg<BN, NPASS>;
+  constexpr int ring = Cfg::STAGE_BYTES * STAGES, store = Cfg::NBUF * STORE_BUF_BYTES;
+  // BN = 256 tiles never stage a residual (umma_linear picks BN <= 128 when R is given)
+  constexpr int res_max = BN == 256 ? 0 : Cfg::NBUF * RES_BUF_BYTES;
+  constexpr int smem_max = (ring > store ? ring : store) + res_max + 1024;
+  static_assert(smem_max <= 227 * 1024, "shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
-    SEEME_CUDA(cudaFuncSetAttribute(umma_linear_kernel<BN, NPASS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SEEME_CUDA(cudaFuncSetAttribute(umma_linear_kernel<BN, NPASS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     configured = true;
   }
+  SEEME_REQUIRE(!(e.has_r && BN == 256), SEEME_EINVAL, "umma_linear: residual staging is not available for 256-wide tiles");
+  const int smem = (ring > store ? ring : store) + (e.has_r ? res_max : 0) + 1024;
   dim3 grid(g.N / BN, (g.M + 127) / 128);
   ProfScope prof(g.prof_id - 1, s);
-  umma_linear_kernel<BN, NPASS, STAGES><<<grid, 192, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], e);
+  umma_linear_kernel<BN, NPASS, STAGES><<<grid, 192, smem, s>>>(maps, e);
   SEEME_LAUNCH_CHECK();
   return SEEME_OK;
 }
@@ -275,24 +352,35 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
   SEEME_REQUIRE(npass == 1 || npass == 3, SEEME_EINVAL, "umma_linear: npass must be 1 or 3");
   SEEME_REQUIRE(npass == 1 || (g.A1.lo && g.W.lo && (g.K2 == 0 || g.A2.lo)), SEEME_EINVAL, "umma_linear: split-bf16 needs lo operands");
   SEEME_REQUIRE(!g.colmax || g.colmax_group_rows >= 128, SEEME_EINVAL, "umma_linear: colmax groups must have >= 128 rows");
+  SEEME_REQUIRE(!(g.Y && g.Zh), SEEME_EINVAL, "umma_linear: the fp32 output and the relu bf16 output share staging slots");
+  SEEME_REQUIRE((!g.Yl || g.Yh) && (!g.Zl || g.Zh), SEEME_EINVAL, "umma_linear: lo outputs need their hi companion");
   // few rows (the latency-bound sampler / per-sample GEMMs): narrow tiles spread one GEMM over more SMs;
-  // many rows: the widest tile that divides N
-  const int BN = (g.M <= 2048 && !g.colmax) ? 64 : ((g.N % 256 == 0) ? 256 : 128);
-  SEEME_REQUIRE(g.N % BN == 0, SEEME_EINVAL, "umma_linear: N=%d must be a multiple of %d", g.N, BN);
-  CUtensorMap maps[6];
-  memset(maps, 0, sizeof(maps));
-  SEEME_TRY(make_map(&maps[0], g.A1.hi, g.M, g.K1, g.A1.ld, 128));
-  if (npass == 3) SEEME_TRY(make_map(&maps[1], g.A1.lo, g.M, g.K1, g.A1.ld, 128)); else maps[1] = maps[0];
+  // many rows: the widest tile that divides N (128 when a residual tile has to be staged as well)
+  int BN = (g.M <= 2048 && !g.colmax) ? 64 : ((g.N % 256 == 0 && !g.R) ? 256 : 128);
+  if (g.N % BN != 0) BN = 64;
+  SEEME_REQUIRE(g.N % BN == 0, SEEME_EINVAL, "umma_linear: N=%d must be a multiple of 64", g.N);
+  UmmaMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  SEEME_TRY(make_map(&maps.a1h, g.A1.hi, false, g.M, g.K1, g.A1.ld, 128));
+  if (npass == 3) SEEME_TRY(make_map(&maps.a1l, g.A1.lo, false, g.M, g.K1, g.A1.ld, 128)); else maps.a1l = maps.a1h;
   if (g.K2) {
-    SEEME_TRY(make_map(&maps[2], g.A2.hi, g.M, g.K2, g.A2.ld, 128));
-    if (npass == 3) SEEME_TRY(make_map(&maps[3], g.A2.lo, g.M, g.K2, g.A2.ld, 128)); else maps[3] = maps[2];
-  } else { maps[2] = maps[0]; maps[3] = maps[1]; }
-  SEEME_TRY(make_map(&maps[4], g.W.hi, g.N, K, g.W.ld, BN));
-  if (npass == 3) SEEME_TRY(make_map(&maps[5], g.W.lo, g.N, K, g.W.ld, BN)); else maps[5] = maps[4];
+    SEEME_TRY(make_map(&maps.a2h, g.A2.hi, false, g.M, g.K2, g.A2.ld, 128));
+    if (npass == 3) SEEME_TRY(make_map(&maps.a2l, g.A2.lo, false, g.M, g.K2, g.A2.ld, 128)); else maps.a2l = maps.a2h;
+  } else { maps.a2h = maps.a1h; maps.a2l = maps.a1l; }
+  SEEME_TRY(make_map(&maps.wh, g.W.hi, false, g.N, K, g.W.ld, BN));
+  if (npass == 3) SEEME_TRY(make_map(&maps.wl, g.W.lo, false, g.N, K, g.W.ld, BN)); else maps.wl = maps.wh;
+  maps.yh = maps.yl = maps.zh = maps.zl = maps.yf = maps.rf = maps.a1h;   // placeholders for unused outputs
+  if (g.Yh) SEEME_TRY(make_map(&maps.yh, g.Yh, false, g.M, g.N, g.ldb, 128));
+  if (g.Yl) SEEME_TRY(make_map(&maps.yl, g.Yl, false, g.M, g.N, g.ldb, 128));
+  if (g.Zh) SEEME_TRY(make_map(&maps.zh, g.Zh, false, g.M, g.N, g.ldb, 128));
+  if (g.Zl) SEEME_TRY(make_map(&maps.zl, g.Zl, false, g.M, g.N, g.ldb, 128));
+  if (g.Y) SEEME_TRY(make_map(&maps.yf, g.Y, true, g.M, g.N, g.ldy, 128));
+  if (g.R) SEEME_TRY(make_map(&maps.rf, g.R, true, g.M, g.N, g.ldr, 128));
   UmmaEpi e;
   e.M = g.M; e.N = g.N; e.nkb1 = g.K1 / 64; e.nkb = K / 64;
   e.bias = g.bias; e.bias_group_rows = g.bias_group_rows; e.pfold = g.pfold; e.xyz = g.xyz; e.act = g.act;
-  e.R = g.R; e.ldr = g.ldr; e.Y = g.Y; e.ldy = g.ldy; e.Yh = g.Yh; e.Yl = g.Yl; e.Zh = g.Zh; e.Zl = g.Zl; e.ldb = g.ldb;
+  e.has_r = g.R != nullptr; e.has_yf = g.Y != nullptr; e.has_yh = g.Yh != nullptr; e.has_yl = g.Yl != nullptr;
+  e.has_zh = g.Zh != nullptr; e.has_zl = g.Zl != nullptr;
   e.colmax = g.colmax; e.colmax_group_rows = g.colmax_group_rows;
   if (BN == 256) return npass == 1 ? launch<256, 1, 2>(g, maps, e, s) : launch<256, 3, 2>(g, maps, e, s);
   if (BN == 64) return npass == 1 ? launch<64, 1, 4>(g, maps, e, s) : launch<64, 3, 4>(g, maps, e, s);
@@ -350,19 +438,28 @@ int run_linear(const PackedLinear& W, const ActBuf& A, const ActBuf* A2, int M, 
   return umma_linear(g, npass, s);
 }
 
+__global__ void bf16_join_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, float* __restrict__ out,
+                                 size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+}
+
 }  // namespace seeme
 
 // ---- test entry point: Y = act(A W^T + bias) (+R) with fp32 inputs converted on the fly -----------------
 extern "C" int seeme_test_umma_linear(const float* A, const float* W, const float* bias, const float* R, float* Y, int M, int N,
-                                      int K, int act, int npass, unsigned* colmax, int colmax_group_rows, void* stream) {
+                                      int K, int act, int npass, unsigned* colmax, int colmax_group_rows, float* Ysplit,
+                                      float* Zsplit, void* stream) {
   using namespace seeme;
-  SEEME_REQUIRE(A && W && Y, SEEME_EINVAL, "seeme_test_umma_linear: null argument");
+  SEEME_REQUIRE(A && W && (Y || Ysplit), SEEME_EINVAL, "seeme_test_umma_linear: null argument");
   cudaStream_t s = (cudaStream_t)stream;
-  __nv_bfloat16 *ah, *al, *wh, *wl;
+  __nv_bfloat16 *ah, *al, *wh, *wl, *ob = nullptr;
   SEEME_CUDA(cudaMalloc(&ah, (size_t)M * K * 2));
   SEEME_CUDA(cudaMalloc(&al, (size_t)M * K * 2));
   SEEME_CUDA(cudaMalloc(&wh, (size_t)N * K * 2));
   SEEME_CUDA(cudaMalloc(&wl, (size_t)N * K * 2));
+  SEEME_CUDA(cudaMalloc(&ob, (size_t)M * N * 2 * 4));
+  const size_t mn = (size_t)M * N;
   int rc = to_bf16_split(A, K, M, K, ah, al, K, 0, s);
   if (!rc) rc = to_bf16_split(W, K, N, K, wh, wl, K, 0, s);
   if (!rc) {
@@ -373,11 +470,17 @@ extern "C" int seeme_test_umma_linear(const float* A, const float* W, const floa
       g.K1 = K / 2; g.K2 = K / 2;
       g.A2 = {ah + K / 2, al + K / 2, K};
     }
-    g.bias = bias; g.act = act; g.R = R; g.ldr = N; g.Y = Y; g.ldy = N;
+    g.bias = bias; g.act = act; g.R = R; g.ldr = N;
+    if (Y && !Zsplit) { g.Y = Y; g.ldy = N; }
+    if (Ysplit) { g.Yh = ob; g.Yl = ob + mn; g.ldb = N; }
+    if (Zsplit) { g.Zh = ob + 2 * mn; g.Zl = ob + 3 * mn; g.ldb = N; }
     g.colmax = colmax; g.colmax_group_rows = colmax_group_rows;
     rc = umma_linear(g, npass, s);
+    if (!rc && Ysplit) bf16_join_kernel<<<(unsigned)((mn + 255) / 256), 256, 0, s>>>(ob, ob + mn, Ysplit, mn);
+    if (!rc && Zsplit) bf16_join_kernel<<<(unsigned)((mn + 255) / 256), 256, 0, s>>>(ob + 2 * mn, ob + 3 * mn, Zsplit, mn);
   }
-  cudaStreamSynchronize(s);
-  cudaFree(ah); cudaFree(al); cudaFree(wh); cudaFree(wl);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(ah); cudaFree(al); cudaFree(wh); cudaFree(wl); cudaFree(ob);
+  if (!rc && e != cudaSuccess) { set_error("seeme_test_umma_linear: %s", cudaGetErrorString(e)); rc = SEEME_ECUDA; }
   return rc;
 }
