@@ -48,7 +48,6 @@ struct UmmaCfg {
   static constexpr int W_BYTES = BN * 64 * 2;
   static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES) * (NPASS == 3 ? 2 : 1);
   static constexpr int NG = BN / 64;             // 64-column store groups
-  static constexpr int NBUF = NG > 1 ? 2 : 1;
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
@@ -61,14 +60,26 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// (a, b) -> packed bf16x2 hi = rn(a), rn(b) and lo = rn(a - hi_a), rn(b - hi_b): two cvt.rn.bf16x2.f32
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);          // .x = a (low 16 bits), .y = b
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // byte offset of logical 16-byte chunk j of row r inside a 128-byte-swizzled [128 x 128 B] tile
 __device__ __forceinline__ uint32_t sw128(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
-template <int BN, int NPASS, int STAGES>
-__global__ void __launch_bounds__(192) umma_linear_kernel(const __grid_constant__ UmmaMaps tm, const UmmaEpi e) {
+// STAGES: depth of the operand ring; NBUF: store-staging (and residual) buffers; MINB: CTAs per SM the
+// register allocation must allow (small-footprint configurations co-reside so that one CTA's epilogue
+// overlaps another's main loop)
+template <int BN, int NPASS, int STAGES, int NBUF, int MINB>
+__global__ void __launch_bounds__(192, MINB) umma_linear_kernel(const __grid_constant__ UmmaMaps tm, const UmmaEpi e) {
   using Cfg = UmmaCfg<BN, NPASS>;
   constexpr int RING_BYTES = Cfg::STAGE_BYTES * STAGES;
-  constexpr int STORE_BYTES = Cfg::NBUF * STORE_BUF_BYTES;
+  constexpr int STORE_BYTES = NBUF * STORE_BUF_BYTES;
   constexpr int MAIN_BYTES = RING_BYTES > STORE_BYTES ? RING_BYTES : STORE_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.  Layout: [ring, reused as store staging after the last MMA | residual staging]
@@ -146,7 +157,7 @@ __global__ void __launch_bounds__(192) umma_linear_kernel(const __grid_constant_
     const bool elected = (warp == 2 && lane == 0);
     // residual tiles of the first store groups travel while the main loop runs
     if (e.has_r && elected) {
-      for (int g = 0; g < Cfg::NBUF; ++g) {
+      for (int g = 0; g < NBUF && g < Cfg::NG; ++g) {
         mbar_arrive_expect_tx(&res_bar[g], RES_BUF_BYTES);
         tma_load_2d(res_stage + g * RES_BUF_BYTES, &tm.rf, &res_bar[g], n0 + g * 64, m0);
         tma_load_2d(res_stage + g * RES_BUF_BYTES + TILE_BYTES, &tm.rf, &res_bar[g], n0 + g * 64 + 32, m0);
@@ -162,13 +173,13 @@ __global__ void __launch_bounds__(192) umma_linear_kernel(const __grid_constant_
     tc_fence_after();
 #pragma unroll 1
     for (int g = 0; g < Cfg::NG; ++g) {
-      const int buf = g & (Cfg::NBUF - 1);
+      const int buf = g % NBUF;
       uint8_t* sbuf = smem + buf * STORE_BUF_BYTES;
-      if (g >= 2) {                     // the stores of group g-2 must have drained this staging buffer
-        if (elected) tma_store_wait_read<1>();
+      if (g >= NBUF) {                  // the stores of group g-NBUF must have drained this staging buffer
+        if (elected) tma_store_wait_read<NBUF - 1>();
         epi_bar_sync();
       }
-      if (e.has_r) mbar_wait(&res_bar[buf], (g >> 1) & 1);
+      if (e.has_r) mbar_wait(&res_bar[buf], (g / NBUF) & 1);
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         const int c0 = g * 64 + half * 32;
@@ -212,32 +223,32 @@ __global__ void __launch_bounds__(192) umma_linear_kernel(const __grid_constant_
             *reinterpret_cast<float4*>(t + sw128(row, j)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         }
         if (e.has_yh) {
-          __align__(16) __nv_bfloat16 hb[32], lb[32];
+          uint32_t hb[16], lb[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { hb[i] = __float2bfloat16_rn(f[i]); lb[i] = __float2bfloat16_rn(f[i] - __bfloat162float(hb[i])); }
+          for (int i = 0; i < 16; ++i) split_bf16x2(f[2 * i], f[2 * i + 1], hb[i], lb[i]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(sbuf + sw128(row, half * 4 + j)) = reinterpret_cast<const uint4*>(hb)[j];
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(sbuf + sw128(row, half * 4 + j)) = make_uint4(hb[4 * j], hb[4 * j + 1], hb[4 * j + 2], hb[4 * j + 3]);
           if (e.has_yl) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(sbuf + TILE_BYTES + sw128(row, half * 4 + j)) = reinterpret_cast<const uint4*>(lb)[j];
+              *reinterpret_cast<uint4*>(sbuf + TILE_BYTES + sw128(row, half * 4 + j)) =
+                  make_uint4(lb[4 * j], lb[4 * j + 1], lb[4 * j + 2], lb[4 * j + 3]);
           }
         }
         if (e.has_zh) {
-          __align__(16) __nv_bfloat16 hb[32], lb[32];
+          uint32_t hb[16], lb[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float r = fmaxf(f[i], 0.f);
-            hb[i] = __float2bfloat16_rn(r);
-            lb[i] = __float2bfloat16_rn(r - __bfloat162float(hb[i]));
-          }
+          for (int i = 0; i < 16; ++i) split_bf16x2(fmaxf(f[2 * i], 0.f), fmaxf(f[2 * i + 1], 0.f), hb[i], lb[i]);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(sbuf + 2 * TILE_BYTES + sw128(row, half * 4 + j)) = reinterpret_cast<const uint4*>(hb)[j];
+            *reinterpret_cast<uint4*>(sbuf + 2 * TILE_BYTES + sw128(row, half * 4 + j)) =
+                make_uint4(hb[4 * j], hb[4 * j + 1], hb[4 * j + 2], hb[4 * j + 3]);
           if (e.has_zl) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(sbuf + 3 * TILE_BYTES + sw128(row, half * 4 + j)) = reinterpret_cast<const uint4*>(lb)[j];
+              *reinterpret_cast<uint4*>(sbuf + 3 * TILE_BYTES + sw128(row, half * 4 + j)) =
+                  make_uint4(lb[4 * j], lb[4 * j + 1], lb[4 * j + 2], lb[4 * j + 3]);
           }
         }
         if (e.colmax) {
@@ -267,10 +278,10 @@ __global__ void __launch_bounds__(192) umma_linear_kernel(const __grid_constant_
           tma_store_2d(&tm.yf, sbuf + 3 * TILE_BYTES, c + 32, m0);
         }
         tma_store_commit();
-        if (e.has_r && g + 2 < Cfg::NG) {   // everyone is past the reads of this residual buffer
+        if (e.has_r && g + NBUF < Cfg::NG) {   // everyone is past the reads of this residual buffer
           mbar_arrive_expect_tx(&res_bar[buf], RES_BUF_BYTES);
-          tma_load_2d(res_stage + buf * RES_BUF_BYTES, &tm.rf, &res_bar[buf], n0 + (g + 2) * 64, m0);
-          tma_load_2d(res_stage + buf * RES_BUF_BYTES + TILE_BYTES, &tm.rf, &res_bar[buf], n0 + (g + 2) * 64 + 32, m0);
+          tma_load_2d(res_stage + buf * RES_BUF_BYTES, &tm.rf, &res_bar[buf], n0 + (g + NBUF) * 64, m0);
+          tma_load_2d(res_stage + buf * RES_BUF_BYTES + TILE_BYTES, &tm.rf, &res_bar[buf], n0 + (g + NBUF) * 64 + 32, m0);
         }
       }
     }
@@ -322,24 +333,25 @@ static int make_map(CUtensorMap* map, const void* ptr, bool f32, int rows, int c
   return SEEME_OK;
 }
 
-template <int BN, int NPASS, int STAGES>
+template <int BN, int NPASS, int STAGES, int NBUF, int MINB>
 static int launch(const UmmaLinear& g, const UmmaMaps& maps, const UmmaEpi& e, cudaStream_t s) {
   using Cfg = UmmaCfg<BN, NPASS>;
-  constexpr int ring = Cfg::STAGE_BYTES * STAGES, store = Cfg::NBUF * STORE_BUF_BYTES;
+  constexpr int ring = Cfg::STAGE_BYTES * STAGES, store = NBUF * STORE_BUF_BYTES;
   // BN = 256 tiles never stage a residual (umma_linear picks BN <= 128 when R is given)
-  constexpr int res_max = BN == 256 ? 0 : Cfg::NBUF * RES_BUF_BYTES;
+  constexpr int res_max = BN == 256 ? 0 : NBUF * RES_BUF_BYTES;
   constexpr int smem_max = (ring > store ? ring : store) + res_max + 1024;
   static_assert(smem_max <= 227 * 1024, "shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
-    SEEME_CUDA(cudaFuncSetAttribute(umma_linear_kernel<BN, NPASS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    SEEME_CUDA(cudaFuncSetAttribute(umma_linear_kernel<BN, NPASS, STAGES, NBUF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    smem_max));
     configured = true;
   }
   SEEME_REQUIRE(!(e.has_r && BN == 256), SEEME_EINVAL, "umma_linear: residual staging is not available for 256-wide tiles");
   const int smem = (ring > store ? ring : store) + (e.has_r ? res_max : 0) + 1024;
   dim3 grid(g.N / BN, (g.M + 127) / 128);
   ProfScope prof(g.prof_id - 1, s);
-  umma_linear_kernel<BN, NPASS, STAGES><<<grid, 192, smem, s>>>(maps, e);
+  umma_linear_kernel<BN, NPASS, STAGES, NBUF, MINB><<<grid, 192, smem, s>>>(maps, e);
   SEEME_LAUNCH_CHECK();
   return SEEME_OK;
 }
@@ -356,7 +368,7 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
   SEEME_REQUIRE((!g.Yl || g.Yh) && (!g.Zl || g.Zh), SEEME_EINVAL, "umma_linear: lo outputs need their hi companion");
   // few rows (the latency-bound sampler / per-sample GEMMs): narrow tiles spread one GEMM over more SMs;
   // many rows: the widest tile that divides N (128 when a residual tile has to be staged as well)
-  int BN = (g.M <= 2048 && !g.colmax) ? 64 : ((g.N % 256 == 0 && !g.R) ? 256 : 128);
+  int BN = (g.M <= 2048 && !g.colmax) ? 64 : 128;
   if (g.N % BN != 0) BN = 64;
   SEEME_REQUIRE(g.N % BN == 0, SEEME_EINVAL, "umma_linear: N=%d must be a multiple of 64", g.N);
   UmmaMaps maps;
@@ -382,9 +394,11 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
   e.has_r = g.R != nullptr; e.has_yf = g.Y != nullptr; e.has_yh = g.Yh != nullptr; e.has_yl = g.Yl != nullptr;
   e.has_zh = g.Zh != nullptr; e.has_zl = g.Zl != nullptr;
   e.colmax = g.colmax; e.colmax_group_rows = g.colmax_group_rows;
-  if (BN == 256) return npass == 1 ? launch<256, 1, 2>(g, maps, e, s) : launch<256, 3, 2>(g, maps, e, s);
-  if (BN == 64) return npass == 1 ? launch<64, 1, 4>(g, maps, e, s) : launch<64, 3, 4>(g, maps, e, s);
-  return npass == 1 ? launch<128, 1, 4>(g, maps, e, s) : launch<128, 3, 2>(g, maps, e, s);
+  // 64-wide tiles: the whole K = 256 of a latency-bound GEMM is in flight at once (4 stages), one CTA per SM.
+  // 128-wide tiles (many rows): a shallow ring (64 KB in split mode) and one staging buffer keep the footprint
+  // small enough for 2-3 CTAs per SM, which is what overlaps TMA, MMA and epilogue phases across tiles.
+  if (BN == 64) return npass == 1 ? launch<64, 1, 4, 1, 1>(g, maps, e, s) : launch<64, 3, 4, 1, 1>(g, maps, e, s);
+  return npass == 1 ? launch<128, 1, 2, 1, 2>(g, maps, e, s) : launch<128, 3, 1, 1, 2>(g, maps, e, s);
 }
 
 __global__ void to_bf16_split_kernel(const float* __restrict__ x, int ldx, int rows, int cols, __nv_bfloat16* __restrict__ hi,
