@@ -189,7 +189,7 @@ def main():
     def timed(fn, steps, prof=False):
         barrier()
         if prof:
-            for i in range(6):
+            for i in range(8):
                 _lib.prof_read(i)
             _lib.prof_enable(True)
         n0 = _lib.launch_count()
@@ -214,6 +214,7 @@ def main():
     t_res, launches, rs = timed(step_resident, args.steps, prof=True)
     clk = clocks.stop() if clocks else None
     prof = {name: _lib.prof_read(i) for i, name in enumerate(["pointnet_gemm", "smpl_skin", "smpl_pose", "sampler_graph"])}
+    prof["pointnet_fused"] = _lib.prof_read(6)
     value = world * B * args.steps / t_res
 
     # the per-epoch metric gather (the path's only collective): all-reduce(sum) of the EgoMetric state vector
@@ -243,7 +244,7 @@ def main():
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         ach = flops / (pn_ms / 1e3) / 1e12 if pn_ms > 0 else None
         prec = os.environ.get("SEEME_POINTNET_PRECISION", "3")
-        kname = {"3": "umma_linear_kernel<256,3,2> (tcgen05, split-bf16: 3 MMAs per algorithmic MAC)",
+        kname = {"16": "fp16 fused", "17": "fp16 fused (smem H)", "3": "umma_linear_kernel<256,3,2> (tcgen05, split-bf16: 3 MMAs per algorithmic MAC)",
                  "1": "umma_linear_kernel<256,1,2> (tcgen05, bf16)", "0": "gemm_f32_kernel<128,128,8,8> (fp32 CUDA cores)"}[prec]
         roofline = {"kernel": "scene-encoder GEMM launches: " + kname, "bound": "tensor", "achieved": ach,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": (ach / peak_tf) if ach else None, "traffic": None,
@@ -256,7 +257,8 @@ def main():
         other = {"smpl_skin": {"bound": "hbm", "achieved": sk_ach, "peak": hbm, "unit": "GB/s", "frac": (sk_ach / hbm) if sk_ach else None,
                                "launches": sk_n, "avg_launch_ms": sk_ms / sk_n if sk_n else None},
                  "sampler_graph_ms_per_step": prof["sampler_graph"][0] / max(prof["sampler_graph"][1], 1),
-                 "smpl_pose_ms_per_launch": prof["smpl_pose"][0] / max(prof["smpl_pose"][1], 1)}
+                 "smpl_pose_ms_per_launch": prof["smpl_pose"][0] / max(prof["smpl_pose"][1], 1),
+                 "pointnet_fused_ms": prof["pointnet_fused"][0], "pointnet_fused_launches": prof["pointnet_fused"][1]}
         cpu_baseline = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

@@ -75,6 +75,15 @@ typedef struct seeme_pointnet* seeme_pointnet_t;
 #define SEEME_POINTNET_NUM_TENSORS 26
 int seeme_pointnet_create(seeme_pointnet_t* out, const float* const* weights /*HOST array of device ptrs*/,
                           int n_weights, int max_batch, int max_points);
+/* Same with an explicit GEMM operand format for the per-point contractions (fp32 accumulation everywhere):
+ *   3  split-bf16 (hi.hi + lo.hi + hi.lo, ~16 mantissa bits; the default of seeme_pointnet_create unless the
+ *      environment variable SEEME_POINTNET_PRECISION overrides it), layer-by-layer tcgen05 GEMMs;
+ *   1  plain bf16, layer-by-layer;   0  fp32 CUDA-core GEMMs, layer-by-layer;
+ *   16 fp16 operands, residual blocks 1..3 fused into one persistent tcgen05 kernel each (activations stay in
+ *      shared/tensor memory between the block's three GEMMs); 17 = 16 with the hidden activation staged through
+ *      shared memory instead of tensor memory. */
+int seeme_pointnet_create_ex(seeme_pointnet_t* out, const float* const* weights, int n_weights, int max_batch,
+                             int max_points, int precision);
 /* pcd [B,N,3] -> feat512 [B,512] (= encode_scene, may be NULL) and emb256 [B,256]
  * (= output_scene(encode_scene), may be NULL). */
 int seeme_pointnet_forward(seeme_pointnet_t h, const float* pcd, int B, int N, float* feat512,

@@ -26,6 +26,7 @@ SIGNATURES = {
     "seeme_test_umma_linear": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_int, C.c_void_p, C.c_int, c_float_p, c_float_p, C.c_void_p]),
     "seeme_pointnet_create": (C.c_int, [C.POINTER(c_handle), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]),
+    "seeme_pointnet_create_ex": (C.c_int, [C.POINTER(c_handle), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]),
     "seeme_pointnet_forward": (C.c_int, [c_handle, c_float_p, C.c_int, C.c_int, c_float_p, c_float_p, C.c_void_p]),
     "seeme_pointnet_destroy": (C.c_int, [c_handle]),
     "seeme_vae_create": (C.c_int, [C.POINTER(c_handle), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -56,7 +56,7 @@ inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
 // When enabled with seeme_prof_enable(1), each instrumented launch is bracketed by a cudaEvent pair on
 // its own stream; seeme_prof_read() synchronises and returns the summed duration and launch count.
 enum ProfId { PROF_POINTNET_GEMM = 0, PROF_SMPL_SKIN = 1, PROF_SMPL_POSE = 2, PROF_SAMPLER_GRAPH = 3, PROF_VAE_ATTN = 4,
-              PROF_UMMA_GEMM = 5, PROF_COUNT = 8 };
+              PROF_UMMA_GEMM = 5, PROF_POINTNET_FUSED = 6, PROF_COUNT = 8 };
 extern bool g_prof_on;
 void prof_begin(int id, cudaStream_t s);
 void prof_end(int id, cudaStream_t s);

@@ -20,6 +20,8 @@
 // the layer-by-layer path kept for accuracy studies).
 #include "common.cuh"
 #include "umma.cuh"
+#include "pointnet_fused.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace seeme {
@@ -48,7 +50,7 @@ __global__ void ord_decode_kernel(const unsigned* __restrict__ in, float* __rest
 // xr0[m, c] = bf16 split of relu(Wp[c,:] . p[m] + bp[c]); thread = 8 consecutive channels, grid-stride over points
 __global__ void __launch_bounds__(256) fcpos_relu_bf16_kernel(const float* __restrict__ p, const float* __restrict__ Wp,
                                                               const float* __restrict__ bp, __nv_bfloat16* __restrict__ hi,
-                                                              __nv_bfloat16* __restrict__ lo, int rows) {
+                                                              __nv_bfloat16* __restrict__ lo, int rows, int fp16) {
   const int cg = threadIdx.x & 63;             // channel group: channels [8 cg, 8 cg + 8)
   float w[8][3], b[8];
 #pragma unroll
@@ -64,8 +66,12 @@ __global__ void __launch_bounds__(256) fcpos_relu_bf16_kernel(const float* __res
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float v = fmaxf(fmaf(w[i][2], z, fmaf(w[i][1], y, fmaf(w[i][0], x, b[i]))), 0.f);
-      h[i] = __float2bfloat16_rn(v);
-      l[i] = __float2bfloat16_rn(v - __bfloat162float(h[i]));
+      if (fp16) {
+        reinterpret_cast<__half*>(h)[i] = __float2half_rn(v);
+      } else {
+        h[i] = __float2bfloat16_rn(v);
+        l[i] = __float2bfloat16_rn(v - __bfloat162float(h[i]));
+      }
     }
     *reinterpret_cast<uint4*>(hi + (size_t)m * 512 + cg * 8) = *reinterpret_cast<const uint4*>(h);
     if (lo) *reinterpret_cast<uint4*>(lo + (size_t)m * 512 + cg * 8) = *reinterpret_cast<const uint4*>(l);
@@ -97,6 +103,21 @@ __global__ void pointnet_fold_kernel(const float* __restrict__ Ws, const float* 
   cst[n] = (float)(a3 + (double)b1[n]);
 }
 
+__global__ void to_f16_kernel(const float* __restrict__ x, int ldx, int rows, int cols, __half* __restrict__ out, int ld_out) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  out[(size_t)r * ld_out + c] = __float2half_rn(x[(size_t)r * ldx + c]);
+}
+
+// fp32 [rows, cols] (pitch ldx) -> fp16 bits in a bf16-typed buffer (default stream, create time)
+static int to_f16(const float* x, int ldx, int rows, int cols, __nv_bfloat16* out, int ld_out) {
+  const size_t n = (size_t)rows * cols;
+  to_f16_kernel<<<(unsigned)((n + 255) / 256), 256>>>(x, ldx, rows, cols, reinterpret_cast<__half*>(out), ld_out);
+  SEEME_LAUNCH_CHECK();
+  return SEEME_OK;
+}
+
 }  // namespace seeme
 
 using namespace seeme;
@@ -117,6 +138,8 @@ struct seeme_pointnet {
   // shared
   float *pool, *c0, *cs, *feat, *padbuf;
   unsigned* pool_ord;
+  // fused fp16 path (precision 16 / 17): per-block weight-chunk blobs for blocks 1..3
+  void* blob[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 static int copy_w(Arena& a, float*& dst, const float* src, size_t n) {
@@ -131,8 +154,7 @@ static void destroy(seeme_pointnet* h) {
   delete h;
 }
 
-extern "C" int seeme_pointnet_create(seeme_pointnet_t* out, const float* const* w, int n_w, int max_batch,
-                                     int max_points) {
+static int pointnet_create(seeme_pointnet_t* out, const float* const* w, int n_w, int max_batch, int max_points, int precision_arg) {
   SEEME_REQUIRE(out && w, SEEME_EINVAL, "seeme_pointnet_create: null argument");
   SEEME_REQUIRE(n_w == SEEME_POINTNET_NUM_TENSORS, SEEME_EINVAL, "seeme_pointnet_create: expected %d tensors, got %d",
                 SEEME_POINTNET_NUM_TENSORS, n_w);
@@ -144,15 +166,17 @@ extern "C" int seeme_pointnet_create(seeme_pointnet_t* out, const float* const* 
   h->max_points = max_points;
   const char* pe = getenv("SEEME_POINTNET_PRECISION");
   h->precision = pe ? atoi(pe) : 3;
-  if (h->precision != 0 && h->precision != 1 && h->precision != 3) {
-    set_error("SEEME_POINTNET_PRECISION must be 0, 1 or 3");
+  if (precision_arg >= 0) h->precision = precision_arg;
+  if (h->precision != 0 && h->precision != 1 && h->precision != 3 && h->precision != 16 && h->precision != 17) {
+    set_error("scene-encoder precision must be 0, 1, 3, 16 or 17 (got %d)", h->precision);
     delete h;
     return SEEME_EINVAL;
   }
   h->chunk = max_batch < 32 ? max_batch : 32;   // samples per pass: bounds the per-point workspace
   const size_t rows = (size_t)h->chunk * (max_points < 128 ? 128 : max_points);
   const bool split = h->precision == 3;
-  size_t wbytes = pad256(512 * 3 * 4) + pad256(512 * 4) + 4 * (pad256(256 * 512 * 4) * 2 + pad256(256 * 256 * 4) + 2 * pad256(256 * 4)) +
+  const bool fused = h->precision >= 16;
+  size_t wbytes = 3 * pad256(pf_blob_bytes()) + pad256(512 * 3 * 4) + pad256(512 * 4) + 4 * (pad256(256 * 512 * 4) * 2 + pad256(256 * 256 * 4) + 2 * pad256(256 * 4)) +
                   pad256(512 * 256 * 4) + pad256(512 * 4) + pad256(256 * 512 * 4) + pad256(256 * 4) +
                   8 * 2 * pad256(256 * 512 * 2) + pad256(256 * 4 * 4) + pad256(256 * 4);
   size_t ws = 4 * pad256((size_t)max_batch * 256 * 4) + pad256((size_t)max_batch * 512 * 4) + pad256((size_t)max_batch * 128 * 3 * 4);
@@ -207,9 +231,17 @@ extern "C" int seeme_pointnet_create(seeme_pointnet_t* out, const float* const* 
     ok = ok && h->xrh[1] && (!split || h->xrl[1]);
     if (ok) {
       // pack the tensor-path weights (default stream, create time)
-      rc = to_bf16_split(h->w0[0], 512, 256, 512, h->g1h[0], h->g1l[0], 512, 0, 0);
-      if (!rc) rc = to_bf16_split(h->w1[0], 256, 256, 256, h->g2h[0], h->g2l[0], 256, 0, 0);
-      for (int i = 1; i < 4 && !rc; ++i) {
+      if (fused) {
+        rc = to_f16(h->w0[0], 512, 256, 512, h->g1h[0], 512);
+        if (!rc) rc = to_f16(h->w1[0], 256, 256, 256, h->g2h[0], 256);
+        for (int i = 1; i < 4 && !rc; ++i) {
+          h->blob[i] = h->arena.take<char>(pf_blob_bytes());
+          if (!h->blob[i]) { set_error("pointnet: arena exhausted (weight blobs)"); rc = SEEME_ENOMEM; break; }
+          rc = pf_pack_block(h->ws[i], h->w0[i], h->w1[i], h->blob[i]);
+        }
+      } else rc = to_bf16_split(h->w0[0], 512, 256, 512, h->g1h[0], h->g1l[0], 512, 0, 0);
+      if (!rc && !fused) rc = to_bf16_split(h->w1[0], 256, 256, 256, h->g2h[0], h->g2l[0], 256, 0, 0);
+      for (int i = 1; i < 4 && !rc && !fused; ++i) {
         rc = to_bf16_split(h->w0[i], 512, 256, 256, h->g1h[i], h->g1l[i], 256, 0, 0);
         if (!rc) rc = to_bf16_split(h->ws[i], 512, 256, 256, h->g2h[i], h->g2l[i], 512, 0, 0);          // columns [0,256)
         if (!rc) rc = to_bf16_split(h->w1[i], 256, 256, 256, h->g2h[i] + 256, h->g2l[i] + 256, 512, 0, 0);  // columns [256,512)
@@ -290,7 +322,7 @@ static int blocks_tensor(seeme_pointnet* h, const float* p, int C, int N, cudaSt
     const int ppb = 4;
     int grid = (rows + ppb - 1) / ppb;
     if (grid > NUM_SMS * 16) grid = NUM_SMS * 16;
-    fcpos_relu_bf16_kernel<<<grid, 256, 0, s>>>(p, h->fc_pos_w, h->fc_pos_b, h->xr0h, h->xr0l, rows);
+    fcpos_relu_bf16_kernel<<<grid, 256, 0, s>>>(p, h->fc_pos_w, h->fc_pos_b, h->xr0h, h->xr0l, rows, 0);
     SEEME_LAUNCH_CHECK();
   }
   int cur = 0;
@@ -342,6 +374,64 @@ static int blocks_tensor(seeme_pointnet* h, const float* p, int C, int N, cudaSt
   return decode_pool(h, C, s);
 }
 
+// ---- fused fp16 path (precision 16: H operand in tensor memory; 17: H through shared memory) ------------------
+// block 0 keeps the two-GEMM form (its input is the 512-wide relu(fc_pos(p)), its shortcut the rank-3 fold); blocks
+// 1..3 are one persistent kernel each (pointnet_fused.cu).
+static int blocks_fused(seeme_pointnet* h, const float* p, int C, int N, cudaStream_t s) {
+  const int rows = C * N;
+  {
+    const int ppb = 4;
+    int grid = (rows + ppb - 1) / ppb;
+    if (grid > NUM_SMS * 16) grid = NUM_SMS * 16;
+    fcpos_relu_bf16_kernel<<<grid, 256, 0, s>>>(p, h->fc_pos_w, h->fc_pos_b, h->xr0h, nullptr, rows, 1);
+    SEEME_LAUNCH_CHECK();
+  }
+  UmmaLinear g1;   // hr = relu(W0 . xr0 + b0)
+  g1.fp16 = 1;
+  g1.A1 = {h->xr0h, nullptr, 512};
+  g1.W = {h->g1h[0], nullptr, 512};
+  g1.M = rows; g1.N = 256; g1.K1 = 512;
+  g1.bias = h->b0[0];
+  g1.act = ACT_RELU;
+  g1.Yh = h->hrh; g1.ldb = 256;
+  g1.prof_id = PROF_POINTNET_GEMM + 1;
+  SEEME_TRY(umma_linear(g1, 1, s));
+  SEEME_CUDA(cudaMemsetAsync(h->pool_ord, 0, (size_t)C * 256 * sizeof(unsigned), s));
+  UmmaLinear g2;   // net = W1 . hr + rank-3 fold of the shortcut
+  g2.fp16 = 1;
+  g2.A1 = {h->hrh, nullptr, 256};
+  g2.W = {h->g2h[0], nullptr, 256};
+  g2.M = rows; g2.N = 256; g2.K1 = 256;
+  g2.bias = h->cst0;
+  g2.pfold = h->pfold;
+  g2.xyz = p;
+  g2.Yh = h->xh[0]; g2.ldb = 256;
+  g2.colmax = h->pool_ord;
+  g2.colmax_group_rows = N;
+  g2.prof_id = PROF_POINTNET_GEMM + 1;
+  SEEME_TRY(umma_linear(g2, 1, s));
+  int cur = 0;
+  for (int i = 1; i < 4; ++i) {
+    SEEME_TRY(decode_pool(h, C, s));
+    SEEME_TRY(pooled_bias(h, i, C, s));
+    SEEME_CUDA(cudaMemsetAsync(h->pool_ord, 0, (size_t)C * 256 * sizeof(unsigned), s));
+    SEEME_TRY(pf_block_forward(h->xh[cur], i < 3 ? h->xh[cur ^ 1] : nullptr, h->blob[i], h->c0, h->cs, h->pool_ord, C, N,
+                               h->precision == 16, PROF_POINTNET_FUSED + 1, s));
+    cur ^= 1;
+  }
+  return decode_pool(h, C, s);
+}
+
+extern "C" int seeme_pointnet_create(seeme_pointnet_t* out, const float* const* w, int n_w, int max_batch, int max_points) {
+  return pointnet_create(out, w, n_w, max_batch, max_points, -1);
+}
+
+extern "C" int seeme_pointnet_create_ex(seeme_pointnet_t* out, const float* const* w, int n_w, int max_batch, int max_points,
+                                        int precision) {
+  SEEME_REQUIRE(precision >= 0, SEEME_EINVAL, "seeme_pointnet_create_ex: bad precision %d", precision);
+  return pointnet_create(out, w, n_w, max_batch, max_points, precision);
+}
+
 extern "C" int seeme_pointnet_forward(seeme_pointnet_t h, const float* pcd, int B, int N, float* feat512,
                                       float* emb256, void* stream) {
   SEEME_REQUIRE(h && pcd, SEEME_EINVAL, "seeme_pointnet_forward: null argument");
@@ -359,6 +449,7 @@ extern "C" int seeme_pointnet_forward(seeme_pointnet_t h, const float* pcd, int 
     const int C = (B - b0 < h->chunk) ? (B - b0) : h->chunk;
     const float* p = pcd + (size_t)b0 * N * 3;
     if (h->precision == 0) SEEME_TRY(blocks_fp32(h, p, C, N, s));
+    else if (h->precision >= 16) SEEME_TRY(blocks_fused(h, p, C, N, s));
     else SEEME_TRY(blocks_tensor(h, p, C, N, s));
     // fc_c(relu(pool)) -> [C,512]; output_scene: Linear(relu(.)) -> [C,256]
     GemmP gc = gemm_params(h->pool, 256, h->wc, 256, h->bc, h->feat + (size_t)b0 * 512, 512, C, 512, 256);

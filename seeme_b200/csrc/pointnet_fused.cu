@@ -1,0 +1,452 @@
+// Fused ResnetBlockFC for the scene encoder (EgoHMR/models/respointnet.py:88-97 applied to [net | pooled],
+// :36-48) -- one persistent tcgen05 kernel per residual block i >= 1, fp16 operands, fp32 accumulation.
+//
+// Per 128-point tile (points of ONE sample; the pooled half of the reference's concat is a per-sample bias,
+// see pointnet.cu) the whole block runs on chip:
+//
+//     X   = net tile [128, 256] fp16                       TMA load (3-D map [256, N, B], OOB rows = 0)
+//     S   : OUT  = X . Ws^T                                 tcgen05.mma, A and B from shared memory
+//     relu: X   <- relu(X) in place                         epilogue warps, K-chunk by K-chunk behind S
+//     G1  : H    = relu(X) . W0^T                           two N-halves, each committed separately
+//     epiH: H16 = fp16(relu(H + c0[b]))                     TMEM -> registers -> TMEM (in place, packed 2/column)
+//     G2  : OUT += H16 . W1^T                               tcgen05.mma with the A operand read from TMEM
+//     epiOUT: out = OUT + cs[b]; per-sample column max (pooling); fp16 tile staged in the (now free) X buffer
+//             and written back with TMA stores
+//
+// The activations never leave the SM between the three GEMMs; HBM sees 512 B in + 512 B out per point and block.
+// The weights of a block (3 x 256x256 fp16 = 384 KB) are streamed from L2 as 24 chunks of [128 n, 64 k] per tile
+// through a 6-deep ring.  TMEM (512 columns) holds two 256-column regions that alternate between the OUT
+// accumulator of tile j and the H accumulator of tile j+1, so tile j's output epilogue overlaps tile j+1's
+// shortcut GEMM.
+//
+//   warp 0      weight-ring TMA producer
+//   warp 1      TMEM allocator + the single MMA-issuing thread
+//   warps 2..9  8 epilogue warps (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4): in-place relu,
+//               H epilogue, OUT epilogue, X-tile TMA loads (one elected thread)
+#include "umma.cuh"
+#include "pointnet_fused.cuh"
+#include <cudaTypedefs.h>
+#include <cuda_fp16.h>
+
+namespace seeme {
+
+constexpr int PF_NST = 6;                           // weight ring depth
+constexpr int PF_CHUNK = 128 * 128;                 // [128 rows x 64 fp16], SWIZZLE_128B
+constexpr int PF_XBUF = 4 * PF_CHUNK;               // one activation tile [128 x 256] fp16
+constexpr int PF_THREADS = 320;
+constexpr int PF_WCHUNKS = 24;                      // weight chunks per tile: S 8, G1 8, G2 8
+constexpr int PF_SMEM = 2 * PF_XBUF + PF_NST * PF_CHUNK + 1024;
+
+struct PfMaps { CUtensorMap xin, xout, w; };
+struct PfArgs {
+  int n_points, tiles_per_sample, n_tiles;
+  const float* bias_h;   // [samples, 256]  c0: added to H before its relu
+  const float* bias_o;   // [samples, 256]  cs: added to OUT
+  unsigned* colmax;      // [samples, 256]  order-preserving uint, zeroed by the caller
+  int store_out;
+};
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void pf_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void pf_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void pf_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T : the A tile sits in TMEM as 128 lanes x (K/2) columns, two fp16 per column
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float m;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+  return m;
+}
+__device__ __forceinline__ uint32_t pf_pack(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pf_sw128(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+
+// H_TMEM: G2 reads its A operand (H) from tensor memory; false = H is written over relu(X) in shared memory
+template <bool H_TMEM>
+__global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __grid_constant__ PfMaps tm, const PfArgs a) {
+  extern __shared__ __align__(1024) uint8_t pf_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pf_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* xbuf = smem;
+  uint8_t* wring = smem + 2 * PF_XBUF;
+  __shared__ __align__(8) uint64_t w_full[PF_NST], w_empty[PF_NST], x_full[2], s_done[2][4], r_done[2][4], h_full[2][2],
+      h_ready[2][4], out_full[2], out_drained[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ unsigned colmax_s[256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = a.n_tiles / (int)gridDim.x, rem = a.n_tiles % (int)gridDim.x;
+  const int t_begin = (int)blockIdx.x * per + ((int)blockIdx.x < rem ? (int)blockIdx.x : rem);
+  const int nt = per + ((int)blockIdx.x < rem ? 1 : 0);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm.xin);
+    tma_prefetch_desc(&tm.w);
+    tma_prefetch_desc(&tm.xout);
+    for (int i = 0; i < PF_NST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&x_full[b], 1);
+      mbar_init(&out_full[b], 1);
+      mbar_init(&out_drained[b], 8);
+      for (int k = 0; k < 4; ++k) { mbar_init(&s_done[b][k], 1); mbar_init(&r_done[b][k], 8); mbar_init(&h_ready[b][k], 4); }
+      mbar_init(&h_full[b][0], 1);
+      mbar_init(&h_full[b][1], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  if (threadIdx.x < 256) colmax_s[threadIdx.x] = 0u;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ---- weight-ring producer -------------------------------------------------------------------------
+    if (lane == 0) {
+      uint32_t c = 0;
+      for (int j = 0; j < nt; ++j) {
+        for (int i = 0; i < PF_WCHUNKS; ++i, ++c) {
+          const uint32_t st = c % PF_NST;
+          mbar_wait(&w_empty[st], ((c / PF_NST) & 1) ^ 1);
+          mbar_arrive_expect_tx(&w_full[st], PF_CHUNK);
+          tma_load_2d(wring + st * PF_CHUNK, &tm.w, &w_full[st], 0, i * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ------------------------------------------------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(128);
+      uint32_t c = 0;
+      auto next_w = [&]() -> uint32_t {
+        const uint32_t st = c % PF_NST;
+        mbar_wait(&w_full[st], (c / PF_NST) & 1);
+        tc_fence_after();
+        return smem_u32(wring + st * PF_CHUNK);
+      };
+      auto release_w = [&]() {
+        umma_commit(&w_empty[c % PF_NST]);
+        ++c;
+      };
+      for (int j = 0; j < nt; ++j) {
+        const int b = j & 1;
+        const uint32_t p2 = (uint32_t)(j >> 1) & 1u;
+        const uint32_t Ra = tmem_base + (uint32_t)b * 256u, Rb = tmem_base + (uint32_t)(b ^ 1) * 256u;
+        const uint32_t xb = smem_u32(xbuf + b * PF_XBUF);
+        mbar_wait(&x_full[b], p2);
+        tc_fence_after();
+        // S: OUT = X . Ws^T  (weight chunk order: kc outer, n-half inner)
+        for (int kc = 0; kc < 4; ++kc) {
+          for (int nh = 0; nh < 2; ++nh) {
+            const uint32_t sw = next_w();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16(Ra + nh * 128, umma_desc_k128(xb + kc * PF_CHUNK + ks * 32), umma_desc_k128(sw + ks * 32), idesc, (kc | ks) != 0);
+            release_w();
+          }
+          umma_commit(&s_done[b][kc]);
+        }
+        // the H region of this tile was the OUT region of the previous one: its epilogue must have drained it
+        if (j > 0) {
+          mbar_wait(&out_drained[b ^ 1], (uint32_t)((j - 1) >> 1) & 1u);
+          tc_fence_after();
+        }
+        // G1: H = relu(X) . W0^T  (n-half outer so that the first half's epilogue overlaps the second half's MMAs)
+        for (int nh = 0; nh < 2; ++nh) {
+          for (int kc = 0; kc < 4; ++kc) {
+            if (nh == 0) {
+              mbar_wait(&r_done[b][kc], p2);
+              tc_fence_after();
+            }
+            const uint32_t sw = next_w();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16(Rb + nh * 128, umma_desc_k128(xb + kc * PF_CHUNK + ks * 32), umma_desc_k128(sw + ks * 32), idesc, (kc | ks) != 0);
+            release_w();
+          }
+          umma_commit(&h_full[b][nh]);
+        }
+        // G2: OUT += H16 . W1^T  (kc outer, n-half inner)
+        for (int kc = 0; kc < 4; ++kc) {
+          mbar_wait(&h_ready[b][kc], p2);
+          tc_fence_after();
+          for (int nh = 0; nh < 2; ++nh) {
+            const uint32_t sw = next_w();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              if (H_TMEM)
+                umma_f16_ts(Ra + nh * 128, Rb + (uint32_t)((kc >> 1) * 128 + (kc & 1) * 32 + ks * 8), umma_desc_k128(sw + ks * 32), idesc, 1);
+              else
+                umma_bf16(Ra + nh * 128, umma_desc_k128(xb + kc * PF_CHUNK + ks * 32), umma_desc_k128(sw + ks * 32), idesc, 1);
+            }
+            release_w();
+          }
+        }
+        umma_commit(&out_full[b]);
+      }
+    }
+  } else {
+    // ---- epilogue warps --------------------------------------------------------------------------------------
+    const int te = (int)threadIdx.x - 64;          // 0..255
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int hsel = (warp - 2) >> 2;               // column half
+    const int row = q * 32 + lane;
+    const bool elected = te == 0;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    auto load_x = [&](int j) {
+      const int t = t_begin + j, b = j & 1;
+      const int sample = t / a.tiles_per_sample, n0 = (t % a.tiles_per_sample) * 128;
+      mbar_arrive_expect_tx(&x_full[b], PF_XBUF);
+      for (int kc = 0; kc < 4; ++kc) tma_load_3d(xbuf + b * PF_XBUF + kc * PF_CHUNK, &tm.xin, &x_full[b], kc * 64, n0, sample);
+    };
+    auto flush_colmax = [&](int sample) {   // all 256 epilogue threads
+      pf_epi_sync();
+      const unsigned v = colmax_s[te];
+      if (v) atomicMax(a.colmax + (size_t)sample * 256 + te, v);
+      colmax_s[te] = 0u;
+      pf_epi_sync();
+    };
+    if (elected) {
+      if (nt > 0) load_x(0);
+      if (nt > 1) load_x(1);
+    }
+    int cur_sample = -1;
+    for (int j = 0; j < nt; ++j) {
+      const int b = j & 1;
+      const uint32_t p2 = (uint32_t)(j >> 1) & 1u;
+      const int t = t_begin + j;
+      const int sample = t / a.tiles_per_sample, n0 = (t % a.tiles_per_sample) * 128;
+      uint8_t* xb = xbuf + b * PF_XBUF;
+      // -- relu(X) in place, one K-chunk behind the shortcut GEMM
+      for (int kc = 0; kc < 4; ++kc) {
+        mbar_wait(&s_done[b][kc], p2);
+        uint4* p = reinterpret_cast<uint4*>(xb + kc * PF_CHUNK) + te;
+        const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 v = p[i * 256];
+          __half2* h = reinterpret_cast<__half2*>(&v);
+          h[0] = __hmax2(h[0], z); h[1] = __hmax2(h[1], z); h[2] = __hmax2(h[2], z); h[3] = __hmax2(h[3], z);
+          p[i * 256] = v;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&r_done[b][kc]);
+      }
+      // -- H epilogue
+      {
+        const float* bh = a.bias_h + (size_t)sample * 256 + hsel * 128;
+        const uint32_t th = tmem_base + (uint32_t)(b ^ 1) * 256u + (uint32_t)hsel * 128u + lane_off;
+        mbar_wait(&h_full[b][hsel], p2);
+        if (!H_TMEM) mbar_wait(&h_full[b][hsel ^ 1], p2);   // relu(X) is overwritten: both halves of G1 must be done
+        tc_fence_after();
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          uint32_t raw[32];
+          tmem_ld32(th + g * 32, raw);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(bh + g * 32) + i);
+            const float f0 = fmaxf(__uint_as_float(raw[4 * i]) + bv.x, 0.f), f1 = fmaxf(__uint_as_float(raw[4 * i + 1]) + bv.y, 0.f);
+            const float f2 = fmaxf(__uint_as_float(raw[4 * i + 2]) + bv.z, 0.f), f3 = fmaxf(__uint_as_float(raw[4 * i + 3]) + bv.w, 0.f);
+            pk[2 * i] = pf_pack(f0, f1);
+            pk[2 * i + 1] = pf_pack(f2, f3);
+          }
+          if (H_TMEM) {
+            tmem_st16(th + g * 16, pk);          // in place: these 16 columns were read in this or an earlier group
+          } else {
+            uint8_t* ct = xb + (hsel * 2 + (g >> 1)) * PF_CHUNK;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              *reinterpret_cast<uint4*>(ct + pf_sw128(row, (g & 1) * 4 + jj)) = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+          }
+          if (g & 1) {
+            if (H_TMEM) { tmem_st_wait(); tc_fence_before(); }
+            else fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_ready[b][hsel * 2 + (g >> 1)]);
+          }
+        }
+      }
+      // -- OUT epilogue
+      {
+        mbar_wait(&out_full[b], p2);
+        tc_fence_after();
+        if (sample != cur_sample) {
+          if (cur_sample >= 0) flush_colmax(cur_sample);
+          cur_sample = sample;
+        }
+        const float* bo = a.bias_o + (size_t)sample * 256 + hsel * 128;
+        const uint32_t to = tmem_base + (uint32_t)b * 256u + (uint32_t)hsel * 128u + lane_off;
+        const bool valid = n0 + row < a.n_points;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          uint32_t raw[32];
+          tmem_ld32(to + g * 32, raw);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(bo + g * 32) + i);
+            f[4 * i] = __uint_as_float(raw[4 * i]) + bv.x; f[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + bv.y;
+            f[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + bv.z; f[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + bv.w;
+          }
+          float mine = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float m = warp_max_f32(valid ? f[i] : -INFINITY);
+            if (lane == i) mine = m;
+          }
+          atomicMax(&colmax_s[hsel * 128 + g * 32 + lane], f2ord(mine));
+          if (a.store_out) {
+            uint8_t* ct = xb + (hsel * 2 + (g >> 1)) * PF_CHUNK;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              *reinterpret_cast<uint4*>(ct + pf_sw128(row, (g & 1) * 4 + jj)) =
+                  make_uint4(pf_pack(f[8 * jj], f[8 * jj + 1]), pf_pack(f[8 * jj + 2], f[8 * jj + 3]), pf_pack(f[8 * jj + 4], f[8 * jj + 5]),
+                             pf_pack(f[8 * jj + 6], f[8 * jj + 7]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&out_drained[b]);
+        if (a.store_out) fence_proxy_async();
+        pf_epi_sync();
+        if (elected) {
+          if (a.store_out) {
+            for (int kc = 0; kc < 4; ++kc) tma_store_3d(&tm.xout, xb + kc * PF_CHUNK, kc * 64, n0, sample);
+            pf_store_commit();
+            pf_store_wait_read();
+          }
+          if (j + 2 < nt) load_x(j + 2);
+        }
+      }
+    }
+    if (cur_sample >= 0) flush_colmax(cur_sample);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_pf_encode = nullptr;
+static int pf_encoder() {
+  if (g_pf_encode) return SEEME_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  SEEME_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  SEEME_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, SEEME_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  g_pf_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return SEEME_OK;
+}
+
+// activations [samples, n_points, 256] fp16 as a 3-D map (channels, points, samples), box [64, 128, 1]
+static int pf_act_map(CUtensorMap* map, const void* ptr, int samples, int n_points) {
+  cuuint64_t gdim[3] = {256, (cuuint64_t)n_points, (cuuint64_t)samples};
+  cuuint64_t gstr[2] = {512, (cuuint64_t)n_points * 512};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_pf_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SEEME_REQUIRE(r == CUDA_SUCCESS, SEEME_ECUDA, "cuTensorMapEncodeTiled (activations) failed with CUresult %d", (int)r);
+  return SEEME_OK;
+}
+
+static int pf_w_map(CUtensorMap* map, const void* ptr) {
+  cuuint64_t gdim[2] = {64, (cuuint64_t)PF_WCHUNKS * 128};
+  cuuint64_t gstr[1] = {128};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_pf_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SEEME_REQUIRE(r == CUDA_SUCCESS, SEEME_ECUDA, "cuTensorMapEncodeTiled (weights) failed with CUresult %d", (int)r);
+  return SEEME_OK;
+}
+
+// chunk blob layout (24 x [128, 64] fp16): S (kc, nh) from Ws[:, :256]; G1 (nh, kc) from W0[:, :256]; G2 (kc, nh) from W1
+__global__ void pf_pack_weights_kernel(const float* __restrict__ ws, const float* __restrict__ w0, const float* __restrict__ w1,
+                                       __half* __restrict__ blob) {
+  const int chunk = blockIdx.x;
+  const int phase = chunk / 8, idx = chunk % 8;
+  int kc, nh;
+  if (phase == 1) { nh = idx / 4; kc = idx % 4; } else { kc = idx / 2; nh = idx % 2; }
+  const float* src = phase == 0 ? ws : phase == 1 ? w0 : w1;
+  const int ld = phase == 2 ? 256 : 512;
+  for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) {
+    const int r = i / 64, cc = i % 64;
+    blob[(size_t)chunk * 128 * 64 + i] = __float2half_rn(src[(size_t)(nh * 128 + r) * ld + kc * 64 + cc]);
+  }
+}
+
+int pf_pack_block(const float* ws, const float* w0, const float* w1, void* blob) {
+  pf_pack_weights_kernel<<<PF_WCHUNKS, 256>>>(ws, w0, w1, reinterpret_cast<__half*>(blob));
+  SEEME_LAUNCH_CHECK();
+  return SEEME_OK;
+}
+
+size_t pf_blob_bytes() { return (size_t)PF_WCHUNKS * 128 * 64 * 2; }
+
+int pf_block_forward(const void* x_in, void* x_out, const void* w_blob, const float* bias_h, const float* bias_o, unsigned* colmax,
+                     int samples, int n_points, int h_in_tmem, int prof_id, cudaStream_t s) {
+  SEEME_TRY(pf_encoder());
+  SEEME_REQUIRE(n_points >= 128, SEEME_EINVAL, "pf_block_forward: needs >= 128 points per sample (got %d)", n_points);
+  PfMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  SEEME_TRY(pf_act_map(&maps.xin, x_in, samples, n_points));
+  if (x_out) SEEME_TRY(pf_act_map(&maps.xout, x_out, samples, n_points)); else maps.xout = maps.xin;
+  SEEME_TRY(pf_w_map(&maps.w, w_blob));
+  PfArgs a;
+  a.n_points = n_points;
+  a.tiles_per_sample = (n_points + 127) / 128;
+  a.n_tiles = a.tiles_per_sample * samples;
+  a.bias_h = bias_h; a.bias_o = bias_o; a.colmax = colmax;
+  a.store_out = x_out != nullptr;
+  static bool configured = false;
+  if (!configured) {
+    SEEME_CUDA(cudaFuncSetAttribute(pointnet_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    SEEME_CUDA(cudaFuncSetAttribute(pointnet_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    configured = true;
+  }
+  const int grid = a.n_tiles < NUM_SMS ? a.n_tiles : NUM_SMS;
+  ProfScope prof(prof_id - 1, s);
+  if (h_in_tmem) pointnet_block_kernel<true><<<grid, PF_THREADS, PF_SMEM, s>>>(maps, a);
+  else pointnet_block_kernel<false><<<grid, PF_THREADS, PF_SMEM, s>>>(maps, a);
+  SEEME_LAUNCH_CHECK();
+  return SEEME_OK;
+}
+
+}  // namespace seeme

@@ -97,6 +97,10 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
+// same with fp16 operands (a_format = b_format = 0): 10 mantissa bits instead of 7 at the same MMA rate
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
 
 // ---- host-side description of one tcgen05 linear -----------------------------------------------
 // D[M,N] = epilogue( [A1 | A2][M, K1+K2] . W[N, K1+K2]^T ), operands bf16 (optionally split hi+lo for
@@ -124,6 +128,7 @@ struct UmmaLinear {
   unsigned* colmax = nullptr;    // [G,N] order-preserving uint max over the rows of each group (nullable)
   int colmax_group_rows = 0;
   int prof_id = 0;
+  int fp16 = 0;                  // operands and 16-bit outputs are IEEE fp16 (stored in the bf16-typed buffers); npass 1 only
 };
 // precision: 1 = single bf16 pass, 3 = split-bf16 (hi.hi + lo.hi + hi.lo)
 int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s);

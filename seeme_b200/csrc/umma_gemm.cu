@@ -21,6 +21,7 @@
 // bits at 3x the MMA count -- used where the reference's fp32 results must be tracked closely.
 #include "umma.cuh"
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 
 namespace seeme {
 
@@ -36,6 +37,7 @@ struct UmmaEpi {
   int act;
   int has_r, has_yf, has_yh, has_yl, has_zh, has_zl;
   unsigned* colmax; int colmax_group_rows;
+  int fp16;
 };
 
 constexpr int TILE_BYTES = 128 * 128;            // one 128-row x 128-byte swizzled staging tile
@@ -67,6 +69,12 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
   const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
   const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// fp16 flavour: hi = packed half2 of (a, b); there is no lo part
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 // byte offset of logical 16-byte chunk j of row r inside a 128-byte-swizzled [128 x 128 B] tile
@@ -127,7 +135,7 @@ __global__ void __launch_bounds__(192, MINB) umma_linear_kernel(const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BN);
+      const uint32_t idesc = e.fp16 ? umma_idesc_f16(BN) : umma_idesc_bf16(BN);
       for (int kb = 0; kb < e.nkb; ++kb) {
         const int st = kb % STAGES;
         mbar_wait(&full_bar[st], (kb / STAGES) & 1);
@@ -225,7 +233,10 @@ __global__ void __launch_bounds__(192, MINB) umma_linear_kernel(const __grid_con
         if (e.has_yh) {
           uint32_t hb[16], lb[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) split_bf16x2(f[2 * i], f[2 * i + 1], hb[i], lb[i]);
+          for (int i = 0; i < 16; ++i) {
+            if (e.fp16) { hb[i] = pack_f16x2(f[2 * i], f[2 * i + 1]); lb[i] = 0u; }
+            else split_bf16x2(f[2 * i], f[2 * i + 1], hb[i], lb[i]);
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<uint4*>(sbuf + sw128(row, half * 4 + j)) = make_uint4(hb[4 * j], hb[4 * j + 1], hb[4 * j + 2], hb[4 * j + 3]);
@@ -239,7 +250,10 @@ __global__ void __launch_bounds__(192, MINB) umma_linear_kernel(const __grid_con
         if (e.has_zh) {
           uint32_t hb[16], lb[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) split_bf16x2(fmaxf(f[2 * i], 0.f), fmaxf(f[2 * i + 1], 0.f), hb[i], lb[i]);
+          for (int i = 0; i < 16; ++i) {
+            if (e.fp16) { hb[i] = pack_f16x2(fmaxf(f[2 * i], 0.f), fmaxf(f[2 * i + 1], 0.f)); lb[i] = 0u; }
+            else split_bf16x2(fmaxf(f[2 * i], 0.f), fmaxf(f[2 * i + 1], 0.f), hb[i], lb[i]);
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<uint4*>(sbuf + 2 * TILE_BYTES + sw128(row, half * 4 + j)) =
@@ -362,6 +376,7 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
   SEEME_REQUIRE(g.M > 0 && g.N > 0 && g.K1 > 0 && g.K1 % 64 == 0 && g.K2 % 64 == 0, SEEME_EINVAL,
                 "umma_linear: unsupported shape M=%d N=%d K1=%d K2=%d (K multiples of 64)", g.M, g.N, g.K1, g.K2);
   SEEME_REQUIRE(npass == 1 || npass == 3, SEEME_EINVAL, "umma_linear: npass must be 1 or 3");
+  SEEME_REQUIRE(!g.fp16 || (npass == 1 && !g.Yl && !g.Zl), SEEME_EINVAL, "umma_linear: fp16 operands are single-pass (no lo parts)");
   SEEME_REQUIRE(npass == 1 || (g.A1.lo && g.W.lo && (g.K2 == 0 || g.A2.lo)), SEEME_EINVAL, "umma_linear: split-bf16 needs lo operands");
   SEEME_REQUIRE(!g.colmax || g.colmax_group_rows >= 128, SEEME_EINVAL, "umma_linear: colmax groups must have >= 128 rows");
   SEEME_REQUIRE(!(g.Y && g.Zh), SEEME_EINVAL, "umma_linear: the fp32 output and the relu bf16 output share staging slots");
@@ -394,6 +409,7 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
   e.has_r = g.R != nullptr; e.has_yf = g.Y != nullptr; e.has_yh = g.Yh != nullptr; e.has_yl = g.Yl != nullptr;
   e.has_zh = g.Zh != nullptr; e.has_zl = g.Zl != nullptr;
   e.colmax = g.colmax; e.colmax_group_rows = g.colmax_group_rows;
+  e.fp16 = g.fp16;
   // 64-wide tiles: the whole K = 256 of a latency-bound GEMM is in flight at once (4 stages), one CTA per SM.
   // 128-wide tiles (many rows): a shallow ring (64 KB in split mode) and one staging buffer keep the footprint
   // small enough for 2-3 CTAs per SM, which is what overlaps TMA, MMA and epilogue phases across tiles.

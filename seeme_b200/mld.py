@@ -82,7 +82,12 @@ class MLD(nn.Module):
         except AttributeError:
             self.vae_type = cfg.model.motion_vae.target.split(".")[-1].lower().replace("vae", "")   # -> "mld"
         if "scene" in self.condition:
-            self.proscene = ProHMRScene(cfg.get("PROSCENE"), max_batch=max_batch, max_points=n_points)
+            # scene_precision: operand format of the scene encoder's per-point GEMMs ("fp16-fused" = 16, the
+            # default; "split-bf16" = 3 tracks the fp32 reference to ~1e-5 at 3x the MMA count)
+            sp = kwargs.get("scene_precision", cfg.model.get("scene_precision", "fp16-fused"))
+            sp = {"fp16-fused": 16, "fp16-fused-smem": 17, "split-bf16": 3, "bf16": 1, "fp32": 0}.get(sp, sp)
+            self.scene_precision = int(sp)
+            self.proscene = ProHMRScene(cfg.get("PROSCENE"), max_batch=max_batch, max_points=n_points, precision=int(sp))
             self.output_scene = nn.Sequential(nn.ReLU(), nn.Linear(512, 256))                        # mld.py:257-261
         mv = cfg.model.motion_vae
         mv_params = dict(mv.get("params", {}))

@@ -188,11 +188,13 @@ class ResnetPointnet(_PackedModule):
     """``EgoHMR.models.respointnet.ResnetPointnet`` (out_dim 512, hidden 256).  ``output_scene`` is fused
     behind the same handle; ``forward`` returns the 512-d code like the reference."""
 
-    def __init__(self, out_dim: int = 512, hidden_dim: int = 256, max_batch: int = 512, max_points: int = 20000):
+    def __init__(self, out_dim: int = 512, hidden_dim: int = 256, max_batch: int = 512, max_points: int = 20000,
+                 precision: int = -1):
         super().__init__()
         if out_dim != 512 or hidden_dim != 256:
             raise NotImplementedError("ResnetPointnet (sm_100a): out_dim 512 / hidden_dim 256 only")
         self.out_dim = out_dim
+        self.precision = int(precision)      # operand format of the per-point GEMMs (seeme_pointnet_create_ex)
         self.max_batch, self.max_points = max_batch, max_points
         _register_spec(self, synthetic.pointnet_spec())
 
@@ -214,12 +216,12 @@ class ResnetPointnet(_PackedModule):
         sig_extra = (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version)
         cache = self.__dict__.setdefault("_op_cache", {})
         ent = cache.get("pn")
-        sig = (self._signature(), sig_extra)
+        sig = (self._signature(), sig_extra, self.precision)
         if ent is None or ent[0] != sig:
             if ent is not None:
                 ent[1].close()
             cache["pn"] = (sig, ops.PointNetOp(self.state_dict(), {"1.weight": lin.weight, "1.bias": lin.bias},
-                                               self.max_batch, self.max_points))
+                                               self.max_batch, self.max_points, precision=self.precision))
         return cache["pn"][1]
 
     def forward(self, p):
@@ -232,9 +234,9 @@ class ProHMRScene(nn.Module):
     ``encode_scene`` (:51,102-104).  The ResNet-50 backbone / flow / discriminator sub-trees are never
     run at SEE-ME test time and are not built (load reference checkpoints with ``strict=False``)."""
 
-    def __init__(self, cfg=None, max_batch: int = 512, max_points: int = 20000, **kwargs):
+    def __init__(self, cfg=None, max_batch: int = 512, max_points: int = 20000, precision: int = -1, **kwargs):
         super().__init__()
-        self.scene_enc = ResnetPointnet(512, 256, max_batch, max_points)
+        self.scene_enc = ResnetPointnet(512, 256, max_batch, max_points, precision=precision)
 
     def encode_scene(self, scene_pcd_verts):
         return self.scene_enc(scene_pcd_verts)

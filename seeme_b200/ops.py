@@ -102,14 +102,21 @@ class PointNetOp(_Handle):
     _destroy = "seeme_pointnet_destroy"
 
     def __init__(self, scene_enc_sd: Dict[str, torch.Tensor], output_scene_sd: Dict[str, torch.Tensor], max_batch: int,
-                 max_points: int = 20000):
+                 max_points: int = 20000, precision: int = -1):
+        """precision: GEMM operand format of the per-point contractions (include/seeme_b200.h,
+        ``seeme_pointnet_create_ex``); -1 = library default (split-bf16 unless SEEME_POINTNET_PRECISION is set)."""
         super().__init__()
         ts = [_dev_f32(scene_enc_sd[k], k) for k in pointnet_keys()]
         ts += [_dev_f32(output_scene_sd["1.weight"], "output_scene.1.weight"), _dev_f32(output_scene_sd["1.bias"], "output_scene.1.bias")]
         self.device = ts[0].device
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().seeme_pointnet_create(C.byref(self.h), _ptr_array(ts), len(ts), max_batch, max_points),
-                       "seeme_pointnet_create")
+            if precision < 0:
+                _lib.check(_lib.lib().seeme_pointnet_create(C.byref(self.h), _ptr_array(ts), len(ts), max_batch, max_points),
+                           "seeme_pointnet_create")
+            else:
+                _lib.check(_lib.lib().seeme_pointnet_create_ex(C.byref(self.h), _ptr_array(ts), len(ts), max_batch, max_points,
+                                                               int(precision)), "seeme_pointnet_create_ex")
+        self.precision = precision
         self.max_batch, self.max_points = max_batch, max_points
 
     def __call__(self, pcd: torch.Tensor, want_feat: bool = False):

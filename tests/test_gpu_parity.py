@@ -176,6 +176,42 @@ def test_pointnet_full_size_properties(pn_op, weights):
     assert (pn_op(pr.to(DEV)).cpu() - ref).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize("precision", [16, 17])
+def test_pointnet_fused_fp16_vs_oracle(weights, precision):
+    """Fused residual-block kernel (fp16 operands, fp32 accumulation; 16 = H operand in tensor memory, 17 = H through
+    shared memory).  Bound: fp16 rounding of operands (2^-11 relative) through 9 chained contractions -> a few 1e-3 of
+    the output scale; a layout / synchronisation bug gives O(1) errors."""
+    from oracle import restate as O
+    from seeme_b200 import ops, synthetic as S
+    op = ops.PointNetOp(cu(weights["pointnet"]), cu(weights["output_scene"]), max_batch=3, max_points=20000, precision=precision)
+    for B, N, seed in ((3, 777, 6), (2, 20000, 3), (1, 128, 9), (2, 50, 11)):
+        p = S.egobody_scene(B, N, torch.Generator().manual_seed(seed))
+        with torch.no_grad():
+            ref_feat = O.pointnet_forward(weights["pointnet"], p)
+            ref = O.scene_embed(weights["pointnet"], weights["output_scene"], p)
+        emb, feat = op(p.to(DEV), want_feat=True)
+        ef = float((feat.cpu() - ref_feat).abs().max() / ref_feat.abs().max())
+        ee = float((emb.cpu() - ref).abs().max() / ref.abs().max())
+        assert ef < 5e-3 and ee < 5e-3, (B, N, ef, ee)
+        emb2 = op(p.to(DEV))
+        assert torch.equal(emb, emb2)          # deterministic (max-pool atomics are order-independent)
+    # permutation invariance at full size
+    p = S.egobody_scene(2, 20000, torch.Generator().manual_seed(3)).to(DEV)
+    perm = torch.randperm(20000, generator=torch.Generator().manual_seed(4)).to(DEV)
+    assert (op(p) - op(p[:, perm])).abs().max() < 1e-5
+
+
+def test_pointnet_fused_variants_agree(weights):
+    """the tensor-memory and shared-memory H paths perform the same arithmetic in the same order"""
+    from seeme_b200 import ops, synthetic as S
+    p = S.egobody_scene(2, 5000, torch.Generator().manual_seed(13)).to(DEV)
+    outs = []
+    for precision in (16, 17):
+        op = ops.PointNetOp(cu(weights["pointnet"]), cu(weights["output_scene"]), max_batch=2, max_points=5000, precision=precision)
+        outs.append(op(p, want_feat=True)[1])
+    assert torch.equal(outs[0], outs[1])
+
+
 # ---- SMPL -------------------------------------------------------------------------------------------------------
 def test_smpl_vs_oracle(smpl_op, smpl_buffers):
     from oracle import restate as O
@@ -263,6 +299,31 @@ def test_smpl_full_size_properties(smpl_buffers):
 @pytest.mark.parametrize("name,config,gs", [("egobody_cfg", "config_mld_egobody.yaml", 7.5),
                                             ("egobody_nocfg", "config_mld_egobody.yaml", 1.0),
                                             ("gimo_cfg", "config_mld_gimo.yaml", 7.5)])
+def test_ego_eval_fp16_scene_encoder_bound(name, config, gs):
+    """Default product configuration (scene encoder with fp16 GEMM operands): north_star's bound for reduced-precision
+    GEMMs is MPJPE drift < 0.5 mm against the reference; max-abs joint error stays below 2 mm on these goldens."""
+    import seeme_b200
+    from seeme_b200 import synthetic as S
+    g = dict(np.load(os.path.join(GOLDEN, f"ego_eval_{name}.npz")))
+    B = g["joints_rst"].shape[0]
+    model = seeme_b200.build_model(config, device=DEV, guidance_scale=gs, max_batch=B, n_points=1000)
+    assert model.scene_precision == 16
+    batch = S.make_batch(B, n_points=1000, ragged=True, dataset=model.name_dataset)
+    batch = tuple(x.to(DEV) if torch.is_tensor(x) else x for x in batch)
+    noise = {k[6:]: T(v).to(DEV) for k, v in g.items() if k.startswith("noise_")}
+    rs = model.ego_eval(batch, noise)
+    d = rs["joints_rst"].double().cpu() - T(g["joints_rst"]).double()
+    mpjpe_drift_mm = float(d.norm(dim=-1).mean()) * 1000
+    max_abs_mm = float(d.abs().max()) * 1000
+    print(f"{name}: MPJPE drift {mpjpe_drift_mm:.4f} mm, max-abs {max_abs_mm:.4f} mm")
+    assert mpjpe_drift_mm < 0.5, mpjpe_drift_mm
+    assert max_abs_mm < 2.0, max_abs_mm
+    assert (rs["joints_ref"].double().cpu() - T(g["joints_ref"]).double()).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("name,config,gs", [("egobody_cfg", "config_mld_egobody.yaml", 7.5),
+                                            ("egobody_nocfg", "config_mld_egobody.yaml", 1.0),
+                                            ("gimo_cfg", "config_mld_gimo.yaml", 7.5)])
 def test_ego_eval_vs_unmodified_reference_golden(name, config, gs):
     """MLD.ego_eval (CUDA) vs the rs_set the UNMODIFIED reference ego_eval produced on the same weights,
     batch and noise (tests/golden/ego_eval_*.npz).  Joint tolerance 1e-3 m (north_star); observed ~1e-5."""
@@ -270,7 +331,7 @@ def test_ego_eval_vs_unmodified_reference_golden(name, config, gs):
     from seeme_b200 import synthetic as S
     g = dict(np.load(os.path.join(GOLDEN, f"ego_eval_{name}.npz")))
     B = g["joints_rst"].shape[0]
-    model = seeme_b200.build_model(config, device=DEV, guidance_scale=gs, max_batch=B, n_points=1000)
+    model = seeme_b200.build_model(config, device=DEV, guidance_scale=gs, max_batch=B, n_points=1000, scene_precision="split-bf16")
     batch = S.make_batch(B, n_points=1000, ragged=True, dataset=model.name_dataset)
     batch = tuple(x.to(DEV) if torch.is_tensor(x) else x for x in batch)
     noise = {k[6:]: T(v).to(DEV) for k, v in g.items() if k.startswith("noise_")}
