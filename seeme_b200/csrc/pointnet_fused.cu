@@ -21,8 +21,10 @@
 //
 //   warp 0      weight-ring TMA producer
 //   warp 1      TMEM allocator + the single MMA-issuing thread
-//   warps 2..9  8 epilogue warps (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4): in-place relu,
-//               H epilogue, OUT epilogue, X-tile TMA loads (one elected thread)
+//   warps 2..5  H group (TMEM lane quarter = warp % 4): in-place relu of X behind the shortcut GEMM, H epilogue
+//   warps 6..13 O group (lane quarter x column half): OUT epilogue (bias, pooled column max via a transpose-reduce
+//               butterfly, fp16 staging), TMA stores and the X-tile TMA loads (one elected thread)
+// The two groups run concurrently, so tile j's OUT epilogue overlaps tile j+1's shortcut GEMM, relu pass and G1.
 #include "umma.cuh"
 #include "pointnet_fused.cuh"
 #include <cudaTypedefs.h>
@@ -33,7 +35,7 @@ namespace seeme {
 constexpr int PF_NST = 6;                           // weight ring depth
 constexpr int PF_CHUNK = 128 * 128;                 // [128 rows x 64 fp16], SWIZZLE_128B
 constexpr int PF_XBUF = 4 * PF_CHUNK;               // one activation tile [128 x 256] fp16
-constexpr int PF_THREADS = 320;
+constexpr int PF_THREADS = 448;            // 2 control warps + 4 H-group warps + 8 O-group warps
 constexpr int PF_WCHUNKS = 24;                      // weight chunks per tile: S 8, G1 8, G2 8
 constexpr int PF_SMEM = 2 * PF_XBUF + PF_NST * PF_CHUNK + 1024;
 
@@ -87,7 +89,33 @@ __device__ __forceinline__ uint32_t pf_pack(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+// one lane of a converged warp (the same lane every time)
+__device__ __forceinline__ bool pf_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// advance the 14-bit start-address field of a shared-memory matrix descriptor by off16 (units of 16 bytes)
+__device__ __forceinline__ uint64_t pf_desc_add(uint64_t d, uint32_t off16) {
+  return (d & 0xffffffff00000000ull) | (uint64_t)((uint32_t)d + off16);
+}
 __device__ __forceinline__ uint32_t pf_sw128(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+
+// per-warp column max of a 32x32 block held one row per lane: returns the max of column `lane`
+// (transpose-reduce butterfly: 31 shuffles; v is destroyed)
+__device__ __forceinline__ float pf_colmax32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float keep = up ? v[i + off] : v[i];
+      const float send = up ? v[i] : v[i + off];
+      v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
+    }
+  }
+  return v[0];
+}
 
 // H_TMEM: G2 reads its A operand (H) from tensor memory; false = H is written over relu(X) in shared memory
 template <bool H_TMEM>
@@ -115,7 +143,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       mbar_init(&x_full[b], 1);
       mbar_init(&out_full[b], 1);
       mbar_init(&out_drained[b], 8);
-      for (int k = 0; k < 4; ++k) { mbar_init(&s_done[b][k], 1); mbar_init(&r_done[b][k], 8); mbar_init(&h_ready[b][k], 4); }
+      for (int k = 0; k < 4; ++k) { mbar_init(&s_done[b][k], 1); mbar_init(&r_done[b][k], 4); mbar_init(&h_ready[b][k], 4); }
       mbar_init(&h_full[b][0], 1);
       mbar_init(&h_full[b][1], 1);
     }
@@ -131,93 +159,169 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
   if (warp == 0) {
     // ---- weight-ring producer -------------------------------------------------------------------------
     if (lane == 0) {
-      uint32_t c = 0;
+      uint32_t st = 0, ph = 1;
       for (int j = 0; j < nt; ++j) {
-        for (int i = 0; i < PF_WCHUNKS; ++i, ++c) {
-          const uint32_t st = c % PF_NST;
-          mbar_wait(&w_empty[st], ((c / PF_NST) & 1) ^ 1);
+        for (int i = 0; i < PF_WCHUNKS; ++i) {
+          mbar_wait(&w_empty[st], ph);
           mbar_arrive_expect_tx(&w_full[st], PF_CHUNK);
           tma_load_2d(wring + st * PF_CHUNK, &tm.w, &w_full[st], 0, i * 128);
+          if (++st == PF_NST) { st = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ---- MMA issuer ------------------------------------------------------------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(128);
-      uint32_t c = 0;
-      auto next_w = [&]() -> uint32_t {
-        const uint32_t st = c % PF_NST;
-        mbar_wait(&w_full[st], (c / PF_NST) & 1);
-        tc_fence_after();
-        return smem_u32(wring + st * PF_CHUNK);
-      };
-      auto release_w = [&]() {
-        umma_commit(&w_empty[c % PF_NST]);
-        ++c;
-      };
-      for (int j = 0; j < nt; ++j) {
-        const int b = j & 1;
-        const uint32_t p2 = (uint32_t)(j >> 1) & 1u;
-        const uint32_t Ra = tmem_base + (uint32_t)b * 256u, Rb = tmem_base + (uint32_t)(b ^ 1) * 256u;
-        const uint32_t xb = smem_u32(xbuf + b * PF_XBUF);
-        mbar_wait(&x_full[b], p2);
-        tc_fence_after();
-        // S: OUT = X . Ws^T  (weight chunk order: kc outer, n-half inner)
-        for (int kc = 0; kc < 4; ++kc) {
-          for (int nh = 0; nh < 2; ++nh) {
-            const uint32_t sw = next_w();
+    // ---- MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues tcgen05.mma / commit ----
+    constexpr uint32_t idesc128 = umma_idesc_f16(128), idesc256 = umma_idesc_f16(256);
+    const uint64_t wdesc0 = umma_desc_k128(smem_u32(wring));
+    uint32_t st = 0, wph = 0;          // weight-ring slot and its phase parity
+    for (int j = 0; j < nt; ++j) {
+      const int b = j & 1;
+      const uint32_t p2 = (uint32_t)(j >> 1) & 1u;
+      // TMEM: OUT(j) lives in region j & 1, H(j) in the other one, i.e. where OUT(j-1) was: tile j's shortcut GEMM
+      // overlaps tile j-1's output epilogue
+      const uint32_t Ra = tmem_base + (uint32_t)b * 256u, Rb = tmem_base + (uint32_t)(b ^ 1) * 256u;
+      const uint64_t xdesc = umma_desc_k128(smem_u32(xbuf + b * PF_XBUF));
+      mbar_wait(&x_full[b], p2);
+      // S: OUT = X . Ws^T  -- per K-chunk one N = 256 MMA group over two adjacent ring slots (n-halves)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_bf16(Ra + nh * 128, umma_desc_k128(xb + kc * PF_CHUNK + ks * 32), umma_desc_k128(sw + ks * 32), idesc, (kc | ks) != 0);
-            release_w();
-          }
+      for (int kc = 0; kc < 4; ++kc) {
+        mbar_wait(&w_full[st], wph);
+        mbar_wait(&w_full[st + 1], wph);
+        tc_fence_after();
+        if (pf_elect_one()) {
+          const uint64_t wd = pf_desc_add(wdesc0, st * (PF_CHUNK >> 4));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(Ra, pf_desc_add(xdesc, kc * (PF_CHUNK >> 4) + ks * 2), pf_desc_add(wd, ks * 2), idesc256, (kc | ks) != 0);
+          umma_commit(&w_empty[st]);
+          umma_commit(&w_empty[st + 1]);
           umma_commit(&s_done[b][kc]);
         }
-        // the H region of this tile was the OUT region of the previous one: its epilogue must have drained it
-        if (j > 0) {
-          mbar_wait(&out_drained[b ^ 1], (uint32_t)((j - 1) >> 1) & 1u);
+        __syncwarp();
+        st += 2;
+        if (st == PF_NST) { st = 0; wph ^= 1u; }
+      }
+      // the H region of this tile was the OUT region of the previous one: its epilogue must have drained it
+      if (j > 0) mbar_wait(&out_drained[b ^ 1], (uint32_t)((j - 1) >> 1) & 1u);
+      // G1: H = relu(X) . W0^T  (n-half outer so that the first half's epilogue overlaps the second half's MMAs)
+#pragma unroll
+      for (int nh = 0; nh < 2; ++nh) {
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+          if (nh == 0) mbar_wait(&r_done[b][kc], p2);
+          mbar_wait(&w_full[st], wph);
           tc_fence_after();
-        }
-        // G1: H = relu(X) . W0^T  (n-half outer so that the first half's epilogue overlaps the second half's MMAs)
-        for (int nh = 0; nh < 2; ++nh) {
-          for (int kc = 0; kc < 4; ++kc) {
-            if (nh == 0) {
-              mbar_wait(&r_done[b][kc], p2);
-              tc_fence_after();
-            }
-            const uint32_t sw = next_w();
+          if (pf_elect_one()) {
+            const uint64_t wd = pf_desc_add(wdesc0, st * (PF_CHUNK >> 4));
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_bf16(Rb + nh * 128, umma_desc_k128(xb + kc * PF_CHUNK + ks * 32), umma_desc_k128(sw + ks * 32), idesc, (kc | ks) != 0);
-            release_w();
+              umma_bf16(Rb + nh * 128, pf_desc_add(xdesc, kc * (PF_CHUNK >> 4) + ks * 2), pf_desc_add(wd, ks * 2), idesc128, (kc | ks) != 0);
+            umma_commit(&w_empty[st]);
+            if (kc == 3) umma_commit(&h_full[b][nh]);
           }
-          umma_commit(&h_full[b][nh]);
+          __syncwarp();
+          if (++st == PF_NST) { st = 0; wph ^= 1u; }
         }
-        // G2: OUT += H16 . W1^T  (kc outer, n-half inner)
-        for (int kc = 0; kc < 4; ++kc) {
-          mbar_wait(&h_ready[b][kc], p2);
-          tc_fence_after();
-          for (int nh = 0; nh < 2; ++nh) {
-            const uint32_t sw = next_w();
+      }
+      // G2: OUT += H16 . W1^T  (N = 256 per K-chunk)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              if (H_TMEM)
-                umma_f16_ts(Ra + nh * 128, Rb + (uint32_t)((kc >> 1) * 128 + (kc & 1) * 32 + ks * 8), umma_desc_k128(sw + ks * 32), idesc, 1);
-              else
-                umma_bf16(Ra + nh * 128, umma_desc_k128(xb + kc * PF_CHUNK + ks * 32), umma_desc_k128(sw + ks * 32), idesc, 1);
-            }
-            release_w();
+      for (int kc = 0; kc < 4; ++kc) {
+        mbar_wait(&h_ready[b][kc], p2);
+        mbar_wait(&w_full[st], wph);
+        mbar_wait(&w_full[st + 1], wph);
+        tc_fence_after();
+        if (pf_elect_one()) {
+          const uint64_t wd = pf_desc_add(wdesc0, st * (PF_CHUNK >> 4));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (H_TMEM)
+              umma_f16_ts(Ra, Rb + (uint32_t)((kc >> 1) * 128 + (kc & 1) * 32 + ks * 8), pf_desc_add(wd, ks * 2), idesc256, 1);
+            else
+              umma_bf16(Ra, pf_desc_add(xdesc, kc * (PF_CHUNK >> 4) + ks * 2), pf_desc_add(wd, ks * 2), idesc256, 1);
+          }
+          umma_commit(&w_empty[st]);
+          umma_commit(&w_empty[st + 1]);
+          if (kc == 3) umma_commit(&out_full[b]);
+        }
+        __syncwarp();
+        st += 2;
+        if (st == PF_NST) { st = 0; wph ^= 1u; }
+      }
+    }
+  } else if (warp < 6) {
+    // ---- H group (4 warps, one per TMEM lane quarter): in-place relu of X, then the H epilogue ----------------
+    const int th = (int)threadIdx.x - 64;           // 0..127
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    for (int j = 0; j < nt; ++j) {
+      const int b = j & 1;
+      const uint32_t p2 = (uint32_t)(j >> 1) & 1u;
+      const int sample = (t_begin + j) / a.tiles_per_sample;
+      uint8_t* xb = xbuf + b * PF_XBUF;
+      for (int kc = 0; kc < 4; ++kc) {
+        mbar_wait(&s_done[b][kc], p2);
+        uint4* p = reinterpret_cast<uint4*>(xb + kc * PF_CHUNK) + th;
+        const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint4 v = p[i * 128];
+          __half2* h = reinterpret_cast<__half2*>(&v);
+          h[0] = __hmax2(h[0], z); h[1] = __hmax2(h[1], z); h[2] = __hmax2(h[2], z); h[3] = __hmax2(h[3], z);
+          p[i * 128] = v;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&r_done[b][kc]);
+      }
+      const float* bh = a.bias_h + (size_t)sample * 256;
+      const uint32_t tbase = tmem_base + (uint32_t)(b ^ 1) * 256u + lane_off;
+      if (!H_TMEM) { mbar_wait(&h_full[b][0], p2); mbar_wait(&h_full[b][1], p2); }   // relu(X) is overwritten: G1 must be done
+#pragma unroll 1
+      for (int hsel = 0; hsel < 2; ++hsel) {
+        if (H_TMEM) mbar_wait(&h_full[b][hsel], p2);
+        tc_fence_after();
+        const uint32_t thh = tbase + (uint32_t)hsel * 128u;
+        uint32_t raw[2][32];
+        tmem_ld32(thh, raw[0]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float4 bv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bh + hsel * 128 + g * 32) + i);
+          tmem_ld_wait();
+          if (g < 3) tmem_ld32(thh + (g + 1) * 32, raw[(g + 1) & 1]);
+          const uint32_t* r = raw[g & 1];
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float f0 = fmaxf(__uint_as_float(r[4 * i]) + bv[i].x, 0.f), f1 = fmaxf(__uint_as_float(r[4 * i + 1]) + bv[i].y, 0.f);
+            const float f2 = fmaxf(__uint_as_float(r[4 * i + 2]) + bv[i].z, 0.f), f3 = fmaxf(__uint_as_float(r[4 * i + 3]) + bv[i].w, 0.f);
+            pk[2 * i] = pf_pack(f0, f1);
+            pk[2 * i + 1] = pf_pack(f2, f3);
+          }
+          if (H_TMEM) {
+            tmem_st16(thh + g * 16, pk);         // in place: these 16 columns were read in this or an earlier group
+          } else {
+            uint8_t* ct = xb + (hsel * 2 + (g >> 1)) * PF_CHUNK;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              *reinterpret_cast<uint4*>(ct + pf_sw128(row, (g & 1) * 4 + jj)) = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+          }
+          if (g & 1) {
+            if (H_TMEM) { tmem_st_wait(); tc_fence_before(); }
+            else fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_ready[b][hsel * 2 + (g >> 1)]);
           }
         }
-        umma_commit(&out_full[b]);
       }
     }
   } else {
-    // ---- epilogue warps --------------------------------------------------------------------------------------
-    const int te = (int)threadIdx.x - 64;          // 0..255
-    const int q = warp & 3;                         // TMEM lane quarter this warp may access
-    const int hsel = (warp - 2) >> 2;               // column half
+    // ---- O group (8 warps: lane quarter x column half): OUT epilogue, pooled column max, TMA stores, X-tile loads ---------
+    const int te = (int)threadIdx.x - 192;         // 0..255
+    const int q = warp & 3;
+    const int hsel = (warp - 6) >> 2;
     const int row = q * 32 + lane;
     const bool elected = te == 0;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -227,7 +331,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       mbar_arrive_expect_tx(&x_full[b], PF_XBUF);
       for (int kc = 0; kc < 4; ++kc) tma_load_3d(xbuf + b * PF_XBUF + kc * PF_CHUNK, &tm.xin, &x_full[b], kc * 64, n0, sample);
     };
-    auto flush_colmax = [&](int sample) {   // all 256 epilogue threads
+    auto flush_colmax = [&](int sample) {
       pf_epi_sync();
       const unsigned v = colmax_s[te];
       if (v) atomicMax(a.colmax + (size_t)sample * 256 + te, v);
@@ -245,111 +349,61 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       const int t = t_begin + j;
       const int sample = t / a.tiles_per_sample, n0 = (t % a.tiles_per_sample) * 128;
       uint8_t* xb = xbuf + b * PF_XBUF;
-      // -- relu(X) in place, one K-chunk behind the shortcut GEMM
-      for (int kc = 0; kc < 4; ++kc) {
-        mbar_wait(&s_done[b][kc], p2);
-        uint4* p = reinterpret_cast<uint4*>(xb + kc * PF_CHUNK) + te;
-        const __half2 z = __float2half2_rn(0.f);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 v = p[i * 256];
-          __half2* h = reinterpret_cast<__half2*>(&v);
-          h[0] = __hmax2(h[0], z); h[1] = __hmax2(h[1], z); h[2] = __hmax2(h[2], z); h[3] = __hmax2(h[3], z);
-          p[i * 256] = v;
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&r_done[b][kc]);
+      if (sample != cur_sample) {
+        if (cur_sample >= 0) flush_colmax(cur_sample);
+        cur_sample = sample;
       }
-      // -- H epilogue
-      {
-        const float* bh = a.bias_h + (size_t)sample * 256 + hsel * 128;
-        const uint32_t th = tmem_base + (uint32_t)(b ^ 1) * 256u + (uint32_t)hsel * 128u + lane_off;
-        mbar_wait(&h_full[b][hsel], p2);
-        if (!H_TMEM) mbar_wait(&h_full[b][hsel ^ 1], p2);   // relu(X) is overwritten: both halves of G1 must be done
-        tc_fence_after();
-#pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          uint32_t raw[32];
-          tmem_ld32(th + g * 32, raw);
-          tmem_ld_wait();
-          uint32_t pk[16];
+      const float* bo = a.bias_o + (size_t)sample * 256 + hsel * 128;
+      const uint32_t to = tmem_base + (uint32_t)b * 256u + (uint32_t)hsel * 128u + lane_off;
+      const bool valid = n0 + row < a.n_points;
+      mbar_wait(&out_full[b], p2);
+      tc_fence_after();
+      uint32_t raw[2][32];
+      tmem_ld32(to, raw[0]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(bh + g * 32) + i);
-            const float f0 = fmaxf(__uint_as_float(raw[4 * i]) + bv.x, 0.f), f1 = fmaxf(__uint_as_float(raw[4 * i + 1]) + bv.y, 0.f);
-            const float f2 = fmaxf(__uint_as_float(raw[4 * i + 2]) + bv.z, 0.f), f3 = fmaxf(__uint_as_float(raw[4 * i + 3]) + bv.w, 0.f);
-            pk[2 * i] = pf_pack(f0, f1);
-            pk[2 * i + 1] = pf_pack(f2, f3);
-          }
-          if (H_TMEM) {
-            tmem_st16(th + g * 16, pk);          // in place: these 16 columns were read in this or an earlier group
-          } else {
-            uint8_t* ct = xb + (hsel * 2 + (g >> 1)) * PF_CHUNK;
+      for (int g = 0; g < 4; ++g) {
+        float4 bv[8];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-              *reinterpret_cast<uint4*>(ct + pf_sw128(row, (g & 1) * 4 + jj)) = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
-          }
-          if (g & 1) {
-            if (H_TMEM) { tmem_st_wait(); tc_fence_before(); }
-            else fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&h_ready[b][hsel * 2 + (g >> 1)]);
-          }
+        for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bo + g * 32) + i);
+        tmem_ld_wait();
+        if (g < 3) {
+          tmem_ld32(to + (g + 1) * 32, raw[(g + 1) & 1]);
+        } else {                                   // all of this warp's TMEM reads are complete
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&out_drained[b]);
         }
+        const uint32_t* r = raw[g & 1];
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          f[4 * i] = __uint_as_float(r[4 * i]) + bv[i].x; f[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bv[i].y;
+          f[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bv[i].z; f[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bv[i].w;
+        }
+        if (a.store_out) {
+          uint8_t* ct = xb + (hsel * 2 + (g >> 1)) * PF_CHUNK;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            *reinterpret_cast<uint4*>(ct + pf_sw128(row, (g & 1) * 4 + jj)) =
+                make_uint4(pf_pack(f[8 * jj], f[8 * jj + 1]), pf_pack(f[8 * jj + 2], f[8 * jj + 3]), pf_pack(f[8 * jj + 4], f[8 * jj + 5]),
+                           pf_pack(f[8 * jj + 6], f[8 * jj + 7]));
+        }
+        if (!valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = -INFINITY;
+        }
+        const float mine = pf_colmax32(f, lane);
+        atomicMax(&colmax_s[hsel * 128 + g * 32 + lane], f2ord(mine));
       }
-      // -- OUT epilogue
-      {
-        mbar_wait(&out_full[b], p2);
-        tc_fence_after();
-        if (sample != cur_sample) {
-          if (cur_sample >= 0) flush_colmax(cur_sample);
-          cur_sample = sample;
+      if (a.store_out) fence_proxy_async();
+      pf_epi_sync();
+      if (elected) {
+        if (a.store_out) {
+          for (int kc = 0; kc < 4; ++kc) tma_store_3d(&tm.xout, xb + kc * PF_CHUNK, kc * 64, n0, sample);
+          pf_store_commit();
+          pf_store_wait_read();
         }
-        const float* bo = a.bias_o + (size_t)sample * 256 + hsel * 128;
-        const uint32_t to = tmem_base + (uint32_t)b * 256u + (uint32_t)hsel * 128u + lane_off;
-        const bool valid = n0 + row < a.n_points;
-#pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          uint32_t raw[32];
-          tmem_ld32(to + g * 32, raw);
-          tmem_ld_wait();
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(bo + g * 32) + i);
-            f[4 * i] = __uint_as_float(raw[4 * i]) + bv.x; f[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + bv.y;
-            f[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + bv.z; f[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + bv.w;
-          }
-          float mine = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float m = warp_max_f32(valid ? f[i] : -INFINITY);
-            if (lane == i) mine = m;
-          }
-          atomicMax(&colmax_s[hsel * 128 + g * 32 + lane], f2ord(mine));
-          if (a.store_out) {
-            uint8_t* ct = xb + (hsel * 2 + (g >> 1)) * PF_CHUNK;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-              *reinterpret_cast<uint4*>(ct + pf_sw128(row, (g & 1) * 4 + jj)) =
-                  make_uint4(pf_pack(f[8 * jj], f[8 * jj + 1]), pf_pack(f[8 * jj + 2], f[8 * jj + 3]), pf_pack(f[8 * jj + 4], f[8 * jj + 5]),
-                             pf_pack(f[8 * jj + 6], f[8 * jj + 7]));
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&out_drained[b]);
-        if (a.store_out) fence_proxy_async();
-        pf_epi_sync();
-        if (elected) {
-          if (a.store_out) {
-            for (int kc = 0; kc < 4; ++kc) tma_store_3d(&tm.xout, xb + kc * PF_CHUNK, kc * 64, n0, sample);
-            pf_store_commit();
-            pf_store_wait_read();
-          }
-          if (j + 2 < nt) load_x(j + 2);
-        }
+        if (j + 2 < nt) load_x(j + 2);
       }
     }
     if (cur_sample >= 0) flush_colmax(cur_sample);

@@ -93,6 +93,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// advance the 14-bit start-address field of a descriptor by off16 (units of 16 bytes; shared memory is < 256 KB: no carry)
+__device__ __forceinline__ uint64_t umma_desc_add(uint64_t d, uint32_t off16) {
+  return (d & 0xffffffff00000000ull) | (uint64_t)((uint32_t)d + off16);
+}
+// one lane of a converged warp (the same lane every time)
+__device__ __forceinline__ bool umma_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);

@@ -134,27 +134,31 @@ __global__ void __launch_bounds__(192, MINB) umma_linear_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = e.fp16 ? umma_idesc_f16(BN) : umma_idesc_bf16(BN);
-      for (int kb = 0; kb < e.nkb; ++kb) {
-        const int st = kb % STAGES;
-        mbar_wait(&full_bar[st], (kb / STAGES) & 1);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)st * Cfg::STAGE_BYTES);
-        const uint32_t sw = sa + Cfg::A_BYTES * (NPASS == 3 ? 2 : 1);
+    // the whole warp runs the (uniform) loop; one elected lane issues the MMAs and commits -- this lets ptxas keep the
+    // descriptors in uniform registers and issue the tcgen05.mma instructions back to back
+    const uint32_t idesc = e.fp16 ? umma_idesc_f16(BN) : umma_idesc_bf16(BN);
+    const uint64_t d0 = umma_desc_k128(smem_u32(smem));
+    for (int kb = 0; kb < e.nkb; ++kb) {
+      const int st = kb % STAGES;
+      mbar_wait(&full_bar[st], (kb / STAGES) & 1);
+      tc_fence_after();
+      if (umma_elect_one()) {
+        const uint64_t da0 = umma_desc_add(d0, (uint32_t)(st * (Cfg::STAGE_BYTES >> 4)));
+        const uint64_t dw0 = umma_desc_add(da0, (uint32_t)((Cfg::A_BYTES * (NPASS == 3 ? 2 : 1)) >> 4));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {     // 4 x (K = 16) inside the 128-byte swizzle atom: +32 bytes each
-          const uint64_t da = umma_desc_k128(sa + k * 32), dw = umma_desc_k128(sw + k * 32);
+          const uint64_t da = umma_desc_add(da0, k * 2), dw = umma_desc_add(dw0, k * 2);
           umma_bf16(tmem_base, da, dw, idesc, (kb | k) != 0);
           if (NPASS == 3) {
-            const uint64_t dal = umma_desc_k128(sa + Cfg::A_BYTES + k * 32), dwl = umma_desc_k128(sw + Cfg::W_BYTES + k * 32);
+            const uint64_t dal = umma_desc_add(da, Cfg::A_BYTES >> 4), dwl = umma_desc_add(dw, Cfg::W_BYTES >> 4);
             umma_bf16(tmem_base, dal, dw, idesc, 1);
             umma_bf16(tmem_base, da, dwl, idesc, 1);
           }
         }
         umma_commit(&empty_bar[st]);      // slot reusable once these MMAs have read it
+        if (kb == e.nkb - 1) umma_commit(&tmem_full_bar);   // accumulator complete
       }
-      umma_commit(&tmem_full_bar);        // accumulator complete
+      __syncwarp();
     }
   } else {
     // ---- epilogue: warp w may only touch TMEM lanes [32 (w % 4), 32 (w % 4) + 32) ----------------------
