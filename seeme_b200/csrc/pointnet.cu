@@ -140,6 +140,7 @@ struct seeme_pointnet {
   unsigned* pool_ord;
   // fused fp16 path (precision 16 / 17): per-block weight-chunk blobs for blocks 1..3
   void* blob[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* wpb = nullptr;     // [512] float4 (Wp row, bp) for the on-chip fc_pos of the fused block 0
 };
 
 static int copy_w(Arena& a, float*& dst, const float* src, size_t n) {
@@ -176,7 +177,7 @@ static int pointnet_create(seeme_pointnet_t* out, const float* const* w, int n_w
   const size_t rows = (size_t)h->chunk * (max_points < 128 ? 128 : max_points);
   const bool split = h->precision == 3;
   const bool fused = h->precision >= 16;
-  size_t wbytes = 3 * pad256(pf_blob_bytes()) + pad256(512 * 3 * 4) + pad256(512 * 4) + 4 * (pad256(256 * 512 * 4) * 2 + pad256(256 * 256 * 4) + 2 * pad256(256 * 4)) +
+  size_t wbytes = 4 * pad256(pf_blob_bytes()) + pad256(512 * 16) + pad256(512 * 3 * 4) + pad256(512 * 4) + 4 * (pad256(256 * 512 * 4) * 2 + pad256(256 * 256 * 4) + 2 * pad256(256 * 4)) +
                   pad256(512 * 256 * 4) + pad256(512 * 4) + pad256(256 * 512 * 4) + pad256(256 * 4) +
                   8 * 2 * pad256(256 * 512 * 2) + pad256(256 * 4 * 4) + pad256(256 * 4);
   size_t ws = 4 * pad256((size_t)max_batch * 256 * 4) + pad256((size_t)max_batch * 512 * 4) + pad256((size_t)max_batch * 128 * 3 * 4);
@@ -232,8 +233,10 @@ static int pointnet_create(seeme_pointnet_t* out, const float* const* w, int n_w
     if (ok) {
       // pack the tensor-path weights (default stream, create time)
       if (fused) {
-        rc = to_f16(h->w0[0], 512, 256, 512, h->g1h[0], 512);
-        if (!rc) rc = to_f16(h->w1[0], 256, 256, 256, h->g2h[0], 256);
+        h->blob[0] = h->arena.take<char>(pf_blob_bytes());
+        h->wpb = h->arena.take<char>(512 * 16);
+        if (!h->blob[0] || !h->wpb) { set_error("pointnet: arena exhausted (weight blobs)"); rc = SEEME_ENOMEM; }
+        else rc = pf_pack_block0(h->w0[0], h->w1[0], h->fc_pos_w, h->fc_pos_b, h->blob[0], h->wpb);
         for (int i = 1; i < 4 && !rc; ++i) {
           h->blob[i] = h->arena.take<char>(pf_blob_bytes());
           if (!h->blob[i]) { set_error("pointnet: arena exhausted (weight blobs)"); rc = SEEME_ENOMEM; break; }
@@ -375,41 +378,12 @@ static int blocks_tensor(seeme_pointnet* h, const float* p, int C, int N, cudaSt
 }
 
 // ---- fused fp16 path (precision 16: H operand in tensor memory; 17: H through shared memory) ------------------
-// block 0 keeps the two-GEMM form (its input is the 512-wide relu(fc_pos(p)), its shortcut the rank-3 fold); blocks
-// 1..3 are one persistent kernel each (pointnet_fused.cu).
+// one persistent kernel per residual block (pointnet_fused.cu); block 0 also evaluates fc_pos on chip and its
+// shortcut as a rank-3 fold in the epilogue.
 static int blocks_fused(seeme_pointnet* h, const float* p, int C, int N, cudaStream_t s) {
-  const int rows = C * N;
-  {
-    const int ppb = 4;
-    int grid = (rows + ppb - 1) / ppb;
-    if (grid > NUM_SMS * 16) grid = NUM_SMS * 16;
-    fcpos_relu_bf16_kernel<<<grid, 256, 0, s>>>(p, h->fc_pos_w, h->fc_pos_b, h->xr0h, nullptr, rows, 1);
-    SEEME_LAUNCH_CHECK();
-  }
-  UmmaLinear g1;   // hr = relu(W0 . xr0 + b0)
-  g1.fp16 = 1;
-  g1.A1 = {h->xr0h, nullptr, 512};
-  g1.W = {h->g1h[0], nullptr, 512};
-  g1.M = rows; g1.N = 256; g1.K1 = 512;
-  g1.bias = h->b0[0];
-  g1.act = ACT_RELU;
-  g1.Yh = h->hrh; g1.ldb = 256;
-  g1.prof_id = PROF_POINTNET_GEMM + 1;
-  SEEME_TRY(umma_linear(g1, 1, s));
   SEEME_CUDA(cudaMemsetAsync(h->pool_ord, 0, (size_t)C * 256 * sizeof(unsigned), s));
-  UmmaLinear g2;   // net = W1 . hr + rank-3 fold of the shortcut
-  g2.fp16 = 1;
-  g2.A1 = {h->hrh, nullptr, 256};
-  g2.W = {h->g2h[0], nullptr, 256};
-  g2.M = rows; g2.N = 256; g2.K1 = 256;
-  g2.bias = h->cst0;
-  g2.pfold = h->pfold;
-  g2.xyz = p;
-  g2.Yh = h->xh[0]; g2.ldb = 256;
-  g2.colmax = h->pool_ord;
-  g2.colmax_group_rows = N;
-  g2.prof_id = PROF_POINTNET_GEMM + 1;
-  SEEME_TRY(umma_linear(g2, 1, s));
+  SEEME_TRY(pf_block0_forward(p, h->xh[0], h->blob[0], h->wpb, h->b0[0], h->cst0, h->pfold, h->pool_ord, C, N,
+                              PROF_POINTNET_FUSED + 1, s));
   int cur = 0;
   for (int i = 1; i < 4; ++i) {
     SEEME_TRY(decode_pool(h, C, s));

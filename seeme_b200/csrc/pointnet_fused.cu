@@ -416,6 +416,295 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Block 0 (+ fc_pos): the block's input relu(fc_pos(p)) [128, 512] is GENERATED on chip from the xyz coordinates (K = 3,
+// CUDA cores) chunk by chunk into a 4-slot shared-memory ring -- it never exists in HBM -- and its shortcut, an affine
+// map of p (rank 3, see pointnet.cu), is evaluated in the output epilogue.
+//     gen : A[:, kc] = fp16(relu(Wp[kc] p + bp[kc]))          H group, one K-chunk ahead of the MMAs
+//     G1  : H   = A . W0^T  (K = 512)                          8 N=256 MMA groups
+//     epiH: H16 = fp16(relu(H + b0)) in place in TMEM          H group
+//     G2  : OUT = H16 . W1^T                                   A operand from TMEM
+//     epiOUT: out = OUT + cst0 + Pf p; pooled column max; fp16 tile -> staging -> TMA store      O group
+// TMEM: H in columns [0,256), OUT in [256,512); G1 of tile j+1 overlaps the OUT epilogue of tile j.
+constexpr int P0_ASLOTS = 4;
+constexpr int P0_SMEM = P0_ASLOTS * PF_CHUNK + PF_XBUF + PF_NST * PF_CHUNK + 1024;
+
+struct P0Args {
+  int n_points, tiles_per_sample, n_tiles;
+  const float* xyz;      // [samples, n_points, 3]
+  const float4* wpb;     // [512] (Wp[c][0..2], bp[c])
+  const float* b0;       // [256]
+  const float* cst0;     // [256]  Ws bp + b1
+  const float4* pfold;   // [256]  (Ws Wp)[c][0..2], 0
+  unsigned* colmax;
+};
+
+__global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block0_kernel(const __grid_constant__ PfMaps tm, const P0Args a) {
+  extern __shared__ __align__(1024) uint8_t pf_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pf_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* aring = smem;                                  // 4 x 16 KB generated A chunks
+  uint8_t* stage = smem + P0_ASLOTS * PF_CHUNK;           // 64 KB output staging
+  uint8_t* wring = stage + PF_XBUF;
+  __shared__ __align__(8) uint64_t w_full[PF_NST], w_empty[PF_NST], a_ready[P0_ASLOTS], a_free[P0_ASLOTS], h_full, h_ready[4], h_free,
+      out_full, out_drained;
+  __shared__ uint32_t tmem_slot;
+  __shared__ unsigned colmax_s[256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = a.n_tiles / (int)gridDim.x, rem = a.n_tiles % (int)gridDim.x;
+  const int t_begin = (int)blockIdx.x * per + ((int)blockIdx.x < rem ? (int)blockIdx.x : rem);
+  const int nt = per + ((int)blockIdx.x < rem ? 1 : 0);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm.w);
+    tma_prefetch_desc(&tm.xout);
+    for (int i = 0; i < PF_NST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < P0_ASLOTS; ++i) { mbar_init(&a_ready[i], 4); mbar_init(&a_free[i], 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(&h_ready[i], 4);
+    mbar_init(&h_full, 1);
+    mbar_init(&h_free, 1);
+    mbar_init(&out_full, 1);
+    mbar_init(&out_drained, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  if (threadIdx.x < 256) colmax_s[threadIdx.x] = 0u;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t RH = tmem_base, RO = tmem_base + 256u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t st = 0, ph = 1;
+      for (int j = 0; j < nt; ++j) {
+        for (int i = 0; i < PF_WCHUNKS; ++i) {
+          mbar_wait(&w_empty[st], ph);
+          mbar_arrive_expect_tx(&w_full[st], PF_CHUNK);
+          tma_load_2d(wring + st * PF_CHUNK, &tm.w, &w_full[st], 0, i * 128);
+          if (++st == PF_NST) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc256 = umma_idesc_f16(256);
+    const uint64_t wdesc0 = umma_desc_k128(smem_u32(wring));
+    const uint64_t adesc0 = umma_desc_k128(smem_u32(aring));
+    uint32_t st = 0, wph = 0;
+    for (int j = 0; j < nt; ++j) {
+      const uint32_t pj = (uint32_t)j & 1u;
+      // G1 writes the H region: G2 of the previous tile (which read H16 from it) is ordered before by the MMA pipe
+#pragma unroll
+      for (int kc = 0; kc < 8; ++kc) {
+        const int as = kc & 3;
+        mbar_wait(&a_ready[as], (uint32_t)(kc >> 2) & 1u);          // 8 chunks per tile = exactly 2 ring rounds per tile
+        mbar_wait(&w_full[st], wph);
+        mbar_wait(&w_full[st + 1], wph);
+        tc_fence_after();
+        if (pf_elect_one()) {
+          const uint64_t wd = pf_desc_add(wdesc0, st * (PF_CHUNK >> 4));
+          const uint64_t ad = pf_desc_add(adesc0, as * (PF_CHUNK >> 4));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_bf16(RH, pf_desc_add(ad, ks * 2), pf_desc_add(wd, ks * 2), idesc256, (kc | ks) != 0);
+          umma_commit(&w_empty[st]);
+          umma_commit(&w_empty[st + 1]);
+          umma_commit(&a_free[as]);
+          if (kc == 7) umma_commit(&h_full);
+        }
+        __syncwarp();
+        st += 2;
+        if (st == PF_NST) { st = 0; wph ^= 1u; }
+      }
+      // G2 writes the OUT region: the previous tile's output epilogue must have drained it
+      if (j > 0) mbar_wait(&out_drained, (uint32_t)(j - 1) & 1u);
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        mbar_wait(&h_ready[kc], pj);
+        mbar_wait(&w_full[st], wph);
+        mbar_wait(&w_full[st + 1], wph);
+        tc_fence_after();
+        if (pf_elect_one()) {
+          const uint64_t wd = pf_desc_add(wdesc0, st * (PF_CHUNK >> 4));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16_ts(RO, RH + (uint32_t)((kc >> 1) * 128 + (kc & 1) * 32 + ks * 8), pf_desc_add(wd, ks * 2), idesc256, (kc | ks) != 0);
+          umma_commit(&w_empty[st]);
+          umma_commit(&w_empty[st + 1]);
+          if (kc == 3) { umma_commit(&out_full); umma_commit(&h_free); }
+        }
+        __syncwarp();
+        st += 2;
+        if (st == PF_NST) { st = 0; wph ^= 1u; }
+      }
+    }
+  } else if (warp < 6) {
+    // ---- H group: thread = point.  Generates the A chunks, then the H epilogue ---------------------------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    for (int j = 0; j < nt; ++j) {
+      const uint32_t pj = (uint32_t)j & 1u;
+      const int t = t_begin + j;
+      const int sample = t / a.tiles_per_sample, n0 = (t % a.tiles_per_sample) * 128;
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (n0 + row < a.n_points) {
+        const float* pp = a.xyz + ((size_t)sample * a.n_points + n0 + row) * 3;
+        px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2);
+      }
+#pragma unroll 1
+      for (int kc = 0; kc < 8; ++kc) {
+        const int as = kc & 3;
+        // slot reuse: chunk kc of this tile overwrites the chunk consumed 4 chunks earlier (2 ring rounds per tile)
+        mbar_wait(&a_free[as], ((uint32_t)(kc >> 2) & 1u) ^ 1u);
+        uint8_t* ct = aring + as * PF_CHUNK;
+        const float4* wp = a.wpb + kc * 64;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 w0 = __ldg(wp + jj * 8 + 2 * i), w1 = __ldg(wp + jj * 8 + 2 * i + 1);
+            const float v0 = fmaxf(fmaf(w0.z, pz, fmaf(w0.y, py, fmaf(w0.x, px, w0.w))), 0.f);
+            const float v1 = fmaxf(fmaf(w1.z, pz, fmaf(w1.y, py, fmaf(w1.x, px, w1.w))), 0.f);
+            pk[i] = pf_pack(v0, v1);
+          }
+          *reinterpret_cast<uint4*>(ct + pf_sw128(row, jj)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[as]);
+      }
+      // H epilogue (in place in TMEM)
+      mbar_wait(&h_full, pj);
+      tc_fence_after();
+#pragma unroll 1
+      for (int hsel = 0; hsel < 2; ++hsel) {
+        const uint32_t thh = RH + lane_off + (uint32_t)hsel * 128u;
+        uint32_t raw[2][32];
+        tmem_ld32(thh, raw[0]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float4 bv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(a.b0 + hsel * 128 + g * 32) + i);
+          tmem_ld_wait();
+          if (g < 3) tmem_ld32(thh + (g + 1) * 32, raw[(g + 1) & 1]);
+          const uint32_t* r = raw[g & 1];
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float f0 = fmaxf(__uint_as_float(r[4 * i]) + bv[i].x, 0.f), f1 = fmaxf(__uint_as_float(r[4 * i + 1]) + bv[i].y, 0.f);
+            const float f2 = fmaxf(__uint_as_float(r[4 * i + 2]) + bv[i].z, 0.f), f3 = fmaxf(__uint_as_float(r[4 * i + 3]) + bv[i].w, 0.f);
+            pk[2 * i] = pf_pack(f0, f1);
+            pk[2 * i + 1] = pf_pack(f2, f3);
+          }
+          tmem_st16(thh + g * 16, pk);
+          if (g & 1) {
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_ready[hsel * 2 + (g >> 1)]);
+          }
+        }
+      }
+      // the next tile's G1 may only overwrite the H region after this tile's G2 has consumed H16: that is MMA-pipe
+      // order; but this group's NEXT H epilogue reads the region only after h_full, so nothing to wait for here.
+      (void)h_free;
+    }
+  } else {
+    // ---- O group ---------------------------------------------------------------------------------------------------
+    const int te = (int)threadIdx.x - 192;
+    const int q = warp & 3;
+    const int hsel = (warp - 6) >> 2;
+    const int row = q * 32 + lane;
+    const bool elected = te == 0;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    auto flush_colmax = [&](int sample) {
+      pf_epi_sync();
+      const unsigned v = colmax_s[te];
+      if (v) atomicMax(a.colmax + (size_t)sample * 256 + te, v);
+      colmax_s[te] = 0u;
+      pf_epi_sync();
+    };
+    int cur_sample = -1;
+    for (int j = 0; j < nt; ++j) {
+      const uint32_t pj = (uint32_t)j & 1u;
+      const int t = t_begin + j;
+      const int sample = t / a.tiles_per_sample, n0 = (t % a.tiles_per_sample) * 128;
+      if (sample != cur_sample) {
+        if (cur_sample >= 0) flush_colmax(cur_sample);
+        cur_sample = sample;
+      }
+      const bool valid = n0 + row < a.n_points;
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (valid) {
+        const float* pp = a.xyz + ((size_t)sample * a.n_points + n0 + row) * 3;
+        px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2);
+      }
+      const uint32_t to = RO + lane_off + (uint32_t)hsel * 128u;
+      mbar_wait(&out_full, pj);
+      tc_fence_after();
+      uint32_t raw[2][32];
+      tmem_ld32(to, raw[0]);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int c0 = hsel * 128 + g * 32;
+        tmem_ld_wait();
+        if (g < 3) {
+          tmem_ld32(to + (g + 1) * 32, raw[(g + 1) & 1]);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&out_drained);
+        }
+        const uint32_t* r = raw[g & 1];
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(a.cst0 + c0) + i);
+          f[4 * i] = __uint_as_float(r[4 * i]) + bv.x; f[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bv.y;
+          f[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bv.z; f[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bv.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float4 pfv = __ldg(a.pfold + c0 + i);
+          f[i] = fmaf(pfv.z, pz, fmaf(pfv.y, py, fmaf(pfv.x, px, f[i])));
+        }
+        {
+          uint8_t* ct = stage + (hsel * 2 + (g >> 1)) * PF_CHUNK;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            *reinterpret_cast<uint4*>(ct + pf_sw128(row, (g & 1) * 4 + jj)) =
+                make_uint4(pf_pack(f[8 * jj], f[8 * jj + 1]), pf_pack(f[8 * jj + 2], f[8 * jj + 3]), pf_pack(f[8 * jj + 4], f[8 * jj + 5]),
+                           pf_pack(f[8 * jj + 6], f[8 * jj + 7]));
+        }
+        if (!valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = -INFINITY;
+        }
+        const float mine = pf_colmax32(f, lane);
+        atomicMax(&colmax_s[c0 + lane], f2ord(mine));
+      }
+      fence_proxy_async();
+      pf_epi_sync();
+      if (elected) {
+        for (int kc = 0; kc < 4; ++kc) tma_store_3d(&tm.xout, stage + kc * PF_CHUNK, kc * 64, n0, sample);
+        pf_store_commit();
+        pf_store_wait_read();
+      }
+      pf_epi_sync();        // the staging buffer is free again for the next tile's writes
+    }
+    if (cur_sample >= 0) flush_colmax(cur_sample);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 g_pf_encode = nullptr;
 static int pf_encoder() {
@@ -464,6 +753,63 @@ __global__ void pf_pack_weights_kernel(const float* __restrict__ ws, const float
     const int r = i / 64, cc = i % 64;
     blob[(size_t)chunk * 128 * 64 + i] = __float2half_rn(src[(size_t)(nh * 128 + r) * ld + kc * 64 + cc]);
   }
+}
+
+// block 0 blob: G1 (kc 0..7, nh) from W0 [256,512]; G2 (kc 0..3, nh) from W1 [256,256]
+__global__ void pf_pack_weights0_kernel(const float* __restrict__ w0, const float* __restrict__ w1, __half* __restrict__ blob) {
+  const int chunk = blockIdx.x;
+  const bool g1 = chunk < 16;
+  const int idx = g1 ? chunk : chunk - 16;
+  const int kc = idx / 2, nh = idx % 2;
+  const float* src = g1 ? w0 : w1;
+  const int ld = g1 ? 512 : 256;
+  for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) {
+    const int r = i / 64, cc = i % 64;
+    blob[(size_t)chunk * 128 * 64 + i] = __float2half_rn(src[(size_t)(nh * 128 + r) * ld + kc * 64 + cc]);
+  }
+}
+
+__global__ void pf_pack_wpb_kernel(const float* __restrict__ wp, const float* __restrict__ bp, float4* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < 512) out[c] = make_float4(wp[c * 3], wp[c * 3 + 1], wp[c * 3 + 2], bp[c]);
+}
+
+int pf_pack_block0(const float* w0, const float* w1, const float* wp, const float* bp, void* blob, void* wpb) {
+  pf_pack_weights0_kernel<<<PF_WCHUNKS, 256>>>(w0, w1, reinterpret_cast<__half*>(blob));
+  SEEME_LAUNCH_CHECK();
+  pf_pack_wpb_kernel<<<2, 256>>>(wp, bp, reinterpret_cast<float4*>(wpb));
+  SEEME_LAUNCH_CHECK();
+  return SEEME_OK;
+}
+
+int pf_block0_forward(const float* xyz, void* x_out, const void* w_blob, const void* wpb, const float* b0, const float* cst0,
+                      const float* pfold, unsigned* colmax, int samples, int n_points, int prof_id, cudaStream_t s) {
+  SEEME_TRY(pf_encoder());
+  SEEME_REQUIRE(n_points >= 128, SEEME_EINVAL, "pf_block0_forward: needs >= 128 points per sample (got %d)", n_points);
+  PfMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  SEEME_TRY(pf_act_map(&maps.xout, x_out, samples, n_points));
+  maps.xin = maps.xout;
+  SEEME_TRY(pf_w_map(&maps.w, w_blob));
+  P0Args a;
+  a.n_points = n_points;
+  a.tiles_per_sample = (n_points + 127) / 128;
+  a.n_tiles = a.tiles_per_sample * samples;
+  a.xyz = xyz;
+  a.wpb = reinterpret_cast<const float4*>(wpb);
+  a.b0 = b0; a.cst0 = cst0;
+  a.pfold = reinterpret_cast<const float4*>(pfold);
+  a.colmax = colmax;
+  static bool configured = false;
+  if (!configured) {
+    SEEME_CUDA(cudaFuncSetAttribute(pointnet_block0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P0_SMEM));
+    configured = true;
+  }
+  const int grid = a.n_tiles < NUM_SMS ? a.n_tiles : NUM_SMS;
+  ProfScope prof(prof_id - 1, s);
+  pointnet_block0_kernel<<<grid, PF_THREADS, P0_SMEM, s>>>(maps, a);
+  SEEME_LAUNCH_CHECK();
+  return SEEME_OK;
 }
 
 int pf_pack_block(const float* ws, const float* w0, const float* w1, void* blob) {
