@@ -238,17 +238,30 @@ def main():
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(pk):
             peaks = json.load(open(pk))
-        # dominant kernel class: the scene-encoder GEMMs (tensor-bound class)
-        pn_ms, pn_n = prof["pointnet_gemm"]
-        flops = POINTNET_FLOP_PER_POINT * N_POINTS * B * args.steps - 2 * 3 * 512 * N_POINTS * B * args.steps  # fc_pos (K=3) is not in this class
+        # dominant kernel class: the scene encoder's fused residual-block kernels (tensor-bound class).
+        # Algorithmic work: SURVEY 8(d)/App. E essential count, 1.838 MFLOP per point for the whole encoder (fc_pos + 4
+        # residual blocks with the pooled half of each concat hoisted), i.e. 0.4595 MFLOP per point per block launch;
+        # one launch processes (32-cloud chunk) x 20 000 points.
+        pn_ms, pn_n = prof["pointnet_fused"]
+        flops = POINTNET_FLOP_PER_POINT * N_POINTS * B * args.steps
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         ach = flops / (pn_ms / 1e3) / 1e12 if pn_ms > 0 else None
-        prec = os.environ.get("SEEME_POINTNET_PRECISION", "3")
-        kname = {"16": "fp16 fused", "17": "fp16 fused (smem H)", "3": "umma_linear_kernel<256,3,2> (tcgen05, split-bf16: 3 MMAs per algorithmic MAC)",
-                 "1": "umma_linear_kernel<256,1,2> (tcgen05, bf16)", "0": "gemm_f32_kernel<128,128,8,8> (fp32 CUDA cores)"}[prec]
-        roofline = {"kernel": "scene-encoder GEMM launches: " + kname, "bound": "tensor", "achieved": ach,
-                    "peak": peak_tf, "unit": "TFLOP/s", "frac": (ach / peak_tf) if ach else None, "traffic": None,
-                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_pointnet_block_kernel_ncu.json")
+        if os.path.exists(tp):
+            try:
+                k0 = json.load(open(tp))[0]
+                traffic = (k0["dram__bytes_read.sum"]["value"] + k0["dram__bytes_write.sum"]["value"]) * 1e6
+            except Exception:
+                traffic = None
+        roofline = {"kernel": "scene-encoder fused residual-block kernels pointnet_block0_kernel + pointnet_block_kernel<true> "
+                              "(tcgen05 fp16 x fp16 -> fp32, TMA, TMEM-resident hidden activation)",
+                    "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": (ach / peak_tf) if ach else None,
+                    "traffic": traffic,
+                    "traffic_note": "dram read+write bytes of one pointnet_block_kernel launch (32 clouds x 20000 points) from "
+                                    "profiles/r1_pointnet_block_kernel_ncu.json; algorithmic 655 MB (fp16 tile in + out)",
+                    "algorithmic_flop_per_launch": POINTNET_FLOP_PER_POINT * N_POINTS * min(B, 32) / 4,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
                     "launches": pn_n, "avg_launch_ms": pn_ms / pn_n if pn_n else None,
                     "share_of_step": (pn_ms / 1e3) / t_res if t_res else None}
         sk_ms, sk_n = prof["smpl_skin"]
@@ -274,7 +287,8 @@ def main():
                             "sample": f"1 pass over a batch of {Bc} sequences of the same per-sequence workload ({dt:.1f} s), oracle/restate.py fp32"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": workload(B), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+                "dtype": "fp16 (scene encoder) / split-bf16 x3 (denoiser, VAE) tensor-core operands, fp32 accumulation; f32 elsewhere",
+                "data": "synthetic", "config": workload(B), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "kernels": other, "cpu_baseline": cpu_baseline,
                 "metric_gather": {"collective": "all_reduce(sum) of the EgoMetric state vector", "sequences": n_seq_metric}}
         print(json.dumps(line), flush=True)
