@@ -66,6 +66,29 @@ struct ProfScope {
   ~ProfScope() { if (on) prof_end(id, s); }
 };
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------
+// Kernels of a dependent chain call pdl_prologue() before touching any data produced by earlier kernels: it lets
+// the NEXT kernel of the stream/graph start its own prologue (launch latency, barrier init, TMEM allocation, tensor-map
+// prefetch) while this one is still running, then blocks until the PREVIOUS kernel has completed and flushed.  Both
+// instructions are no-ops for a kernel launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+extern bool g_pdl_on;   // SEEME_PDL=1 enables the attribute (default: plain stream order)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl_on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- a tiny bump allocator over one cudaMalloc'd slab (everything allocated at create) -------
 struct Arena {
   char* base = nullptr;

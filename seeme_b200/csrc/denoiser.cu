@@ -22,6 +22,7 @@ namespace seeme {
 // x[r] = lat[r % B] + pe[0]      (torch.cat([latents]*2), mld.py:469-473; query_pos, mld_denoiser.py:210)
 __global__ void den_prep_kernel(const float* __restrict__ lat, const float* __restrict__ pe0, float* __restrict__ x,
                                 __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ xl, int R, int B) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -38,6 +39,7 @@ __global__ void den_prep_kernel(const float* __restrict__ lat, const float* __re
 __global__ void den_sa_attn_kernel(const float* __restrict__ qkv, const float* __restrict__ kvc,
                                    const float* __restrict__ tkv, int Nc, int R, __nv_bfloat16* __restrict__ oh,
                                    __nv_bfloat16* __restrict__ ol) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -91,6 +93,7 @@ __device__ __forceinline__ Row8 film_silu(const Row8& y, const float* __restrict
 __global__ void den_ca_kernel(const float* __restrict__ q, const float* __restrict__ kv2, int Nc, int R,
                               const float* __restrict__ film, const float* __restrict__ g, const float* __restrict__ b,
                               __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -131,6 +134,7 @@ __global__ void den_ca_kernel(const float* __restrict__ q, const float* __restri
 __global__ void den_film_kernel(const float* __restrict__ y, const float* __restrict__ film, const float* __restrict__ g,
                                 const float* __restrict__ b, __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol,
                                 int R) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -144,6 +148,7 @@ __global__ void den_ln_kernel(const float* __restrict__ x, const float* __restri
                               float* __restrict__ y, __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl,
                               const float* __restrict__ g2, const float* __restrict__ b2, __nv_bfloat16* __restrict__ y2h,
                               __nv_bfloat16* __restrict__ y2l, int R) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -160,6 +165,7 @@ __global__ void den_ln_kernel(const float* __restrict__ x, const float* __restri
 __global__ void den_final_ddim_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
                                       float* __restrict__ lat, int B, int cfg, const float* __restrict__ coef,
                                       const float* __restrict__ gscale) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
@@ -319,6 +325,16 @@ extern "C" int seeme_denoiser_create(seeme_denoiser_t* out, const float* const* 
   if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_error("seeme_denoiser_create: weight packing failed"); rc = SEEME_ECUDA; }
   if (rc) { h->arena.release(); delete h; return rc; }
   SEEME_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+  if (!(getenv("SEEME_NO_CARVEOUT") && getenv("SEEME_NO_CARVEOUT")[0] == '1')) {
+    // the row-wise kernels use no shared memory; asking for the maximum carve-out anyway keeps the SMs in the
+    // configuration of the 193 KB GEMM kernels they alternate with (no L1/shared re-partitioning between launches)
+    cudaFuncSetAttribute(den_prep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(den_sa_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(den_ca_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(den_film_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(den_ln_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(den_final_ddim_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
   *out = h;
   return SEEME_OK;
 }
@@ -384,29 +400,29 @@ static int den_block(seeme_denoiser* h, int l, int ti, const ActBuf& xin, const 
   ActBuf y; y.f = h->y; y.ld = 256;
   // self-attention over {x, cond tokens, time token}, token 0 only (H1)
   SEEME_TRY(run_linear(h->Wqkv[l], xin, nullptr, R, ACT_NONE, nullptr, 0, qkv, np, s));
-  den_sa_attn_kernel<<<nb, 256, 0, s>>>(h->qkv, h->kvc[l], h->tkv[l] + (size_t)ti * 512, Nc, R, h->att.h, h->att.l);
+  SEEME_CUDA(launch_pdl(den_sa_attn_kernel, dim3(nb), dim3(256), 0, s, h->qkv, h->kvc[l], h->tkv[l] + (size_t)ti * 512, Nc, R, h->att.h, h->att.l));
   SEEME_LAUNCH_CHECK();
   SEEME_TRY(run_linear(h->Wout[l], h->att, nullptr, R, ACT_NONE, xin.f, 256, t0, np, s));
-  den_ln_kernel<<<nb, 256, 0, s>>>(h->t0, blkw(h, l, SA_N1_W), blkw(h, l, SA_N1_B), h->x1.f, h->x1.h, h->x1.l, nullptr, nullptr,
-                                   nullptr, nullptr, R);
+  SEEME_CUDA(launch_pdl(den_ln_kernel, dim3(nb), dim3(256), 0, s, h->t0, blkw(h, l, SA_N1_W), blkw(h, l, SA_N1_B), h->x1.f, h->x1.h, h->x1.l, nullptr, nullptr,
+                                   nullptr, nullptr, R));
   SEEME_LAUNCH_CHECK();
   SEEME_TRY(run_linear(h->Wl1[l], h->x1, nullptr, R, ACT_RELU, nullptr, 0, h->ff, np, s));
   SEEME_TRY(run_linear(h->Wl2[l], h->ff, nullptr, R, ACT_NONE, h->x1.f, 256, t0, np, s));
   // x2 = norm2(.) and the cross-attention's input norm chained in one kernel
-  den_ln_kernel<<<nb, 256, 0, s>>>(h->t0, blkw(h, l, SA_N2_W), blkw(h, l, SA_N2_B), h->x2.f, nullptr, nullptr, blkw(h, l, CA_N_W),
-                                   blkw(h, l, CA_N_B), h->ln.h, h->ln.l, R);
+  SEEME_CUDA(launch_pdl(den_ln_kernel, dim3(nb), dim3(256), 0, s, h->t0, blkw(h, l, SA_N2_W), blkw(h, l, SA_N2_B), h->x2.f, nullptr, nullptr, blkw(h, l, CA_N_W),
+                                   blkw(h, l, CA_N_B), h->ln.h, h->ln.l, R));
   SEEME_LAUNCH_CHECK();
   // linear cross-attention to the cond tokens (H2) + FiLM
   SEEME_TRY(run_linear(h->Wcaq[l], h->ln, nullptr, R, ACT_NONE, nullptr, 0, caq, np, s));
-  den_ca_kernel<<<nb, 256, 0, s>>>(h->caq, h->kv2[l], Nc, R, h->film_ca[l] + (size_t)ti * 512, blkw(h, l, CA_PN_W),
-                                   blkw(h, l, CA_PN_B), h->hb.h, h->hb.l);
+  SEEME_CUDA(launch_pdl(den_ca_kernel, dim3(nb), dim3(256), 0, s, h->caq, h->kv2[l], Nc, R, h->film_ca[l] + (size_t)ti * 512, blkw(h, l, CA_PN_W),
+                                   blkw(h, l, CA_PN_B), h->hb.h, h->hb.l));
   SEEME_LAUNCH_CHECK();
   SEEME_TRY(run_linear(h->Wcaout[l], h->hb, nullptr, R, ACT_NONE, h->x2.f, 256, h->x1, np, s));    // x3 -> x1 (fp32 + bf16)
   // FFN + FiLM
   SEEME_TRY(run_linear(h->Wf1[l], h->x1, nullptr, R, ACT_GELU, nullptr, 0, h->g1, np, s));
   SEEME_TRY(run_linear(h->Wf2[l], h->g1, nullptr, R, ACT_NONE, nullptr, 0, y, np, s));
-  den_film_kernel<<<nb, 256, 0, s>>>(h->y, h->film_ff[l] + (size_t)ti * 512, blkw(h, l, FF_PN_W), blkw(h, l, FF_PN_B), h->hb.h,
-                                     h->hb.l, R);
+  SEEME_CUDA(launch_pdl(den_film_kernel, dim3(nb), dim3(256), 0, s, h->y, h->film_ff[l] + (size_t)ti * 512, blkw(h, l, FF_PN_W), blkw(h, l, FF_PN_B), h->hb.h,
+                                     h->hb.l, R));
   SEEME_LAUNCH_CHECK();
   SEEME_TRY(run_linear(h->Wfout[l], h->hb, nullptr, R, ACT_NONE, h->x1.f, 256, xout, np, s));
   return SEEME_OK;
@@ -441,7 +457,7 @@ extern "C" int seeme_denoiser_forward(seeme_denoiser_t h, const float* sample, i
   if (!(h->table_ts.size() == 1 && h->table_ts[0] == timestep)) SEEME_TRY(den_build_tables(h, &timestep, 1, nullptr, s));
   SEEME_CUDA(cudaMemcpyAsync(h->cond, cond, (size_t)Nc * R * 256 * 4, cudaMemcpyDeviceToDevice, s));
   SEEME_TRY(den_cond_precompute(h, Nc, R, s));
-  den_prep_kernel<<<(R + 7) / 8, 256, 0, s>>>(sample, h->w[DN_PE], h->x.f, h->x.h, h->x.l, R, R);
+  SEEME_CUDA(launch_pdl(den_prep_kernel, dim3((R + 7) / 8), dim3(256), 0, s, sample, h->w[DN_PE], h->x.f, h->x.h, h->x.l, R, R));
   SEEME_LAUNCH_CHECK();
   SEEME_TRY(den_stack(h, 0, Nc, R, s));
   SEEME_TRY(layernorm256(h->L[4].f, nullptr, 0, h->w[DN_NORM_W], h->w[DN_NORM_B], out, R, s));
@@ -457,11 +473,11 @@ extern "C" int seeme_denoiser_set_time_table(seeme_denoiser_t h, const int32_t* 
 static int sampler_enqueue(seeme_denoiser* h, int Nc, int B, int R, int cfg, int n_steps, cudaStream_t s) {
   SEEME_TRY(den_cond_precompute(h, Nc, R, s));
   for (int i = 0; i < n_steps; ++i) {
-    den_prep_kernel<<<(R + 7) / 8, 256, 0, s>>>(h->lat, h->w[DN_PE], h->x.f, h->x.h, h->x.l, R, B);
+    SEEME_CUDA(launch_pdl(den_prep_kernel, dim3((R + 7) / 8), dim3(256), 0, s, h->lat, h->w[DN_PE], h->x.f, h->x.h, h->x.l, R, B));
     SEEME_LAUNCH_CHECK();
     SEEME_TRY(den_stack(h, i, Nc, R, s));
-    den_final_ddim_kernel<<<(B + 7) / 8, 256, 0, s>>>(h->L[4].f, h->w[DN_NORM_W], h->w[DN_NORM_B], h->lat, B, cfg,
-                                                      h->d_coef + 4 * i, h->d_gscale);
+    SEEME_CUDA(launch_pdl(den_final_ddim_kernel, dim3((B + 7) / 8), dim3(256), 0, s, h->L[4].f, h->w[DN_NORM_W], h->w[DN_NORM_B], h->lat, B, cfg,
+                                                      h->d_coef + 4 * i, h->d_gscale));
     SEEME_LAUNCH_CHECK();
   }
   return SEEME_OK;

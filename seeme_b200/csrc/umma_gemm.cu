@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(192, MINB) umma_linear_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_prologue();     // everything above overlaps the previous kernel of the chain; its outputs are read only below
 
   if (warp == 0) {
     if (lane == 0) {
@@ -369,7 +370,7 @@ static int launch(const UmmaLinear& g, const UmmaMaps& maps, const UmmaEpi& e, c
   const int smem = (ring > store ? ring : store) + (e.has_r ? res_max : 0) + 1024;
   dim3 grid(g.N / BN, (g.M + 127) / 128);
   ProfScope prof(g.prof_id - 1, s);
-  umma_linear_kernel<BN, NPASS, STAGES, NBUF, MINB><<<grid, 192, smem, s>>>(maps, e);
+  SEEME_CUDA(launch_pdl(umma_linear_kernel<BN, NPASS, STAGES, NBUF, MINB>, grid, dim3(192), (size_t)smem, s, maps, e));
   SEEME_LAUNCH_CHECK();
   return SEEME_OK;
 }
