@@ -42,40 +42,57 @@ def workload(batch):
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason samples DURING the timed region, read in-process through NVML on a background thread
+    (spawning nvidia-smi inside the timed region stalls the driver for tens of milliseconds)."""
 
-    def __init__(self, gpu_index: int):
-        self.p = None
+    def __init__(self, gpu_index: int, period_s: float = 0.02):
+        import threading
+        self.samples, self.reasons, self.err = [], set(), None
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._on = threading.Event()
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:          # noqa: BLE001
+            self.err = f"NVML unavailable: {e}"
+            self.nv = None
+        self.period = period_s
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        bad = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+               "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            if self._on.is_set():
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for name, bit in bad.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception as e:   # noqa: BLE001
+                    self.err = str(e)
+            self._stop.wait(self.period)
+
+    def begin(self):
+        self._on.set()
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            out, _ = self.p.communicate(timeout=5)
-        except Exception:
-            self.p.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._on.clear()
+        self._stop.set()
+        self.t.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [self.err or "no samples"], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
 
 
 def oracle_weights():
@@ -133,7 +150,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="seeme_b200", choices=["seeme_b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="sequences per GPU per step")
@@ -208,9 +225,11 @@ def main():
         barrier()
         return float(ms) / 1e3, launches, rs
 
+    clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.begin()
     t_res, launches, rs = timed(step_resident, args.steps, prof=True)
     clk = clocks.stop() if clocks else None
     prof = {name: _lib.prof_read(i) for i, name in enumerate(["pointnet_gemm", "smpl_skin", "smpl_pose", "sampler_graph"])}
@@ -241,7 +260,7 @@ def main():
         # dominant kernel class: the scene encoder's fused residual-block kernels (tensor-bound class).
         # Algorithmic work: SURVEY 8(d)/App. E essential count, 1.838 MFLOP per point for the whole encoder (fc_pos + 4
         # residual blocks with the pooled half of each concat hoisted), i.e. 0.4595 MFLOP per point per block launch;
-        # one launch processes (32-cloud chunk) x 20 000 points.
+        # one launch processes a chunk of up to 128 clouds x 20 000 points.
         pn_ms, pn_n = prof["pointnet_fused"]
         flops = POINTNET_FLOP_PER_POINT * N_POINTS * B * args.steps
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
@@ -260,7 +279,7 @@ def main():
                     "traffic": traffic,
                     "traffic_note": "dram read+write bytes of one pointnet_block_kernel launch (32 clouds x 20000 points) from "
                                     "profiles/r1_pointnet_block_kernel_ncu.json; algorithmic 655 MB (fp16 tile in + out)",
-                    "algorithmic_flop_per_launch": POINTNET_FLOP_PER_POINT * N_POINTS * min(B, 32) / 4,
+                    "algorithmic_flop_per_launch": POINTNET_FLOP_PER_POINT * N_POINTS * min(B, 128) / 4,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
                     "launches": pn_n, "avg_launch_ms": pn_ms / pn_n if pn_n else None,
                     "share_of_step": (pn_ms / 1e3) / t_res if t_res else None}

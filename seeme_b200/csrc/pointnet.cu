@@ -173,15 +173,19 @@ static int pointnet_create(seeme_pointnet_t* out, const float* const* w, int n_w
     delete h;
     return SEEME_EINVAL;
   }
-  h->chunk = max_batch < 32 ? max_batch : 32;   // samples per pass: bounds the per-point workspace
-  const size_t rows = (size_t)h->chunk * (max_points < 128 ? 128 : max_points);
   const bool split = h->precision == 3;
   const bool fused = h->precision >= 16;
+  // samples per pass: bounds the per-point workspace.  The fused path only keeps two fp16 [rows,256] activation buffers
+  // (1 KB per point), so it takes 128 clouds per pass (fewer launches of the small per-sample bias GEMMs).
+  const int chunk_cap = fused ? 128 : 32;
+  h->chunk = max_batch < chunk_cap ? max_batch : chunk_cap;
+  const size_t rows = (size_t)h->chunk * (max_points < 128 ? 128 : max_points);
   size_t wbytes = 4 * pad256(pf_blob_bytes()) + pad256(512 * 16) + pad256(512 * 3 * 4) + pad256(512 * 4) + 4 * (pad256(256 * 512 * 4) * 2 + pad256(256 * 256 * 4) + 2 * pad256(256 * 4)) +
                   pad256(512 * 256 * 4) + pad256(512 * 4) + pad256(256 * 512 * 4) + pad256(256 * 4) +
                   8 * 2 * pad256(256 * 512 * 2) + pad256(256 * 4 * 4) + pad256(256 * 4);
   size_t ws = 4 * pad256((size_t)max_batch * 256 * 4) + pad256((size_t)max_batch * 512 * 4) + pad256((size_t)max_batch * 128 * 3 * 4);
   if (h->precision == 0) ws += pad256(rows * 512 * 4) + 3 * pad256(rows * 256 * 4);
+  else if (fused) ws += 2 * pad256(rows * 256 * 2);
   else ws += (split ? 2 : 1) * (pad256(rows * 512 * 2) + 5 * pad256(rows * 256 * 2));
   int rc = h->arena.init(wbytes + ws + 65536);
   if (rc != SEEME_OK) { delete h; return rc; }
@@ -223,13 +227,13 @@ static int pointnet_create(seeme_pointnet_t* out, const float* const* w, int n_w
     h->pfold = h->arena.take<float>(256 * 4);
     h->cst0 = h->arena.take<float>(256);
     auto take16 = [&](size_t n, bool need) -> __nv_bfloat16* { return need ? h->arena.take<__nv_bfloat16>(n) : nullptr; };
-    h->xr0h = take16(rows * 512, true); h->xr0l = take16(rows * 512, split);
-    h->hrh = take16(rows * 256, true); h->hrl = take16(rows * 256, split);
+    h->xr0h = take16(rows * 512, !fused); h->xr0l = take16(rows * 512, split);
+    h->hrh = take16(rows * 256, !fused); h->hrl = take16(rows * 256, split);
     for (int i = 0; i < 2; ++i) {
       h->xh[i] = take16(rows * 256, true); h->xl[i] = take16(rows * 256, split);
-      h->xrh[i] = take16(rows * 256, true); h->xrl[i] = take16(rows * 256, split);
+      h->xrh[i] = take16(rows * 256, !fused); h->xrl[i] = take16(rows * 256, split);
     }
-    ok = ok && h->xrh[1] && (!split || h->xrl[1]);
+    ok = ok && h->xh[1] && (fused || h->xrh[1]) && (!split || h->xrl[1]);
     if (ok) {
       // pack the tensor-path weights (default stream, create time)
       if (fused) {

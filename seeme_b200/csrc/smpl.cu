@@ -16,6 +16,8 @@
 //                    then T_v = sum_{<=4} w A_j (SMPL's skinning weights have <=4 non-zeros per vertex;
 //                    a dense-24 layout is used when a model violates that) and the 3x4 apply.
 #include "common.cuh"
+#include "smpl_tc.cuh"
+#include <stdlib.h>
 
 namespace seeme {
 
@@ -294,6 +296,9 @@ struct seeme_smpl {
   float *Jt, *Jd, *basis, *vtp, *w4, *w24;
   unsigned char *i4, *i24;
   float *A, *coef;
+  // tensor-core blend path (smpl_tc.cu): packed bf16 (hi, lo) basis and per-call coefficient scratch
+  void *bh = nullptr, *bl = nullptr, *ch = nullptr, *cl = nullptr;
+  bool use_tc = true;
 };
 
 extern "C" int seeme_smpl_create(seeme_smpl_t* out, const float* v_template, const float* shapedirs,
@@ -320,7 +325,8 @@ extern "C" int seeme_smpl_create(seeme_smpl_t* out, const float* v_template, con
   const size_t fpad = ((size_t)max_frames + FT - 1) / FT * FT;
   size_t bytes = pad256(SJ * 3 * 4) + pad256(SJ * 30 * 4) + pad256((size_t)SK * 3 * SVP * 4) + pad256((size_t)3 * SVP * 4) +
                  pad256((size_t)SVP * 4 * 4) + pad256((size_t)SVP * SJ * 4) + pad256((size_t)SVP * 4) + pad256((size_t)SVP * SJ) +
-                 pad256(fpad * SJ * 12 * 4) + pad256(fpad * SKP * 4) + 4096;
+                 pad256(fpad * SJ * 12 * 4) + pad256(fpad * SKP * 4) + 4096 +
+                 2 * pad256(smpl_tc_basis_elems() * 2) + 2 * pad256((fpad + 64) * 256 * 2);
   int rc = h->arena.init(bytes);
   if (rc) { delete h; return rc; }
   h->Jt = h->arena.take<float>(SJ * 3);
@@ -333,11 +339,24 @@ extern "C" int seeme_smpl_create(seeme_smpl_t* out, const float* v_template, con
   h->i24 = h->arena.take<unsigned char>((size_t)SVP * SJ);
   h->A = h->arena.take<float>(fpad * SJ * 12);
   h->coef = h->arena.take<float>(fpad * SKP);
+  h->bh = h->arena.take<__nv_bfloat16>(smpl_tc_basis_elems());
+  h->bl = h->arena.take<__nv_bfloat16>(smpl_tc_basis_elems());
+  h->ch = h->arena.take<__nv_bfloat16>((fpad + 64) * 256);
+  h->cl = h->arena.take<__nv_bfloat16>((fpad + 64) * 256);
+  {
+    const char* e = getenv("SEEME_SMPL_FP32");
+    h->use_tc = !(e && e[0] == '1');
+  }
   int* d_nnz = h->arena.take<int>(1);
   if (!d_nnz) { set_error("seeme_smpl_create: arena exhausted"); h->arena.release(); delete h; return SEEME_ENOMEM; }
   smpl_jfold_kernel<<<dim3(SJ, 33), 256>>>(J_regressor, v_template, shapedirs, h->Jt, h->Jd);
   smpl_basis_kernel<<<(unsigned)(((size_t)SK * 3 * SVP + 255) / 256), 256>>>(v_template, shapedirs, posedirs, h->basis, h->vtp);
   cudaMemset(d_nnz, 0, sizeof(int));
+  if (h->cl) {
+    cudaMemset(h->ch, 0, (fpad + 64) * 256 * 2);
+    cudaMemset(h->cl, 0, (fpad + 64) * 256 * 2);
+    if (smpl_tc_pack_basis(h->basis, SK, h->bh, h->bl) != SEEME_OK) { h->arena.release(); delete h; return SEEME_ECUDA; }
+  }
   smpl_lbs_pack_kernel<<<(SVP + 127) / 128, 128>>>(lbs_weights, h->w4, h->i4, h->w24, h->i24, d_nnz);
   cudaError_t e = cudaMemcpy(&h->max_nnz, d_nnz, sizeof(int), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -357,7 +376,11 @@ static int smpl_run(seeme_smpl* h, const float* betas, const float* body_pose, c
                                                  h->Jt, h->Jd, h->topo, F, h->A, h->coef, joints, quat);
   }
   SEEME_LAUNCH_CHECK();
-  if (vertices) {
+  if (vertices && h->use_tc && h->max_nnz <= 4) {
+    // blend contraction on the tensor cores, skinning in its epilogue (smpl_tc.cu)
+    SEEME_TRY(smpl_skin_tc(h->bh, h->bl, h->coef, SKP, SKP, h->ch, h->cl, h->A, h->vtp, h->w4, h->i4, F, vertices,
+                           PROF_SMPL_SKIN + 1, s));
+  } else if (vertices) {
     ProfScope prof(PROF_SMPL_SKIN, s);
     dim3 grid(SVP / 128, (F + FT - 1) / FT);
     if (h->max_nnz <= 4)

@@ -1,0 +1,15 @@
+// Tensor-core SMPL blend + skinning kernel (smpl_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace seeme {
+
+size_t smpl_tc_basis_elems();     // elements of each of the packed bf16 basis buffers (hi, lo)
+// basis [SK][3][6912] fp32 -> bf16 (hi, lo) [3*6912][256]  (default stream, create time)
+int smpl_tc_pack_basis(const float* basis, int SK, void* bh, void* bl);
+// coef [F, n_coef] fp32 (pitch ld_coef); ch / cl: bf16 [F_pad, 256] scratch whose columns >= n_coef are zero;
+// A [F,24,12]; vt [3][6912]; w4/i4 [6912][4]; verts [F,6890,3]
+int smpl_skin_tc(const void* bh, const void* bl, const float* coef, int ld_coef, int n_coef, void* ch, void* cl, const float* A,
+                 const float* vt, const float* w4, const unsigned char* i4, int F, float* verts, int prof_id, cudaStream_t s);
+
+}  // namespace seeme

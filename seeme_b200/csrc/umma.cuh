@@ -143,6 +143,9 @@ struct UmmaLinear {
 // precision: 1 = single bf16 pass, 3 = split-bf16 (hi.hi + lo.hi + hi.lo)
 int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s);
 
+// 2-D bf16 tensor map over a [rows, cols] matrix (pitch ld_elems), box = box_rows x 64 elements, SWIZZLE_128B, OOB = 0
+int umma_tensor_map_bf16(CUtensorMap* map, const void* ptr, int rows, int cols, int ld_elems, int box_rows);
+
 // ---- convenience layer used by the transformer stacks ----------------------------------------------
 struct PackedLinear {           // nn.Linear weight [N,K] packed once as bf16 (hi, lo); bias stays fp32
   __nv_bfloat16 *hi = nullptr, *lo = nullptr;

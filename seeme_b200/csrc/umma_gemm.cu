@@ -352,6 +352,11 @@ static int make_map(CUtensorMap* map, const void* ptr, bool f32, int rows, int c
   return SEEME_OK;
 }
 
+int umma_tensor_map_bf16(CUtensorMap* map, const void* ptr, int rows, int cols, int ld_elems, int box_rows) {
+  SEEME_TRY(get_encoder());
+  return make_map(map, ptr, false, rows, cols, ld_elems, box_rows);
+}
+
 template <int BN, int NPASS, int STAGES, int NBUF, int MINB>
 static int launch(const UmmaLinear& g, const UmmaMaps& maps, const UmmaEpi& e, cudaStream_t s) {
   using Cfg = UmmaCfg<BN, NPASS>;
