@@ -60,6 +60,116 @@ __global__ void __launch_bounds__(256) mha1_kernel(const float* __restrict__ qkv
   }
 }
 
+
+// Register-tiled version of the same attention (S <= 64, d = 256): one CTA per sample, Q/K/V staged in shared memory
+// with a 260-float row pitch, each thread owns a 4x4 tile of the 64x64 score matrix (rows ty + 16 i, keys tx + 16 j:
+// consecutive rows per quarter-warp -> conflict-free 16-byte reads), row softmax by one warp per row, then a 4 x 16
+// tile of P.V per thread.  ~10x fewer instructions than one warp-reduction per (query, key) pair.
+constexpr int MH_P = 260;      // Q/K/V row pitch (floats)
+constexpr int MH_PP = 65;      // P row pitch
+constexpr int MH_SMEM = (3 * 64 * MH_P + 64 * MH_PP) * 4;
+__global__ void __launch_bounds__(256) mha1_tiled_kernel(const float* __restrict__ qkv, const int* __restrict__ lengths,
+                                                         int n_prefix, int S, __nv_bfloat16* __restrict__ oh,
+                                                         __nv_bfloat16* __restrict__ ol) {
+  extern __shared__ __align__(16) float sm[];
+  float* Qs = sm;
+  float* Ks = Qs + 64 * MH_P;
+  float* Vs = Ks + 64 * MH_P;
+  float* Ps = Vs + 64 * MH_P;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* base = qkv + (size_t)b * S * 768;
+  for (int i = tid; i < 64 * 64 * 3; i += 256) {           // 64 rows x 192 float4 (q | k | v)
+    const int row = i / 192, c4 = i % 192;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < S) v = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * 768) + c4);
+    float* dst = (c4 < 64 ? Qs : c4 < 128 ? Ks : Vs) + row * MH_P + (c4 & 63) * 4;
+    *reinterpret_cast<float4*>(dst) = v;
+  }
+  __syncthreads();
+  int nvalid = n_prefix + lengths[b];
+  nvalid = nvalid < S ? nvalid : S;
+  const int tx = tid & 15, ty = tid >> 4;
+  {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < 256; c += 4) {
+      float4 q[4], k[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) q[i] = *reinterpret_cast<const float4*>(Qs + (ty + 16 * i) * MH_P + c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) k[j] = *reinterpret_cast<const float4*>(Ks + (tx + 16 * j) * MH_P + c);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          acc[i][j] = fmaf(q[i].w, k[j].w, fmaf(q[i].z, k[j].z, fmaf(q[i].y, k[j].y, fmaf(q[i].x, k[j].x, acc[i][j]))));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Ps[(ty + 16 * i) * MH_PP + tx + 16 * j] = (tx + 16 * j) < nvalid ? acc[i][j] : -INFINITY;
+  }
+  __syncthreads();
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp; r < 64; r += 8) {
+      const float s0 = Ps[r * MH_PP + lane], s1 = Ps[r * MH_PP + lane + 32];
+      const float m = warp_max(fmaxf(s0, s1));
+      const float e0 = (s0 == -INFINITY) ? 0.f : expf(s0 - m);
+      const float e1 = (s1 == -INFINITY) ? 0.f : expf(s1 - m);
+      const float inv = 1.0f / warp_sum(e0 + e1);
+      Ps[r * MH_PP + lane] = e0 * inv;
+      Ps[r * MH_PP + lane + 32] = e1 * inv;
+    }
+  }
+  __syncthreads();
+  {
+    float4 acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kk = 0; kk < nvalid; ++kk) {
+      float p[4];
+      float4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p[i] = Ps[(ty + 16 * i) * MH_PP + kk];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(Vs + kk * MH_P + tx * 4 + 64 * j);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j].x = fmaf(p[i], v[j].x, acc[i][j].x); acc[i][j].y = fmaf(p[i], v[j].y, acc[i][j].y);
+          acc[i][j].z = fmaf(p[i], v[j].z, acc[i][j].z); acc[i][j].w = fmaf(p[i], v[j].w, acc[i][j].w);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = ty + 16 * i;
+      if (row < S) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float f[4] = {acc[i][j].x, acc[i][j].y, acc[i][j].z, acc[i][j].w};
+          __align__(8) __nv_bfloat16 h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            h[e] = __float2bfloat16_rn(f[e]);
+            l[e] = __float2bfloat16_rn(f[e] - __bfloat162float(h[e]));
+          }
+          const size_t o = ((size_t)b * S + row) * 256 + tx * 4 + 64 * j;
+          *reinterpret_cast<uint2*>(oh + o) = *reinterpret_cast<const uint2*>(h);
+          *reinterpret_cast<uint2*>(ol + o) = *reinterpret_cast<const uint2*>(l);
+        }
+      }
+    }
+  }
+}
+
 // xseq[b, s] = (s < 2 ? global_motion_token[s] : emb[b, s-2]) + pe[s]     (mld_vae.py:147-164)
 __global__ void vae_enc_assemble_kernel(const float* __restrict__ emb, const float* __restrict__ token,
                                         const float* __restrict__ pe, float* __restrict__ x,
@@ -146,6 +256,7 @@ struct seeme_vae {
   float* w[SEEME_VAE_NUM_TENSORS];
   float *emb, *qkv, *t0, *ca[5], *vtmp;
   int npass = 3;
+  bool tiled_attn = true;
   // per stack (0 encoder, 1 decoder) and block: packed (hi, lo) weights of the tcgen05 linears
   PackedLinear Wqkv[2][5], Wout[2][5], Wl1[2][5], Wl2[2][5], Wskip[2][2];
   ActBuf x0, x, L[5], att, x1, x2, ff;
@@ -243,6 +354,11 @@ extern "C" int seeme_vae_create(seeme_vae_t* out, const float* const* w, int n_w
   if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_error("seeme_vae_create: weight packing failed"); rc = SEEME_ECUDA; }
   if (rc) { h->arena.release(); delete h; return rc; }
   SEEME_CUDA(cudaFuncSetAttribute(mha1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 256 * 4));
+  SEEME_CUDA(cudaFuncSetAttribute(mha1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MH_SMEM));
+  {
+    const char* e = getenv("SEEME_VAE_ATTN");
+    h->tiled_attn = !(e && e[0] == '0');
+  }
   *out = h;
   return SEEME_OK;
 }
@@ -260,7 +376,8 @@ static int vae_layer(seeme_vae* h, int st, int l, const ActBuf& xin, const ActBu
   SEEME_TRY(run_linear(h->Wqkv[st][l], xin, nullptr, rows, ACT_NONE, nullptr, 0, qkv, np, s));
   {
     ProfScope prof(PROF_VAE_ATTN, s);
-    mha1_kernel<<<B, 256, (size_t)2 * S * 256 * 4, s>>>(h->qkv, lengths, n_prefix, S, h->att.h, h->att.l);
+    if (h->tiled_attn) mha1_tiled_kernel<<<B, 256, MH_SMEM, s>>>(h->qkv, lengths, n_prefix, S, h->att.h, h->att.l);
+    else mha1_kernel<<<B, 256, (size_t)2 * S * 256 * 4, s>>>(h->qkv, lengths, n_prefix, S, h->att.h, h->att.l);
   }
   SEEME_LAUNCH_CHECK();
   SEEME_TRY(run_linear(h->Wout[st][l], h->att, nullptr, rows, ACT_NONE, xin.f, 256, t0, np, s));

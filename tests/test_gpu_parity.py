@@ -120,12 +120,13 @@ def test_vae_vs_reference_golden(vae_op, golden_stages):
     g = golden_stages
     lens = T(g["vae_lens"])
     z, mu, std = vae_op.encode(T(g["vae_f"]).to(DEV), lens, T(g["vae_eps"]).to(DEV))
-    assert (z.cpu() - T(g["vae_z"])[0]).abs().max() < 1e-4
-    assert (mu.cpu() - T(g["vae_mu"])[0]).abs().max() < 1e-4
-    assert (std.cpu() - T(g["vae_std"])[0]).abs().max() < 1e-4
+    ez, em, es = (float((a.cpu() - T(g[k])[0]).abs().max()) for a, k in ((z, "vae_z"), (mu, "vae_mu"), (std, "vae_std")))
+    # z = mu + std * eps carries the std error times |eps| (up to ~4.5 in this draw): 2e-4; mu / std themselves 1e-4
+    assert ez < 2e-4 and em < 1e-4 and es < 1e-4, (ez, em, es)
     dec = vae_op.decode(T(g["vae_z"]).to(DEV), lens, 60).cpu()
     assert dec.shape == (4, 60, 75)
-    assert (dec - T(g["vae_dec"])).abs().max() < 1e-4      # includes the un-masked padded frames (mld_vae.py:253)
+    ed = float((dec - T(g["vae_dec"])).abs().max())
+    assert ed < 1e-4, ed                                   # includes the un-masked padded frames (mld_vae.py:253)
 
 
 def test_vae_short_and_single_frame_vs_oracle(vae_op, weights):
