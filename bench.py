@@ -244,6 +244,40 @@ def main():
         dist.all_reduce(state)
     n_seq_metric = float(state[STATE_KEYS.index("count")]) / 60.0
 
+    # SURVEY 8(d) sub-metrics, one extra pass each (device-timed, batch resident):
+    #  (ii) the reference's own timing window (interactee encode + 50-step reverse + VAE decode, mld.py:1267-1368)
+    #  (iii) the chain with the scene embeddings cached (replication protocol: repetitions of a sequence reuse them)
+    #  (iv) SMPL alone (predicted-body skinning of B x 60 frames)
+    def device_ms(fn, n=3):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    sub = {}
+    try:
+        scene_dev = dev_batch[4]
+        emb_cached = model._encode_scene(scene_dev)
+        orig = model._encode_scene
+        t_scene = device_ms(lambda: orig(scene_dev))
+        model._encode_scene = lambda scene: emb_cached
+        t_cached = device_ms(step_resident)
+        model._encode_scene = orig
+        F = B * 60
+        bet = torch.zeros(F, 10, device=dev); pz = torch.zeros(F, 69, device=dev); gz = torch.zeros(F, 3, device=dev)
+        sop = model.smpl_model.op
+        t_smpl = device_ms(lambda: sop.forward(bet, pz, gz, None))
+        sub = {"scene_encoder_ms": t_scene, "chain_cached_scene_ms": t_cached,
+               "sequences_per_s_cached_scene": world * B / (t_cached / 1e3),
+               "reference_window_ms_estimate": t_cached - t_smpl, "smpl_only_ms": t_smpl,
+               "smpl_only_frames_per_s": world * F / (t_smpl / 1e3)}
+    except Exception as e:      # noqa: BLE001
+        sub = {"error": str(e)}
+
     e2e = None
     if not args.no_e2e:
         for _ in range(2):
@@ -290,7 +324,8 @@ def main():
                                "launches": sk_n, "avg_launch_ms": sk_ms / sk_n if sk_n else None},
                  "sampler_graph_ms_per_step": prof["sampler_graph"][0] / max(prof["sampler_graph"][1], 1),
                  "smpl_pose_ms_per_launch": prof["smpl_pose"][0] / max(prof["smpl_pose"][1], 1),
-                 "pointnet_fused_ms": prof["pointnet_fused"][0], "pointnet_fused_launches": prof["pointnet_fused"][1]}
+                 "pointnet_fused_ms": prof["pointnet_fused"][0], "pointnet_fused_launches": prof["pointnet_fused"][1],
+                 "sub_metrics": sub}
         cpu_baseline = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

@@ -12,9 +12,11 @@
 //
 //   warp 0      TMA producer: basis chunks [128 v x 64 k] (hi, lo) through a 5-slot ring
 //   warp 1      MMA issuer (elected lane); accumulators double-buffered in TMEM (2 x 3 x 64 columns)
-//   warps 2..9  epilogue: lane quarter x frame half; tcgen05.ld of x/y/z for 32 frames, sparse (<= 4) skinning, stores
+//   warps 2..17 epilogue: lane quarter x frame quarter; tcgen05.ld of x/y/z for 16 frames, sparse (<= 4) skinning, stores
+//               (16 warps: the per-frame LDS -> FFMA chains are latency-bound, so occupancy is what hides them)
 #include "umma.cuh"
 #include "smpl_tc.cuh"
+#include <stdlib.h>
 
 namespace seeme {
 
@@ -24,7 +26,7 @@ constexpr int ST_BCHUNK = 64 * 128;                  // [64 f x 64 k] bf16
 constexpr int ST_B_BYTES = 4 * 2 * ST_BCHUNK;        // 4 k-chunks x (hi, lo)
 constexpr int ST_A_BYTES = ST_NF * ST_J * 12 * 4;    // joint transforms of the frame group
 constexpr int ST_SMEM = ST_B_BYTES + ST_A_BYTES + ST_NST * ST_CHUNK + 1024;
-constexpr int ST_THREADS = 320;
+constexpr int ST_THREADS = 576;                     // 2 control warps + 16 epilogue warps
 
 struct StMaps { CUtensorMap bh, bl, ch, cl; };
 struct StArgs {
@@ -36,6 +38,19 @@ struct StArgs {
   int F, tiles_per_cta;
 };
 
+__device__ __forceinline__ void st_tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// CL: thread-block cluster size along the frame-group axis.  The CTAs of a cluster work on different frame groups but the
+// SAME vertex tiles, so the basis chunk stream is identical: chunk n is fetched from L2 once, by CTA n % CL, and multicast
+// into the ring slot of every CTA of the cluster (the kernel is bound by this L2 -> SM stream, not by the MMAs).
+template <int CL>
 __global__ void __launch_bounds__(ST_THREADS, 1) smpl_skin_tc_kernel(const __grid_constant__ StMaps tm, const StArgs a) {
   extern __shared__ __align__(1024) uint8_t st_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(st_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -51,9 +66,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) smpl_skin_tc_kernel(const __gri
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm.bh); tma_prefetch_desc(&tm.bl); tma_prefetch_desc(&tm.ch); tma_prefetch_desc(&tm.cl);
-    for (int i = 0; i < ST_NST; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 1); }
+    for (int i = 0; i < ST_NST; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], CL); }
     mbar_init(&b_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], 16); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_slot, 512);
@@ -67,6 +82,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) smpl_skin_tc_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  uint32_t crank = 0;
+  if (CL > 1) {
+    cluster_sync_all();          // every CTA's barriers exist before any remote arrive / multicast write
+    crank = cluster_ctarank();
+  }
+  constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -75,15 +96,17 @@ __global__ void __launch_bounds__(ST_THREADS, 1) smpl_skin_tc_kernel(const __gri
         tma_load_2d(bop + (kc * 2 + 0) * ST_BCHUNK, &tm.ch, &b_full, kc * 64, f0);
         tma_load_2d(bop + (kc * 2 + 1) * ST_BCHUNK, &tm.cl, &b_full, kc * 64, f0);
       }
-      uint32_t st = 0, ph = 1;
+      uint32_t st = 0, ph = 1, n = 0;
       for (int i = 0; i < nt; ++i) {
         const int tile = t0 + i;
         for (int c = 0; c < 3; ++c)
           for (int kc = 0; kc < 4; ++kc)
-            for (int hl = 0; hl < 2; ++hl) {
-              mbar_wait(&r_empty[st], ph);
+            for (int hl = 0; hl < 2; ++hl, ++n) {
+              mbar_wait(&r_empty[st], ph);        // the slot has been consumed by every CTA of the cluster
               mbar_arrive_expect_tx(&r_full[st], ST_CHUNK);
-              tma_load_2d(ring + st * ST_CHUNK, hl ? &tm.bl : &tm.bh, &r_full[st], kc * 64, c * ST_VP + tile * 128);
+              if (CL == 1) tma_load_2d(ring + st * ST_CHUNK, hl ? &tm.bl : &tm.bh, &r_full[st], kc * 64, c * ST_VP + tile * 128);
+              else if (n % CL == crank)
+                tma_load_2d_mc(ring + st * ST_CHUNK, hl ? &tm.bl : &tm.bh, &r_full[st], kc * 64, c * ST_VP + tile * 128, cmask);
               if (++st == ST_NST) { st = 0; ph ^= 1u; }
             }
       }
@@ -115,7 +138,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) smpl_skin_tc_kernel(const __gri
               umma_bf16(d, umma_desc_add(ad, ks * 2), umma_desc_add(bh, ks * 2), idesc, (kc | ks) != 0);
               umma_bf16(d, umma_desc_add(ad, ks * 2), umma_desc_add(bl, ks * 2), idesc, 1);
             }
-            umma_commit(&r_empty[st]);
+            if (CL == 1) umma_commit(&r_empty[st]); else umma_commit_mc(&r_empty[st], cmask);
           }
           __syncwarp();
           if (++st == ST_NST) { st = 0; ph ^= 1u; }
@@ -126,7 +149,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) smpl_skin_tc_kernel(const __gri
             const uint64_t ad = umma_desc_add(rdesc0, st * (ST_CHUNK >> 4));
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) umma_bf16(d, umma_desc_add(ad, ks * 2), umma_desc_add(bh, ks * 2), idesc, 1);
-            umma_commit(&r_empty[st]);
+            if (CL == 1) umma_commit(&r_empty[st]); else umma_commit_mc(&r_empty[st], cmask);
             if (c == 2 && kc == 3) umma_commit(&acc_full[p]);
           }
           __syncwarp();
@@ -136,7 +159,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) smpl_skin_tc_kernel(const __gri
     }
   } else {
     const int q = warp & 3;                  // TMEM lane quarter
-    const int fh = (warp - 2) >> 2;          // frame half: frames [32 fh, 32 fh + 32) of the group
+    const int fq = (warp - 2) >> 2;          // frame quarter: frames [16 fq, 16 fq + 16) of the group
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     for (int i = 0; i < nt; ++i) {
       const int p = i & 1;
@@ -152,22 +175,22 @@ __global__ void __launch_bounds__(ST_THREADS, 1) smpl_skin_tc_kernel(const __gri
       const float vx = __ldg(a.vt + v), vy = __ldg(a.vt + ST_VP + v), vz = __ldg(a.vt + 2 * ST_VP + v);
       mbar_wait(&acc_full[p], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
-      uint32_t X[32], Y[32], Z[32];
-      const uint32_t tb = tmem_base + lane_off + (uint32_t)(p * 192 + fh * 32);
-      tmem_ld32(tb, X);
-      tmem_ld32(tb + 64, Y);
-      tmem_ld32(tb + 128, Z);
+      uint32_t X[16], Y[16], Z[16];
+      const uint32_t tb = tmem_base + lane_off + (uint32_t)(p * 192 + fq * 16);
+      st_tmem_ld16(tb, X);
+      st_tmem_ld16(tb + 64, Y);
+      st_tmem_ld16(tb + 128, Z);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_free[p]);     // the accumulators are in registers: the MMAs of tile i+2 may proceed
       if (v < ST_V) {
-        float* out = a.verts + ((size_t)(f0 + fh * 32) * ST_V + v) * 3;
-        const int nf = a.F - (f0 + fh * 32);
+        float* out = a.verts + ((size_t)(f0 + fq * 16) * ST_V + v) * 3;
+        const int nf = a.F - (f0 + fq * 16);
 #pragma unroll
-        for (int f = 0; f < 32; ++f) {
+        for (int f = 0; f < 16; ++f) {
           if (f < nf) {
-            const float* Af = As + (fh * 32 + f) * (ST_J * 12);
+            const float* Af = As + (fq * 16 + f) * (ST_J * 12);
             float T[12];
 #pragma unroll
             for (int e = 0; e < 12; ++e) T[e] = 0.f;
@@ -191,6 +214,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) smpl_skin_tc_kernel(const __gri
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -231,7 +255,14 @@ int smpl_skin_tc(const void* bh, const void* bl, const float* coef, int ld_coef,
   SEEME_TRY(umma_tensor_map_bf16(&maps.bl, bl, 3 * ST_VP, ST_KP, ST_KP, 128));
   SEEME_TRY(umma_tensor_map_bf16(&maps.ch, ch, F, ST_KP, ST_KP, ST_NF));
   SEEME_TRY(umma_tensor_map_bf16(&maps.cl, cl, F, ST_KP, ST_KP, ST_NF));
-  const int groups = (F + ST_NF - 1) / ST_NF;
+  static int csz = -1;
+  if (csz < 0) {
+    const char* e = getenv("SEEME_SMPL_CLUSTER");
+    csz = e ? atoi(e) : 1;   // measured on B200: multicast halves the L2 reads but not the time (the SM-inbound side bounds it)
+    if (csz != 1 && csz != 2 && csz != 4) csz = 1;
+  }
+  // frame groups padded to a multiple of the cluster size: a ghost group (f0 >= F) only consumes the chunk stream
+  const int groups = ((F + ST_NF - 1) / ST_NF + csz - 1) / csz * csz;
   // split the 54 vertex tiles so that the grid has a few waves of CTAs; the split must divide 54
   static const int divs[8] = {1, 2, 3, 6, 9, 18, 27, 54};
   int vsplit = 54;
@@ -242,11 +273,23 @@ int smpl_skin_tc(const void* bh, const void* bl, const float* coef, int ld_coef,
   a.tiles_per_cta = 54 / vsplit;
   static bool configured = false;
   if (!configured) {
-    SEEME_CUDA(cudaFuncSetAttribute(smpl_skin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+    SEEME_CUDA(cudaFuncSetAttribute(smpl_skin_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+    SEEME_CUDA(cudaFuncSetAttribute(smpl_skin_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+    SEEME_CUDA(cudaFuncSetAttribute(smpl_skin_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
     configured = true;
   }
   ProfScope prof(prof_id - 1, s);
-  smpl_skin_tc_kernel<<<dim3(groups, vsplit), ST_THREADS, ST_SMEM, s>>>(maps, a);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(groups, vsplit); cfg.blockDim = dim3(ST_THREADS); cfg.dynamicSmemBytes = ST_SMEM; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csz; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = csz > 1 ? 1 : 0;
+  if (csz == 1) SEEME_CUDA(cudaLaunchKernelEx(&cfg, smpl_skin_tc_kernel<1>, maps, a));
+  else if (csz == 2) SEEME_CUDA(cudaLaunchKernelEx(&cfg, smpl_skin_tc_kernel<2>, maps, a));
+  else SEEME_CUDA(cudaLaunchKernelEx(&cfg, smpl_skin_tc_kernel<4>, maps, a));
   SEEME_LAUNCH_CHECK();
   return SEEME_OK;
 }
