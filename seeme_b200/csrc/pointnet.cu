@@ -168,8 +168,8 @@ static int pointnet_create(seeme_pointnet_t* out, const float* const* w, int n_w
   const char* pe = getenv("SEEME_POINTNET_PRECISION");
   h->precision = pe ? atoi(pe) : 3;
   if (precision_arg >= 0) h->precision = precision_arg;
-  if (h->precision != 0 && h->precision != 1 && h->precision != 3 && h->precision != 16 && h->precision != 17) {
-    set_error("scene-encoder precision must be 0, 1, 3, 16 or 17 (got %d)", h->precision);
+  if (h->precision != 0 && h->precision != 1 && h->precision != 3 && h->precision != 16 && h->precision != 17 && h->precision != 18) {
+    set_error("scene-encoder precision must be 0, 1, 3, 16, 17 or 18 (got %d)", h->precision);
     delete h;
     return SEEME_EINVAL;
   }
@@ -394,7 +394,7 @@ static int blocks_fused(seeme_pointnet* h, const float* p, int C, int N, cudaStr
     SEEME_TRY(pooled_bias(h, i, C, s));
     SEEME_CUDA(cudaMemsetAsync(h->pool_ord, 0, (size_t)C * 256 * sizeof(unsigned), s));
     SEEME_TRY(pf_block_forward(h->xh[cur], i < 3 ? h->xh[cur ^ 1] : nullptr, h->blob[i], h->c0, h->cs, h->pool_ord, C, N,
-                               h->precision == 16, PROF_POINTNET_FUSED + 1, s));
+                               h->precision == 18 ? 2 : (h->precision == 16 ? 1 : 0), PROF_POINTNET_FUSED + 1, s));
     cur ^= 1;
   }
   return decode_pool(h, C, s);

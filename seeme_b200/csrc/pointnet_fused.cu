@@ -705,6 +705,390 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block0_kernel(const __
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair version of pointnet_block_kernel: tcgen05.mma.cta_group::2, M = 256 (two 128-point tiles, one per SM), N = 256.
+// Each CTA holds only ITS half of every weight K-chunk ([128 n x 64 k]: CTA 0 the output columns 0-127, CTA 1 128-255),
+// so the per-SM weight traffic from L2 -- what bounds the single-CTA kernel -- halves and the 6-slot ring holds 6 K-steps.
+// Protocol: the leader CTA's warp 1 issues every MMA; tcgen05.commit multicasts completion to the barriers of both CTAs;
+// the peer CTA's warp 1 relays "my X tile / my weight slot has landed" to the leader with remote mbarrier arrives; the
+// epilogue warps of the peer arrive remotely on the leader's r_done / h_ready / out_drained barriers.
+__device__ __forceinline__ uint32_t pf_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void pf_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// arrive on the leader CTA's copy of a barrier
+__device__ __forceinline__ void pf_arrive_leader(uint64_t* bar, uint32_t rank) {
+  if (rank == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+  else pf_arrive_remote(pf_mapa(smem_u32(bar), 0));
+}
+// wait with cluster-scope acquire (the barrier receives arrivals from the peer CTA)
+__device__ __forceinline__ void pf_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  printf("seeme_b200: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void umma2_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of this thread's cta_group::2 MMAs -> the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__host__ __device__ constexpr uint32_t umma2_idesc_f16(int n) {     // M = 256 over the CTA pair
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+constexpr int PF2_WSTEPS = 12;      // weight K-steps per tile: S 4, G1 4, G2 4 (each CTA loads its 128-row half)
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PF_THREADS, 1)
+    pointnet_block_pair_kernel(const __grid_constant__ PfMaps tm, const PfArgs a) {
+  extern __shared__ __align__(1024) uint8_t pf_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pf_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* xbuf = smem;
+  uint8_t* wring = smem + 2 * PF_XBUF;
+  // local barriers (every CTA): w_full, x_full (TMA), w_empty, s_done, h_full, out_full (multicast commits)
+  // leader-only use: wp_full, xp_full (relayed by the peer), r_done, h_ready, out_drained (both CTAs' epilogue warps)
+  __shared__ __align__(8) uint64_t w_full[PF_NST], w_empty[PF_NST], wp_full[PF_NST], x_full[2], xp_full[2], s_done[2][4], r_done[2][4],
+      h_full[2], h_ready[2][4], out_full[2], out_drained[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ unsigned colmax_s[256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = (int)blockIdx.x >> 1, npairs = (int)gridDim.x >> 1;
+  // tile pairs [pb, pb + np) of this CTA pair; this CTA takes tile 2 * (pb + j) + rank (a ghost tile beyond the end has
+  // no valid rows: zero-filled loads, clipped stores, no pooling contribution)
+  const int tile_pairs = (a.n_tiles + 1) / 2;
+  const int per = tile_pairs / npairs, rem = tile_pairs % npairs;
+  const int pb = pair * per + (pair < rem ? pair : rem);
+  const int np = per + (pair < rem ? 1 : 0);
+  auto tile_of = [&](int j, int& sample, int& n0) {
+    const int t = 2 * (pb + j) + (int)rank;
+    if (t < a.n_tiles) { sample = t / a.tiles_per_sample; n0 = (t % a.tiles_per_sample) * 128; }
+    else { sample = (a.n_tiles - 1) / a.tiles_per_sample; n0 = a.tiles_per_sample * 128; }      // ghost: rows >= n_points
+  };
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm.xin);
+    tma_prefetch_desc(&tm.w);
+    tma_prefetch_desc(&tm.xout);
+    for (int i = 0; i < PF_NST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); mbar_init(&wp_full[i], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&x_full[b], 1);
+      mbar_init(&xp_full[b], 1);
+      mbar_init(&out_full[b], 1);
+      mbar_init(&out_drained[b], 16);
+      mbar_init(&h_full[b], 1);
+      for (int k = 0; k < 4; ++k) { mbar_init(&s_done[b][k], 1); mbar_init(&r_done[b][k], 8); mbar_init(&h_ready[b][k], 8); }
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(&tmem_slot, 512);
+  if (threadIdx.x < 256) colmax_s[threadIdx.x] = 0u;
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // both CTAs' barriers and TMEM exist before any cross-CTA traffic
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ---- weight producer: this CTA's half (128 output columns) of each K-step ---------------------------------------
+    if (lane == 0) {
+      uint32_t st = 0, ph = 1;
+      for (int j = 0; j < np; ++j) {
+        for (int i = 0; i < PF2_WSTEPS; ++i) {
+          const int phase = i >> 2, kc = i & 3;
+          // blob chunk order: S (kc, nh), G1 (nh, kc), G2 (kc, nh)
+          const int chunk = phase == 1 ? 8 + (int)rank * 4 + kc : phase * 8 + kc * 2 + (int)rank;
+          mbar_wait(&w_empty[st], ph);
+          mbar_arrive_expect_tx(&w_full[st], PF_CHUNK);
+          tma_load_2d(wring + st * PF_CHUNK, &tm.w, &w_full[st], 0, chunk * 128);
+          if (++st == PF_NST) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 1) {
+    // ---- peer relay: tell the leader's MMA thread when this CTA's X tile / weight slot has landed ---------------------
+    if (lane == 0) {
+      uint32_t st = 0, wph = 0;
+      for (int j = 0; j < np; ++j) {
+        const int b = j & 1;
+        mbar_wait(&x_full[b], (uint32_t)(j >> 1) & 1u);
+        pf_arrive_remote(pf_mapa(smem_u32(&xp_full[b]), 0));
+        for (int i = 0; i < PF2_WSTEPS; ++i) {
+          mbar_wait(&w_full[st], wph);
+          pf_arrive_remote(pf_mapa(smem_u32(&wp_full[st]), 0));
+          if (++st == PF_NST) { st = 0; wph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer (leader CTA): M = 256 over the pair ---------------------------------------------------------------
+    constexpr uint32_t idesc = umma2_idesc_f16(256);
+    const uint64_t wdesc0 = umma_desc_k128(smem_u32(wring));
+    uint32_t st = 0, wph = 0;
+    auto wait_w = [&]() {
+      mbar_wait(&w_full[st], wph);
+      pf_wait_cluster(&wp_full[st], wph);
+    };
+    auto next_w = [&]() {
+      if (++st == PF_NST) { st = 0; wph ^= 1u; }
+    };
+    for (int j = 0; j < np; ++j) {
+      const int b = j & 1;
+      const uint32_t p2 = (uint32_t)(j >> 1) & 1u;
+      const uint32_t Ra = tmem_base + (uint32_t)b * 256u, Rb = tmem_base + (uint32_t)(b ^ 1) * 256u;
+      const uint64_t xdesc = umma_desc_k128(smem_u32(xbuf + b * PF_XBUF));
+      mbar_wait(&x_full[b], p2);
+      pf_wait_cluster(&xp_full[b], p2);
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {          // S: OUT = X . Ws^T
+        wait_w();
+        tc_fence_after();
+        if (pf_elect_one()) {
+          const uint64_t wd = pf_desc_add(wdesc0, st * (PF_CHUNK >> 4));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma2_f16_ss(Ra, pf_desc_add(xdesc, kc * (PF_CHUNK >> 4) + ks * 2), pf_desc_add(wd, ks * 2), idesc, (kc | ks) != 0);
+          umma2_commit(&w_empty[st]);
+          umma2_commit(&s_done[b][kc]);
+        }
+        __syncwarp();
+        next_w();
+      }
+      if (j > 0) pf_wait_cluster(&out_drained[b ^ 1], (uint32_t)((j - 1) >> 1) & 1u);
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {          // G1: H = relu(X) . W0^T
+        pf_wait_cluster(&r_done[b][kc], p2);
+        wait_w();
+        tc_fence_after();
+        if (pf_elect_one()) {
+          const uint64_t wd = pf_desc_add(wdesc0, st * (PF_CHUNK >> 4));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma2_f16_ss(Rb, pf_desc_add(xdesc, kc * (PF_CHUNK >> 4) + ks * 2), pf_desc_add(wd, ks * 2), idesc, (kc | ks) != 0);
+          umma2_commit(&w_empty[st]);
+          if (kc == 3) umma2_commit(&h_full[b]);
+        }
+        __syncwarp();
+        next_w();
+      }
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {          // G2: OUT += H16 . W1^T, A operand from TMEM
+        pf_wait_cluster(&h_ready[b][kc], p2);
+        wait_w();
+        tc_fence_after();
+        if (pf_elect_one()) {
+          const uint64_t wd = pf_desc_add(wdesc0, st * (PF_CHUNK >> 4));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma2_f16_ts(Ra, Rb + (uint32_t)((kc >> 1) * 128 + (kc & 1) * 32 + ks * 8), pf_desc_add(wd, ks * 2), idesc, 1);
+          umma2_commit(&w_empty[st]);
+          if (kc == 3) umma2_commit(&out_full[b]);
+        }
+        __syncwarp();
+        next_w();
+      }
+    }
+  } else if (warp < 6) {
+    // ---- H group ------------------------------------------------------------------------------------------------------
+    const int th = (int)threadIdx.x - 64;
+    const int q = warp & 3;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    for (int j = 0; j < np; ++j) {
+      const int b = j & 1;
+      const uint32_t p2 = (uint32_t)(j >> 1) & 1u;
+      int sample, n0;
+      tile_of(j, sample, n0);
+      uint8_t* xb = xbuf + b * PF_XBUF;
+      for (int kc = 0; kc < 4; ++kc) {
+        mbar_wait(&s_done[b][kc], p2);
+        uint4* p = reinterpret_cast<uint4*>(xb + kc * PF_CHUNK) + th;
+        const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint4 v = p[i * 128];
+          __half2* h = reinterpret_cast<__half2*>(&v);
+          h[0] = __hmax2(h[0], z); h[1] = __hmax2(h[1], z); h[2] = __hmax2(h[2], z); h[3] = __hmax2(h[3], z);
+          p[i * 128] = v;
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");     // generic writes -> async proxy (the leader's MMA reads this tile)
+        __syncwarp();
+        if (lane == 0) pf_arrive_leader(&r_done[b][kc], rank);
+      }
+      const float* bh = a.bias_h + (size_t)sample * 256;
+      const uint32_t tbase = tmem_base + (uint32_t)(b ^ 1) * 256u + lane_off;
+      mbar_wait(&h_full[b], p2);
+      tc_fence_after();
+#pragma unroll 1
+      for (int hsel = 0; hsel < 2; ++hsel) {
+        const uint32_t thh = tbase + (uint32_t)hsel * 128u;
+        uint32_t raw[2][32];
+        tmem_ld32(thh, raw[0]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float4 bv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bh + hsel * 128 + g * 32) + i);
+          tmem_ld_wait();
+          if (g < 3) tmem_ld32(thh + (g + 1) * 32, raw[(g + 1) & 1]);
+          const uint32_t* r = raw[g & 1];
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float f0 = fmaxf(__uint_as_float(r[4 * i]) + bv[i].x, 0.f), f1 = fmaxf(__uint_as_float(r[4 * i + 1]) + bv[i].y, 0.f);
+            const float f2 = fmaxf(__uint_as_float(r[4 * i + 2]) + bv[i].z, 0.f), f3 = fmaxf(__uint_as_float(r[4 * i + 3]) + bv[i].w, 0.f);
+            pk[2 * i] = pf_pack(f0, f1);
+            pk[2 * i + 1] = pf_pack(f2, f3);
+          }
+          tmem_st16(thh + g * 16, pk);
+          if (g & 1) {
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) pf_arrive_leader(&h_ready[b][hsel * 2 + (g >> 1)], rank);
+          }
+        }
+      }
+    }
+  } else {
+    // ---- O group ------------------------------------------------------------------------------------------------------
+    const int te = (int)threadIdx.x - 192;
+    const int q = warp & 3;
+    const int hsel = (warp - 6) >> 2;
+    const int row = q * 32 + lane;
+    const bool elected = te == 0;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    auto load_x = [&](int j) {
+      int sample, n0;
+      tile_of(j, sample, n0);
+      const int b = j & 1;
+      mbar_arrive_expect_tx(&x_full[b], PF_XBUF);
+      for (int kc = 0; kc < 4; ++kc) tma_load_3d(xbuf + b * PF_XBUF + kc * PF_CHUNK, &tm.xin, &x_full[b], kc * 64, n0, sample);
+    };
+    auto flush_colmax = [&](int sample) {
+      pf_epi_sync();
+      const unsigned v = colmax_s[te];
+      if (v) atomicMax(a.colmax + (size_t)sample * 256 + te, v);
+      colmax_s[te] = 0u;
+      pf_epi_sync();
+    };
+    if (elected) {
+      if (np > 0) load_x(0);
+      if (np > 1) load_x(1);
+    }
+    int cur_sample = -1;
+    for (int j = 0; j < np; ++j) {
+      const int b = j & 1;
+      const uint32_t p2 = (uint32_t)(j >> 1) & 1u;
+      int sample, n0;
+      tile_of(j, sample, n0);
+      uint8_t* xb = xbuf + b * PF_XBUF;
+      if (sample != cur_sample) {
+        if (cur_sample >= 0) flush_colmax(cur_sample);
+        cur_sample = sample;
+      }
+      const float* bo = a.bias_o + (size_t)sample * 256 + hsel * 128;
+      const uint32_t to = tmem_base + (uint32_t)b * 256u + (uint32_t)hsel * 128u + lane_off;
+      const bool valid = n0 + row < a.n_points;
+      mbar_wait(&out_full[b], p2);
+      tc_fence_after();
+      uint32_t raw[2][32];
+      tmem_ld32(to, raw[0]);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float4 bv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bo + g * 32) + i);
+        tmem_ld_wait();
+        if (g < 3) {
+          tmem_ld32(to + (g + 1) * 32, raw[(g + 1) & 1]);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) pf_arrive_leader(&out_drained[b], rank);
+        }
+        const uint32_t* r = raw[g & 1];
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          f[4 * i] = __uint_as_float(r[4 * i]) + bv[i].x; f[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bv[i].y;
+          f[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bv[i].z; f[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bv[i].w;
+        }
+        if (a.store_out) {
+          uint8_t* ct = xb + (hsel * 2 + (g >> 1)) * PF_CHUNK;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            *reinterpret_cast<uint4*>(ct + pf_sw128(row, (g & 1) * 4 + jj)) =
+                make_uint4(pf_pack(f[8 * jj], f[8 * jj + 1]), pf_pack(f[8 * jj + 2], f[8 * jj + 3]), pf_pack(f[8 * jj + 4], f[8 * jj + 5]),
+                           pf_pack(f[8 * jj + 6], f[8 * jj + 7]));
+        }
+        if (!valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = -INFINITY;
+        }
+        const float mine = pf_colmax32(f, lane);
+        atomicMax(&colmax_s[hsel * 128 + g * 32 + lane], f2ord(mine));
+      }
+      if (a.store_out) fence_proxy_async();
+      pf_epi_sync();
+      if (elected) {
+        if (a.store_out) {
+          for (int kc = 0; kc < 4; ++kc) tma_store_3d(&tm.xout, xb + kc * PF_CHUNK, kc * 64, n0, sample);
+          pf_store_commit();
+          pf_store_wait_read();
+        }
+        if (j + 2 < np) load_x(j + 2);
+      }
+    }
+    if (cur_sample >= 0) flush_colmax(cur_sample);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // the peer may still be reading this CTA's shared / tensor memory through the pair MMAs
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 g_pf_encode = nullptr;
 static int pf_encoder() {
@@ -841,8 +1225,19 @@ int pf_block_forward(const void* x_in, void* x_out, const void* w_blob, const fl
     SEEME_CUDA(cudaFuncSetAttribute(pointnet_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
     configured = true;
   }
-  const int grid = a.n_tiles < NUM_SMS ? a.n_tiles : NUM_SMS;
+  static bool configured2 = false;
+  if (!configured2) {
+    SEEME_CUDA(cudaFuncSetAttribute(pointnet_block_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    configured2 = true;
+  }
   ProfScope prof(prof_id - 1, s);
+  if (h_in_tmem == 2) {            // CTA pairs (cta_group::2): 74 clusters of 2
+    const int pairs = (a.n_tiles + 1) / 2 < NUM_SMS / 2 ? (a.n_tiles + 1) / 2 : NUM_SMS / 2;
+    pointnet_block_pair_kernel<<<2 * pairs, PF_THREADS, PF_SMEM, s>>>(maps, a);
+    SEEME_LAUNCH_CHECK();
+    return SEEME_OK;
+  }
+  const int grid = a.n_tiles < NUM_SMS ? a.n_tiles : NUM_SMS;
   if (h_in_tmem) pointnet_block_kernel<true><<<grid, PF_THREADS, PF_SMEM, s>>>(maps, a);
   else pointnet_block_kernel<false><<<grid, PF_THREADS, PF_SMEM, s>>>(maps, a);
   SEEME_LAUNCH_CHECK();

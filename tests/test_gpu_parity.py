@@ -177,7 +177,7 @@ def test_pointnet_full_size_properties(pn_op, weights):
     assert (pn_op(pr.to(DEV)).cpu() - ref).abs().max() < 1e-4
 
 
-@pytest.mark.parametrize("precision", [16, 17])
+@pytest.mark.parametrize("precision", [16, 17, 18])
 def test_pointnet_fused_fp16_vs_oracle(weights, precision):
     """Fused residual-block kernel (fp16 operands, fp32 accumulation; 16 = H operand in tensor memory, 17 = H through
     shared memory).  Bound: fp16 rounding of operands (2^-11 relative) through 9 chained contractions -> a few 1e-3 of
@@ -207,10 +207,10 @@ def test_pointnet_fused_variants_agree(weights):
     from seeme_b200 import ops, synthetic as S
     p = S.egobody_scene(2, 5000, torch.Generator().manual_seed(13)).to(DEV)
     outs = []
-    for precision in (16, 17):
+    for precision in (16, 17, 18):
         op = ops.PointNetOp(cu(weights["pointnet"]), cu(weights["output_scene"]), max_batch=2, max_points=5000, precision=precision)
         outs.append(op(p, want_feat=True)[1])
-    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
 # ---- SMPL -------------------------------------------------------------------------------------------------------
