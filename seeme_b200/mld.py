@@ -26,6 +26,23 @@ from .config import instantiate_from_config
 from .modules import MldDenoiser, MldVae, ProHMRScene, SMPL, time_sinusoid
 
 
+class PendingEval:
+    """Result of ``MLD.ego_eval_async``: the ``rs_set`` tensors are being produced on ``stream``."""
+
+    def __init__(self, rs_set, last_vertices, last_latent, event, stream):
+        self.rs_set, self.last_vertices, self.last_latent, self.event, self.stream = rs_set, last_vertices, last_latent, event, stream
+
+    def result(self):
+        """make the caller's current stream wait for the slot, then hand out the rs_set (device tensors)"""
+        torch.cuda.current_stream().wait_event(self.event)
+        return self.rs_set
+
+    def synchronize(self):
+        """block the host until the slot's work (including any device-to-host copies enqueued on ``stream``) is done"""
+        self.event.synchronize()
+        return self.rs_set
+
+
 class MLD(nn.Module):
     def __init__(self, cfg, datamodule, smpl_buffers: Optional[Dict[str, torch.Tensor]] = None, **kwargs):
         super().__init__()
@@ -109,6 +126,11 @@ class MLD(nn.Module):
         # which bodies get the 6890-vertex skinning: "rst" (predicted, default), "all", or "none";
         # the reference skins all three and discards the vertices (only joints reach rs_set)
         self.compute_vertices = kwargs.get("compute_vertices", "rst")
+        # concurrent sub-batches (see ego_eval): at most `lanes` lanes of at least `min_lane_batch` sequences each
+        self.lanes = int(kwargs.get("lanes", cfg.model.get("lanes", 1)))
+        self.min_lane_batch = int(kwargs.get("min_lane_batch", cfg.model.get("min_lane_batch", 32)))
+        # batches in flight for ego_eval_async / run_test_batches
+        self.pipeline_depth = int(kwargs.get("pipeline_depth", cfg.model.get("pipeline_depth", 4)))
         self.last_vertices: Dict[str, torch.Tensor] = {}
         self._uncond_scene = None
         self.eval()
@@ -157,10 +179,10 @@ class MLD(nn.Module):
             self.__dict__["_coef"] = self.scheduler.step_coefficients()
             self.__dict__["_sinus"] = time_sinusoid(self.scheduler.timesteps)
         op = self.denoiser.op
-        key = (id(op), tuple(ts))
-        if self.__dict__.get("_table_key") != key:
+        tables = self.__dict__.setdefault("_table_keys", {})          # per kernel-side handle (one per lane)
+        if tables.get(id(op)) != tuple(ts):
             op.set_time_table(ts, self.__dict__["_sinus"])
-            self.__dict__["_table_key"] = key
+            tables[id(op)] = tuple(ts)
         cond = encoder_hidden_states.permute(1, 0, 2).contiguous()         # [Nc,B',256] as the denoiser receives it
         z = op.sample(latents.reshape(bsz, 256), cond, self.guidance_scale, ts, self.__dict__["_coef"])
         return z.view(bsz, 1, 256).permute(1, 0, 2)
@@ -173,16 +195,128 @@ class MLD(nn.Module):
             return emb[None]
         # encode_scene(zeros) is input independent (every point identical -> the max-pool is that point,
         # SURVEY App. H8): computed once on a tiny all-zero cloud and cached per packed-weights handle
-        if self._uncond_scene is None or self._uncond_scene[0] is not op:
-            self._uncond_scene = (op, op(torch.zeros(1, 8, 3, device=scene.device)))
-        unc = self._uncond_scene[1].expand(emb.shape[0], -1)
+        cache = self._uncond_scene if isinstance(self._uncond_scene, dict) else {}
+        self._uncond_scene = cache
+        if id(op) not in cache or cache[id(op)][0] is not op:
+            cache[id(op)] = (op, op(torch.zeros(1, 8, 3, device=scene.device)))
+        unc = cache[id(op)][1].expand(emb.shape[0], -1)
         return torch.cat([emb, unc], dim=0)[None]                          # mld.py:1157-1158 (COND first)
 
     def ego_eval(self, batch, noise: Optional[Dict[str, torch.Tensor]] = None):
         """mld.py:1076-1905 (scene / scene+interactee / interactee-only branches).
         ``noise`` = {"eps_int", "eps_unc" [1,B,256], "x_T" [B,1,256]} injects the three draws; missing
-        entries are drawn with torch.randn in the reference's order."""
-        noise = noise or {}
+        entries are drawn with torch.randn in the reference's order.
+
+        Large batches are split into ``self.lanes`` contiguous sub-batches that run concurrently on their own CUDA
+        streams with their own kernel-side handles: the 50-step sampler is a latency-bound chain of small kernels that
+        leaves most SMs idle, so one lane's sampler overlaps the other lanes' scene encoder / VAE / SMPL work.  Every
+        stage is per-sample, so the results are those of the unsplit batch."""
+        noise = dict(noise or {})
+        B = batch[0].shape[0]
+        lanes = max(1, min(int(self.lanes), B // max(int(self.min_lane_batch), 1)))
+        if lanes <= 1 or not batch[0].is_cuda:
+            return self._ego_eval_one(batch, noise)
+        dev = batch[0].device
+        # the draws happen once, for the whole batch and in the reference's order (mld_vae.py:190-192, mld.py:449-453)
+        if "interactee" in self.condition:
+            if noise.get("eps_int") is None:
+                noise["eps_int"] = torch.randn(1, B, 256, device=dev, dtype=torch.float32)
+            if self.do_classifier_free_guidance and noise.get("eps_unc") is None:
+                noise["eps_unc"] = torch.randn(1, B, 256, device=dev, dtype=torch.float32)
+        if noise.get("x_T") is None:
+            noise["x_T"] = torch.randn((B, self.latent_dim[0], self.latent_dim[-1]), device=dev, dtype=torch.float)
+        from . import modules as _m
+        from .dist import shard_range
+        main = torch.cuda.current_stream(dev)
+        # one device->host read of the lengths for the whole batch (mld.py:1264); every lane decodes to max(lengths)
+        lengths_all = batch[5 if "scene" in self.condition else 4].long().reshape(-1).tolist()
+        t_max = int(max(lengths_all))
+        streams = self.__dict__.setdefault("_lane_streams", {})
+        outs = []
+        for k in range(lanes):
+            lo, hi = shard_range(B, k, lanes)
+            st = streams.get((dev, k))
+            if st is None:
+                st = streams[(dev, k)] = torch.cuda.Stream(device=dev)
+            sub = tuple((x[lo:hi] if torch.is_tensor(x) else x) for x in batch)
+            sub_noise = {"eps_int": None, "eps_unc": None, "x_T": noise["x_T"][lo:hi]}
+            for key in ("eps_int", "eps_unc"):
+                if noise.get(key) is not None:
+                    sub_noise[key] = noise[key][:, lo:hi].contiguous()
+            st.wait_stream(main)
+            _m._LANE[0] = k
+            try:
+                with torch.cuda.stream(st):
+                    outs.append(self._ego_eval_one(sub, sub_noise, defer_random=True, t_max=t_max, lengths=lengths_all[lo:hi]))
+            finally:
+                _m._LANE[0] = 0
+        # the lanes' outputs are consumed on the caller's stream after this join; the next call makes every lane stream
+        # wait for the caller's stream again before reusing memory, so no record_stream bookkeeping is needed
+        for k in range(lanes):
+            main.wait_stream(streams[(dev, k)])
+        rs_set = {}
+        for key, v0 in outs[0].items():
+            if torch.is_tensor(v0):
+                rs_set[key] = torch.cat([o[key] for o in outs], dim=0)
+            elif key == "lengths":
+                rs_set[key] = [x for o in outs for x in o[key]]
+            else:
+                rs_set[key] = v0
+        if "interactee" not in self.condition:                                # mld.py:1572-1574 (RNG side effect kept)
+            joints_int = torch.rand_like(rs_set["joints_rst"])
+            rs_set["joints_interactee"] = joints_int
+            rs_set["root_interactee"] = joints_int[:, :, 0:1, :]
+            rs_set["orientation_quat_int"] = torch.rand_like(rs_set["orientation_quat_rst"])
+        lv = [o.pop("_last_vertices") for o in outs]
+        self.last_vertices = {k: (None if lv[0][k] is None else torch.cat([d[k] for d in lv], dim=0)) for k in lv[0]}
+        self.last_latent = torch.cat([o.pop("_last_latent") for o in outs], dim=1)
+        rs_set.pop("_last_vertices", None)
+        rs_set.pop("_last_latent", None)
+        return rs_set
+
+    # ------------------------------------------------------------------------------------------
+    def ego_eval_async(self, batch, noise: Optional[Dict[str, torch.Tensor]] = None) -> "PendingEval":
+        """Enqueue ``ego_eval(batch)`` on the next pipeline slot and return immediately.
+
+        The 50-step sampler is a ~26 ms latency-bound chain of small kernels that leaves most SMs idle, while the scene
+        encoder / VAE / SMPL stages are throughput-bound; with ``pipeline_depth`` batches in flight -- each slot has its
+        own CUDA stream and its own kernel-side handles (workspaces, sampler graph) -- batch k+1's scene encoder runs
+        under batch k's sampler.  CPU tensors in ``batch`` / ``noise`` (pinned host memory) are copied on the slot's
+        stream, so the copies overlap other slots' compute as well.  ``PendingEval.result()`` makes the caller's current
+        stream wait for the slot and returns the ``rs_set``; slots are reused round-robin, so at most
+        ``pipeline_depth`` results should be outstanding."""
+        from . import modules as _m
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("MLD (sm_100a): parameters are on the CPU; seeme_b200 runs on CUDA only")
+        depth = max(1, int(self.pipeline_depth))
+        slot = self.__dict__.get("_next_slot", 0) % depth
+        self.__dict__["_next_slot"] = slot + 1
+        streams = self.__dict__.setdefault("_slot_streams", {})
+        st = streams.get((dev, slot))
+        if st is None:
+            st = streams[(dev, slot)] = torch.cuda.Stream(device=dev)
+        st.wait_stream(torch.cuda.current_stream(dev))          # device inputs were produced on the caller's stream
+        lane = _m._LANE[0]
+        _m._LANE[0] = 1000 + slot                                # handles of this slot (distinct from the lanes' handles)
+        try:
+            with torch.cuda.stream(st):
+                b = tuple((x.to(dev, non_blocking=True) if torch.is_tensor(x) and not x.is_cuda else x) for x in batch)
+                n = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and not v.is_cuda else v) for k, v in (noise or {}).items()}
+                rs = self._ego_eval_one(b, n, defer_random=True)
+                if "interactee" not in self.condition:            # mld.py:1572-1574 (RNG side effect kept)
+                    joints_int = torch.rand_like(rs["joints_rst"])
+                    rs["joints_interactee"] = joints_int
+                    rs["root_interactee"] = joints_int[:, :, 0:1, :]
+                    rs["orientation_quat_int"] = torch.rand_like(rs["orientation_quat_rst"])
+                ev = torch.cuda.Event()
+                ev.record(st)
+        finally:
+            _m._LANE[0] = lane
+        return PendingEval(rs, rs.pop("_last_vertices"), rs.pop("_last_latent"), ev, st)
+
+    def _ego_eval_one(self, batch, noise, defer_random: bool = False, t_max: Optional[int] = None, lengths=None):
+        """one (sub-)batch on the current stream with the current lane's handles"""
         if "scene" in self.condition:
             feats_ref, transl, beta, utils_, scene, length, dict_images = batch
             scene_emb = self._encode_scene(scene)                          # [1,B or 2B,256]
@@ -191,16 +325,17 @@ class MLD(nn.Module):
             scene_emb = None
         feats_ref, transl, beta = feats_ref.float(), transl.float(), beta.float()
         dev = feats_ref.device
-        lengths = length.long().reshape(-1).tolist()                       # mld.py:1264
+        if lengths is None:
+            lengths = length.long().reshape(-1).tolist()                   # mld.py:1264
         len_dev = length.reshape(-1).to(torch.int32)
         start = time.time()
         f_ref_int = None
         if "interactee" in self.condition:
             f_ref_int = torch.cat([feats_ref[:, :, 1, :], transl[:, 1, :, :]], dim=-1).contiguous()
             B, T, _ = f_ref_int.shape
-            text_emb, _ = self.vae.encode(f_ref_int, None, lengths, eps=noise.get("eps_int"))
+            text_emb, _ = self.vae.encode(f_ref_int, None, lengths, eps=noise.get("eps_int"), lengths_dev=len_dev)
             if self.do_classifier_free_guidance:
-                unc, _ = self.vae.encode(torch.zeros_like(f_ref_int), None, lengths, eps=noise.get("eps_unc"))
+                unc, _ = self.vae.encode(torch.zeros_like(f_ref_int), None, lengths, eps=noise.get("eps_unc"), lengths_dev=len_dev)
                 text_emb = torch.cat([unc, text_emb], dim=1)               # mld.py:1290 (UNCOND first)
             cond_emb = torch.cat([text_emb, scene_emb], dim=0) if scene_emb is not None else text_emb
         else:
@@ -208,7 +343,7 @@ class MLD(nn.Module):
         if cond_emb is None:
             raise NotImplementedError("MLD (sm_100a): at least one of scene / interactee conditioning is required")
         z = self._diffusion_reverse(cond_emb.permute(1, 0, 2), lengths, latents=noise.get("x_T"))
-        feats_rst = self.vae.decode(z, lengths)                            # [B,max(lengths),nfeats_net]
+        feats_rst = self.vae.decode(z, lengths, T=t_max, lengths_dev=len_dev)   # [B,max(lengths),nfeats_net]
         self.times.append(time.time() - start)                             # mld.py:1367-1368 (no device sync, like the reference)
 
         min_len = min(feats_ref.shape[1], feats_rst.shape[1])
@@ -240,16 +375,21 @@ class MLD(nn.Module):
             _, v_int, joints_int, quat_int = self._body(f_ref_int[:, :min_len].contiguous(), beta[:, 1, :min_len, :].contiguous(),
                                                         mean, std, 69, want_all, want_m=False)
             rs_set["joints_interactee"] = joints_int
-            rs_set["root_interactee"] = joints_int[:, :, [0], :]
+            rs_set["root_interactee"] = joints_int[:, :, 0:1, :]
             rs_set["orientation_quat_int"] = quat_int
-        else:
+        elif not defer_random:
             joints_int = torch.rand_like(joints_rst)                        # mld.py:1572-1574 (RNG side effect kept)
             rs_set["joints_interactee"] = joints_int
-            rs_set["root_interactee"] = joints_int[:, :, [0], :]
+            rs_set["root_interactee"] = joints_int[:, :, 0:1, :]
             rs_set["orientation_quat_int"] = torch.rand_like(quat_rst)
-        self.last_vertices = {k: (None if v is None else v.view(Bsz, min_len, 6890, 3))
-                              for k, v in (("rst", v_rst), ("ref", v_ref), ("int", v_int))}
-        self.last_latent = z
+        last_vertices = {k: (None if v is None else v.view(Bsz, min_len, 6890, 3))
+                         for k, v in (("rst", v_rst), ("ref", v_ref), ("int", v_int))}
+        if defer_random:       # lane mode: the caller merges these
+            rs_set["_last_vertices"] = last_vertices
+            rs_set["_last_latent"] = z
+        else:
+            self.last_vertices = last_vertices
+            self.last_latent = z
         return rs_set
 
     def _body(self, feats, betas, mean, std, n_body, want_v, want_m=True):
@@ -270,6 +410,28 @@ class MLD(nn.Module):
 
     def test_step(self, batch, batch_idx):                                  # base.py:44-53
         return self.allsplit_step("test", batch, batch_idx)
+
+    def run_test_batches(self, batches, split: str = "test"):
+        """The test loop of ``trainer.test`` (base.py:44-53 per batch) with ``pipeline_depth`` batches in flight:
+        batch k's metric update runs while batches k+1.. are on the GPU.  Yields ``joints_rst`` per batch, in order."""
+        from collections import deque
+        pending = deque()
+
+        def retire():
+            rs_set = pending.popleft().result()
+            for metric in self.metrics_dict:
+                getattr(self, metric).update(
+                    split, rs_set["joints_rst"], rs_set["joints_ref"], rs_set["orientation_quat_rst"],
+                    rs_set["orientation_quat_ref"], rs_set["root_interactee"], rs_set["joints_interactee"],
+                    rs_set["orientation_quat_int"], rs_set["joints_interactee_gt"], rs_set["lengths"], rs_set["list_names"])
+            return rs_set["joints_rst"]
+
+        for batch in batches:
+            pending.append(self.ego_eval_async(batch))
+            if len(pending) >= max(1, int(self.pipeline_depth)):
+                yield retire()
+        while pending:
+            yield retire()
 
     def validation_step(self, batch, batch_idx):
         return self.allsplit_step("val", batch, batch_idx)

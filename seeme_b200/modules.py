@@ -30,6 +30,11 @@ def _register_spec(root: nn.Module, spec: Dict[str, tuple]) -> None:
         mod.register_parameter(parts[-1], nn.Parameter(torch.zeros(shape), requires_grad=False))
 
 
+# Execution lane (see MLD.ego_eval): kernel-side handles own their workspace and are not re-entrant, so every lane --
+# a sub-batch running on its own CUDA stream -- gets its own handle.  Set by ``MLD`` around a lane's calls.
+_LANE = [0]
+
+
 class _PackedModule(nn.Module):
     """Tracks parameter versions/devices so the C-side packed weights are rebuilt when they change."""
 
@@ -37,6 +42,7 @@ class _PackedModule(nn.Module):
         return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
 
     def _op(self, key, factory):
+        key = (key, _LANE[0])
         cache = self.__dict__.setdefault("_op_cache", {})
         sig = self._signature()
         ent = cache.get(key)
@@ -166,21 +172,26 @@ class MldVae(_PackedModule):
         z, dist = self.encode(features, None, lengths)
         return self.decode(z, lengths), z, dist
 
-    def encode(self, features, images=None, lengths: Optional[List[int]] = None, eps: Optional[torch.Tensor] = None):
+    def encode(self, features, images=None, lengths: Optional[List[int]] = None, eps: Optional[torch.Tensor] = None,
+               lengths_dev: Optional[torch.Tensor] = None):
         """[B,T,nfeats] -> (latent [1,B,256], Normal(mu,std)).  ``eps`` ([1,B,256]) is the N(0,1) draw of
-        ``rsample``; when None it is drawn with ``torch.randn`` on the features' device."""
+        ``rsample``; when None it is drawn with ``torch.randn`` on the features' device.  ``lengths_dev``: the same
+        lengths already on the device (avoids a blocking host-to-device copy in the middle of the stream)."""
         if lengths is None:
             lengths = [len(f) for f in features]
         B = features.shape[0]
         if eps is None:
             eps = torch.randn(1, B, self.latent_dim, device=features.device, dtype=torch.float32)
-        z, mu, std = self.op.encode(features, torch.as_tensor(lengths), eps)
+        z, mu, std = self.op.encode(features, lengths_dev if lengths_dev is not None else torch.as_tensor(lengths), eps)
         dist = torch.distributions.Normal(mu.unsqueeze(0), std.unsqueeze(0), validate_args=False)
         return z.unsqueeze(0), dist
 
-    def decode(self, z, lengths: List[int]):
-        """z [1,B,256] -> [B,max(lengths),nfeats]"""
-        T = int(max(lengths))
+    def decode(self, z, lengths: List[int], T: Optional[int] = None, lengths_dev: Optional[torch.Tensor] = None):
+        """z [1,B,256] -> [B,max(lengths),nfeats]  (``T`` overrides max(lengths): a sub-batch decoded to the frame count of
+        the whole batch; ``lengths_dev``: the lengths already on the device)"""
+        T = int(max(lengths)) if T is None else int(T)
+        if lengths_dev is not None:
+            return self.op.decode(z.reshape(-1, self.latent_dim), lengths_dev, T)
         return self.op.decode(z.reshape(-1, self.latent_dim), torch.as_tensor(lengths), T)
 
 
@@ -215,14 +226,15 @@ class ResnetPointnet(_PackedModule):
         lin = output_scene[1]
         sig_extra = (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version)
         cache = self.__dict__.setdefault("_op_cache", {})
-        ent = cache.get("pn")
+        key = ("pn", _LANE[0])
+        ent = cache.get(key)
         sig = (self._signature(), sig_extra, self.precision)
         if ent is None or ent[0] != sig:
             if ent is not None:
                 ent[1].close()
-            cache["pn"] = (sig, ops.PointNetOp(self.state_dict(), {"1.weight": lin.weight, "1.bias": lin.bias},
-                                               self.max_batch, self.max_points, precision=self.precision))
-        return cache["pn"][1]
+            cache[key] = (sig, ops.PointNetOp(self.state_dict(), {"1.weight": lin.weight, "1.bias": lin.bias},
+                                              self.max_batch, self.max_points, precision=self.precision))
+        return cache[key][1]
 
     def forward(self, p):
         _, feat = self.op()(p, want_feat=True)

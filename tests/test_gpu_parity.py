@@ -357,6 +357,64 @@ def test_ego_eval_vs_unmodified_reference_golden(name, config, gs):
     assert "Metrics/MPJPE" in m
 
 
+def test_ego_eval_lanes_match_single_lane():
+    """sub-batches on concurrent streams (lanes) give the results of the unsplit batch: every stage is per-sample"""
+    import seeme_b200
+    from seeme_b200 import synthetic as S
+    B = 70                                     # ragged split: 35 + 35 with min_lane_batch 32
+    batch = S.make_batch(B, n_points=600, ragged=True)
+    batch = tuple(x.to(DEV) if torch.is_tensor(x) else x for x in batch)
+    g = torch.Generator().manual_seed(11)
+    noise = {"eps_int": torch.randn(1, B, 256, generator=g).to(DEV), "eps_unc": torch.randn(1, B, 256, generator=g).to(DEV),
+             "x_T": torch.randn(B, 1, 256, generator=g).to(DEV)}
+    res = []
+    for lanes in (1, 2):
+        model = seeme_b200.build_model("config_mld_egobody.yaml", device=DEV, guidance_scale=7.5, max_batch=B, n_points=600, lanes=lanes)
+        rs = model.ego_eval(batch, noise)
+        torch.cuda.synchronize()
+        res.append((rs, model.last_vertices["rst"].clone(), model.last_latent.clone()))
+    (a, va, za), (b, vb, zb) = res
+    assert a["lengths"] == b["lengths"]
+    for k in ("m_rst", "joints_rst", "joints_ref", "orientation_quat_rst", "joints_interactee", "orientation_quat_int"):
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(va, vb) and torch.equal(za, zb)
+    # the no-noise path draws for the whole batch up front, in the reference's order
+    torch.manual_seed(5)
+    r1 = res[1][0]  # keep model alive
+    model = seeme_b200.build_model("config_mld_egobody.yaml", device=DEV, guidance_scale=7.5, max_batch=B, n_points=600, lanes=2)
+    out = model.test_step(batch, 0)
+    assert out.shape == (B, 60, 24, 3) and bool(torch.isfinite(out).all())
+
+
+def test_ego_eval_async_pipeline_matches_sync():
+    """several batches in flight on the pipeline slots (own streams + handles, host-resident inputs copied on the slot's
+    stream) give exactly the results of the synchronous call"""
+    import seeme_b200
+    from seeme_b200 import synthetic as S
+    B = 6
+    model = seeme_b200.build_model("config_mld_egobody.yaml", device=DEV, guidance_scale=7.5, max_batch=B, n_points=500, pipeline_depth=2)
+    batches, noises = [], []
+    for i in range(5):
+        b = S.make_batch(B, seed=100 + i, n_points=500, ragged=True)
+        g = torch.Generator().manual_seed(200 + i)
+        batches.append(tuple(x.pin_memory() if torch.is_tensor(x) else x for x in b))
+        noises.append({"eps_int": torch.randn(1, B, 256, generator=g).pin_memory(), "eps_unc": torch.randn(1, B, 256, generator=g).pin_memory(),
+                       "x_T": torch.randn(B, 1, 256, generator=g).pin_memory()})
+    pend = [model.ego_eval_async(b, n) for b, n in zip(batches, noises)]          # more submissions than slots
+    got = [p.synchronize() for p in pend]
+    for b, n, r in zip(batches, noises, got):
+        ref = model.ego_eval(tuple(x.to(DEV) if torch.is_tensor(x) else x for x in b), {k: v.to(DEV) for k, v in n.items()})
+        assert ref["lengths"] == r["lengths"]
+        for k in ("m_rst", "joints_rst", "joints_ref", "orientation_quat_rst", "joints_interactee"):
+            assert torch.equal(ref[k], r[k]), k
+    # the pipelined test loop updates the metric for every batch, in order
+    model.EgoMetric.reset()
+    outs = list(model.run_test_batches(batches))
+    assert len(outs) == 5 and all(o.shape == (B, 60, 24, 3) for o in outs)
+    m = model.on_test_epoch_end()
+    assert "Metrics/MPJPE" in m
+
+
 def test_error_conventions(den_op, vae_op):
     with pytest.raises(RuntimeError, match="capacity"):
         den_op.forward(torch.zeros(65, 256, device=DEV), 1, torch.zeros(1, 65, 256, device=DEV))
