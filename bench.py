@@ -39,7 +39,7 @@ def workload(batch):
                         "of the predicted body, joints for GT and interactee bodies",
             "batch_per_gpu": batch, "ddim_steps": 50, "guidance_scale": GUIDANCE, "scene_points": N_POINTS, "frames": 60,
             "l2_policy": "per-step inputs+activations (>= 1.3 GB per 128-cloud chunk) exceed the 126 MB L2; no flush needed",
-            "pipeline": "MLD.ego_eval_async with 4 batches in flight, each on its own CUDA stream and kernel-side handles: the "
+            "pipeline": "MLD.ego_eval_async with 6 batches in flight, each on its own CUDA stream and kernel-side handles: the "
                         "latency-bound 50-step sampler chain of batch k overlaps the scene encoder / VAE / SMPL kernels of "
                         "batches k+1..; kernels.single_batch_* gives the unpipelined numbers"}
 

@@ -22,6 +22,7 @@
 #include "umma.cuh"
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace seeme {
 
@@ -423,7 +424,11 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
   // 64-wide tiles: the whole K = 256 of a latency-bound GEMM is in flight at once (4 stages), one CTA per SM.
   // 128-wide tiles (many rows): a shallow ring (64 KB in split mode) and one staging buffer keep the footprint
   // small enough for 2-3 CTAs per SM, which is what overlaps TMA, MMA and epilogue phases across tiles.
-  if (BN == 64) return npass == 1 ? launch<64, 1, 4, 1, 1>(g, maps, e, s) : launch<64, 3, 4, 1, 1>(g, maps, e, s);
+  if (BN == 64) {
+    static const bool small = !(getenv("SEEME_UMMA64_STAGES4") && getenv("SEEME_UMMA64_STAGES4")[0] == '1');
+    if (npass == 1) return launch<64, 1, 4, 1, 1>(g, maps, e, s);
+    return small ? launch<64, 3, 2, 1, 2>(g, maps, e, s) : launch<64, 3, 4, 1, 1>(g, maps, e, s);
+  }
   return npass == 1 ? launch<128, 1, 2, 1, 2>(g, maps, e, s) : launch<128, 3, 1, 1, 2>(g, maps, e, s);
 }
 

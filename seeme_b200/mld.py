@@ -130,7 +130,7 @@ class MLD(nn.Module):
         self.lanes = int(kwargs.get("lanes", cfg.model.get("lanes", 1)))
         self.min_lane_batch = int(kwargs.get("min_lane_batch", cfg.model.get("min_lane_batch", 32)))
         # batches in flight for ego_eval_async / run_test_batches
-        self.pipeline_depth = int(kwargs.get("pipeline_depth", cfg.model.get("pipeline_depth", 4)))
+        self.pipeline_depth = int(kwargs.get("pipeline_depth", cfg.model.get("pipeline_depth", 6)))
         self.last_vertices: Dict[str, torch.Tensor] = {}
         self._uncond_scene = None
         self.eval()
