@@ -74,3 +74,15 @@ def test_metric_allreduce_world2_gloo(tmp_path):
     assert got["compute"]["MPJPE"] == pytest.approx(ref.compute()["MPJPE"], rel=1e-12)
     assert got["n_rec"] == 15 and got["work0"] == [(s, r) for s in range(3) for r in range(3)]
     assert got["rec_ranks"] == [0.0] * 9 + [1.0] * 6
+
+
+def test_replication_statistics_match_reference_formula():
+    """seeme_b200.driver.summarize = test.py:32-38,138-148 (mean, 1.96 std / sqrt(n), min, max + raw lists)"""
+    import numpy as np
+    from seeme_b200.driver import summarize
+    vals = [12.5, 11.0, 13.25, 12.0]
+    out = summarize({"Metrics/MPJPE": vals}, 4)
+    a = np.array(vals)
+    assert out["Metrics/MPJPE/mean"] == float(a.mean())
+    assert abs(out["Metrics/MPJPE/conf_interval"] - 1.96 * a.std() / 2.0) < 1e-12
+    assert out["Metrics/MPJPE/min"] == 11.0 and out["Metrics/MPJPE/max"] == 13.25 and out["Metrics/MPJPE"] == vals
