@@ -46,6 +46,7 @@ struct PfArgs {
   const float* bias_o;   // [samples, 256]  cs: added to OUT
   unsigned* colmax;      // [samples, 256]  order-preserving uint, zeroed by the caller
   int store_out;
+  const uint8_t* wblob;  // 24 pre-swizzled 16 KB weight chunks (byte image of the shared-memory tiles)
 };
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -57,6 +58,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
                "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// plain (non-tensor) bulk copy of `bytes` contiguous bytes global -> shared, completion on an mbarrier.  The weight chunks
+// are stored in global memory as the byte image of their SWIZZLE_128B shared-memory tile, so one 16 KB burst replaces a
+// 128-row tiled TMA box (128 separate 128-byte requests).
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
 __device__ __forceinline__ void pf_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -164,7 +173,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
         for (int i = 0; i < PF_WCHUNKS; ++i) {
           mbar_wait(&w_empty[st], ph);
           mbar_arrive_expect_tx(&w_full[st], PF_CHUNK);
-          tma_load_2d(wring + st * PF_CHUNK, &tm.w, &w_full[st], 0, i * 128);
+          bulk_load(wring + st * PF_CHUNK, a.wblob + (size_t)i * PF_CHUNK, PF_CHUNK, &w_full[st]);
           if (++st == PF_NST) { st = 0; ph ^= 1u; }
         }
       }
@@ -437,6 +446,7 @@ struct P0Args {
   const float* cst0;     // [256]  Ws bp + b1
   const float4* pfold;   // [256]  (Ws Wp)[c][0..2], 0
   unsigned* colmax;
+  const uint8_t* wblob;  // 24 pre-swizzled 16 KB weight chunks
 };
 
 __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block0_kernel(const __grid_constant__ PfMaps tm, const P0Args a) {
@@ -482,7 +492,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block0_kernel(const __
         for (int i = 0; i < PF_WCHUNKS; ++i) {
           mbar_wait(&w_empty[st], ph);
           mbar_arrive_expect_tx(&w_full[st], PF_CHUNK);
-          tma_load_2d(wring + st * PF_CHUNK, &tm.w, &w_full[st], 0, i * 128);
+          bulk_load(wring + st * PF_CHUNK, a.wblob + (size_t)i * PF_CHUNK, PF_CHUNK, &w_full[st]);
           if (++st == PF_NST) { st = 0; ph ^= 1u; }
         }
       }
@@ -839,7 +849,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PF_THREADS, 1)
           const int chunk = phase == 1 ? 8 + (int)rank * 4 + kc : phase * 8 + kc * 2 + (int)rank;
           mbar_wait(&w_empty[st], ph);
           mbar_arrive_expect_tx(&w_full[st], PF_CHUNK);
-          tma_load_2d(wring + st * PF_CHUNK, &tm.w, &w_full[st], 0, chunk * 128);
+          bulk_load(wring + st * PF_CHUNK, a.wblob + (size_t)chunk * PF_CHUNK, PF_CHUNK, &w_full[st]);
           if (++st == PF_NST) { st = 0; ph ^= 1u; }
         }
       }
@@ -1124,7 +1134,11 @@ static int pf_w_map(CUtensorMap* map, const void* ptr) {
   return SEEME_OK;
 }
 
-// chunk blob layout (24 x [128, 64] fp16): S (kc, nh) from Ws[:, :256]; G1 (nh, kc) from W0[:, :256]; G2 (kc, nh) from W1
+// element index of (row r, column cc) inside a [128 x 64] fp16 chunk stored as its SWIZZLE_128B shared-memory image
+__device__ __forceinline__ int pf_swz_elem(int r, int cc) { return r * 64 + ((((cc >> 3) ^ (r & 7)) << 3) | (cc & 7)); }
+
+// chunk blob layout (24 x [128, 64] fp16, each the byte image of its swizzled shared-memory tile):
+// S (kc, nh) from Ws[:, :256]; G1 (nh, kc) from W0[:, :256]; G2 (kc, nh) from W1
 __global__ void pf_pack_weights_kernel(const float* __restrict__ ws, const float* __restrict__ w0, const float* __restrict__ w1,
                                        __half* __restrict__ blob) {
   const int chunk = blockIdx.x;
@@ -1135,7 +1149,7 @@ __global__ void pf_pack_weights_kernel(const float* __restrict__ ws, const float
   const int ld = phase == 2 ? 256 : 512;
   for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) {
     const int r = i / 64, cc = i % 64;
-    blob[(size_t)chunk * 128 * 64 + i] = __float2half_rn(src[(size_t)(nh * 128 + r) * ld + kc * 64 + cc]);
+    blob[(size_t)chunk * 128 * 64 + pf_swz_elem(r, cc)] = __float2half_rn(src[(size_t)(nh * 128 + r) * ld + kc * 64 + cc]);
   }
 }
 
@@ -1149,7 +1163,7 @@ __global__ void pf_pack_weights0_kernel(const float* __restrict__ w0, const floa
   const int ld = g1 ? 512 : 256;
   for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) {
     const int r = i / 64, cc = i % 64;
-    blob[(size_t)chunk * 128 * 64 + i] = __float2half_rn(src[(size_t)(nh * 128 + r) * ld + kc * 64 + cc]);
+    blob[(size_t)chunk * 128 * 64 + pf_swz_elem(r, cc)] = __float2half_rn(src[(size_t)(nh * 128 + r) * ld + kc * 64 + cc]);
   }
 }
 
@@ -1184,6 +1198,7 @@ int pf_block0_forward(const float* xyz, void* x_out, const void* w_blob, const v
   a.b0 = b0; a.cst0 = cst0;
   a.pfold = reinterpret_cast<const float4*>(pfold);
   a.colmax = colmax;
+  a.wblob = reinterpret_cast<const uint8_t*>(w_blob);
   static bool configured = false;
   if (!configured) {
     SEEME_CUDA(cudaFuncSetAttribute(pointnet_block0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P0_SMEM));
@@ -1219,6 +1234,7 @@ int pf_block_forward(const void* x_in, void* x_out, const void* w_blob, const fl
   a.n_tiles = a.tiles_per_sample * samples;
   a.bias_h = bias_h; a.bias_o = bias_o; a.colmax = colmax;
   a.store_out = x_out != nullptr;
+  a.wblob = reinterpret_cast<const uint8_t*>(w_blob);
   static bool configured = false;
   if (!configured) {
     SEEME_CUDA(cudaFuncSetAttribute(pointnet_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
