@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libseeme_b200.so")
+# SEEME_B200_LIB selects another build of the SAME library (e.g. the -DPF_TRACE instrumented one of tools/pf_trace.py)
+LIB_PATH = os.environ.get("SEEME_B200_LIB") or os.path.join(_HERE, "lib", "libseeme_b200.so")
 
 _lib = None
 

@@ -140,7 +140,8 @@ struct seeme_pointnet {
   unsigned* pool_ord;
   // fused fp16 path (precision 16 / 17): per-block weight-chunk blobs for blocks 1..3
   void* blob[4] = {nullptr, nullptr, nullptr, nullptr};
-  void* wpb = nullptr;     // [512] float4 (Wp row, bp) for the on-chip fc_pos of the fused block 0
+  void* wpb = nullptr;     // [512] float4 (Wp row, bp) for the on-chip fc_pos of the fused block 0 (CUDA-core generator)
+  void* ctblob = nullptr;  // 2 x 16 KB constant MMA tiles of the tensor-core block 0 (pf_pack_block0_ct)
 };
 
 static int copy_w(Arena& a, float*& dst, const float* src, size_t n) {
@@ -180,7 +181,7 @@ static int pointnet_create(seeme_pointnet_t* out, const float* const* w, int n_w
   const int chunk_cap = fused ? 128 : 32;
   h->chunk = max_batch < chunk_cap ? max_batch : chunk_cap;
   const size_t rows = (size_t)h->chunk * (max_points < 128 ? 128 : max_points);
-  size_t wbytes = 4 * pad256(pf_blob_bytes()) + pad256(512 * 16) + pad256(512 * 3 * 4) + pad256(512 * 4) + 4 * (pad256(256 * 512 * 4) * 2 + pad256(256 * 256 * 4) + 2 * pad256(256 * 4)) +
+  size_t wbytes = 4 * pad256(pf_blob_bytes()) + pad256(512 * 16) + pad256(32768) + pad256(512 * 3 * 4) + pad256(512 * 4) + 4 * (pad256(256 * 512 * 4) * 2 + pad256(256 * 256 * 4) + 2 * pad256(256 * 4)) +
                   pad256(512 * 256 * 4) + pad256(512 * 4) + pad256(256 * 512 * 4) + pad256(256 * 4) +
                   8 * 2 * pad256(256 * 512 * 2) + pad256(256 * 4 * 4) + pad256(256 * 4);
   size_t ws = 4 * pad256((size_t)max_batch * 256 * 4) + pad256((size_t)max_batch * 512 * 4) + pad256((size_t)max_batch * 128 * 3 * 4);
@@ -239,7 +240,8 @@ static int pointnet_create(seeme_pointnet_t* out, const float* const* w, int n_w
       if (fused) {
         h->blob[0] = h->arena.take<char>(pf_blob_bytes());
         h->wpb = h->arena.take<char>(512 * 16);
-        if (!h->blob[0] || !h->wpb) { set_error("pointnet: arena exhausted (weight blobs)"); rc = SEEME_ENOMEM; }
+        h->ctblob = h->arena.take<char>(32768);
+        if (!h->blob[0] || !h->wpb || !h->ctblob) { set_error("pointnet: arena exhausted (weight blobs)"); rc = SEEME_ENOMEM; }
         else rc = pf_pack_block0(h->w0[0], h->w1[0], h->fc_pos_w, h->fc_pos_b, h->blob[0], h->wpb);
         for (int i = 1; i < 4 && !rc; ++i) {
           h->blob[i] = h->arena.take<char>(pf_blob_bytes());
@@ -255,6 +257,10 @@ static int pointnet_create(seeme_pointnet_t* out, const float* const* w, int n_w
       }
       if (rc) { destroy(h); return rc; }
       pointnet_fold_kernel<<<1, 256>>>(h->ws[0], h->fc_pos_w, h->fc_pos_b, h->b1[0], h->pfold, h->cst0);
+      if (fused) {
+        rc = pf_pack_block0_ct(h->fc_pos_w, h->fc_pos_b, h->b0[0], h->pfold, h->cst0, h->ctblob);
+        if (rc) { destroy(h); return rc; }
+      }
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { set_error("seeme_pointnet_create: weight packing failed: %s", cudaGetErrorString(e)); destroy(h); return SEEME_ECUDA; }
     }
@@ -386,8 +392,8 @@ static int blocks_tensor(seeme_pointnet* h, const float* p, int C, int N, cudaSt
 // shortcut as a rank-3 fold in the epilogue.
 static int blocks_fused(seeme_pointnet* h, const float* p, int C, int N, cudaStream_t s) {
   SEEME_CUDA(cudaMemsetAsync(h->pool_ord, 0, (size_t)C * 256 * sizeof(unsigned), s));
-  SEEME_TRY(pf_block0_forward(p, h->xh[0], h->blob[0], h->wpb, h->b0[0], h->cst0, h->pfold, h->pool_ord, C, N,
-                              PROF_POINTNET_FUSED + 1, s));
+  SEEME_TRY(pf_block0_forward(p, h->xh[0], h->blob[0], h->wpb, h->ctblob, h->b0[0], h->cst0, h->pfold, h->pool_ord, C, N,
+                              PROF_POINTNET_FUSED + 2, s));   // block 0 has its own profile slot (7)
   int cur = 0;
   for (int i = 1; i < 4; ++i) {
     SEEME_TRY(decode_pool(h, C, s));

@@ -32,6 +32,19 @@
 
 namespace seeme {
 
+// Optional event trace (build with -DPF_TRACE): CTA 0 records clock64() at protocol events of its first tiles into
+// pf_trace[tile][slot]; read back with seeme_pf_trace_read (tools/pf_trace.py).
+#ifdef PF_TRACE
+constexpr int PF_TRACE_TILES = 24, PF_TRACE_SLOTS = 64;
+__device__ long long pf_trace[PF_TRACE_TILES * PF_TRACE_SLOTS];
+#define PF_TR(tile, slot)                                                                                 \
+  do {                                                                                                    \
+    if (blockIdx.x == 0 && (tile) < PF_TRACE_TILES) pf_trace[(tile) * PF_TRACE_SLOTS + (slot)] = clock64(); \
+  } while (0)
+#else
+#define PF_TR(tile, slot) do { } while (0)
+#endif
+
 constexpr int PF_NST = 6;                           // weight ring depth
 constexpr int PF_CHUNK = 128 * 128;                 // [128 rows x 64 fp16], SWIZZLE_128B
 constexpr int PF_XBUF = 4 * PF_CHUNK;               // one activation tile [128 x 256] fp16
@@ -716,6 +729,368 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block0_kernel(const __
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Block 0, tensor-core generator (default).  ncu on the kernel above showed the 4 generating warps (3 FMA + max + pack per
+// value, 2 400 instructions per thread and tile behind table loads) taking ~4x the tile's MMA time.  Here fc_pos itself, the
+// two biases and the rank-3 shortcut fold all become K = 16 tcgen05 MMAs on a 16-column "coordinate operand"
+//     A16[r] = [xh yh zh | xl yl zl | xh yh zh | 1 1 | 0 0 0 0 0]        (x = xh + xl, two fp16 terms; fp32 accumulation)
+// against constant B rows [wh(3) | wh(3) | wl(3) | bh bl | 0..]: the products are exact in fp32, so the result carries the
+// fp32 affine map to ~2^-22 (the dropped xl.wl term), i.e. the same value the CUDA-core generator rounds to fp16.
+//     F(kc) : TMEM[128 x 64] = A16 . Wp16[kc]^T           one MMA per 64-channel chunk, double-buffered in the OUT region
+//     gen   : A[:, kc] = fp16(relu(F(kc)))                 H group: tcgen05.ld -> cvt.pack -> hmax2 -> swizzled st.shared
+//     G1    : H   = A16 . B0_16^T + A . W0^T  (K = 512)    bias by MMA
+//     epiH  : H16 = fp16(relu(H)) in place in TMEM
+//     G2    : OUT = A16 . PF16^T + H16 . W1^T              shortcut fold + its constant by MMA
+//     epiOUT: pooled column max; fp16 tile -> 32 KB staging (two rounds) -> TMA store
+// The F staging buffers are OUT-region columns [0,64) and [128,192): the output epilogue drains those first and releases
+// them (fr_free) long before the rest (out_drained), so the next tile's generator starts ~2 TMEM loads after G2 completes.
+// Shared memory (14 x 16 KB): A ring 3 | staging 2 | constant tiles 2 | A16 1 | weight ring 6.
+constexpr int P0T_ASLOTS = 3;
+constexpr int P0T_SMEM = (P0T_ASLOTS + 2 + 2 + 1 + PF_NST) * PF_CHUNK + 1024;
+
+struct P0TArgs {
+  int n_points, tiles_per_sample, n_tiles;
+  const float* xyz;       // [samples, n_points, 3]
+  unsigned* colmax;
+  const uint8_t* wblob;   // 24 pre-swizzled 16 KB weight chunks (G1 16, G2 8)
+  const uint8_t* ctblob;  // 2 pre-swizzled 16 KB constant tiles: Wp16 | (B0_16, PF16)
+};
+
+__device__ __forceinline__ uint32_t pf_relu_pack(uint32_t a, uint32_t b) {
+  const __half2 h = __hmax2(__floats2half2_rn(__uint_as_float(a), __uint_as_float(b)), __float2half2_rn(0.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block0_tc_kernel(const __grid_constant__ PfMaps tm, const P0TArgs a) {
+  extern __shared__ __align__(1024) uint8_t pf_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pf_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* aring = smem;                                  // 3 x 16 KB generated A chunks
+  uint8_t* stage = aring + P0T_ASLOTS * PF_CHUNK;         // 2 x 16 KB output staging
+  uint8_t* ct = stage + 2 * PF_CHUNK;                     // constant tiles
+  uint8_t* a16 = ct + 2 * PF_CHUNK;                       // coordinate operand, K-slice (tile & 1)
+  uint8_t* wring = a16 + PF_CHUNK;
+  __shared__ __align__(8) uint64_t w_full[PF_NST], w_empty[PF_NST], a_ready[P0T_ASLOTS], a_free[P0T_ASLOTS], f_full[2], a16_full[2],
+      ct_full, h_full, h_ready[4], out_full, fr_free, out_drained;
+  __shared__ uint32_t tmem_slot;
+  __shared__ unsigned colmax_s[256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = a.n_tiles / (int)gridDim.x, rem = a.n_tiles % (int)gridDim.x;
+  const int t_begin = (int)blockIdx.x * per + ((int)blockIdx.x < rem ? (int)blockIdx.x : rem);
+  const int nt = per + ((int)blockIdx.x < rem ? 1 : 0);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm.xout);
+    for (int i = 0; i < PF_NST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < P0T_ASLOTS; ++i) { mbar_init(&a_ready[i], 4); mbar_init(&a_free[i], 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(&h_ready[i], 4);
+    for (int i = 0; i < 2; ++i) { mbar_init(&f_full[i], 1); mbar_init(&a16_full[i], 4); }
+    mbar_init(&ct_full, 1);
+    mbar_init(&h_full, 1);
+    mbar_init(&out_full, 1);
+    mbar_init(&fr_free, 8);
+    mbar_init(&out_drained, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  if (threadIdx.x < 256) colmax_s[threadIdx.x] = 0u;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t RH = tmem_base, RO = tmem_base + 256u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&ct_full, 2 * PF_CHUNK);
+      bulk_load(ct, a.ctblob, 2 * PF_CHUNK, &ct_full);
+      uint32_t st = 0, ph = 1;
+      for (int j = 0; j < nt; ++j) {
+        for (int i = 0; i < PF_WCHUNKS; ++i) {
+          mbar_wait(&w_empty[st], ph);
+          mbar_arrive_expect_tx(&w_full[st], PF_CHUNK);
+          bulk_load(wring + st * PF_CHUNK, a.wblob + (size_t)i * PF_CHUNK, PF_CHUNK, &w_full[st]);
+          if (++st == PF_NST) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc256 = umma_idesc_f16(256), idesc128 = umma_idesc_f16(128), idesc64 = umma_idesc_f16(64);
+    const uint64_t wdesc0 = umma_desc_k128(smem_u32(wring));
+    const uint64_t adesc0 = umma_desc_k128(smem_u32(aring));
+    const uint64_t ct1desc = umma_desc_k128(smem_u32(ct)), ct2desc = umma_desc_k128(smem_u32(ct + PF_CHUNK));
+    const uint64_t a16desc0 = umma_desc_k128(smem_u32(a16));
+    uint32_t st = 0, wph = 0;
+    uint32_t as = 0, aph = 0;            // A-ring slot and its phase parity (running over tiles)
+    // F(kc): 64 channels kc*64.. = K-slice (kc >> 1), rows (kc & 1) * 64.. of the Wp16 tile
+    auto issue_f = [&](uint64_t ad, int kc) {
+      umma_bf16(RO + (uint32_t)(kc & 1) * 128u, ad, pf_desc_add(ct1desc, (uint32_t)(kc & 1) * (64 * 128 >> 4) + (uint32_t)(kc >> 1) * 2), idesc64, 0);
+      umma_commit(&f_full[kc & 1]);
+    };
+    mbar_wait(&ct_full, 0);
+    for (int j = 0; j < nt; ++j) {
+      const uint32_t pj = (uint32_t)j & 1u;
+      const uint64_t ad16 = pf_desc_add(a16desc0, pj * 2);
+      mbar_wait(&a16_full[pj], (uint32_t)(j >> 1) & 1u);
+      if (j > 0) mbar_wait(&fr_free, (uint32_t)(j - 1) & 1u);
+      tc_fence_after();
+      if (pf_elect_one()) {
+        PF_TR(j, 0);
+        issue_f(ad16, 0);
+        issue_f(ad16, 1);
+        // H = bias (accumulate = 0): G2 of the previous tile, which read H16 from this region, is ordered before by the MMA pipe
+        umma_bf16(RH, ad16, ct2desc, idesc128, 0);
+        umma_bf16(RH + 128u, ad16, pf_desc_add(ct2desc, 2), idesc128, 0);
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int kc = 0; kc < 8; ++kc) {
+        mbar_wait(&a_ready[as], aph);
+        if (lane == 0) PF_TR(j, 1 + 2 * kc);
+        mbar_wait(&w_full[st], wph);
+        mbar_wait(&w_full[st + 1], wph);
+        tc_fence_after();
+        if (pf_elect_one()) {
+          PF_TR(j, 2 + 2 * kc);
+          const uint64_t wd = pf_desc_add(wdesc0, st * (PF_CHUNK >> 4));
+          const uint64_t ad = pf_desc_add(adesc0, as * (PF_CHUNK >> 4));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_bf16(RH, pf_desc_add(ad, ks * 2), pf_desc_add(wd, ks * 2), idesc256, 1);
+          umma_commit(&w_empty[st]);
+          umma_commit(&w_empty[st + 1]);
+          umma_commit(&a_free[as]);
+          // chunk kc has been converted (a_ready), so its F buffer (kc & 1) is free for chunk kc + 2
+          if (kc + 2 < 8) issue_f(ad16, kc + 2);
+          if (kc == 7) umma_commit(&h_full);
+        }
+        __syncwarp();
+        st += 2;
+        if (st == PF_NST) { st = 0; wph ^= 1u; }
+        if (++as == P0T_ASLOTS) { as = 0; aph ^= 1u; }
+      }
+      // G2 writes the whole OUT region (incl. the F buffers, all read by now): the previous tile's epilogue must have drained it
+      if (j > 0) mbar_wait(&out_drained, (uint32_t)(j - 1) & 1u);
+      tc_fence_after();
+      if (pf_elect_one()) {
+        PF_TR(j, 17);
+        umma_bf16(RO, ad16, pf_desc_add(ct2desc, 4), idesc128, 0);
+        umma_bf16(RO + 128u, ad16, pf_desc_add(ct2desc, 6), idesc128, 0);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        mbar_wait(&h_ready[kc], pj);
+        if (lane == 0) PF_TR(j, 18 + 2 * kc);
+        mbar_wait(&w_full[st], wph);
+        mbar_wait(&w_full[st + 1], wph);
+        tc_fence_after();
+        if (pf_elect_one()) {
+          PF_TR(j, 19 + 2 * kc);
+          const uint64_t wd = pf_desc_add(wdesc0, st * (PF_CHUNK >> 4));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16_ts(RO, RH + (uint32_t)((kc >> 1) * 128 + (kc & 1) * 32 + ks * 8), pf_desc_add(wd, ks * 2), idesc256, 1);
+          umma_commit(&w_empty[st]);
+          umma_commit(&w_empty[st + 1]);
+          if (kc == 3) umma_commit(&out_full);
+        }
+        __syncwarp();
+        st += 2;
+        if (st == PF_NST) { st = 0; wph ^= 1u; }
+      }
+    }
+  } else if (warp < 6) {
+    // ---- H group: thread = point.  Coordinate operand, generator epilogue, H epilogue -----------------------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    bool pvalid = false;
+    auto load_xyz = [&](int j) {
+      px = py = pz = 0.f;
+      pvalid = false;
+      if (j < nt) {
+        const int t = t_begin + j;
+        const int sample = t / a.tiles_per_sample, n0 = (t % a.tiles_per_sample) * 128;
+        if (n0 + row < a.n_points) {
+          const float* pp = a.xyz + ((size_t)sample * a.n_points + n0 + row) * 3;
+          px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2);
+          pvalid = true;
+        }
+      }
+    };
+    auto write_a16 = [&](int buf) {
+      const __half xh = __float2half_rn(px), yh = __float2half_rn(py), zh = __float2half_rn(pz);
+      const __half xl = __float2half_rn(px - __half2float(xh)), yl = __float2half_rn(py - __half2float(yh)),
+                   zl = __float2half_rn(pz - __half2float(zh));
+      const __half one = __float2half_rn(pvalid ? 1.f : 0.f), zero = __float2half_rn(0.f);
+      auto pk = [](__half lo, __half hi) { return (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16); };
+      *reinterpret_cast<uint4*>(a16 + pf_sw128(row, 2 * buf)) = make_uint4(pk(xh, yh), pk(zh, xl), pk(yl, zl), pk(xh, yh));
+      *reinterpret_cast<uint4*>(a16 + pf_sw128(row, 2 * buf + 1)) = make_uint4(pk(zh, one), pk(one, zero), 0u, 0u);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a16_full[buf]);
+    };
+    load_xyz(0);
+    write_a16(0);
+    load_xyz(1);
+    uint32_t as = 0, aph = 1;            // producer side of the A ring: first round passes immediately
+    for (int j = 0; j < nt; ++j) {
+      const uint32_t pj = (uint32_t)j & 1u;
+#pragma unroll 1
+      for (int kc = 0; kc < 8; ++kc) {
+        // F buffer kc & 1 completes 4 times per tile
+        mbar_wait(&f_full[kc & 1], (uint32_t)(kc >> 1) & 1u);
+        if (threadIdx.x == 64) PF_TR(j, 26 + 2 * kc);
+        tc_fence_after();
+        uint32_t r[64];
+        const uint32_t tf = RO + lane_off + (uint32_t)(kc & 1) * 128u;
+        tmem_ld32(tf, r);
+        tmem_ld32(tf + 32, r + 32);
+        mbar_wait(&a_free[as], aph);
+        uint8_t* ctile = aring + as * PF_CHUNK;
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+          *reinterpret_cast<uint4*>(ctile + pf_sw128(row, jj)) =
+              make_uint4(pf_relu_pack(r[8 * jj], r[8 * jj + 1]), pf_relu_pack(r[8 * jj + 2], r[8 * jj + 3]),
+                         pf_relu_pack(r[8 * jj + 4], r[8 * jj + 5]), pf_relu_pack(r[8 * jj + 6], r[8 * jj + 7]));
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[as]);
+        if (threadIdx.x == 64) PF_TR(j, 27 + 2 * kc);
+        if (++as == P0T_ASLOTS) { as = 0; aph ^= 1u; }
+      }
+      // H epilogue (in place in TMEM): relu + fp16, the bias is already in the accumulator
+      mbar_wait(&h_full, pj);
+      if (threadIdx.x == 64) PF_TR(j, 42);
+      tc_fence_after();
+#pragma unroll 1
+      for (int hsel = 0; hsel < 2; ++hsel) {
+        const uint32_t thh = RH + lane_off + (uint32_t)hsel * 128u;
+        uint32_t raw[2][32];
+        tmem_ld32(thh, raw[0]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          tmem_ld_wait();
+          if (g < 3) tmem_ld32(thh + (g + 1) * 32, raw[(g + 1) & 1]);
+          const uint32_t* r = raw[g & 1];
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pf_relu_pack(r[2 * i], r[2 * i + 1]);
+          tmem_st16(thh + g * 16, pk);
+          if (g & 1) {
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_ready[hsel * 2 + (g >> 1)]);
+          }
+        }
+      }
+      // coordinate operand of the next tile: its K-slice was last read by tile j-1's MMAs, all complete before h_full(j)
+      if (threadIdx.x == 64) PF_TR(j, 43);
+      if (j + 1 < nt) write_a16((j + 1) & 1);
+      load_xyz(j + 2);
+    }
+  } else {
+    // ---- O group ---------------------------------------------------------------------------------------------------
+    const int te = (int)threadIdx.x - 192;
+    const int q = warp & 3;
+    const int hsel = (warp - 6) >> 2;
+    const int row = q * 32 + lane;
+    const bool elected = te == 0;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    auto flush_colmax = [&](int sample) {
+      pf_epi_sync();
+      const unsigned v = colmax_s[te];
+      if (v) atomicMax(a.colmax + (size_t)sample * 256 + te, v);
+      colmax_s[te] = 0u;
+      pf_epi_sync();
+    };
+    uint8_t* ctile = stage + hsel * PF_CHUNK;
+    // 32 columns (hsel * 128 + g * 32 ..) of this thread's row: fp16 into the staging chunk, then the pooled column max
+    auto process = [&](uint32_t (&r)[32], int g, bool valid) {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const __half2 h0 = __floats2half2_rn(__uint_as_float(r[8 * jj]), __uint_as_float(r[8 * jj + 1]));
+        const __half2 h1 = __floats2half2_rn(__uint_as_float(r[8 * jj + 2]), __uint_as_float(r[8 * jj + 3]));
+        const __half2 h2 = __floats2half2_rn(__uint_as_float(r[8 * jj + 4]), __uint_as_float(r[8 * jj + 5]));
+        const __half2 h3 = __floats2half2_rn(__uint_as_float(r[8 * jj + 6]), __uint_as_float(r[8 * jj + 7]));
+        *reinterpret_cast<uint4*>(ctile + pf_sw128(row, (g & 1) * 4 + jj)) =
+            make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                       *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+      }
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = valid ? __uint_as_float(r[i]) : -INFINITY;
+      const float mine = pf_colmax32(f, lane);
+      atomicMax(&colmax_s[hsel * 128 + g * 32 + lane], f2ord(mine));
+    };
+    int cur_sample = -1;
+    for (int j = 0; j < nt; ++j) {
+      const uint32_t pj = (uint32_t)j & 1u;
+      const int t = t_begin + j;
+      const int sample = t / a.tiles_per_sample, n0 = (t % a.tiles_per_sample) * 128;
+      if (sample != cur_sample) {
+        if (cur_sample >= 0) flush_colmax(cur_sample);
+        cur_sample = sample;
+      }
+      const bool valid = n0 + row < a.n_points;
+      const uint32_t to = RO + lane_off + (uint32_t)hsel * 128u;
+      mbar_wait(&out_full, pj);
+      if (elected) PF_TR(j, 44);
+      tc_fence_after();
+      uint32_t raw[2][32];
+      tmem_ld32(to, raw[0]);
+      tmem_ld32(to + 32, raw[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (elected) PF_TR(j, 45);
+      if (lane == 0) mbar_arrive(&fr_free);          // columns [0,64) and [128,192): the next tile's F staging buffers
+      process(raw[0], 0, valid);
+      tmem_ld32(to + 64, raw[0]);
+      process(raw[1], 1, valid);
+      tmem_ld_wait();
+      tmem_ld32(to + 96, raw[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&out_drained);
+      if (elected) PF_TR(j, 46);
+      fence_proxy_async();
+      pf_epi_sync();
+      if (elected) {
+        tma_store_3d(&tm.xout, stage, 0, n0, sample);
+        tma_store_3d(&tm.xout, stage + PF_CHUNK, 128, n0, sample);
+        pf_store_commit();
+        pf_store_wait_read();
+      }
+      pf_epi_sync();        // the staging chunks are free for the second round
+      process(raw[0], 2, valid);
+      process(raw[1], 3, valid);
+      fence_proxy_async();
+      pf_epi_sync();
+      if (elected) {
+        tma_store_3d(&tm.xout, stage, 64, n0, sample);
+        tma_store_3d(&tm.xout, stage + PF_CHUNK, 192, n0, sample);
+        pf_store_commit();
+        pf_store_wait_read();
+      }
+      pf_epi_sync();
+      if (elected) PF_TR(j, 47);
+    }
+    if (cur_sample >= 0) flush_colmax(cur_sample);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // CTA-pair version of pointnet_block_kernel: tcgen05.mma.cta_group::2, M = 256 (two 128-point tiles, one per SM), N = 256.
 // Each CTA holds only ITS half of every weight K-chunk ([128 n x 64 k]: CTA 0 the output columns 0-127, CTA 1 128-255),
 // so the per-SM weight traffic from L2 -- what bounds the single-CTA kernel -- halves and the 6-slot ring holds 6 K-steps.
@@ -1180,8 +1555,56 @@ int pf_pack_block0(const float* w0, const float* w1, const float* wp, const floa
   return SEEME_OK;
 }
 
-int pf_block0_forward(const float* xyz, void* x_out, const void* w_blob, const void* wpb, const float* b0, const float* cst0,
-                      const float* pfold, unsigned* colmax, int samples, int n_points, int prof_id, cudaStream_t s) {
+// constant tiles of the tensor-core block 0: two [128 rows x 64 k] fp16 SWIZZLE_128B images, K-slice s = columns 16 s..
+//   tile 0, slice s   : Wp16 rows of channels 128 s + n      [wh(3) | wh(3) | wl(3) | bh bl | 0 x 5]
+//   tile 1, slice 0/1 : B0_16 of channels n / 128 + n        [0 x 9 | b0h b0l | 0 x 5]
+//   tile 1, slice 2/3 : PF16  of channels n / 128 + n        [ph(3) | ph(3) | pl(3) | ch cl | 0 x 5]   (pfold, cst0)
+__global__ void pf_pack_ct_kernel(const float* __restrict__ wp, const float* __restrict__ bp, const float* __restrict__ b0,
+                                  const float* __restrict__ pfold, const float* __restrict__ cst0, __half* __restrict__ blob) {
+  const int tile = blockIdx.x;
+  for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) {
+    const int n = i / 64, cc = i % 64, sl = cc >> 4, k = cc & 15;
+    float w3[3] = {0.f, 0.f, 0.f}, bias = 0.f;
+    if (tile == 0) {
+      const int c = sl * 128 + n;
+      w3[0] = wp[c * 3]; w3[1] = wp[c * 3 + 1]; w3[2] = wp[c * 3 + 2]; bias = bp[c];
+    } else if (sl < 2) {
+      bias = b0[sl * 128 + n];
+    } else {
+      const int c = (sl - 2) * 128 + n;
+      w3[0] = pfold[c * 4]; w3[1] = pfold[c * 4 + 1]; w3[2] = pfold[c * 4 + 2]; bias = cst0[c];
+    }
+    float v = 0.f;
+    if (k < 9) {
+      const float w = w3[k % 3];
+      const __half hi = __float2half_rn(w);
+      v = k < 6 ? __half2float(hi) : w - __half2float(hi);
+    } else if (k < 11) {
+      const __half hi = __float2half_rn(bias);
+      v = k == 9 ? __half2float(hi) : bias - __half2float(hi);
+    }
+    blob[(size_t)tile * 128 * 64 + pf_swz_elem(n, cc)] = __float2half_rn(v);
+  }
+}
+
+int pf_pack_block0_ct(const float* wp, const float* bp, const float* b0, const float* pfold, const float* cst0, void* ctblob) {
+  pf_pack_ct_kernel<<<2, 256>>>(wp, bp, b0, pfold, cst0, reinterpret_cast<__half*>(ctblob));
+  SEEME_LAUNCH_CHECK();
+  return SEEME_OK;
+}
+
+// SEEME_PF_BLOCK0=cuda selects the CUDA-core generator (pointnet_block0_kernel) for A/B measurements
+static bool pf_block0_use_tc() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SEEME_PF_BLOCK0");
+    v = (e && strcmp(e, "cuda") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+int pf_block0_forward(const float* xyz, void* x_out, const void* w_blob, const void* wpb, const void* ctblob, const float* b0,
+                      const float* cst0, const float* pfold, unsigned* colmax, int samples, int n_points, int prof_id, cudaStream_t s) {
   SEEME_TRY(pf_encoder());
   SEEME_REQUIRE(n_points >= 128, SEEME_EINVAL, "pf_block0_forward: needs >= 128 points per sample (got %d)", n_points);
   PfMaps maps;
@@ -1189,24 +1612,34 @@ int pf_block0_forward(const float* xyz, void* x_out, const void* w_blob, const v
   SEEME_TRY(pf_act_map(&maps.xout, x_out, samples, n_points));
   maps.xin = maps.xout;
   SEEME_TRY(pf_w_map(&maps.w, w_blob));
-  P0Args a;
-  a.n_points = n_points;
-  a.tiles_per_sample = (n_points + 127) / 128;
-  a.n_tiles = a.tiles_per_sample * samples;
-  a.xyz = xyz;
-  a.wpb = reinterpret_cast<const float4*>(wpb);
-  a.b0 = b0; a.cst0 = cst0;
-  a.pfold = reinterpret_cast<const float4*>(pfold);
-  a.colmax = colmax;
-  a.wblob = reinterpret_cast<const uint8_t*>(w_blob);
+  const int tiles_per_sample = (n_points + 127) / 128, n_tiles = tiles_per_sample * samples;
+  const int grid = n_tiles < NUM_SMS ? n_tiles : NUM_SMS;
   static bool configured = false;
   if (!configured) {
     SEEME_CUDA(cudaFuncSetAttribute(pointnet_block0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P0_SMEM));
+    SEEME_CUDA(cudaFuncSetAttribute(pointnet_block0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P0T_SMEM));
     configured = true;
   }
-  const int grid = a.n_tiles < NUM_SMS ? a.n_tiles : NUM_SMS;
   ProfScope prof(prof_id - 1, s);
-  pointnet_block0_kernel<<<grid, PF_THREADS, P0_SMEM, s>>>(maps, a);
+  if (pf_block0_use_tc()) {
+    P0TArgs a;
+    a.n_points = n_points; a.tiles_per_sample = tiles_per_sample; a.n_tiles = n_tiles;
+    a.xyz = xyz;
+    a.colmax = colmax;
+    a.wblob = reinterpret_cast<const uint8_t*>(w_blob);
+    a.ctblob = reinterpret_cast<const uint8_t*>(ctblob);
+    pointnet_block0_tc_kernel<<<grid, PF_THREADS, P0T_SMEM, s>>>(maps, a);
+  } else {
+    P0Args a;
+    a.n_points = n_points; a.tiles_per_sample = tiles_per_sample; a.n_tiles = n_tiles;
+    a.xyz = xyz;
+    a.wpb = reinterpret_cast<const float4*>(wpb);
+    a.b0 = b0; a.cst0 = cst0;
+    a.pfold = reinterpret_cast<const float4*>(pfold);
+    a.colmax = colmax;
+    a.wblob = reinterpret_cast<const uint8_t*>(w_blob);
+    pointnet_block0_kernel<<<grid, PF_THREADS, P0_SMEM, s>>>(maps, a);
+  }
   SEEME_LAUNCH_CHECK();
   return SEEME_OK;
 }
@@ -1216,6 +1649,13 @@ int pf_pack_block(const float* ws, const float* w0, const float* w1, void* blob)
   SEEME_LAUNCH_CHECK();
   return SEEME_OK;
 }
+
+#ifdef PF_TRACE
+extern "C" int seeme_pf_trace_read(long long* host, int n) {
+  const int m = n < PF_TRACE_TILES * PF_TRACE_SLOTS ? n : PF_TRACE_TILES * PF_TRACE_SLOTS;
+  return cudaMemcpyFromSymbol(host, pf_trace, (size_t)m * sizeof(long long)) == cudaSuccess ? m : -1;
+}
+#endif
 
 size_t pf_blob_bytes() { return (size_t)PF_WCHUNKS * 128 * 64 * 2; }
 

@@ -15,9 +15,12 @@ int pf_block_forward(const void* x_in, void* x_out, const void* w_blob, const fl
 
 // block 0 (+ fc_pos): weight-chunk blob from W0 [256,512] / W1 [256,256] and the packed (Wp, bp) table [512] float4
 int pf_pack_block0(const float* w0, const float* w1, const float* wp, const float* bp, void* blob, void* wpb);
+// constant tiles (32 KB) of the tensor-core block 0: fc_pos, the biases and the rank-3 shortcut fold as K = 16 MMA operands.
+// pfold [256] float4 and cst0 [256] must already be computed (device pointers)
+int pf_pack_block0_ct(const float* wp, const float* bp, const float* b0, const float* pfold, const float* cst0, void* ctblob);
 // xyz [samples, n_points, 3] fp32 -> x_out [samples, n_points, 256] fp16 and the pooled column max;
-// b0 [256], cst0 [256] = Ws bp + b1, pfold [256] float4 = rank-3 fold of the shortcut
-int pf_block0_forward(const float* xyz, void* x_out, const void* w_blob, const void* wpb, const float* b0, const float* cst0,
-                      const float* pfold, unsigned* colmax, int samples, int n_points, int prof_id, cudaStream_t s);
+// b0 [256], cst0 [256] = Ws bp + b1, pfold [256] float4 = rank-3 fold of the shortcut (CUDA-core generator only)
+int pf_block0_forward(const float* xyz, void* x_out, const void* w_blob, const void* wpb, const void* ctblob, const float* b0,
+                      const float* cst0, const float* pfold, unsigned* colmax, int samples, int n_points, int prof_id, cudaStream_t s);
 
 }  // namespace seeme

@@ -1,0 +1,63 @@
+"""Event trace of the tensor-core block-0 kernel (CTA 0, first tiles): builds an instrumented copy of the library
+(-DPF_TRACE) next to the product one, runs one scene-encoder pass and prints per-tile event times (cycles).
+
+    python tools/pf_trace.py build      # here (no GPU): writes seeme_b200/lib/libseeme_b200_trace.so
+    python tools/pf_trace.py            # on the GPU box
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TRACE_LIB = os.path.join(ROOT, "seeme_b200", "lib", "libseeme_b200_trace.so")
+
+if len(sys.argv) > 1 and sys.argv[1] == "build":
+    sys.path.insert(0, ROOT)
+    from seeme_b200 import build as B
+    B.build(verbose=False)
+    obj = os.path.join(B.OBJ, "pointnet_fused_trace.o")
+    subprocess.run([B.NVCC, *B.ARCH, *[f for f in B.FLAGS if f not in ("-Xptxas", "-v")], "-DPF_TRACE", "-c",
+                    os.path.join(B.CSRC, "pointnet_fused.cu"), "-o", obj], check=True)
+    objs = [os.path.join(B.OBJ, s[:-3] + ".o") for s in B.sources() if s != "pointnet_fused.cu"] + [obj]
+    subprocess.run([B.NVCC, *B.ARCH, "-shared", "-o", TRACE_LIB, *objs], check=True)
+    print(TRACE_LIB)
+    sys.exit(0)
+
+os.environ["SEEME_B200_LIB"] = TRACE_LIB
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from seeme_b200 import _lib, ops, synthetic as S  # noqa: E402
+
+B = 32
+dev = "cuda:0"
+W = {k: v.to(dev) for k, v in S.pointnet_state(0).items()}
+Wo = {k: v.to(dev) for k, v in S.output_scene_state(0).items()}
+op = ops.PointNetOp(W, Wo, max_batch=B, max_points=20000, precision=16)
+p = S.egobody_scene(B, 20000, torch.Generator().manual_seed(3)).to(dev)
+for _ in range(3):
+    op(p)
+torch.cuda.synchronize()
+TILES, SLOTS = 24, 64
+buf = (C.c_longlong * (TILES * SLOTS))()
+n = _lib.lib().seeme_pf_trace_read(buf, TILES * SLOTS)
+assert n == TILES * SLOTS, n
+t = [[buf[i * SLOTS + k] for k in range(SLOTS)] for i in range(TILES)]
+names = {0: "F0 issue"}
+for kc in range(8):
+    names[1 + 2 * kc] = f"a_ready{kc}"
+    names[2 + 2 * kc] = f"G1({kc}) issue"
+    names[26 + 2 * kc] = f"  H: f_full{kc}"
+    names[27 + 2 * kc] = f"  H: gen{kc} done"
+names[17] = "PF issue (out_drained)"
+for kc in range(4):
+    names[18 + 2 * kc] = f"h_ready{kc}"
+    names[19 + 2 * kc] = f"G2({kc}) issue"
+names.update({42: "  H: h_full", 43: "  H: epiH done", 44: "    O: out_full", 45: "    O: fr_free", 46: "    O: out_drained", 47: "    O: tile done"})
+for j in (8, 9):
+    base = t[j][0]
+    print(f"--- tile {j}: F0 issue of tile {j + 1} at +{t[j + 1][0] - base}")
+    for k, v in sorted(((k, t[j][k]) for k in names), key=lambda kv: kv[1]):
+        print(f"{v - base:8d}  {names[k]}")
+per = [t[j + 1][0] - t[j][0] for j in range(2, TILES - 1)]
+print("tile period (cycles):", per)
