@@ -745,6 +745,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block0_kernel(const __
 // them (fr_free) long before the rest (out_drained), so the next tile's generator starts ~2 TMEM loads after G2 completes.
 // Shared memory (14 x 16 KB): A ring 3 | staging 2 | constant tiles 2 | A16 1 | weight ring 6.
 constexpr int P0T_ASLOTS = 3;
+// Generator groups: 1 = warps 2-5 convert every chunk.  2 adds warps 14-17 for the odd chunks (independent chains), but 18
+// warps leave 96 registers per thread (5 warps per scheduler) and measured slower (1.07 vs 0.90 ms per 128 clouds).
+constexpr int P0T_GEN_GROUPS = 1;
+constexpr int P0T_THREADS = PF_THREADS + (P0T_GEN_GROUPS - 1) * 128;
 constexpr int P0T_SMEM = (P0T_ASLOTS + 2 + 2 + 1 + PF_NST) * PF_CHUNK + 1024;
 
 struct P0TArgs {
@@ -756,20 +760,66 @@ struct P0TArgs {
 };
 
 __device__ __forceinline__ uint32_t pf_relu_pack(uint32_t a, uint32_t b) {
-  const __half2 h = __hmax2(__floats2half2_rn(__uint_as_float(a), __uint_as_float(b)), __float2half2_rn(0.f));
-  return *reinterpret_cast<const uint32_t*>(&h);
+  uint32_t d;      // {lo = fp16(max(a, 0)), hi = fp16(max(b, 0))}: conversion, relu and packing in ONE instruction
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(b)), "f"(__uint_as_float(a)));
+  return d;
 }
 
-__global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block0_tc_kernel(const __grid_constant__ PfMaps tm, const P0TArgs a) {
+// Lean barrier primitives for the statically scheduled kernel below: 32-bit shared addresses computed once, a wait loop
+// the compiler may not unroll (the generic mbar_wait is unrolled x4 with its printf path at every call site, ~150 SASS
+// instructions per wait), the timeout path out of line.
+__device__ __noinline__ void pf_wait_timeout(uint32_t addr) {
+  printf("seeme_b200: mbarrier wait timed out (block %d thread %d barrier 0x%x)\n", blockIdx.x, threadIdx.x, addr);
+  __trap();
+}
+__device__ __forceinline__ void pf_wait(uint32_t addr, uint32_t parity) {
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  pf_wait_timeout(addr);
+}
+__device__ __forceinline__ void pf_arrive(uint32_t addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory"); }
+__device__ __forceinline__ void pf_arrive_tx(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pf_commit(uint32_t addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void pf_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// Schedule (per tile, 12 static steps; step s uses weight-ring pair s % 3 = 32 KB = two adjacent chunks):
+//   steps 0..7  G1(kc): ONE barrier full[kc] collects the 4 generator warps' arrivals for A chunk kc (A-ring slot
+//               kc % 3) AND the weight pair's TMA bytes; ONE commit empty[s % 3] releases both
+//   steps 8..11 G2(kc): g2_full[kc] collects the 4 H-epilogue warps' arrivals and the weight pair's bytes
+// 12 steps = 4 ring rounds per tile, so every slot index and phase parity below is a compile-time constant.
+// F staging: chunks 0 and 1 of tile j+1 are produced DURING tile j's G2 into the H-region columns the in-place fp16
+// conversion has freed ([64,128) after h_ready 0-1, [192,256) after h_ready 2-3), so G1(j+1) starts right behind G2(j);
+// chunks 2..7 use OUT-region columns [0,64) / [128,192) once the output epilogue has released them (fr_free).
+enum P0TBar { B_FULL = 0, B_EMPTY = 8, B_G2FULL = 11, B_FFULL = 15, B_A16 = 23, B_CT = 25, B_HFULL = 26, B_OUTFULL = 27, B_FRFREE = 28,
+              B_DRAINED = 29, B_GEN1 = 30, B_COUNT = 31 };
+
+__global__ void __launch_bounds__(P0T_THREADS, 1) pointnet_block0_tc_kernel(const __grid_constant__ PfMaps tm, const P0TArgs a) {
   extern __shared__ __align__(1024) uint8_t pf_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pf_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* aring = smem;                                  // 3 x 16 KB generated A chunks
   uint8_t* stage = aring + P0T_ASLOTS * PF_CHUNK;         // 2 x 16 KB output staging
   uint8_t* ct = stage + 2 * PF_CHUNK;                     // constant tiles
   uint8_t* a16 = ct + 2 * PF_CHUNK;                       // coordinate operand, K-slice (tile & 1)
-  uint8_t* wring = a16 + PF_CHUNK;
-  __shared__ __align__(8) uint64_t w_full[PF_NST], w_empty[PF_NST], a_ready[P0T_ASLOTS], a_free[P0T_ASLOTS], f_full[2], a16_full[2],
-      ct_full, h_full, h_ready[4], out_full, fr_free, out_drained;
+  uint8_t* wring = a16 + PF_CHUNK;                        // 3 x 32 KB weight pairs
+  __shared__ __align__(8) uint64_t bars[B_COUNT];
   __shared__ uint32_t tmem_slot;
   __shared__ unsigned colmax_s[256];
 
@@ -777,18 +827,22 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block0_tc_kernel(const
   const int per = a.n_tiles / (int)gridDim.x, rem = a.n_tiles % (int)gridDim.x;
   const int t_begin = (int)blockIdx.x * per + ((int)blockIdx.x < rem ? (int)blockIdx.x : rem);
   const int nt = per + ((int)blockIdx.x < rem ? 1 : 0);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [bar0](int i) { return bar0 + (uint32_t)i * 8u; };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm.xout);
-    for (int i = 0; i < PF_NST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < P0T_ASLOTS; ++i) { mbar_init(&a_ready[i], 4); mbar_init(&a_free[i], 1); }
-    for (int i = 0; i < 4; ++i) mbar_init(&h_ready[i], 4);
-    for (int i = 0; i < 2; ++i) { mbar_init(&f_full[i], 1); mbar_init(&a16_full[i], 4); }
-    mbar_init(&ct_full, 1);
-    mbar_init(&h_full, 1);
-    mbar_init(&out_full, 1);
-    mbar_init(&fr_free, 8);
-    mbar_init(&out_drained, 8);
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[B_FULL + i], 5);
+    for (int i = 0; i < 3; ++i) mbar_init(&bars[B_EMPTY + i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[B_G2FULL + i], 5);
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[B_FFULL + i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&bars[B_A16 + i], 4);
+    mbar_init(&bars[B_CT], 1);
+    mbar_init(&bars[B_HFULL], 1);
+    mbar_init(&bars[B_OUTFULL], 1);
+    mbar_init(&bars[B_FRFREE], 8);
+    mbar_init(&bars[B_DRAINED], 8);
+    mbar_init(&bars[B_GEN1], 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_slot, 512);
@@ -800,75 +854,84 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block0_tc_kernel(const
   const uint32_t RH = tmem_base, RO = tmem_base + 256u;
 
   if (warp == 0) {
+    // ---- weight producer: one 32 KB bulk copy per step ---------------------------------------------------------
     if (lane == 0) {
-      mbar_arrive_expect_tx(&ct_full, 2 * PF_CHUNK);
-      bulk_load(ct, a.ctblob, 2 * PF_CHUNK, &ct_full);
-      uint32_t st = 0, ph = 1;
+      const uint32_t wr = smem_u32(wring);
+      pf_arrive_tx(BAR(B_CT), 2 * PF_CHUNK);
+      pf_bulk_load(smem_u32(ct), a.ctblob, 2 * PF_CHUNK, BAR(B_CT));
       for (int j = 0; j < nt; ++j) {
-        for (int i = 0; i < PF_WCHUNKS; ++i) {
-          mbar_wait(&w_empty[st], ph);
-          mbar_arrive_expect_tx(&w_full[st], PF_CHUNK);
-          bulk_load(wring + st * PF_CHUNK, a.wblob + (size_t)i * PF_CHUNK, PF_CHUNK, &w_full[st]);
-          if (++st == PF_NST) { st = 0; ph ^= 1u; }
+#pragma unroll
+        for (int s = 0; s < 12; ++s) {
+          const uint32_t fb = s < 8 ? BAR(B_FULL + s) : BAR(B_G2FULL + s - 8);
+          pf_wait(BAR(B_EMPTY + s % 3), (uint32_t)((s / 3) & 1) ^ 1u);
+          PF_TR(j, 48 + s);
+          pf_arrive_tx(fb, 2 * PF_CHUNK);
+          pf_bulk_load(wr + (uint32_t)(s % 3) * 2 * PF_CHUNK, a.wblob + (size_t)s * 2 * PF_CHUNK, 2 * PF_CHUNK, fb);
         }
       }
     }
   } else if (warp == 1) {
+    // ---- MMA issuer --------------------------------------------------------------------------------------------------
     constexpr uint32_t idesc256 = umma_idesc_f16(256), idesc128 = umma_idesc_f16(128), idesc64 = umma_idesc_f16(64);
     const uint64_t wdesc0 = umma_desc_k128(smem_u32(wring));
     const uint64_t adesc0 = umma_desc_k128(smem_u32(aring));
     const uint64_t ct1desc = umma_desc_k128(smem_u32(ct)), ct2desc = umma_desc_k128(smem_u32(ct + PF_CHUNK));
     const uint64_t a16desc0 = umma_desc_k128(smem_u32(a16));
-    uint32_t st = 0, wph = 0;
-    uint32_t as = 0, aph = 0;            // A-ring slot and its phase parity (running over tiles)
     // F(kc): 64 channels kc*64.. = K-slice (kc >> 1), rows (kc & 1) * 64.. of the Wp16 tile
-    auto issue_f = [&](uint64_t ad, int kc) {
-      umma_bf16(RO + (uint32_t)(kc & 1) * 128u, ad, pf_desc_add(ct1desc, (uint32_t)(kc & 1) * (64 * 128 >> 4) + (uint32_t)(kc >> 1) * 2), idesc64, 0);
-      umma_commit(&f_full[kc & 1]);
+    auto issue_f = [&](uint64_t ad, int kc, bool commit = true) {
+      const uint32_t dst = kc == 0 ? RH + 64u : kc == 1 ? RH + 192u : RO + (uint32_t)(kc & 1) * 128u;
+      umma_bf16(dst, ad, pf_desc_add(ct1desc, (uint32_t)(kc & 1) * (64 * 128 >> 4) + (uint32_t)(kc >> 1) * 2), idesc64, 0);
+      if (commit) pf_commit(BAR(B_FFULL + kc));
     };
-    mbar_wait(&ct_full, 0);
+    pf_wait(BAR(B_CT), 0);
+    pf_wait(BAR(B_A16 + 0), 0);
+    tc_fence_after();
+    if (pf_elect_one()) {
+      issue_f(a16desc0, 0);
+      issue_f(a16desc0, 1);
+    }
+    __syncwarp();
     for (int j = 0; j < nt; ++j) {
       const uint32_t pj = (uint32_t)j & 1u;
       const uint64_t ad16 = pf_desc_add(a16desc0, pj * 2);
-      mbar_wait(&a16_full[pj], (uint32_t)(j >> 1) & 1u);
-      if (j > 0) mbar_wait(&fr_free, (uint32_t)(j - 1) & 1u);
-      tc_fence_after();
-      if (pf_elect_one()) {
-        PF_TR(j, 0);
-        issue_f(ad16, 0);
-        issue_f(ad16, 1);
-        // H = bias (accumulate = 0): G2 of the previous tile, which read H16 from this region, is ordered before by the MMA pipe
-        umma_bf16(RH, ad16, ct2desc, idesc128, 0);
-        umma_bf16(RH + 128u, ad16, pf_desc_add(ct2desc, 2), idesc128, 0);
-      }
-      __syncwarp();
-#pragma unroll 1
+      const uint64_t ad16n = pf_desc_add(a16desc0, (pj ^ 1u) * 2);
+      const bool more = j + 1 < nt;
+#pragma unroll
       for (int kc = 0; kc < 8; ++kc) {
-        mbar_wait(&a_ready[as], aph);
         if (lane == 0) PF_TR(j, 1 + 2 * kc);
-        mbar_wait(&w_full[st], wph);
-        mbar_wait(&w_full[st + 1], wph);
+        pf_wait(BAR(B_FULL + kc), pj);
+        if (kc == 0) pf_wait(BAR(B_GEN1), pj);         // chunk 1 generated too (its weights may still be in flight): both H-region F buffers have been read
         tc_fence_after();
         if (pf_elect_one()) {
           PF_TR(j, 2 + 2 * kc);
-          const uint64_t wd = pf_desc_add(wdesc0, st * (PF_CHUNK >> 4));
-          const uint64_t ad = pf_desc_add(adesc0, as * (PF_CHUNK >> 4));
+          const uint64_t wd = pf_desc_add(wdesc0, (uint32_t)(kc % 3) * (2 * PF_CHUNK >> 4));
+          const uint64_t ad = pf_desc_add(adesc0, (uint32_t)(kc % 3) * (PF_CHUNK >> 4));
+          if (kc == 0) {
+            // H = bias (accumulate = 0): G2 of the previous tile, which read H16 from this region, is ordered before by the MMA pipe
+            umma_bf16(RH, ad16, ct2desc, idesc128, 0);
+            umma_bf16(RH + 128u, ad16, pf_desc_add(ct2desc, 2), idesc128, 0);
+          }
+          if (kc >= 2 && kc + 2 < 8) issue_f(ad16, kc + 2);      // its F buffer (kc & 1) was read for chunk kc
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) umma_bf16(RH, pf_desc_add(ad, ks * 2), pf_desc_add(wd, ks * 2), idesc256, 1);
-          umma_commit(&w_empty[st]);
-          umma_commit(&w_empty[st + 1]);
-          umma_commit(&a_free[as]);
-          // chunk kc has been converted (a_ready), so its F buffer (kc & 1) is free for chunk kc + 2
-          if (kc + 2 < 8) issue_f(ad16, kc + 2);
-          if (kc == 7) umma_commit(&h_full);
+          pf_commit(BAR(B_EMPTY + kc % 3));
+          if (kc == 7) pf_commit(BAR(B_HFULL));
         }
         __syncwarp();
-        st += 2;
-        if (st == PF_NST) { st = 0; wph ^= 1u; }
-        if (++as == P0T_ASLOTS) { as = 0; aph ^= 1u; }
+        if (kc == 0) {
+          // chunks 2 and 3 go to the OUT-region buffers: the previous tile's epilogue must have read those columns
+          if (j > 0) pf_wait(BAR(B_FRFREE), (uint32_t)(j - 1) & 1u);
+          tc_fence_after();
+          if (pf_elect_one()) {
+            issue_f(ad16, 2, false);     // one commit (f_full[3]) covers both; the generator waits on it for chunk 2 as well
+            issue_f(ad16, 3);
+          }
+          __syncwarp();
+        }
       }
       // G2 writes the whole OUT region (incl. the F buffers, all read by now): the previous tile's epilogue must have drained it
-      if (j > 0) mbar_wait(&out_drained, (uint32_t)(j - 1) & 1u);
+      if (j > 0) pf_wait(BAR(B_DRAINED), (uint32_t)(j - 1) & 1u);
+      if (more) pf_wait(BAR(B_A16 + (pj ^ 1u)), (uint32_t)((j + 1) >> 1) & 1u);
       tc_fence_after();
       if (pf_elect_one()) {
         PF_TR(j, 17);
@@ -878,31 +941,33 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block0_tc_kernel(const
       __syncwarp();
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
-        mbar_wait(&h_ready[kc], pj);
+        constexpr int S0 = 8;
         if (lane == 0) PF_TR(j, 18 + 2 * kc);
-        mbar_wait(&w_full[st], wph);
-        mbar_wait(&w_full[st + 1], wph);
+        pf_wait(BAR(B_G2FULL + kc), pj);
         tc_fence_after();
         if (pf_elect_one()) {
           PF_TR(j, 19 + 2 * kc);
-          const uint64_t wd = pf_desc_add(wdesc0, st * (PF_CHUNK >> 4));
+          const uint64_t wd = pf_desc_add(wdesc0, (uint32_t)((S0 + kc) % 3) * (2 * PF_CHUNK >> 4));
+          // next tile's chunk 0 / 1 into the H-region columns freed by the fp16 conversion of H columns [0,128) / [128,256)
+          if (kc == 1 && more) issue_f(ad16n, 0);
+          if (kc == 3 && more) issue_f(ad16n, 1);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             umma_f16_ts(RO, RH + (uint32_t)((kc >> 1) * 128 + (kc & 1) * 32 + ks * 8), pf_desc_add(wd, ks * 2), idesc256, 1);
-          umma_commit(&w_empty[st]);
-          umma_commit(&w_empty[st + 1]);
-          if (kc == 3) umma_commit(&out_full);
+          pf_commit(BAR(B_EMPTY + (S0 + kc) % 3));
+          if (kc == 3) pf_commit(BAR(B_OUTFULL));
         }
         __syncwarp();
-        st += 2;
-        if (st == PF_NST) { st = 0; wph ^= 1u; }
       }
     }
-  } else if (warp < 6) {
-    // ---- H group: thread = point.  Coordinate operand, generator epilogue, H epilogue -----------------------------
+  } else if (warp < 6 || warp >= 14) {
+    // ---- generator groups: thread = point.  Group 0 (warps 2-5) converts the even chunks and writes the coordinate
+    // operand, group 1 (warps 14-17) the odd chunks; each group owns one F staging buffer, so the two chains are independent
+    const int gsel = warp >= 14 ? 1 : 0;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t ar = smem_u32(aring), a16a = smem_u32(a16);
     float px = 0.f, py = 0.f, pz = 0.f;
     bool pvalid = false;
     auto load_xyz = [&](int j) {
@@ -918,79 +983,64 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block0_tc_kernel(const
         }
       }
     };
+    auto st128 = [](uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+    };
     auto write_a16 = [&](int buf) {
       const __half xh = __float2half_rn(px), yh = __float2half_rn(py), zh = __float2half_rn(pz);
       const __half xl = __float2half_rn(px - __half2float(xh)), yl = __float2half_rn(py - __half2float(yh)),
                    zl = __float2half_rn(pz - __half2float(zh));
       const __half one = __float2half_rn(pvalid ? 1.f : 0.f), zero = __float2half_rn(0.f);
       auto pk = [](__half lo, __half hi) { return (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16); };
-      *reinterpret_cast<uint4*>(a16 + pf_sw128(row, 2 * buf)) = make_uint4(pk(xh, yh), pk(zh, xl), pk(yl, zl), pk(xh, yh));
-      *reinterpret_cast<uint4*>(a16 + pf_sw128(row, 2 * buf + 1)) = make_uint4(pk(zh, one), pk(one, zero), 0u, 0u);
+      st128(a16a + pf_sw128(row, 2 * buf), pk(xh, yh), pk(zh, xl), pk(yl, zl), pk(xh, yh));
+      st128(a16a + pf_sw128(row, 2 * buf + 1), pk(zh, one), pk(one, zero), 0u, 0u);
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&a16_full[buf]);
+      if (lane == 0) pf_arrive(BAR(B_A16 + buf));
     };
-    load_xyz(0);
-    write_a16(0);
-    load_xyz(1);
-    uint32_t as = 0, aph = 1;            // producer side of the A ring: first round passes immediately
+    if (gsel == 0) {
+      load_xyz(0);
+      write_a16(0);
+      load_xyz(1);
+    }
     for (int j = 0; j < nt; ++j) {
       const uint32_t pj = (uint32_t)j & 1u;
-#pragma unroll 1
-      for (int kc = 0; kc < 8; ++kc) {
-        // F buffer kc & 1 completes 4 times per tile
-        mbar_wait(&f_full[kc & 1], (uint32_t)(kc >> 1) & 1u);
+#pragma unroll
+      for (int kc2 = 0; kc2 < 8; kc2 += P0T_GEN_GROUPS) {
+        const int kc = kc2 + gsel;
+        pf_wait(BAR(B_FFULL + (kc == 2 ? 3 : kc)), pj);
         if (threadIdx.x == 64) PF_TR(j, 26 + 2 * kc);
         tc_fence_after();
         uint32_t r[64];
-        const uint32_t tf = RO + lane_off + (uint32_t)(kc & 1) * 128u;
+        const uint32_t tf = (kc == 0 ? RH + 64u : kc == 1 ? RH + 192u : RO + (uint32_t)(kc & 1) * 128u) + lane_off;
         tmem_ld32(tf, r);
         tmem_ld32(tf + 32, r + 32);
-        mbar_wait(&a_free[as], aph);
-        uint8_t* ctile = aring + as * PF_CHUNK;
+        // A-ring slot kc % 3: released by the commit of the step that used ring index kc % 3 before (3 steps earlier)
+        pf_wait(BAR(B_EMPTY + kc % 3), (uint32_t)((kc / 3) & 1) ^ 1u);
+        const uint32_t ctile = ar + (uint32_t)(kc % 3) * PF_CHUNK;
+        if (threadIdx.x == 64 && kc == 4) PF_TR(j, 60);
         tmem_ld_wait();
+        if (threadIdx.x == 64 && kc == 4) PF_TR(j, 61);
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj)
-          *reinterpret_cast<uint4*>(ctile + pf_sw128(row, jj)) =
-              make_uint4(pf_relu_pack(r[8 * jj], r[8 * jj + 1]), pf_relu_pack(r[8 * jj + 2], r[8 * jj + 3]),
-                         pf_relu_pack(r[8 * jj + 4], r[8 * jj + 5]), pf_relu_pack(r[8 * jj + 6], r[8 * jj + 7]));
+          st128(ctile + pf_sw128(row, jj), pf_relu_pack(r[8 * jj], r[8 * jj + 1]), pf_relu_pack(r[8 * jj + 2], r[8 * jj + 3]),
+                pf_relu_pack(r[8 * jj + 4], r[8 * jj + 5]), pf_relu_pack(r[8 * jj + 6], r[8 * jj + 7]));
+        if (threadIdx.x == 64 && kc == 4) PF_TR(j, 62);
         tc_fence_before();
         fence_proxy_async();
+        if (threadIdx.x == 64 && kc == 4) PF_TR(j, 63);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a_ready[as]);
-        if (threadIdx.x == 64) PF_TR(j, 27 + 2 * kc);
-        if (++as == P0T_ASLOTS) { as = 0; aph ^= 1u; }
-      }
-      // H epilogue (in place in TMEM): relu + fp16, the bias is already in the accumulator
-      mbar_wait(&h_full, pj);
-      if (threadIdx.x == 64) PF_TR(j, 42);
-      tc_fence_after();
-#pragma unroll 1
-      for (int hsel = 0; hsel < 2; ++hsel) {
-        const uint32_t thh = RH + lane_off + (uint32_t)hsel * 128u;
-        uint32_t raw[2][32];
-        tmem_ld32(thh, raw[0]);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          tmem_ld_wait();
-          if (g < 3) tmem_ld32(thh + (g + 1) * 32, raw[(g + 1) & 1]);
-          const uint32_t* r = raw[g & 1];
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = pf_relu_pack(r[2 * i], r[2 * i + 1]);
-          tmem_st16(thh + g * 16, pk);
-          if (g & 1) {
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&h_ready[hsel * 2 + (g >> 1)]);
-          }
+        if (lane == 0) {
+          pf_arrive(BAR(B_FULL + kc));
+          if (kc == 1) pf_arrive(BAR(B_GEN1));
         }
+        if (threadIdx.x == 64) PF_TR(j, 27 + 2 * kc);
       }
-      // coordinate operand of the next tile: its K-slice was last read by tile j-1's MMAs, all complete before h_full(j)
-      if (threadIdx.x == 64) PF_TR(j, 43);
-      if (j + 1 < nt) write_a16((j + 1) & 1);
-      load_xyz(j + 2);
+      // coordinate operand of the next tile: its K-slice was last read by tile j-1's MMAs, all complete before f_full(j, *)
+      if (gsel == 0) {
+        if (j + 1 < nt) write_a16((j + 1) & 1);
+        load_xyz(j + 2);
+      }
     }
   } else {
     // ---- O group ---------------------------------------------------------------------------------------------------
@@ -1007,24 +1057,31 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block0_tc_kernel(const
       colmax_s[te] = 0u;
       pf_epi_sync();
     };
-    uint8_t* ctile = stage + hsel * PF_CHUNK;
-    // 32 columns (hsel * 128 + g * 32 ..) of this thread's row: fp16 into the staging chunk, then the pooled column max
-    auto process = [&](uint32_t (&r)[32], int g, bool valid) {
+    const uint32_t st0 = smem_u32(stage) + (uint32_t)hsel * PF_CHUNK + (uint32_t)row * 128u;
+    const uint32_t swz = (uint32_t)(row & 7);
+    auto st128 = [](uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+    };
+    auto pack2 = [](uint32_t lo, uint32_t hi) {
+      const __half2 h = __floats2half2_rn(__uint_as_float(lo), __uint_as_float(hi));
+      return *reinterpret_cast<const uint32_t*>(&h);
+    };
+    // pooled column max of 32 columns (hsel * 128 + g * 32 ..) held one row per lane; r is destroyed
+    auto colmax = [&](uint32_t (&r)[32], int g, bool valid) {
+      float(&f)[32] = reinterpret_cast<float(&)[32]>(r);
+      if (!valid) {
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const __half2 h0 = __floats2half2_rn(__uint_as_float(r[8 * jj]), __uint_as_float(r[8 * jj + 1]));
-        const __half2 h1 = __floats2half2_rn(__uint_as_float(r[8 * jj + 2]), __uint_as_float(r[8 * jj + 3]));
-        const __half2 h2 = __floats2half2_rn(__uint_as_float(r[8 * jj + 4]), __uint_as_float(r[8 * jj + 5]));
-        const __half2 h3 = __floats2half2_rn(__uint_as_float(r[8 * jj + 6]), __uint_as_float(r[8 * jj + 7]));
-        *reinterpret_cast<uint4*>(ctile + pf_sw128(row, (g & 1) * 4 + jj)) =
-            make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
-                       *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+        for (int i = 0; i < 32; ++i) f[i] = -INFINITY;
       }
-      float f[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = valid ? __uint_as_float(r[i]) : -INFINITY;
       const float mine = pf_colmax32(f, lane);
       atomicMax(&colmax_s[hsel * 128 + g * 32 + lane], f2ord(mine));
+    };
+    // fp16 of the 32 columns straight into the staging chunk (16-byte chunks (g & 1) * 4 .. of this thread's row)
+    auto stage_from_raw = [&](const uint32_t (&r)[32], int g) {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+        st128(st0 + ((((uint32_t)((g & 1) * 4 + jj)) ^ swz) << 4), pack2(r[8 * jj], r[8 * jj + 1]), pack2(r[8 * jj + 2], r[8 * jj + 3]),
+              pack2(r[8 * jj + 4], r[8 * jj + 5]), pack2(r[8 * jj + 6], r[8 * jj + 7]));
     };
     int cur_sample = -1;
     for (int j = 0; j < nt; ++j) {
@@ -1035,9 +1092,36 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block0_tc_kernel(const
         if (cur_sample >= 0) flush_colmax(cur_sample);
         cur_sample = sample;
       }
+      // H epilogue (in place in TMEM): relu + fp16 of H columns hsel * 128 .., the bias is already in the accumulator.
+      // Done by this group (8 warps, idle between two output epilogues) so that the generator warps keep generating.
+      pf_wait(BAR(B_HFULL), pj);
+      if (elected) PF_TR(j, 42);
+      tc_fence_after();
+      {
+        const uint32_t thh = RH + lane_off + (uint32_t)hsel * 128u;
+        uint32_t raw[2][32];
+        tmem_ld32(thh, raw[0]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          tmem_ld_wait();
+          if (g < 3) tmem_ld32(thh + (g + 1) * 32, raw[(g + 1) & 1]);
+          const uint32_t* r = raw[g & 1];
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pf_relu_pack(r[2 * i], r[2 * i + 1]);
+          tmem_st16(thh + g * 16, pk);
+          if (g & 1) {
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) pf_arrive(BAR(B_G2FULL + hsel * 2 + (g >> 1)));
+          }
+        }
+      }
+      if (elected) PF_TR(j, 43);
       const bool valid = n0 + row < a.n_points;
       const uint32_t to = RO + lane_off + (uint32_t)hsel * 128u;
-      mbar_wait(&out_full, pj);
+      pf_wait(BAR(B_OUTFULL), pj);
       if (elected) PF_TR(j, 44);
       tc_fence_after();
       uint32_t raw[2][32];
@@ -1046,40 +1130,53 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block0_tc_kernel(const
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (elected) PF_TR(j, 45);
-      if (lane == 0) mbar_arrive(&fr_free);          // columns [0,64) and [128,192): the next tile's F staging buffers
-      process(raw[0], 0, valid);
+      if (lane == 0) pf_arrive(BAR(B_FRFREE));       // columns [0,64) and [128,192): the next tile's F staging buffers
+      if (elected) { PF_TR(j, 45); pf_store_wait_read(); }     // the previous tile's second store round has read the staging chunks
+      pf_epi_sync();
+      stage_from_raw(raw[0], 0);
+      colmax(raw[0], 0, valid);
       tmem_ld32(to + 64, raw[0]);
-      process(raw[1], 1, valid);
+      stage_from_raw(raw[1], 1);
+      colmax(raw[1], 1, valid);
       tmem_ld_wait();
       tmem_ld32(to + 96, raw[1]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&out_drained);
-      if (elected) PF_TR(j, 46);
       fence_proxy_async();
       pf_epi_sync();
       if (elected) {
         tma_store_3d(&tm.xout, stage, 0, n0, sample);
         tma_store_3d(&tm.xout, stage + PF_CHUNK, 128, n0, sample);
         pf_store_commit();
-        pf_store_wait_read();
       }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) pf_arrive(BAR(B_DRAINED));
+      if (elected) PF_TR(j, 46);
+      // second round: pack (16 words per 32 columns) and pool first -- that hides the first round's store reading the staging chunks
+      uint32_t pk[2][16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[0][i] = pack2(raw[0][2 * i], raw[0][2 * i + 1]);
+      colmax(raw[0], 2, valid);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[1][i] = pack2(raw[1][2 * i], raw[1][2 * i + 1]);
+      colmax(raw[1], 3, valid);
+      if (elected) pf_store_wait_read();
       pf_epi_sync();        // the staging chunks are free for the second round
-      process(raw[0], 2, valid);
-      process(raw[1], 3, valid);
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          st128(st0 + ((((uint32_t)(h2 * 4 + jj)) ^ swz) << 4), pk[h2][4 * jj], pk[h2][4 * jj + 1], pk[h2][4 * jj + 2], pk[h2][4 * jj + 3]);
       fence_proxy_async();
       pf_epi_sync();
       if (elected) {
         tma_store_3d(&tm.xout, stage, 64, n0, sample);
         tma_store_3d(&tm.xout, stage + PF_CHUNK, 192, n0, sample);
         pf_store_commit();
-        pf_store_wait_read();
+        PF_TR(j, 47);
       }
-      pf_epi_sync();
-      if (elected) PF_TR(j, 47);
     }
+    if (elected) pf_store_wait_read();
     if (cur_sample >= 0) flush_colmax(cur_sample);
   }
   tc_fence_before();
@@ -1628,7 +1725,7 @@ int pf_block0_forward(const float* xyz, void* x_out, const void* w_blob, const v
     a.colmax = colmax;
     a.wblob = reinterpret_cast<const uint8_t*>(w_blob);
     a.ctblob = reinterpret_cast<const uint8_t*>(ctblob);
-    pointnet_block0_tc_kernel<<<grid, PF_THREADS, P0T_SMEM, s>>>(maps, a);
+    pointnet_block0_tc_kernel<<<grid, P0T_THREADS, P0T_SMEM, s>>>(maps, a);
   } else {
     P0Args a;
     a.n_points = n_points; a.tiles_per_sample = tiles_per_sample; a.n_tiles = n_tiles;

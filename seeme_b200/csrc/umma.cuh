@@ -20,9 +20,16 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU box.
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU box.  The loop must NOT be unrolled and the
+// timeout path stays out of line: the unrolled form (x4 with an inlined printf at every call site) was ~150 SASS
+// instructions per wait and the instruction-cache misses showed up as no_inst stalls of the MMA-issuing warp.
+static __device__ __noinline__ void mbar_wait_timeout(uint32_t addr) {
+  printf("seeme_b200: mbarrier wait timed out (block %d,%d thread %d barrier 0x%x)\n", blockIdx.x, blockIdx.y, threadIdx.x, addr);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 24); ++it) {
     uint32_t ok;
     asm volatile(
@@ -34,8 +41,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     if (ok) return;
   }
-  printf("seeme_b200: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-  __trap();
+  mbar_wait_timeout(addr);
 }
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

@@ -49,11 +49,14 @@ def per_sequence_errors(jts_text, jts_ref, ori_quat_text, ori_quat_ref, lengths:
     jp = jp - jp[:, :, [0]]
     mpjpe = ((jp - jr).norm(dim=-1).mean(-1) * fm).sum(1) / ln * 1000.0
     # acceleration error over the valid prefix (compute.py:254-279): frames 0..len-3
-    acc_gt = jr[:, :-2] - 2 * jr[:, 1:-1] + jr[:, 2:]
-    acc_pr = jp[:, :-2] - 2 * jp[:, 1:-1] + jp[:, 2:]
-    am = (torch.arange(T - 2, device=dev)[None, :] < (ln[:, None] - 2)).double()
-    accl = ((acc_pr - acc_gt).norm(dim=-1).mean(-1) * am).sum(1) / (ln - 2).clamp(min=1) * 1000.0
-    accl = torch.where(ln > 2, accl, torch.full_like(accl, float("nan")))     # np.mean of an empty array
+    if T >= 3:
+        acc_gt = jr[:, :-2] - 2 * jr[:, 1:-1] + jr[:, 2:]
+        acc_pr = jp[:, :-2] - 2 * jp[:, 1:-1] + jp[:, 2:]
+        am = (torch.arange(T - 2, device=dev)[None, :] < (ln[:, None] - 2)).double()
+        accl = ((acc_pr - acc_gt).norm(dim=-1).mean(-1) * am).sum(1) / (ln - 2).clamp(min=1) * 1000.0
+        accl = torch.where(ln > 2, accl, torch.full_like(accl, float("nan")))     # np.mean of an empty array
+    else:       # MOTION_LENGTH 1 (config_mld_interactee.yaml:20): no second difference exists, np.mean([]) = nan
+        accl = torch.full((B,), float("nan"), dtype=torch.float64, device=dev)
     # head orientation (compute.py:335-346, 527)
     Rg = quaternion_rotmat(ori_quat_ref.double()).view(B, T, 3, 3)
     Rp = quaternion_rotmat(ori_quat_text.double()).view(B, T, 3, 3)

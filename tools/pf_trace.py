@@ -45,19 +45,22 @@ assert n == TILES * SLOTS, n
 t = [[buf[i * SLOTS + k] for k in range(SLOTS)] for i in range(TILES)]
 names = {0: "F0 issue"}
 for kc in range(8):
-    names[1 + 2 * kc] = f"a_ready{kc}"
+    names[1 + 2 * kc] = f"wait full{kc}"
     names[2 + 2 * kc] = f"G1({kc}) issue"
     names[26 + 2 * kc] = f"  H: f_full{kc}"
     names[27 + 2 * kc] = f"  H: gen{kc} done"
 names[17] = "PF issue (out_drained)"
 for kc in range(4):
-    names[18 + 2 * kc] = f"h_ready{kc}"
+    names[18 + 2 * kc] = f"wait g2_full{kc}"
     names[19 + 2 * kc] = f"G2({kc}) issue"
+for st in range(12):
+    names[48 + st] = f"        P: load step {st}"
+names.update({60: "  H: gen4 after empty wait", 61: "  H: gen4 after tmem ld", 62: "  H: gen4 after cvt+sts", 63: "  H: gen4 after fence"})
 names.update({42: "  H: h_full", 43: "  H: epiH done", 44: "    O: out_full", 45: "    O: fr_free", 46: "    O: out_drained", 47: "    O: tile done"})
 for j in (8, 9):
-    base = t[j][0]
-    print(f"--- tile {j}: F0 issue of tile {j + 1} at +{t[j + 1][0] - base}")
-    for k, v in sorted(((k, t[j][k]) for k in names), key=lambda kv: kv[1]):
+    base = t[j][2]
+    print(f"--- tile {j}: G1(0) issue of tile {j + 1} at +{t[j + 1][2] - base}")
+    for k, v in sorted(((k, t[j][k]) for k in names if t[j][k]), key=lambda kv: kv[1]):
         print(f"{v - base:8d}  {names[k]}")
-per = [t[j + 1][0] - t[j][0] for j in range(2, TILES - 1)]
+per = [t[j + 1][2] - t[j][2] for j in range(2, TILES - 1)]
 print("tile period (cycles):", per)
