@@ -139,6 +139,48 @@ __device__ __forceinline__ float pf_colmax32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// Lean barrier primitives for the statically scheduled kernels below: 32-bit shared addresses computed once, a wait loop
+// the compiler may not unroll (the generic mbar_wait is unrolled x4 with its printf path at every call site, ~150 SASS
+// instructions per wait), the timeout path out of line.
+__device__ __noinline__ void pf_wait_timeout(uint32_t addr) {
+  printf("seeme_b200: mbarrier wait timed out (block %d thread %d barrier 0x%x)\n", blockIdx.x, threadIdx.x, addr);
+  __trap();
+}
+__device__ __forceinline__ void pf_wait(uint32_t addr, uint32_t parity) {
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  pf_wait_timeout(addr);
+}
+__device__ __forceinline__ void pf_arrive(uint32_t addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory"); }
+__device__ __forceinline__ void pf_arrive_tx(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pf_commit(uint32_t addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void pf_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+
+__device__ __forceinline__ uint32_t pf_relu_pack(uint32_t a, uint32_t b) {
+  uint32_t d;      // {lo = fp16(max(a, 0)), hi = fp16(max(b, 0))}: conversion, relu and packing in ONE instruction
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(b)), "f"(__uint_as_float(a)));
+  return d;
+}
+
 // H_TMEM: G2 reads its A operand (H) from tensor memory; false = H is written over relu(X) in shared memory
 template <bool H_TMEM>
 __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __grid_constant__ PfMaps tm, const PfArgs a) {
@@ -146,8 +188,13 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pf_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xbuf = smem;
   uint8_t* wring = smem + 2 * PF_XBUF;
-  __shared__ __align__(8) uint64_t w_full[PF_NST], w_empty[PF_NST], x_full[2], s_done[2][4], r_done[2][4], h_full[2][2],
-      h_ready[2][4], out_full[2], out_drained[2];
+  // Static schedule: 12 steps per tile, step s consumes the 32 KB weight pair s % 3 (chunks 2s, 2s+1 of the blob):
+  //   s = 0..3   S(kc)        step_full[s]: the pair's bytes
+  //   s = 4..7   G1(nh, kp)   K-chunks 2kp, 2kp+1 of N-half nh; step_full[4 + kp] also collects the relu arrivals (4 warps x 2 chunks)
+  //   s = 8..11  G2(kc)       step_full[s] also collects the 4 H-epilogue warps' arrivals
+  // one phase per tile and barrier (parity = tile & 1); w_empty[s % 3] is committed once per step (4 ring rounds per tile, so
+  // its parities are compile-time constants too)
+  __shared__ __align__(8) uint64_t step_full[12], w_empty[3], x_full[2], s_done[2][4], h_full[2][2], out_full[2], out_drained[2];
   __shared__ uint32_t tmem_slot;
   __shared__ unsigned colmax_s[256];
 
@@ -160,12 +207,13 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
     tma_prefetch_desc(&tm.xin);
     tma_prefetch_desc(&tm.w);
     tma_prefetch_desc(&tm.xout);
-    for (int i = 0; i < PF_NST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 12; ++i) mbar_init(&step_full[i], i < 4 ? 1 : i < 6 ? 9 : i < 8 ? 1 : 5);
+    for (int i = 0; i < 3; ++i) mbar_init(&w_empty[i], 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&x_full[b], 1);
       mbar_init(&out_full[b], 1);
       mbar_init(&out_drained[b], 8);
-      for (int k = 0; k < 4; ++k) { mbar_init(&s_done[b][k], 1); mbar_init(&r_done[b][k], 4); mbar_init(&h_ready[b][k], 4); }
+      for (int k = 0; k < 4; ++k) mbar_init(&s_done[b][k], 1);
       mbar_init(&h_full[b][0], 1);
       mbar_init(&h_full[b][1], 1);
     }
@@ -178,16 +226,17 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
+  const uint32_t sf0 = smem_u32(step_full), we0 = smem_u32(w_empty);
   if (warp == 0) {
-    // ---- weight-ring producer -------------------------------------------------------------------------
+    // ---- weight-ring producer: one 32 KB bulk copy per step ---------------------------------------------------
     if (lane == 0) {
-      uint32_t st = 0, ph = 1;
+      const uint32_t wr = smem_u32(wring);
       for (int j = 0; j < nt; ++j) {
-        for (int i = 0; i < PF_WCHUNKS; ++i) {
-          mbar_wait(&w_empty[st], ph);
-          mbar_arrive_expect_tx(&w_full[st], PF_CHUNK);
-          bulk_load(wring + st * PF_CHUNK, a.wblob + (size_t)i * PF_CHUNK, PF_CHUNK, &w_full[st]);
-          if (++st == PF_NST) { st = 0; ph ^= 1u; }
+#pragma unroll
+        for (int s = 0; s < 12; ++s) {
+          pf_wait(we0 + (uint32_t)(s % 3) * 8u, (uint32_t)((s / 3) & 1) ^ 1u);
+          pf_arrive_tx(sf0 + (uint32_t)s * 8u, 2 * PF_CHUNK);
+          pf_bulk_load(wr + (uint32_t)(s % 3) * 2 * PF_CHUNK, a.wblob + (size_t)s * 2 * PF_CHUNK, 2 * PF_CHUNK, sf0 + (uint32_t)s * 8u);
         }
       }
     }
@@ -195,65 +244,69 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
     // ---- MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues tcgen05.mma / commit ----
     constexpr uint32_t idesc128 = umma_idesc_f16(128), idesc256 = umma_idesc_f16(256);
     const uint64_t wdesc0 = umma_desc_k128(smem_u32(wring));
-    uint32_t st = 0, wph = 0;          // weight-ring slot and its phase parity
     for (int j = 0; j < nt; ++j) {
       const int b = j & 1;
-      const uint32_t p2 = (uint32_t)(j >> 1) & 1u;
+      const uint32_t pj = (uint32_t)j & 1u, p2 = (uint32_t)(j >> 1) & 1u;
       // TMEM: OUT(j) lives in region j & 1, H(j) in the other one, i.e. where OUT(j-1) was: tile j's shortcut GEMM
       // overlaps tile j-1's output epilogue
       const uint32_t Ra = tmem_base + (uint32_t)b * 256u, Rb = tmem_base + (uint32_t)(b ^ 1) * 256u;
       const uint64_t xdesc = umma_desc_k128(smem_u32(xbuf + b * PF_XBUF));
+      if (lane == 0) PF_TR(j, 0);
       mbar_wait(&x_full[b], p2);
-      // S: OUT = X . Ws^T  -- per K-chunk one N = 256 MMA group over two adjacent ring slots (n-halves)
+      if (lane == 0) PF_TR(j, 1);
+      // S: OUT = X . Ws^T  -- per K-chunk one N = 256 MMA group over the two chunks (n-halves) of the pair
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
-        mbar_wait(&w_full[st], wph);
-        mbar_wait(&w_full[st + 1], wph);
+        constexpr int S0 = 0;
+        pf_wait(sf0 + (uint32_t)(S0 + kc) * 8u, pj);
         tc_fence_after();
         if (pf_elect_one()) {
-          const uint64_t wd = pf_desc_add(wdesc0, st * (PF_CHUNK >> 4));
+          PF_TR(j, 2 + kc);
+          const uint64_t wd = pf_desc_add(wdesc0, (uint32_t)((S0 + kc) % 3) * (2 * PF_CHUNK >> 4));
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             umma_bf16(Ra, pf_desc_add(xdesc, kc * (PF_CHUNK >> 4) + ks * 2), pf_desc_add(wd, ks * 2), idesc256, (kc | ks) != 0);
-          umma_commit(&w_empty[st]);
-          umma_commit(&w_empty[st + 1]);
+          pf_commit(we0 + (uint32_t)((S0 + kc) % 3) * 8u);
           umma_commit(&s_done[b][kc]);
         }
         __syncwarp();
-        st += 2;
-        if (st == PF_NST) { st = 0; wph ^= 1u; }
       }
       // the H region of this tile was the OUT region of the previous one: its epilogue must have drained it
       if (j > 0) mbar_wait(&out_drained[b ^ 1], (uint32_t)((j - 1) >> 1) & 1u);
-      // G1: H = relu(X) . W0^T  (n-half outer so that the first half's epilogue overlaps the second half's MMAs)
+      if (lane == 0) PF_TR(j, 6);
+      // G1: H = relu(X) . W0^T  (n-half outer so that the first half's epilogue overlaps the second half's MMAs);
+      // one step = two K-chunks of one n-half
 #pragma unroll
       for (int nh = 0; nh < 2; ++nh) {
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc) {
-          if (nh == 0) mbar_wait(&r_done[b][kc], p2);
-          mbar_wait(&w_full[st], wph);
+        for (int kp = 0; kp < 2; ++kp) {
+          const int s = 4 + nh * 2 + kp;
+          pf_wait(sf0 + (uint32_t)s * 8u, pj);
           tc_fence_after();
           if (pf_elect_one()) {
-            const uint64_t wd = pf_desc_add(wdesc0, st * (PF_CHUNK >> 4));
+            PF_TR(j, 3 + s);
+            const uint64_t wd = pf_desc_add(wdesc0, (uint32_t)(s % 3) * (2 * PF_CHUNK >> 4));
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_bf16(Rb + nh * 128, pf_desc_add(xdesc, kc * (PF_CHUNK >> 4) + ks * 2), pf_desc_add(wd, ks * 2), idesc128, (kc | ks) != 0);
-            umma_commit(&w_empty[st]);
-            if (kc == 3) umma_commit(&h_full[b][nh]);
+            for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16(Rb + nh * 128, pf_desc_add(xdesc, (kp * 2 + kk) * (PF_CHUNK >> 4) + ks * 2),
+                          pf_desc_add(wd, kk * (PF_CHUNK >> 4) + ks * 2), idesc128, (kp | kk | ks) != 0);
+            pf_commit(we0 + (uint32_t)(s % 3) * 8u);
+            if (kp == 1) umma_commit(&h_full[b][nh]);
           }
           __syncwarp();
-          if (++st == PF_NST) { st = 0; wph ^= 1u; }
         }
       }
       // G2: OUT += H16 . W1^T  (N = 256 per K-chunk)
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
-        mbar_wait(&h_ready[b][kc], p2);
-        mbar_wait(&w_full[st], wph);
-        mbar_wait(&w_full[st + 1], wph);
+        const int s = 8 + kc;
+        pf_wait(sf0 + (uint32_t)s * 8u, pj);
         tc_fence_after();
         if (pf_elect_one()) {
-          const uint64_t wd = pf_desc_add(wdesc0, st * (PF_CHUNK >> 4));
+          PF_TR(j, 3 + s);
+          const uint64_t wd = pf_desc_add(wdesc0, (uint32_t)(s % 3) * (2 * PF_CHUNK >> 4));
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             if (H_TMEM)
@@ -261,13 +314,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
             else
               umma_bf16(Ra, pf_desc_add(xdesc, kc * (PF_CHUNK >> 4) + ks * 2), pf_desc_add(wd, ks * 2), idesc256, 1);
           }
-          umma_commit(&w_empty[st]);
-          umma_commit(&w_empty[st + 1]);
+          pf_commit(we0 + (uint32_t)(s % 3) * 8u);
           if (kc == 3) umma_commit(&out_full[b]);
         }
         __syncwarp();
-        st += 2;
-        if (st == PF_NST) { st = 0; wph ^= 1u; }
       }
     }
   } else if (warp < 6) {
@@ -283,6 +333,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       uint8_t* xb = xbuf + b * PF_XBUF;
       for (int kc = 0; kc < 4; ++kc) {
         mbar_wait(&s_done[b][kc], p2);
+        if (th == 0) PF_TR(j, 16 + 2 * kc);
         uint4* p = reinterpret_cast<uint4*>(xb + kc * PF_CHUNK) + th;
         const __half2 z = __float2half2_rn(0.f);
 #pragma unroll
@@ -294,7 +345,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&r_done[b][kc]);
+        if (lane == 0) pf_arrive(sf0 + (uint32_t)(4 + (kc >> 1)) * 8u);
+        if (th == 0) PF_TR(j, 17 + 2 * kc);
       }
       const float* bh = a.bias_h + (size_t)sample * 256;
       const uint32_t tbase = tmem_base + (uint32_t)(b ^ 1) * 256u + lane_off;
@@ -302,6 +354,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
 #pragma unroll 1
       for (int hsel = 0; hsel < 2; ++hsel) {
         if (H_TMEM) mbar_wait(&h_full[b][hsel], p2);
+        if (th == 0) PF_TR(j, 24 + 2 * hsel);
         tc_fence_after();
         const uint32_t thh = tbase + (uint32_t)hsel * 128u;
         uint32_t raw[2][32];
@@ -334,9 +387,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
             if (H_TMEM) { tmem_st_wait(); tc_fence_before(); }
             else fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&h_ready[b][hsel * 2 + (g >> 1)]);
+            if (lane == 0) pf_arrive(sf0 + (uint32_t)(8 + hsel * 2 + (g >> 1)) * 8u);
           }
         }
+        if (th == 0) PF_TR(j, 25 + 2 * hsel);
       }
     }
   } else {
@@ -379,6 +433,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       const uint32_t to = tmem_base + (uint32_t)b * 256u + (uint32_t)hsel * 128u + lane_off;
       const bool valid = n0 + row < a.n_points;
       mbar_wait(&out_full[b], p2);
+      if (elected) PF_TR(j, 28);
       tc_fence_after();
       uint32_t raw[2][32];
       tmem_ld32(to, raw[0]);
@@ -394,6 +449,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&out_drained[b]);
+          if (elected) PF_TR(j, 29);
         }
         const uint32_t* r = raw[g & 1];
         float f[32];
@@ -419,6 +475,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       }
       if (a.store_out) fence_proxy_async();
       pf_epi_sync();
+      if (elected) PF_TR(j, 30);
       if (elected) {
         if (a.store_out) {
           for (int kc = 0; kc < 4; ++kc) tma_store_3d(&tm.xout, xb + kc * PF_CHUNK, kc * 64, n0, sample);
@@ -426,6 +483,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
           pf_store_wait_read();
         }
         if (j + 2 < nt) load_x(j + 2);
+        PF_TR(j, 31);
       }
     }
     if (cur_sample >= 0) flush_colmax(cur_sample);
@@ -759,46 +817,6 @@ struct P0TArgs {
   const uint8_t* ctblob;  // 2 pre-swizzled 16 KB constant tiles: Wp16 | (B0_16, PF16)
 };
 
-__device__ __forceinline__ uint32_t pf_relu_pack(uint32_t a, uint32_t b) {
-  uint32_t d;      // {lo = fp16(max(a, 0)), hi = fp16(max(b, 0))}: conversion, relu and packing in ONE instruction
-  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(b)), "f"(__uint_as_float(a)));
-  return d;
-}
-
-// Lean barrier primitives for the statically scheduled kernel below: 32-bit shared addresses computed once, a wait loop
-// the compiler may not unroll (the generic mbar_wait is unrolled x4 with its printf path at every call site, ~150 SASS
-// instructions per wait), the timeout path out of line.
-__device__ __noinline__ void pf_wait_timeout(uint32_t addr) {
-  printf("seeme_b200: mbarrier wait timed out (block %d thread %d barrier 0x%x)\n", blockIdx.x, threadIdx.x, addr);
-  __trap();
-}
-__device__ __forceinline__ void pf_wait(uint32_t addr, uint32_t parity) {
-#pragma unroll 1
-  for (uint32_t it = 0; it < (1u << 24); ++it) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) return;
-  }
-  pf_wait_timeout(addr);
-}
-__device__ __forceinline__ void pf_arrive(uint32_t addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory"); }
-__device__ __forceinline__ void pf_arrive_tx(uint32_t addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void pf_commit(uint32_t addr) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
-}
-__device__ __forceinline__ void pf_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
-               : "memory");
-}
 
 // Schedule (per tile, 12 static steps; step s uses weight-ring pair s % 3 = 32 KB = two adjacent chunks):
 //   steps 0..7  G1(kc): ONE barrier full[kc] collects the 4 generator warps' arrivals for A chunk kc (A-ring slot

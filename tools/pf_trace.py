@@ -38,6 +38,28 @@ p = S.egobody_scene(B, 20000, torch.Generator().manual_seed(3)).to(dev)
 for _ in range(3):
     op(p)
 torch.cuda.synchronize()
+if len(sys.argv) > 1 and sys.argv[1] == "block":
+    # the pointnet_block_kernel launches come after block 0 in a pass: the trace buffer holds the LAST launch (block 3)
+    TILES, SLOTS = 24, 64
+    buf = (C.c_longlong * (TILES * SLOTS))()
+    assert _lib.lib().seeme_pf_trace_read(buf, TILES * SLOTS) == TILES * SLOTS
+    t = [[buf[i * SLOTS + k] for k in range(SLOTS)] for i in range(TILES)]
+    names = {0: "wait x_full", 1: "x_full seen", 6: "out_drained(prev) seen"}
+    for kc in range(4):
+        names[2 + kc] = f"S({kc}) issue"
+        names[7 + kc] = f"G1(nh{kc >> 1},kp{kc & 1}) issue"
+        names[11 + kc] = f"G2({kc}) issue"
+        names[16 + 2 * kc] = f"  H: s_done{kc}"
+        names[17 + 2 * kc] = f"  H: relu{kc} done"
+    names.update({24: "  H: h_full0", 25: "  H: epiH0 done", 26: "  H: h_full1", 27: "  H: epiH1 done", 28: "    O: out_full",
+                  29: "    O: out_drained", 30: "    O: staged", 31: "    O: stored + next X load issued"})
+    for j in (8, 9):
+        base = t[j][2]
+        print(f"--- tile {j}: S(0) issue of tile {j + 1} at +{t[j + 1][2] - base}")
+        for k, v in sorted(((k, t[j][k]) for k in names if t[j][k]), key=lambda kv: kv[1]):
+            print(f"{v - base:8d}  {names[k]}")
+    print("tile period (cycles):", [t[j + 1][2] - t[j][2] for j in range(2, TILES - 1)])
+    sys.exit(0)
 TILES, SLOTS = 24, 64
 buf = (C.c_longlong * (TILES * SLOTS))()
 n = _lib.lib().seeme_pf_trace_read(buf, TILES * SLOTS)
