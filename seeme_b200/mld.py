@@ -299,11 +299,25 @@ class MLD(nn.Module):
         st.wait_stream(torch.cuda.current_stream(dev))          # device inputs were produced on the caller's stream
         lane = _m._LANE[0]
         _m._LANE[0] = 1000 + slot                                # handles of this slot (distinct from the lanes' handles)
+        # the Python list of lengths (mld.py:1264) is read BEFORE anything is enqueued: from the host tensor when the batch
+        # is host-resident, else once per distinct device tensor (a .tolist() after the scene encoder has been enqueued
+        # would block the host until that slot's encoder has finished)
+        length_t = batch[5 if "scene" in self.condition else 4]
+        if torch.is_tensor(length_t) and length_t.is_cuda:
+            cache = self.__dict__.setdefault("_length_cache", {})
+            key = (length_t.data_ptr(), tuple(length_t.shape), length_t._version)
+            if key not in cache:
+                if len(cache) > 64:
+                    cache.clear()
+                cache[key] = length_t.long().reshape(-1).tolist()
+            lengths_host = cache[key]
+        else:
+            lengths_host = torch.as_tensor(length_t).long().reshape(-1).tolist()
         try:
             with torch.cuda.stream(st):
                 b = tuple((x.to(dev, non_blocking=True) if torch.is_tensor(x) and not x.is_cuda else x) for x in batch)
                 n = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and not v.is_cuda else v) for k, v in (noise or {}).items()}
-                rs = self._ego_eval_one(b, n, defer_random=True)
+                rs = self._ego_eval_one(b, n, defer_random=True, lengths=lengths_host)
                 if "interactee" not in self.condition:            # mld.py:1572-1574 (RNG side effect kept)
                     joints_int = torch.rand_like(rs["joints_rst"])
                     rs["joints_interactee"] = joints_int
