@@ -153,7 +153,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="seeme_b200", choices=["seeme_b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="sequences per GPU per step")
@@ -270,9 +270,10 @@ def main():
     clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    for _ in range(max(args.warmup, 3) + depth):     # warm every pipeline slot (handles, sampler graphs)
-        submit_resident()
-    torch.cuda.synchronize()
+    # warm every pipeline slot (handles, sampler graphs) with the SAME submit / hold / synchronize pattern as the timed
+    # loop: the results of `depth` steps are alive at once there, and a caching-allocator miss (cudaMalloc = device-wide
+    # sync) inside the timed region showed up as 2x run-to-run variance
+    timed_pipelined(submit_resident, max(args.warmup, 3) + 2 * depth)
     if clocks:
         clocks.begin()
     t_res, launches, rs = timed_pipelined(submit_resident, args.steps)
@@ -340,8 +341,7 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        for _ in range(depth + 1):
-            submit_e2e().synchronize()
+        timed_pipelined(submit_e2e, max(args.warmup, 3) + 2 * depth, read_host=True)      # warm-up, same pattern as the timed loop
         t_e2e, _, _ = timed_pipelined(submit_e2e, args.steps, read_host=True)
         e2e = {"value": world * B * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(joints_host[0].numel() * 4)}

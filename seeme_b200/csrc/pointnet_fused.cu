@@ -60,6 +60,7 @@ struct PfArgs {
   unsigned* colmax;      // [samples, 256]  order-preserving uint, zeroed by the caller
   int store_out;
   const uint8_t* wblob;  // 24 pre-swizzled 16 KB weight chunks (byte image of the shared-memory tiles)
+  int debug_skip;        // diagnostics only (SEEME_PF_DEBUG_SKIP, wrong results): 1 = no relu pass, 2 = no pooled max, 4 = no H epilogue math
 };
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -137,6 +138,28 @@ __device__ __forceinline__ float pf_colmax32(float (&v)[32], int lane) {
     }
   }
   return v[0];
+}
+
+// same for 32 columns held as 16 packed fp16 pairs (columns 2i, 2i+1 in v[i]): 16 shuffles + 16 HMNMX2 instead of 31 + 31.
+// max and fp16 rounding commute (rounding is monotonic), so this is fp16(max over the fp32 values).  Returns the max of
+// column `lane` as fp32; v is destroyed.
+__device__ __forceinline__ float pf_colmax32_h2(uint32_t (&v)[16], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 2; off >>= 1) {
+    const bool up = (lane & off) != 0;
+    const int n = off >> 1;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const uint32_t keep = up ? v[i + n] : v[i];
+      const uint32_t send = up ? v[i] : v[i + n];
+      const uint32_t got = __shfl_xor_sync(0xffffffffu, send, off);
+      const __half2 m = __hmax2(*reinterpret_cast<const __half2*>(&keep), *reinterpret_cast<const __half2*>(&got));
+      v[i] = *reinterpret_cast<const uint32_t*>(&m);
+    }
+  }
+  const uint32_t got = __shfl_xor_sync(0xffffffffu, v[0], 1);
+  const __half2 m = __hmax2(*reinterpret_cast<const __half2*>(&v[0]), *reinterpret_cast<const __half2*>(&got));
+  return (lane & 1) ? __high2float(m) : __low2float(m);
 }
 
 // Lean barrier primitives for the statically scheduled kernels below: 32-bit shared addresses computed once, a wait loop
@@ -338,6 +361,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
         const __half2 z = __float2half2_rn(0.f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
+          if (a.debug_skip & 1) break;
           uint4 v = p[i * 128];
           __half2* h = reinterpret_cast<__half2*>(&v);
           h[0] = __hmax2(h[0], z); h[1] = __hmax2(h[1], z); h[2] = __hmax2(h[2], z); h[3] = __hmax2(h[3], z);
@@ -435,43 +459,47 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       mbar_wait(&out_full[b], p2);
       if (elected) PF_TR(j, 28);
       tc_fence_after();
-      uint32_t raw[2][32];
-      tmem_ld32(to, raw[0]);
+      // drain first: the accumulator region is the next tile's H region, so G1(j+1) waits for these four loads.  Each
+      // 32-column group is biased and packed to fp16 (16 words) straight away; staging and the pooled max (on the packed
+      // values: max and fp16 rounding commute) come after the region has been released
+      uint32_t pk[4][16];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
+        uint32_t raw[32];
+        tmem_ld32(to + g * 32, raw);
         float4 bv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bo + g * 32) + i);
         tmem_ld_wait();
-        if (g < 3) {
-          tmem_ld32(to + (g + 1) * 32, raw[(g + 1) & 1]);
-        } else {                                   // all of this warp's TMEM reads are complete
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&out_drained[b]);
-          if (elected) PF_TR(j, 29);
-        }
-        const uint32_t* r = raw[g & 1];
-        float f[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          f[4 * i] = __uint_as_float(r[4 * i]) + bv[i].x; f[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bv[i].y;
-          f[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bv[i].z; f[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bv[i].w;
+          pk[g][2 * i] = pf_pack(__uint_as_float(raw[4 * i]) + bv[i].x, __uint_as_float(raw[4 * i + 1]) + bv[i].y);
+          pk[g][2 * i + 1] = pf_pack(__uint_as_float(raw[4 * i + 2]) + bv[i].z, __uint_as_float(raw[4 * i + 3]) + bv[i].w);
         }
-        if (a.store_out) {
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&out_drained[b]);
+      if (elected) PF_TR(j, 29);
+      if (a.store_out) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
           uint8_t* ct = xb + (hsel * 2 + (g >> 1)) * PF_CHUNK;
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj)
-            *reinterpret_cast<uint4*>(ct + pf_sw128(row, (g & 1) * 4 + jj)) =
-                make_uint4(pf_pack(f[8 * jj], f[8 * jj + 1]), pf_pack(f[8 * jj + 2], f[8 * jj + 3]), pf_pack(f[8 * jj + 4], f[8 * jj + 5]),
-                           pf_pack(f[8 * jj + 6], f[8 * jj + 7]));
+            *reinterpret_cast<uint4*>(ct + pf_sw128(row, (g & 1) * 4 + jj)) = make_uint4(pk[g][4 * jj], pk[g][4 * jj + 1], pk[g][4 * jj + 2], pk[g][4 * jj + 3]);
         }
-        if (!valid) {
+      }
+      if (!(a.debug_skip & 2)) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = -INFINITY;
+        for (int g = 0; g < 4; ++g) {
+          if (!valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[g][i] = 0xfc00fc00u;      // -inf, -inf
+          }
+          const float mine = pf_colmax32_h2(pk[g], lane);
+          atomicMax(&colmax_s[hsel * 128 + g * 32 + lane], f2ord(mine));
         }
-        const float mine = pf_colmax32(f, lane);
-        atomicMax(&colmax_s[hsel * 128 + g * 32 + lane], f2ord(mine));
       }
       if (a.store_out) fence_proxy_async();
       pf_epi_sync();
@@ -1564,7 +1592,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PF_THREADS, 1)
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = -INFINITY;
         }
-        const float mine = pf_colmax32(f, lane);
+        const float mine = __half2float(__float2half_rn(pf_colmax32(f, lane)));   // fp16(max) = max over the stored fp16 values, as pointnet_block_kernel pools
         atomicMax(&colmax_s[hsel * 128 + g * 32 + lane], f2ord(mine));
       }
       if (a.store_out) fence_proxy_async();
@@ -1790,6 +1818,8 @@ int pf_block_forward(const void* x_in, void* x_out, const void* w_blob, const fl
   a.bias_h = bias_h; a.bias_o = bias_o; a.colmax = colmax;
   a.store_out = x_out != nullptr;
   a.wblob = reinterpret_cast<const uint8_t*>(w_blob);
+  static const int dbg = getenv("SEEME_PF_DEBUG_SKIP") ? atoi(getenv("SEEME_PF_DEBUG_SKIP")) : 0;
+  a.debug_skip = dbg;
   static bool configured = false;
   if (!configured) {
     SEEME_CUDA(cudaFuncSetAttribute(pointnet_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));

@@ -130,7 +130,7 @@ class MLD(nn.Module):
         self.lanes = int(kwargs.get("lanes", cfg.model.get("lanes", 1)))
         self.min_lane_batch = int(kwargs.get("min_lane_batch", cfg.model.get("min_lane_batch", 32)))
         # batches in flight for ego_eval_async / run_test_batches
-        self.pipeline_depth = int(kwargs.get("pipeline_depth", cfg.model.get("pipeline_depth", 6)))
+        self.pipeline_depth = int(kwargs.get("pipeline_depth", cfg.model.get("pipeline_depth", 8)))
         self.last_vertices: Dict[str, torch.Tensor] = {}
         self._uncond_scene = None
         self.eval()
@@ -329,6 +329,26 @@ class MLD(nn.Module):
             _m._LANE[0] = lane
         return PendingEval(rs, rs.pop("_last_vertices"), rs.pop("_last_latent"), ev, st)
 
+    def _encode_uncond(self, B: int, T: int, nfeats: int, lengths, eps, dev):
+        """``vae.encode(zeros_like(feats), lengths)`` of the CFG branch (mld.py:1280-1290).  The input is all zeros, so the
+        posterior (mu, std) of a row depends on its length only: one zero sequence per DISTINCT length is encoded and the
+        rows are gathered -- every row goes through the same arithmetic as in the full batch -- and the reparameterised
+        sample ``mu + eps * std`` (torch.distributions.Normal.rsample) uses the caller's / a fresh ``eps`` [1,B,256]."""
+        uniq = sorted(set(int(x) for x in lengths))
+        if eps is None:
+            eps = torch.randn(1, B, self.latent_dim[-1], device=dev, dtype=torch.float32)
+        U = len(uniq)
+        ulen = torch.tensor(uniq, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+        _, dist = self.vae.encode(torch.zeros(U, T, nfeats, device=dev), None, uniq,
+                                  eps=torch.zeros(1, U, self.latent_dim[-1], device=dev), lengths_dev=ulen)
+        if U == 1:
+            mu, std = dist.loc, dist.scale                                   # broadcast over the batch
+        else:
+            pos = {l: i for i, l in enumerate(uniq)}
+            idx = torch.tensor([pos[int(x)] for x in lengths], dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
+            mu, std = dist.loc.index_select(1, idx), dist.scale.index_select(1, idx)
+        return mu + eps * std
+
     def _ego_eval_one(self, batch, noise, defer_random: bool = False, t_max: Optional[int] = None, lengths=None):
         """one (sub-)batch on the current stream with the current lane's handles"""
         if "scene" in self.condition:
@@ -349,7 +369,7 @@ class MLD(nn.Module):
             B, T, _ = f_ref_int.shape
             text_emb, _ = self.vae.encode(f_ref_int, None, lengths, eps=noise.get("eps_int"), lengths_dev=len_dev)
             if self.do_classifier_free_guidance:
-                unc, _ = self.vae.encode(torch.zeros_like(f_ref_int), None, lengths, eps=noise.get("eps_unc"), lengths_dev=len_dev)
+                unc = self._encode_uncond(B, T, f_ref_int.shape[-1], lengths, noise.get("eps_unc"), dev)
                 text_emb = torch.cat([unc, text_emb], dim=1)               # mld.py:1290 (UNCOND first)
             cond_emb = torch.cat([text_emb, scene_emb], dim=0) if scene_emb is not None else text_emb
         else:
