@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
   uint8_t* wring = smem + 2 * PF_XBUF;
   // Static schedule: 12 steps per tile, step s consumes the 32 KB weight pair s % 3 (chunks 2s, 2s+1 of the blob):
   //   s = 0..3   S(kc)        step_full[s]: the pair's bytes
-  //   s = 4..7   G1(nh, kp)   K-chunks 2kp, 2kp+1 of N-half nh; step_full[4 + kp] also collects the relu arrivals (4 warps x 2 chunks)
+  //   s = 4..7   G1(kc)       N = 256 (A is read once; N = 128 halves re-read it and ran at the shared-memory bandwidth);
+  //                           step_full[s] also collects the 4 relu-warp arrivals for X chunk kc
   //   s = 8..11  G2(kc)       step_full[s] also collects the 4 H-epilogue warps' arrivals
   // one phase per tile and barrier (parity = tile & 1); w_empty[s % 3] is committed once per step (4 ring rounds per tile, so
   // its parities are compile-time constants too)
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
     tma_prefetch_desc(&tm.xin);
     tma_prefetch_desc(&tm.w);
     tma_prefetch_desc(&tm.xout);
-    for (int i = 0; i < 12; ++i) mbar_init(&step_full[i], i < 4 ? 1 : i < 6 ? 9 : i < 8 ? 1 : 5);
+    for (int i = 0; i < 12; ++i) mbar_init(&step_full[i], i < 4 ? 1 : 5);
     for (int i = 0; i < 3; ++i) mbar_init(&w_empty[i], 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&x_full[b], 1);
@@ -259,13 +260,18 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
         for (int s = 0; s < 12; ++s) {
           pf_wait(we0 + (uint32_t)(s % 3) * 8u, (uint32_t)((s / 3) & 1) ^ 1u);
           pf_arrive_tx(sf0 + (uint32_t)s * 8u, 2 * PF_CHUNK);
-          pf_bulk_load(wr + (uint32_t)(s % 3) * 2 * PF_CHUNK, a.wblob + (size_t)s * 2 * PF_CHUNK, 2 * PF_CHUNK, sf0 + (uint32_t)s * 8u);
+          if (s >= 4 && s < 8) {      // G1(kc): the blob keeps W0 n-half major (chunks 8 + nh * 4 + kc); both halves of K-chunk kc form the pair
+            pf_bulk_load(wr + (uint32_t)(s % 3) * 2 * PF_CHUNK, a.wblob + (size_t)(8 + s - 4) * PF_CHUNK, PF_CHUNK, sf0 + (uint32_t)s * 8u);
+            pf_bulk_load(wr + (uint32_t)(s % 3) * 2 * PF_CHUNK + PF_CHUNK, a.wblob + (size_t)(12 + s - 4) * PF_CHUNK, PF_CHUNK, sf0 + (uint32_t)s * 8u);
+          } else {
+            pf_bulk_load(wr + (uint32_t)(s % 3) * 2 * PF_CHUNK, a.wblob + (size_t)s * 2 * PF_CHUNK, 2 * PF_CHUNK, sf0 + (uint32_t)s * 8u);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ---- MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues tcgen05.mma / commit ----
-    constexpr uint32_t idesc128 = umma_idesc_f16(128), idesc256 = umma_idesc_f16(256);
+    constexpr uint32_t idesc256 = umma_idesc_f16(256);
     const uint64_t wdesc0 = umma_desc_k128(smem_u32(wring));
     for (int j = 0; j < nt; ++j) {
       const int b = j & 1;
@@ -297,29 +303,22 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       // the H region of this tile was the OUT region of the previous one: its epilogue must have drained it
       if (j > 0) mbar_wait(&out_drained[b ^ 1], (uint32_t)((j - 1) >> 1) & 1u);
       if (lane == 0) PF_TR(j, 6);
-      // G1: H = relu(X) . W0^T  (n-half outer so that the first half's epilogue overlaps the second half's MMAs);
-      // one step = two K-chunks of one n-half
+      // G1: H = relu(X) . W0^T  (N = 256 per K-chunk)
 #pragma unroll
-      for (int nh = 0; nh < 2; ++nh) {
+      for (int kc = 0; kc < 4; ++kc) {
+        const int s = 4 + kc;
+        pf_wait(sf0 + (uint32_t)s * 8u, pj);
+        tc_fence_after();
+        if (pf_elect_one()) {
+          PF_TR(j, 3 + s);
+          const uint64_t wd = pf_desc_add(wdesc0, (uint32_t)(s % 3) * (2 * PF_CHUNK >> 4));
 #pragma unroll
-        for (int kp = 0; kp < 2; ++kp) {
-          const int s = 4 + nh * 2 + kp;
-          pf_wait(sf0 + (uint32_t)s * 8u, pj);
-          tc_fence_after();
-          if (pf_elect_one()) {
-            PF_TR(j, 3 + s);
-            const uint64_t wd = pf_desc_add(wdesc0, (uint32_t)(s % 3) * (2 * PF_CHUNK >> 4));
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                umma_bf16(Rb + nh * 128, pf_desc_add(xdesc, (kp * 2 + kk) * (PF_CHUNK >> 4) + ks * 2),
-                          pf_desc_add(wd, kk * (PF_CHUNK >> 4) + ks * 2), idesc128, (kp | kk | ks) != 0);
-            pf_commit(we0 + (uint32_t)(s % 3) * 8u);
-            if (kp == 1) umma_commit(&h_full[b][nh]);
-          }
-          __syncwarp();
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(Rb, pf_desc_add(xdesc, kc * (PF_CHUNK >> 4) + ks * 2), pf_desc_add(wd, ks * 2), idesc256, (kc | ks) != 0);
+          pf_commit(we0 + (uint32_t)(s % 3) * 8u);
+          if (kc == 3) umma_commit(&h_full[b][0]);
         }
+        __syncwarp();
       }
       // G2: OUT += H16 . W1^T  (N = 256 per K-chunk)
 #pragma unroll
@@ -369,52 +368,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) pf_arrive(sf0 + (uint32_t)(4 + (kc >> 1)) * 8u);
+        if (lane == 0) pf_arrive(sf0 + (uint32_t)(4 + kc) * 8u);
         if (th == 0) PF_TR(j, 17 + 2 * kc);
-      }
-      const float* bh = a.bias_h + (size_t)sample * 256;
-      const uint32_t tbase = tmem_base + (uint32_t)(b ^ 1) * 256u + lane_off;
-      if (!H_TMEM) { mbar_wait(&h_full[b][0], p2); mbar_wait(&h_full[b][1], p2); }   // relu(X) is overwritten: G1 must be done
-#pragma unroll 1
-      for (int hsel = 0; hsel < 2; ++hsel) {
-        if (H_TMEM) mbar_wait(&h_full[b][hsel], p2);
-        if (th == 0) PF_TR(j, 24 + 2 * hsel);
-        tc_fence_after();
-        const uint32_t thh = tbase + (uint32_t)hsel * 128u;
-        uint32_t raw[2][32];
-        tmem_ld32(thh, raw[0]);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float4 bv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bh + hsel * 128 + g * 32) + i);
-          tmem_ld_wait();
-          if (g < 3) tmem_ld32(thh + (g + 1) * 32, raw[(g + 1) & 1]);
-          const uint32_t* r = raw[g & 1];
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float f0 = fmaxf(__uint_as_float(r[4 * i]) + bv[i].x, 0.f), f1 = fmaxf(__uint_as_float(r[4 * i + 1]) + bv[i].y, 0.f);
-            const float f2 = fmaxf(__uint_as_float(r[4 * i + 2]) + bv[i].z, 0.f), f3 = fmaxf(__uint_as_float(r[4 * i + 3]) + bv[i].w, 0.f);
-            pk[2 * i] = pf_pack(f0, f1);
-            pk[2 * i + 1] = pf_pack(f2, f3);
-          }
-          if (H_TMEM) {
-            tmem_st16(thh + g * 16, pk);         // in place: these 16 columns were read in this or an earlier group
-          } else {
-            uint8_t* ct = xb + (hsel * 2 + (g >> 1)) * PF_CHUNK;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-              *reinterpret_cast<uint4*>(ct + pf_sw128(row, (g & 1) * 4 + jj)) = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
-          }
-          if (g & 1) {
-            if (H_TMEM) { tmem_st_wait(); tc_fence_before(); }
-            else fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) pf_arrive(sf0 + (uint32_t)(8 + hsel * 2 + (g >> 1)) * 8u);
-          }
-        }
-        if (th == 0) PF_TR(j, 25 + 2 * hsel);
       }
     }
   } else {
@@ -452,6 +407,47 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       if (sample != cur_sample) {
         if (cur_sample >= 0) flush_colmax(cur_sample);
         cur_sample = sample;
+      }
+      // H epilogue of THIS tile (both column halves in parallel on the 8 warps of this group; the 4 relu warps stay on the
+      // relu pass): H16 = fp16(relu(H + c0[b])), in place in TMEM (or over relu(X) in shared memory)
+      {
+        const float* bh = a.bias_h + (size_t)sample * 256 + hsel * 128;
+        const uint32_t thh = tmem_base + (uint32_t)(b ^ 1) * 256u + lane_off + (uint32_t)hsel * 128u;
+        mbar_wait(&h_full[b][0], p2);
+        if (elected) PF_TR(j, 24);
+        tc_fence_after();
+        uint32_t raw[2][32];
+        tmem_ld32(thh, raw[0]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float4 bv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bh + g * 32) + i);
+          tmem_ld_wait();
+          if (g < 3) tmem_ld32(thh + (g + 1) * 32, raw[(g + 1) & 1]);
+          const uint32_t* r = raw[g & 1];
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            pk[2 * i] = pf_relu_pack(__float_as_uint(__uint_as_float(r[4 * i]) + bv[i].x), __float_as_uint(__uint_as_float(r[4 * i + 1]) + bv[i].y));
+            pk[2 * i + 1] = pf_relu_pack(__float_as_uint(__uint_as_float(r[4 * i + 2]) + bv[i].z), __float_as_uint(__uint_as_float(r[4 * i + 3]) + bv[i].w));
+          }
+          if (H_TMEM) {
+            tmem_st16(thh + g * 16, pk);         // in place: these 16 columns were read in this or an earlier group
+          } else {
+            uint8_t* ct = xb + (hsel * 2 + (g >> 1)) * PF_CHUNK;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              *reinterpret_cast<uint4*>(ct + pf_sw128(row, (g & 1) * 4 + jj)) = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+          }
+          if (g & 1) {
+            if (H_TMEM) { tmem_st_wait(); tc_fence_before(); }
+            else fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) pf_arrive(sf0 + (uint32_t)(8 + hsel * 2 + (g >> 1)) * 8u);
+          }
+        }
+        if (elected) PF_TR(j, 25);
       }
       const float* bo = a.bias_o + (size_t)sample * 256 + hsel * 128;
       const uint32_t to = tmem_base + (uint32_t)b * 256u + (uint32_t)hsel * 128u + lane_off;

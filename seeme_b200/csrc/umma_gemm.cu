@@ -394,7 +394,9 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
   SEEME_REQUIRE((!g.Yl || g.Yh) && (!g.Zl || g.Zh), SEEME_EINVAL, "umma_linear: lo outputs need their hi companion");
   // few rows (the latency-bound sampler / per-sample GEMMs): narrow tiles spread one GEMM over more SMs;
   // many rows: the widest tile that divides N (128 when a residual tile has to be staged as well)
-  int BN = (g.M <= 2048 && !g.colmax) ? 64 : 128;
+  // SEEME_UMMA_SMALL_BN=128: experiment knob (fewer, fatter CTAs for the few-row GEMMs of the sampler chain)
+  static const int small_bn = getenv("SEEME_UMMA_SMALL_BN") ? atoi(getenv("SEEME_UMMA_SMALL_BN")) : 64;
+  int BN = (g.M <= 2048 && !g.colmax) ? (small_bn == 128 ? 128 : 64) : 128;
   if (g.N % BN != 0) BN = 64;
   SEEME_REQUIRE(g.N % BN == 0, SEEME_EINVAL, "umma_linear: N=%d must be a multiple of 64", g.N);
   UmmaMaps maps;
