@@ -360,10 +360,10 @@ def main():
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         ach = flops / (pn_ms / 1e3) / 1e12 if pn_ms > 0 else None
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_pointnet_block_kernel_ncu.json")
+        tp = os.path.join(ROOT, "profiles", "r1_pointnet_kernels_s4_ncu.json")
         if os.path.exists(tp):
             try:
-                k0 = json.load(open(tp))[0]
+                k0 = [k for k in json.load(open(tp)) if "pointnet_block_kernel" in k["Kernel Name"]][0]
                 traffic = (k0["dram__bytes_read.sum"]["value"] + k0["dram__bytes_write.sum"]["value"]) * 1e6
             except Exception:
                 traffic = None
@@ -372,7 +372,7 @@ def main():
                     "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": (ach / peak_tf) if ach else None,
                     "traffic": traffic,
                     "traffic_note": "dram read+write bytes of one pointnet_block_kernel launch (32 clouds x 20000 points) from "
-                                    "profiles/r1_pointnet_block_kernel_ncu.json; algorithmic 655 MB (fp16 tile in + out)",
+                                    "profiles/r1_pointnet_kernels_s4_ncu.json; algorithmic 655 MB (fp16 tile in + out)",
                     "algorithmic_flop_per_launch": POINTNET_FLOP_PER_POINT * N_POINTS * min(B, 128) / 4,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
                     "launches": pn_n, "avg_launch_ms": pn_ms / pn_n if pn_n else None,
