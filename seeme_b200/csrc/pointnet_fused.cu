@@ -50,7 +50,8 @@ constexpr int PF_CHUNK = 128 * 128;                 // [128 rows x 64 fp16], SWI
 constexpr int PF_XBUF = 4 * PF_CHUNK;               // one activation tile [128 x 256] fp16
 constexpr int PF_THREADS = 448;            // 2 control warps + 4 H-group warps + 8 O-group warps
 constexpr int PF_WCHUNKS = 24;                      // weight chunks per tile: S 8, G1 8, G2 8
-constexpr int PF_SMEM = 2 * PF_XBUF + PF_NST * PF_CHUNK + 1024;
+constexpr int PF_SMEM = 2 * PF_XBUF + PF_NST * PF_CHUNK + 1024;     // pair kernel (manual 1 KB alignment slack)
+constexpr int PF_SMEM_BLK = 2 * PF_XBUF + PF_NST * PF_CHUNK;       // pointnet_block_kernel (1 KB of static bias copy instead)
 
 struct PfMaps { CUtensorMap xin, xout, w; };
 struct PfArgs {
@@ -207,8 +208,11 @@ __device__ __forceinline__ uint32_t pf_relu_pack(uint32_t a, uint32_t b) {
 // H_TMEM: G2 reads its A operand (H) from tensor memory; false = H is written over relu(X) in shared memory
 template <bool H_TMEM>
 __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __grid_constant__ PfMaps tm, const PfArgs a) {
+  // no manual alignment slack here: the 1 KB goes to the per-sample bias copy below (the static + dynamic total is exactly
+  // the 227 KB limit); the declared alignment of the dynamic array is checked instead
   extern __shared__ __align__(1024) uint8_t pf_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pf_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = pf_smem_raw;
+  if ((smem_u32(pf_smem_raw) & 1023u) != 0u) __trap();
   uint8_t* xbuf = smem;
   uint8_t* wring = smem + 2 * PF_XBUF;
   // Static schedule: 12 steps per tile, step s consumes the 32 KB weight pair s % 3 (chunks 2s, 2s+1 of the blob):
@@ -221,6 +225,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
   __shared__ __align__(8) uint64_t step_full[12], w_empty[3], x_full[2], s_done[2][4], h_full[2][2], out_full[2], out_drained[2];
   __shared__ uint32_t tmem_slot;
   __shared__ unsigned colmax_s[256];
+  __shared__ __align__(16) float bias_o_s[256];     // cs[b] of the current sample: the L1 next to 225 KB of shared memory is tiny and the
+                                                   // output-epilogue drain waited ~800 cycles per 32 columns on __ldg of it
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = a.n_tiles / (int)gridDim.x, rem = a.n_tiles % (int)gridDim.x;
@@ -405,7 +411,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       const int sample = t / a.tiles_per_sample, n0 = (t % a.tiles_per_sample) * 128;
       uint8_t* xb = xbuf + b * PF_XBUF;
       if (sample != cur_sample) {
-        if (cur_sample >= 0) flush_colmax(cur_sample);
+        if (cur_sample >= 0) flush_colmax(cur_sample);       // (ends with a group barrier: nobody reads the old bias any more)
+        bias_o_s[te] = __ldg(a.bias_o + (size_t)sample * 256 + te);
+        pf_epi_sync();
         cur_sample = sample;
       }
       // H epilogue of THIS tile (both column halves in parallel on the 8 warps of this group; the 4 relu warps stay on the
@@ -413,6 +421,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       {
         const float* bh = a.bias_h + (size_t)sample * 256 + hsel * 128;
         const uint32_t thh = tmem_base + (uint32_t)(b ^ 1) * 256u + lane_off + (uint32_t)hsel * 128u;
+        float4 bv0[8];                                       // the first group's bias is fetched before the wait
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bv0[i] = __ldg(reinterpret_cast<const float4*>(bh) + i);
         mbar_wait(&h_full[b][0], p2);
         if (elected) PF_TR(j, 24);
         tc_fence_after();
@@ -422,7 +433,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
         for (int g = 0; g < 4; ++g) {
           float4 bv[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bh + g * 32) + i);
+          for (int i = 0; i < 8; ++i) bv[i] = g == 0 ? bv0[i] : __ldg(reinterpret_cast<const float4*>(bh + g * 32) + i);
           tmem_ld_wait();
           if (g < 3) tmem_ld32(thh + (g + 1) * 32, raw[(g + 1) & 1]);
           const uint32_t* r = raw[g & 1];
@@ -449,7 +460,6 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
         }
         if (elected) PF_TR(j, 25);
       }
-      const float* bo = a.bias_o + (size_t)sample * 256 + hsel * 128;
       const uint32_t to = tmem_base + (uint32_t)b * 256u + (uint32_t)hsel * 128u + lane_off;
       const bool valid = n0 + row < a.n_points;
       mbar_wait(&out_full[b], p2);
@@ -465,7 +475,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
         tmem_ld32(to + g * 32, raw);
         float4 bv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bo + g * 32) + i);
+        for (int i = 0; i < 8; ++i) bv[i] = *(reinterpret_cast<const float4*>(bias_o_s + hsel * 128 + g * 32) + i);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -1732,6 +1742,19 @@ int pf_pack_block0_ct(const float* wp, const float* bp, const float* b0, const f
   return SEEME_OK;
 }
 
+// Persistent grid size of the scene-encoder kernels.  Their CTAs take a whole SM each (225 KB of shared memory), so a full
+// grid excludes every other kernel while it runs; SEEME_PF_GRID < 148 leaves SMs to the other pipeline slots' kernels (the
+// latency-bound sampler chain, VAE, SMPL), see DESIGN.md 4.4.
+static int pf_grid_limit() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SEEME_PF_GRID");
+    v = e ? atoi(e) : NUM_SMS;
+    if (v < 1 || v > NUM_SMS) v = NUM_SMS;
+  }
+  return v;
+}
+
 // SEEME_PF_BLOCK0=cuda selects the CUDA-core generator (pointnet_block0_kernel) for A/B measurements
 static bool pf_block0_use_tc() {
   static int v = -1;
@@ -1752,7 +1775,7 @@ int pf_block0_forward(const float* xyz, void* x_out, const void* w_blob, const v
   maps.xin = maps.xout;
   SEEME_TRY(pf_w_map(&maps.w, w_blob));
   const int tiles_per_sample = (n_points + 127) / 128, n_tiles = tiles_per_sample * samples;
-  const int grid = n_tiles < NUM_SMS ? n_tiles : NUM_SMS;
+  const int grid = n_tiles < pf_grid_limit() ? n_tiles : pf_grid_limit();
   static bool configured = false;
   if (!configured) {
     SEEME_CUDA(cudaFuncSetAttribute(pointnet_block0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P0_SMEM));
@@ -1818,8 +1841,8 @@ int pf_block_forward(const void* x_in, void* x_out, const void* w_blob, const fl
   a.debug_skip = dbg;
   static bool configured = false;
   if (!configured) {
-    SEEME_CUDA(cudaFuncSetAttribute(pointnet_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
-    SEEME_CUDA(cudaFuncSetAttribute(pointnet_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    SEEME_CUDA(cudaFuncSetAttribute(pointnet_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BLK));
+    SEEME_CUDA(cudaFuncSetAttribute(pointnet_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BLK));
     configured = true;
   }
   static bool configured2 = false;
@@ -1834,9 +1857,9 @@ int pf_block_forward(const void* x_in, void* x_out, const void* w_blob, const fl
     SEEME_LAUNCH_CHECK();
     return SEEME_OK;
   }
-  const int grid = a.n_tiles < NUM_SMS ? a.n_tiles : NUM_SMS;
-  if (h_in_tmem) pointnet_block_kernel<true><<<grid, PF_THREADS, PF_SMEM, s>>>(maps, a);
-  else pointnet_block_kernel<false><<<grid, PF_THREADS, PF_SMEM, s>>>(maps, a);
+  const int grid = a.n_tiles < pf_grid_limit() ? a.n_tiles : pf_grid_limit();
+  if (h_in_tmem) pointnet_block_kernel<true><<<grid, PF_THREADS, PF_SMEM_BLK, s>>>(maps, a);
+  else pointnet_block_kernel<false><<<grid, PF_THREADS, PF_SMEM_BLK, s>>>(maps, a);
   SEEME_LAUNCH_CHECK();
   return SEEME_OK;
 }

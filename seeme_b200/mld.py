@@ -15,6 +15,7 @@ wrapped or used as the ``LightningModule`` base by passing ``base=`` to ``make_l
 """
 from __future__ import annotations
 
+import os
 import time
 from typing import Dict, List, Optional
 
@@ -27,20 +28,49 @@ from .modules import MldDenoiser, MldVae, ProHMRScene, SMPL, time_sinusoid
 
 
 class PendingEval:
-    """Result of ``MLD.ego_eval_async``: the ``rs_set`` tensors are being produced on ``stream``."""
+    """Result of ``MLD.ego_eval_async``: the ``rs_set`` tensors are being produced on ``stream``.
 
-    def __init__(self, rs_set, last_vertices, last_latent, event, stream):
-        self.rs_set, self.last_vertices, self.last_latent, self.event, self.stream = rs_set, last_vertices, last_latent, event, stream
+    With sampler coalescing (``MLD.sampler_group`` > 1) a batch's decode stage is only enqueued once its group's shared
+    sampler chain has been launched; every accessor below first closes the group if it is still open."""
+
+    def __init__(self, model, stream, slot):
+        self._model, self.stream, self.slot = model, stream, slot
+        self._rs_set = self.last_vertices = self.last_latent = self.event = None
+        self._ctx = self._enc_event = None
+        self._callbacks = []
+
+    def _ready(self):
+        if self._rs_set is None:
+            self._model._flush_group()
+        return self
+
+    @property
+    def rs_set(self):
+        return self._ready()._rs_set
+
+    def then(self, fn):
+        """``fn(rs_set)`` runs on the slot's stream right after the batch's last kernel has been enqueued (e.g. a
+        device-to-host copy of a result); ``event`` / ``synchronize`` cover what it enqueues."""
+        if self._rs_set is not None:
+            with torch.cuda.stream(self.stream):
+                fn(self._rs_set)
+                self.event = torch.cuda.Event()
+                self.event.record(self.stream)
+        else:
+            self._callbacks.append(fn)
+        return self
 
     def result(self):
         """make the caller's current stream wait for the slot, then hand out the rs_set (device tensors)"""
+        self._ready()
         torch.cuda.current_stream().wait_event(self.event)
-        return self.rs_set
+        return self._rs_set
 
     def synchronize(self):
         """block the host until the slot's work (including any device-to-host copies enqueued on ``stream``) is done"""
+        self._ready()
         self.event.synchronize()
-        return self.rs_set
+        return self._rs_set
 
 
 class MLD(nn.Module):
@@ -130,7 +160,10 @@ class MLD(nn.Module):
         self.lanes = int(kwargs.get("lanes", cfg.model.get("lanes", 1)))
         self.min_lane_batch = int(kwargs.get("min_lane_batch", cfg.model.get("min_lane_batch", 32)))
         # batches in flight for ego_eval_async / run_test_batches
-        self.pipeline_depth = int(kwargs.get("pipeline_depth", cfg.model.get("pipeline_depth", 8)))
+        self.pipeline_depth = int(kwargs.get("pipeline_depth", cfg.model.get("pipeline_depth", os.environ.get("SEEME_PIPELINE_DEPTH", 8))))
+        # ego_eval_async / run_test_batches: consecutive batches whose 50-step sampler runs as ONE chain over all their rows
+        # (the chain is latency-bound: 3 750 dependent kernels take the same ~27 ms for 512 or 2 048 rows)
+        self.sampler_group = int(kwargs.get("sampler_group", cfg.model.get("sampler_group", os.environ.get("SEEME_SAMPLER_GROUP", 1))))
         self.last_vertices: Dict[str, torch.Tensor] = {}
         self._uncond_scene = None
         self.eval()
@@ -159,7 +192,7 @@ class MLD(nn.Module):
         return cache[device]
 
     # ------------------------------------------------------------------------------------------
-    def _diffusion_reverse(self, encoder_hidden_states, lengths=None, latents=None):
+    def _diffusion_reverse(self, encoder_hidden_states, lengths=None, latents=None, op=None):
         """mld.py:432-511.  encoder_hidden_states [B',Nc,256] (B' = 2B under CFG) -> [1,B,256].
         ``latents`` ([B,1,256]) injects the initial noise; when None it is drawn with ``torch.randn``
         exactly where the reference draws it (:449-453)."""
@@ -178,7 +211,7 @@ class MLD(nn.Module):
         if self.__dict__.get("_coef") is None:
             self.__dict__["_coef"] = self.scheduler.step_coefficients()
             self.__dict__["_sinus"] = time_sinusoid(self.scheduler.timesteps)
-        op = self.denoiser.op
+        op = self.denoiser.op if op is None else op
         tables = self.__dict__.setdefault("_table_keys", {})          # per kernel-side handle (one per lane)
         if tables.get(id(op)) != tuple(ts):
             op.set_time_table(ts, self.__dict__["_sinus"])
@@ -313,21 +346,91 @@ class MLD(nn.Module):
             lengths_host = cache[key]
         else:
             lengths_host = torch.as_tensor(length_t).long().reshape(-1).tolist()
+        pend = PendingEval(self, st, slot)
         try:
             with torch.cuda.stream(st):
                 b = tuple((x.to(dev, non_blocking=True) if torch.is_tensor(x) and not x.is_cuda else x) for x in batch)
                 n = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and not v.is_cuda else v) for k, v in (noise or {}).items()}
-                rs = self._ego_eval_one(b, n, defer_random=True, lengths=lengths_host)
-                if "interactee" not in self.condition:            # mld.py:1572-1574 (RNG side effect kept)
-                    joints_int = torch.rand_like(rs["joints_rst"])
-                    rs["joints_interactee"] = joints_int
-                    rs["root_interactee"] = joints_int[:, :, 0:1, :]
-                    rs["orientation_quat_int"] = torch.rand_like(rs["orientation_quat_rst"])
-                ev = torch.cuda.Event()
-                ev.record(st)
+                pend._ctx = self._stage_encode(b, n, lengths_host)
+                pend._enc_event = torch.cuda.Event()
+                pend._enc_event.record(st)
         finally:
             _m._LANE[0] = lane
-        return PendingEval(rs, rs.pop("_last_vertices"), rs.pop("_last_latent"), ev, st)
+        group = self.__dict__.setdefault("_group_open", [])
+        group.append(pend)
+        if len(group) >= max(1, min(int(self.sampler_group), depth)):
+            self._flush_group()
+        return pend
+
+    def _flush_group(self):
+        """Launch the sampler of the open group -- ONE chain over the rows of all its batches, on a group stream with its
+        own denoiser handle -- and enqueue every member's decode stage (VAE decode, SMPL) on the member's slot stream."""
+        from . import modules as _m
+        members = self.__dict__.get("_group_open") or []
+        if not members:
+            return
+        self.__dict__["_group_open"] = []
+        dev = members[0]._ctx["cond_emb"].device
+        lane = _m._LANE[0]
+        try:
+            if len(members) == 1:
+                m = members[0]
+                _m._LANE[0] = 1000 + m.slot
+                with torch.cuda.stream(m.stream):
+                    z = self._diffusion_reverse(m._ctx["cond_emb"].permute(1, 0, 2), m._ctx["lengths"], latents=m._ctx["x_T"])
+                zs = [z]
+            else:
+                k = self.__dict__.get("_group_count", 0)
+                self.__dict__["_group_count"] = k + 1
+                n_gs = max(2, -(-max(1, int(self.pipeline_depth)) // len(members)) + 1)
+                gstreams = self.__dict__.setdefault("_group_streams", {})
+                gs = gstreams.get((dev, k % n_gs))
+                if gs is None:
+                    gs = gstreams[(dev, k % n_gs)] = torch.cuda.Stream(device=dev)
+                sizes = [m._ctx["x_T"].shape[0] for m in members]
+                for m in members:
+                    gs.wait_event(m._enc_event)
+                _m._LANE[0] = 2000 + (k % n_gs)
+                with torch.cuda.stream(gs):
+                    conds = [m._ctx["cond_emb"] for m in members]                     # [Nc, B or 2B, 256] each
+                    for c in conds:
+                        c.record_stream(gs)
+                    if self.do_classifier_free_guidance:                               # the kernel pairs row i with row i + B_total
+                        cond_all = torch.cat([c[:, :b] for c, b in zip(conds, sizes)] + [c[:, b:] for c, b in zip(conds, sizes)], dim=1)
+                    else:
+                        cond_all = torch.cat(conds, dim=1)
+                    for m in members:
+                        m._ctx["x_T"].record_stream(gs)
+                    lat_all = torch.cat([m._ctx["x_T"] for m in members], dim=0)
+                    rows = cond_all.shape[1]
+                    cap = -(-rows // 512) * 512
+                    z_all = self._diffusion_reverse(cond_all.permute(1, 0, 2), None, latents=lat_all, op=self.denoiser.op_rows(cap))
+                    ev_z = torch.cuda.Event()
+                    ev_z.record(gs)
+                zs, o = [], 0
+                for m, b in zip(members, sizes):
+                    m.stream.wait_event(ev_z)
+                    z_all.record_stream(m.stream)
+                    zs.append(z_all[:, o:o + b])
+                    o += b
+            for m, z in zip(members, zs):
+                _m._LANE[0] = 1000 + m.slot
+                with torch.cuda.stream(m.stream):
+                    rs = self._stage_decode(m._ctx, z.contiguous(), defer_random=True)
+                    if "interactee" not in self.condition:            # mld.py:1572-1574 (RNG side effect kept)
+                        joints_int = torch.rand_like(rs["joints_rst"])
+                        rs["joints_interactee"] = joints_int
+                        rs["root_interactee"] = joints_int[:, :, 0:1, :]
+                        rs["orientation_quat_int"] = torch.rand_like(rs["orientation_quat_rst"])
+                    m.last_vertices, m.last_latent = rs.pop("_last_vertices"), rs.pop("_last_latent")
+                    for fn in m._callbacks:
+                        fn(rs)
+                    m._callbacks = []
+                    m.event = torch.cuda.Event()
+                    m.event.record(m.stream)
+                    m._rs_set, m._ctx = rs, None
+        finally:
+            _m._LANE[0] = lane
 
     def _encode_uncond(self, B: int, T: int, nfeats: int, lengths, eps, dev):
         """``vae.encode(zeros_like(feats), lengths)`` of the CFG branch (mld.py:1280-1290).  The input is all zeros, so the
@@ -351,6 +454,12 @@ class MLD(nn.Module):
 
     def _ego_eval_one(self, batch, noise, defer_random: bool = False, t_max: Optional[int] = None, lengths=None):
         """one (sub-)batch on the current stream with the current lane's handles"""
+        ctx = self._stage_encode(batch, noise, lengths)
+        z = self._diffusion_reverse(ctx["cond_emb"].permute(1, 0, 2), ctx["lengths"], latents=ctx["x_T"])
+        return self._stage_decode(ctx, z, defer_random=defer_random, t_max=t_max)
+
+    def _stage_encode(self, batch, noise, lengths=None):
+        """scene encoder + interactee VAE encode (cond and CFG-uncond) -> the denoiser's conditioning and the initial noise"""
         if "scene" in self.condition:
             feats_ref, transl, beta, utils_, scene, length, dict_images = batch
             scene_emb = self._encode_scene(scene)                          # [1,B or 2B,256]
@@ -376,9 +485,18 @@ class MLD(nn.Module):
             cond_emb = scene_emb
         if cond_emb is None:
             raise NotImplementedError("MLD (sm_100a): at least one of scene / interactee conditioning is required")
-        z = self._diffusion_reverse(cond_emb.permute(1, 0, 2), lengths, latents=noise.get("x_T"))
+        x_T = noise.get("x_T")
+        if x_T is None:                                                    # drawn where the reference draws it (mld.py:449-453)
+            x_T = torch.randn((feats_ref.shape[0], self.latent_dim[0], self.latent_dim[-1]), device=dev, dtype=torch.float)
+        return {"feats_ref": feats_ref, "transl": transl, "beta": beta, "lengths": lengths, "len_dev": len_dev,
+                "f_ref_int": f_ref_int, "cond_emb": cond_emb, "x_T": x_T, "start": start}
+
+    def _stage_decode(self, ctx, z, defer_random: bool = False, t_max: Optional[int] = None):
+        """VAE decode of the sampled latents [1,B,256], renorm + SMPL of the three bodies -> rs_set (mld.py:1355-1905)"""
+        feats_ref, transl, beta, lengths, len_dev, f_ref_int = (ctx[k] for k in ("feats_ref", "transl", "beta", "lengths", "len_dev", "f_ref_int"))
+        dev = feats_ref.device
         feats_rst = self.vae.decode(z, lengths, T=t_max, lengths_dev=len_dev)   # [B,max(lengths),nfeats_net]
-        self.times.append(time.time() - start)                             # mld.py:1367-1368 (no device sync, like the reference)
+        self.times.append(time.time() - ctx["start"])                      # mld.py:1367-1368 (no device sync, like the reference)
 
         min_len = min(feats_ref.shape[1], feats_rst.shape[1])
         idx_ref = 0 if self.estimate == "wearer" else 1

@@ -106,6 +106,12 @@ class MldDenoiser(_PackedModule):
         self._require_cuda()
         return self._op("den", lambda: ops.DenoiserOp(self.state_dict(), self.max_rows))
 
+    def op_rows(self, rows: int) -> ops.DenoiserOp:
+        """a handle of the current lane with room for ``rows`` denoiser rows (the coalesced sampler of several batches)"""
+        self._require_cuda()
+        rows = max(int(rows), 1)
+        return self._op(("den", rows), lambda: ops.DenoiserOp(self.state_dict(), rows))
+
     def forward(self, sample, timestep, encoder_hidden_states, lengths=None, **kwargs):
         """sample [B',1,256], timestep 0-d tensor/int, encoder_hidden_states [Nc,B',256] -> ([B',1,256],)"""
         if sample.dim() != 3 or sample.shape[1] != 1 or sample.shape[2] != 256:

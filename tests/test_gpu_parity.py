@@ -407,6 +407,19 @@ def test_ego_eval_async_pipeline_matches_sync():
         assert ref["lengths"] == r["lengths"]
         for k in ("m_rst", "joints_rst", "joints_ref", "orientation_quat_rst", "joints_interactee"):
             assert torch.equal(ref[k], r[k]), k
+    # sampler coalescing: the 50-step chain of 2 (then 3: more than the slots) consecutive batches runs as ONE chain over all
+    # their rows on a group stream / handle; rows are independent, so the results are bit-identical
+    for G in (2, 3):
+        model.sampler_group = G
+        pend = [model.ego_eval_async(b, n) for b, n in zip(batches, noises)]
+        seen = []
+        pend[1].then(lambda rs: seen.append(rs["joints_rst"].shape))           # callback registered before the group closes
+        for p_, r in zip(pend, got):
+            r2 = p_.synchronize()
+            for k in ("m_rst", "joints_rst", "joints_ref", "orientation_quat_rst", "joints_interactee"):
+                assert torch.equal(r2[k], r[k]), (G, k)
+        assert seen == [(B, 60, 24, 3)]
+    model.sampler_group = 1
     # the pipelined test loop updates the metric for every batch, in order
     model.EgoMetric.reset()
     outs = list(model.run_test_batches(batches))
