@@ -270,7 +270,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
             pf_bulk_load(wr + (uint32_t)(s % 3) * 2 * PF_CHUNK, a.wblob + (size_t)(8 + s - 4) * PF_CHUNK, PF_CHUNK, sf0 + (uint32_t)s * 8u);
             pf_bulk_load(wr + (uint32_t)(s % 3) * 2 * PF_CHUNK + PF_CHUNK, a.wblob + (size_t)(12 + s - 4) * PF_CHUNK, PF_CHUNK, sf0 + (uint32_t)s * 8u);
           } else {
-            pf_bulk_load(wr + (uint32_t)(s % 3) * 2 * PF_CHUNK, a.wblob + (size_t)s * 2 * PF_CHUNK, 2 * PF_CHUNK, sf0 + (uint32_t)s * 8u);
+            // G2 runs its K-chunks in the order 0, 2, 1, 3: the H epilogue converts both column halves in parallel, so
+            // chunks 0 and 2 are ready together (then 1 and 3)
+            const int pair = s < 8 ? s : 8 + (((s - 8) & 1) << 1 | ((s - 8) >> 1));
+            pf_bulk_load(wr + (uint32_t)(s % 3) * 2 * PF_CHUNK, a.wblob + (size_t)pair * 2 * PF_CHUNK, 2 * PF_CHUNK, sf0 + (uint32_t)s * 8u);
           }
         }
       }
@@ -328,8 +331,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       }
       // G2: OUT += H16 . W1^T  (N = 256 per K-chunk)
 #pragma unroll
-      for (int kc = 0; kc < 4; ++kc) {
-        const int s = 8 + kc;
+      for (int i4 = 0; i4 < 4; ++i4) {
+        const int s = 8 + i4;
+        const int kc = ((i4 & 1) << 1) | (i4 >> 1);      // 0, 2, 1, 3
         pf_wait(sf0 + (uint32_t)s * 8u, pj);
         tc_fence_after();
         if (pf_elect_one()) {
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
               umma_bf16(Ra, pf_desc_add(xdesc, kc * (PF_CHUNK >> 4) + ks * 2), pf_desc_add(wd, ks * 2), idesc256, 1);
           }
           pf_commit(we0 + (uint32_t)(s % 3) * 8u);
-          if (kc == 3) umma_commit(&out_full[b]);
+          if (i4 == 3) umma_commit(&out_full[b]);
         }
         __syncwarp();
       }
@@ -455,7 +459,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
             if (H_TMEM) { tmem_st_wait(); tc_fence_before(); }
             else fence_proxy_async();
             __syncwarp();
-            if (lane == 0) pf_arrive(sf0 + (uint32_t)(8 + hsel * 2 + (g >> 1)) * 8u);
+            if (lane == 0) pf_arrive(sf0 + (uint32_t)(8 + (((g >> 1) << 1) | hsel)) * 8u);      // K-chunk hsel * 2 + (g >> 1) is step 8 + 2 (g >> 1) + hsel
           }
         }
         if (elected) PF_TR(j, 25);

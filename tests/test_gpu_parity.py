@@ -203,14 +203,17 @@ def test_pointnet_fused_fp16_vs_oracle(weights, precision):
 
 
 def test_pointnet_fused_variants_agree(weights):
-    """the tensor-memory and shared-memory H paths perform the same arithmetic in the same order"""
+    """the tensor-memory and shared-memory H paths perform the same arithmetic in the same order; the CTA-pair kernel the same
+    arithmetic in another accumulation order"""
     from seeme_b200 import ops, synthetic as S
     p = S.egobody_scene(2, 5000, torch.Generator().manual_seed(13)).to(DEV)
     outs = []
     for precision in (16, 17, 18):
         op = ops.PointNetOp(cu(weights["pointnet"]), cu(weights["output_scene"]), max_batch=2, max_points=5000, precision=precision)
         outs.append(op(p, want_feat=True)[1])
-    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert torch.equal(outs[0], outs[1])
+    # the CTA-pair kernel accumulates G1 / G2 in a different K order (fp32 re-association only)
+    assert (outs[0] - outs[2]).abs().max() <= 2e-3 * outs[0].abs().max()
 
 
 # ---- SMPL -------------------------------------------------------------------------------------------------------
