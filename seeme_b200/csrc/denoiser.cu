@@ -36,22 +36,28 @@ __global__ void den_prep_kernel(const float* __restrict__ lat, const float* __re
 
 // token-0 self-attention over keys {x_r, cond_0..cond_{Nc-1}, time}; qkv [R,768] (q pre-scaled),
 // kvc [Nc*R,512] = (k|v) of the cond tokens (row n*R + r), tkv [512] = (k|v) of the time token.
+// NC = number of cond tokens as a template parameter: with a run-time count the per-token arrays lived in local memory
+template <int NC>
 __global__ void den_sa_attn_kernel(const float* __restrict__ qkv, const float* __restrict__ kvc,
-                                   const float* __restrict__ tkv, int Nc, int R, __nv_bfloat16* __restrict__ oh,
+                                   const float* __restrict__ tkv, int Nc_unused, int R, __nv_bfloat16* __restrict__ oh,
                                    __nv_bfloat16* __restrict__ ol) {
+  constexpr int Nc = NC;
   pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
   const float* base = qkv + (size_t)row * 768;
   const Row8 q = row_load(base, lane);
-  float sc[SEEME_MAX_COND_TOKENS + 2];
+  float sc[NC + 2];
   sc[0] = row_dot(q, row_load(base + 256, lane));
+#pragma unroll
   for (int n = 0; n < Nc; ++n) sc[1 + n] = row_dot(q, row_load(kvc + ((size_t)n * R + row) * 512, lane));
   sc[1 + Nc] = row_dot(q, row_load(tkv, lane));
   float m = sc[0];
+#pragma unroll
   for (int j = 1; j < Nc + 2; ++j) m = fmaxf(m, sc[j]);
   float sum = 0.f;
+#pragma unroll
   for (int j = 0; j < Nc + 2; ++j) { sc[j] = expf(sc[j] - m); sum += sc[j]; }
   const float inv = 1.0f / sum;
   Row8 acc;
@@ -61,6 +67,7 @@ __global__ void den_sa_attn_kernel(const float* __restrict__ qkv, const float* _
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc.v[i] = p * v.v[i];
   }
+#pragma unroll
   for (int n = 0; n < Nc; ++n) {
     const Row8 v = row_load(kvc + ((size_t)n * R + row) * 512 + 256, lane);
     const float p = sc[1 + n] * inv;
@@ -90,7 +97,8 @@ __device__ __forceinline__ Row8 film_silu(const Row8& y, const float* __restrict
 // LinearTemporalCrossAttention core (mdiff_transformer.py:219-237) for one query token, H = 1:
 //   qs = softmax_d(q); ks_n = softmax over the Nc tokens (per channel); y = sum_n (qs . ks_n) v_n
 // followed by the FiLM tail.  q [R,256]; kv2 [Nc*R,512] = (key|value) rows n*R + r.
-__global__ void den_ca_kernel(const float* __restrict__ q, const float* __restrict__ kv2, int Nc, int R,
+template <int NC>
+__global__ void den_ca_kernel(const float* __restrict__ q, const float* __restrict__ kv2, int Nc_unused, int R,
                               const float* __restrict__ film, const float* __restrict__ g, const float* __restrict__ b,
                               __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol) {
   pdl_prologue();
@@ -108,20 +116,26 @@ __global__ void den_ca_kernel(const float* __restrict__ q, const float* __restri
   const float inv = 1.0f / warp_sum(sum);
 #pragma unroll
   for (int i = 0; i < 8; ++i) qs.v[i] *= inv;
-  Row8 ks[SEEME_MAX_COND_TOKENS];
+  constexpr int Nc = NC;
+  Row8 ks[NC];
+#pragma unroll
   for (int n = 0; n < Nc; ++n) ks[n] = row_load(kv2 + ((size_t)n * R + row) * 512, lane);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float km = ks[0].v[i];
+#pragma unroll
     for (int n = 1; n < Nc; ++n) km = fmaxf(km, ks[n].v[i]);
     float s = 0.f;
+#pragma unroll
     for (int n = 0; n < Nc; ++n) { ks[n].v[i] = expf(ks[n].v[i] - km); s += ks[n].v[i]; }
     const float is = 1.0f / s;
+#pragma unroll
     for (int n = 0; n < Nc; ++n) ks[n].v[i] *= is;
   }
   Row8 y;
 #pragma unroll
   for (int i = 0; i < 8; ++i) y.v[i] = 0.f;
+#pragma unroll
   for (int n = 0; n < Nc; ++n) {
     const float w = row_dot(qs, ks[n]);
     const Row8 v = row_load(kv2 + ((size_t)n * R + row) * 512 + 256, lane);
@@ -329,8 +343,14 @@ extern "C" int seeme_denoiser_create(seeme_denoiser_t* out, const float* const* 
     // the row-wise kernels use no shared memory; asking for the maximum carve-out anyway keeps the SMs in the
     // configuration of the 193 KB GEMM kernels they alternate with (no L1/shared re-partitioning between launches)
     cudaFuncSetAttribute(den_prep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(den_sa_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(den_ca_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(den_sa_attn_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(den_sa_attn_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(den_sa_attn_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(den_sa_attn_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(den_ca_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(den_ca_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(den_ca_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(den_ca_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(den_film_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(den_ln_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(den_final_ddim_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -400,7 +420,10 @@ static int den_block(seeme_denoiser* h, int l, int ti, const ActBuf& xin, const 
   ActBuf y; y.f = h->y; y.ld = 256;
   // self-attention over {x, cond tokens, time token}, token 0 only (H1)
   SEEME_TRY(run_linear(h->Wqkv[l], xin, nullptr, R, ACT_NONE, nullptr, 0, qkv, np, s));
-  SEEME_CUDA(launch_pdl(den_sa_attn_kernel, dim3(nb), dim3(256), 0, s, h->qkv, h->kvc[l], h->tkv[l] + (size_t)ti * 512, Nc, R, h->att.h, h->att.l));
+  {
+    auto k = Nc == 1 ? den_sa_attn_kernel<1> : Nc == 2 ? den_sa_attn_kernel<2> : Nc == 3 ? den_sa_attn_kernel<3> : den_sa_attn_kernel<4>;
+    SEEME_CUDA(launch_pdl(k, dim3(nb), dim3(256), 0, s, h->qkv, h->kvc[l], h->tkv[l] + (size_t)ti * 512, Nc, R, h->att.h, h->att.l));
+  }
   SEEME_LAUNCH_CHECK();
   SEEME_TRY(run_linear(h->Wout[l], h->att, nullptr, R, ACT_NONE, xin.f, 256, t0, np, s));
   SEEME_CUDA(launch_pdl(den_ln_kernel, dim3(nb), dim3(256), 0, s, h->t0, blkw(h, l, SA_N1_W), blkw(h, l, SA_N1_B), h->x1.f, h->x1.h, h->x1.l, nullptr, nullptr,
@@ -414,8 +437,11 @@ static int den_block(seeme_denoiser* h, int l, int ti, const ActBuf& xin, const 
   SEEME_LAUNCH_CHECK();
   // linear cross-attention to the cond tokens (H2) + FiLM
   SEEME_TRY(run_linear(h->Wcaq[l], h->ln, nullptr, R, ACT_NONE, nullptr, 0, caq, np, s));
-  SEEME_CUDA(launch_pdl(den_ca_kernel, dim3(nb), dim3(256), 0, s, h->caq, h->kv2[l], Nc, R, h->film_ca[l] + (size_t)ti * 512, blkw(h, l, CA_PN_W),
-                                   blkw(h, l, CA_PN_B), h->hb.h, h->hb.l));
+  {
+    auto k = Nc == 1 ? den_ca_kernel<1> : Nc == 2 ? den_ca_kernel<2> : Nc == 3 ? den_ca_kernel<3> : den_ca_kernel<4>;
+    SEEME_CUDA(launch_pdl(k, dim3(nb), dim3(256), 0, s, h->caq, h->kv2[l], Nc, R, h->film_ca[l] + (size_t)ti * 512, blkw(h, l, CA_PN_W),
+                          blkw(h, l, CA_PN_B), h->hb.h, h->hb.l));
+  }
   SEEME_LAUNCH_CHECK();
   SEEME_TRY(run_linear(h->Wcaout[l], h->hb, nullptr, R, ACT_NONE, h->x2.f, 256, h->x1, np, s));    // x3 -> x1 (fp32 + bf16)
   // FFN + FiLM
