@@ -51,6 +51,30 @@ streams = [torch.cuda.Stream() for _ in range(D)]
 lengths = [60] * B
 
 
+if os.environ.get("PROBE_ASYNC"):      # the public async API (slots, sampler_group) instead of raw lanes
+    from collections import deque
+    model.pipeline_depth = D
+    n = int(os.environ.get("PROBE_STEPS", "48"))
+
+    def run(n):
+        pend = deque()
+        for _ in range(n):
+            pend.append(model.ego_eval_async(batch, noise))
+            if len(pend) >= D:
+                pend.popleft().synchronize()
+        while pend:
+            pend.popleft().synchronize()
+
+    run(3 * D)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run(n)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / n * 1e3
+    print(f"async depth {D} group {model.sampler_group}: {dt:.2f} ms per step -> {B / dt * 1e3:.0f} sequences/s")
+    sys.exit(0)
+
+
 def submit(k):
     s = k % D
     M._LANE[0] = s
