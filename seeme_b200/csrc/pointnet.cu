@@ -144,6 +144,13 @@ struct seeme_pointnet {
   void* ctblob = nullptr;  // 2 x 16 KB constant MMA tiles of the tensor-core block 0 (pf_pack_block0_ct)
 };
 
+// clouds per pass of the fused path (two fp16 [rows,256] activation buffers = 1 KB per point: 2.6 GB at 128 clouds x 20 000)
+static int pf_chunk_cap() {
+  const char* e = getenv("SEEME_PF_CHUNK");
+  const int v = e ? atoi(e) : 128;
+  return v < 1 ? 128 : v;
+}
+
 static int copy_w(Arena& a, float*& dst, const float* src, size_t n) {
   dst = a.take<float>(n);
   SEEME_REQUIRE(dst != nullptr, SEEME_ENOMEM, "pointnet: arena exhausted");
@@ -178,7 +185,7 @@ static int pointnet_create(seeme_pointnet_t* out, const float* const* w, int n_w
   const bool fused = h->precision >= 16;
   // samples per pass: bounds the per-point workspace.  The fused path only keeps two fp16 [rows,256] activation buffers
   // (1 KB per point), so it takes 128 clouds per pass (fewer launches of the small per-sample bias GEMMs).
-  const int chunk_cap = fused ? 128 : 32;
+  const int chunk_cap = fused ? pf_chunk_cap() : 32;
   h->chunk = max_batch < chunk_cap ? max_batch : chunk_cap;
   const size_t rows = (size_t)h->chunk * (max_points < 128 ? 128 : max_points);
   size_t wbytes = 4 * pad256(pf_blob_bytes()) + pad256(512 * 16) + pad256(32768) + pad256(512 * 3 * 4) + pad256(512 * 4) + 4 * (pad256(256 * 512 * 4) * 2 + pad256(256 * 256 * 4) + 2 * pad256(256 * 4)) +

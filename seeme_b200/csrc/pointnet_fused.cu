@@ -353,15 +353,11 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       }
     }
   } else if (warp < 6) {
-    // ---- H group (4 warps, one per TMEM lane quarter): in-place relu of X, then the H epilogue ----------------
+    // ---- H group (4 warps): in-place relu of X, chunk by chunk behind the shortcut GEMM ------------------------
     const int th = (int)threadIdx.x - 64;           // 0..127
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     for (int j = 0; j < nt; ++j) {
       const int b = j & 1;
       const uint32_t p2 = (uint32_t)(j >> 1) & 1u;
-      const int sample = (t_begin + j) / a.tiles_per_sample;
       uint8_t* xb = xbuf + b * PF_XBUF;
       for (int kc = 0; kc < 4; ++kc) {
         mbar_wait(&s_done[b][kc], p2);
