@@ -297,8 +297,9 @@ struct seeme_smpl {
   unsigned char *i4, *i24;
   float *A, *coef;
   // tensor-core blend path (smpl_tc.cu): packed bf16 (hi, lo) basis and per-call coefficient scratch
-  void *bh = nullptr, *bl = nullptr, *ch = nullptr, *cl = nullptr;
+  void *bh = nullptr, *bl = nullptr, *ch = nullptr, *cl = nullptr, *wblob = nullptr, *aopblob = nullptr;
   bool use_tc = true;
+  int tc_version = 2;      // SEEME_SMPL_TC=1: sparse skinning in the epilogue from shared memory (<= 4 weights per vertex)
 };
 
 extern "C" int seeme_smpl_create(seeme_smpl_t* out, const float* v_template, const float* shapedirs,
@@ -326,7 +327,7 @@ extern "C" int seeme_smpl_create(seeme_smpl_t* out, const float* v_template, con
   size_t bytes = pad256(SJ * 3 * 4) + pad256(SJ * 30 * 4) + pad256((size_t)SK * 3 * SVP * 4) + pad256((size_t)3 * SVP * 4) +
                  pad256((size_t)SVP * 4 * 4) + pad256((size_t)SVP * SJ * 4) + pad256((size_t)SVP * 4) + pad256((size_t)SVP * SJ) +
                  pad256(fpad * SJ * 12 * 4) + pad256(fpad * SKP * 4) + 4096 +
-                 2 * pad256(smpl_tc_basis_elems() * 2) + 2 * pad256((fpad + 64) * 256 * 2);
+                 2 * pad256(smpl_tc_basis_elems() * 2) + 2 * pad256((fpad + 64) * 256 * 2) + pad256(smpl_tc_wblob_bytes()) + pad256(smpl_tc_aop_bytes(fpad));
   int rc = h->arena.init(bytes);
   if (rc) { delete h; return rc; }
   h->Jt = h->arena.take<float>(SJ * 3);
@@ -343,9 +344,13 @@ extern "C" int seeme_smpl_create(seeme_smpl_t* out, const float* v_template, con
   h->bl = h->arena.take<__nv_bfloat16>(smpl_tc_basis_elems());
   h->ch = h->arena.take<__nv_bfloat16>((fpad + 64) * 256);
   h->cl = h->arena.take<__nv_bfloat16>((fpad + 64) * 256);
+  h->wblob = h->arena.take<char>(smpl_tc_wblob_bytes());
+  h->aopblob = h->arena.take<char>(smpl_tc_aop_bytes(fpad));
   {
     const char* e = getenv("SEEME_SMPL_FP32");
     h->use_tc = !(e && e[0] == '1');
+    const char* v = getenv("SEEME_SMPL_TC");
+    h->tc_version = (v && v[0] == '1') ? 1 : 2;
   }
   int* d_nnz = h->arena.take<int>(1);
   if (!d_nnz) { set_error("seeme_smpl_create: arena exhausted"); h->arena.release(); delete h; return SEEME_ENOMEM; }
@@ -358,6 +363,7 @@ extern "C" int seeme_smpl_create(seeme_smpl_t* out, const float* v_template, con
     if (smpl_tc_pack_basis(h->basis, SK, h->bh, h->bl) != SEEME_OK) { h->arena.release(); delete h; return SEEME_ECUDA; }
   }
   smpl_lbs_pack_kernel<<<(SVP + 127) / 128, 128>>>(lbs_weights, h->w4, h->i4, h->w24, h->i24, d_nnz);
+  if (h->wblob && smpl_tc_pack_wtiles(h->w24, h->wblob) != SEEME_OK) { h->arena.release(); delete h; return SEEME_ECUDA; }
   cudaError_t e = cudaMemcpy(&h->max_nnz, d_nnz, sizeof(int), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { set_error("seeme_smpl_create: packing failed: %s", cudaGetErrorString(e)); h->arena.release(); delete h; return SEEME_ECUDA; }
@@ -376,7 +382,10 @@ static int smpl_run(seeme_smpl* h, const float* betas, const float* body_pose, c
                                                  h->Jt, h->Jd, h->topo, F, h->A, h->coef, joints, quat);
   }
   SEEME_LAUNCH_CHECK();
-  if (vertices && h->use_tc && h->max_nnz <= 4) {
+  if (vertices && h->use_tc && h->tc_version == 2 && h->wblob && h->aopblob) {
+    // blend shapes AND the skinning-transform blend on the tensor cores (smpl_tc.cu, version 2)
+    SEEME_TRY(smpl_skin_tc2(h->bh, h->bl, h->coef, SKP, SKP, h->ch, h->cl, h->A, h->vtp, h->wblob, h->aopblob, F, vertices, PROF_SMPL_SKIN + 1, s));
+  } else if (vertices && h->use_tc && h->max_nnz <= 4) {
     // blend contraction on the tensor cores, skinning in its epilogue (smpl_tc.cu)
     SEEME_TRY(smpl_skin_tc(h->bh, h->bl, h->coef, SKP, SKP, h->ch, h->cl, h->A, h->vtp, h->w4, h->i4, F, vertices,
                            PROF_SMPL_SKIN + 1, s));

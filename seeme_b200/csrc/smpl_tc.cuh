@@ -12,4 +12,12 @@ int smpl_tc_pack_basis(const float* basis, int SK, void* bh, void* bl);
 int smpl_skin_tc(const void* bh, const void* bl, const float* coef, int ld_coef, int n_coef, void* ch, void* cl, const float* A,
                  const float* vt, const float* w4, const unsigned char* i4, int F, float* verts, int prof_id, cudaStream_t s);
 
+// version 2 (transform blend on the tensor cores as well; any number of skinning weights per vertex):
+// w24 [6912][24] dense fp32 -> wblob (smpl_tc_wblob_bytes()) at create; same call otherwise
+size_t smpl_tc_wblob_bytes();
+size_t smpl_tc_aop_bytes(size_t frames);      // per-call scratch for the fp16 transform operands
+int smpl_tc_pack_wtiles(const float* w24, void* wblob);
+int smpl_skin_tc2(const void* bh, const void* bl, const float* coef, int ld_coef, int n_coef, void* ch, void* cl, const float* A,
+                  const float* vt, const void* wblob, void* aopblob, int F, float* verts, int prof_id, cudaStream_t s);
+
 }  // namespace seeme
