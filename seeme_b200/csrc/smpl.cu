@@ -360,7 +360,7 @@ extern "C" int seeme_smpl_create(seeme_smpl_t* out, const float* v_template, con
   if (h->cl) {
     cudaMemset(h->ch, 0, (fpad + 64) * 256 * 2);
     cudaMemset(h->cl, 0, (fpad + 64) * 256 * 2);
-    if (smpl_tc_pack_basis(h->basis, SK, h->bh, h->bl) != SEEME_OK) { h->arena.release(); delete h; return SEEME_ECUDA; }
+    if ((h->tc_version == 2 ? smpl_tc_pack_basis_f16(h->basis, SK, h->bh, h->bl) : smpl_tc_pack_basis(h->basis, SK, h->bh, h->bl)) != SEEME_OK) { h->arena.release(); delete h; return SEEME_ECUDA; }
   }
   smpl_lbs_pack_kernel<<<(SVP + 127) / 128, 128>>>(lbs_weights, h->w4, h->i4, h->w24, h->i24, d_nnz);
   if (h->wblob && smpl_tc_pack_wtiles(h->w24, h->wblob) != SEEME_OK) { h->arena.release(); delete h; return SEEME_ECUDA; }

@@ -279,14 +279,17 @@ extern "C" int seeme_test_umma_interleave(const void* A, const void* B, float* D
 // in split fp16 (hi.hi + lo.hi + hi.lo, fp32 accumulation: ~2^-22), and the epilogue reads the 12 blended entries of a
 // (vertex, frame) from tensor memory (its own lane) next to x, y, z: no shared-memory reads at all, and dense skinning
 // weights cost the same as sparse ones.
-//   warp 0      producer: per tile the 16 KB W tile (pre-packed no-swizzle image, double-buffered), then 24 basis chunks (6-slot ring)
+//   warp 0      producer: per tile the 16 KB W tile (pre-packed no-swizzle image, double-buffered), then 15 basis chunks
+//               (fp16 hi for all K, lo for K-chunk 0 only; 5-slot ring)
 //   warp 1      blend-shape MMA issuer (single accumulator set: x / y / z = 3 x 64 columns; the epilogue copies it to registers first)
 //   warps 2-17  epilogue, lane quarter q x frame quarter fq (16 frames).  Per tile and 4-frame sub-block the 4 warps of a
 //               frame quarter convert the sub-block's joint transforms to fp16 (hi, lo) into their own 6 KB operand buffer
 //               (next sub-block prefetched from L2 into registers), wait for T, apply it, store.
 //   warp 18     transform-blend MMA issuer: round-robin over the 4 frame quarters, 6 MMAs (N = 48) per sub-block into the
 //               quarter's own 48 TMEM columns
-constexpr int S2_NST = 4;
+__global__ void smpl_coef_split_f16_kernel(const float* __restrict__ coef, int ld, int F, int n, __half* __restrict__ ch, __half* __restrict__ cl);
+
+constexpr int S2_NST = 5;
 constexpr int S2_WT = 128 * 64 * 2;                    // W tile: hi 8 KB | lo 8 KB
 constexpr int S2_AOP = 48 * 64 * 2;                    // Aop buffer of one frame quarter: hi 3 KB | lo 3 KB
 constexpr int S2_SMEM = ST_B_BYTES + S2_NST * ST_CHUNK + 2 * S2_WT + 8 * S2_AOP + 1024;     // Aop: 2 buffers per frame quarter
@@ -360,9 +363,11 @@ __global__ void __launch_bounds__(S2_THREADS, 1) smpl_skin_tc2_kernel(const __gr
         mbar_wait(&wt_free[i & 1], ((uint32_t)(i >> 1) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&wt_full[i & 1], S2_WT);
         st_bulk_load(wt + (i & 1) * S2_WT, a.wblob + (size_t)tile * S2_WT, S2_WT, &wt_full[i & 1]);
+        // fp16 basis: the lo halves are streamed for the first K-chunk only (the 10 shape directions + 54 pose directions);
+        // a pose-direction term carries a few millimetres at most, so its fp16 rounding (2^-12) stays below 1e-6 m
         for (int c = 0; c < 3; ++c)
           for (int kc = 0; kc < 4; ++kc)
-            for (int hl = 0; hl < 2; ++hl) {
+            for (int hl = 0; hl < (kc == 0 ? 2 : 1); ++hl) {
               mbar_wait(&r_empty[st], ph);
               mbar_arrive_expect_tx(&r_full[st], ST_CHUNK);
               tma_load_2d(ring + st * ST_CHUNK, hl ? &tm.bl : &tm.bh, &r_full[st], kc * 64, c * ST_VP + tile * 128);
@@ -371,8 +376,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1) smpl_skin_tc2_kernel(const __gr
       }
     }
   } else if (warp == 1) {
-    // ---- blend-shape GEMM: x / y / z planes, [128 v x 256 k] x [256 k x 64 f] each, split bf16 ---------------------
-    constexpr uint32_t idesc = umma_idesc_bf16(ST_NF);
+    // ---- blend-shape GEMM: x / y / z planes, [128 v x 256 k] x [256 k x 64 f] each, split fp16 (basis lo: K-chunk 0 only) ----
+    constexpr uint32_t idesc = umma_idesc_f16(ST_NF);
     const uint64_t rdesc0 = umma_desc_k128(smem_u32(ring));
     const uint64_t bdesc0 = umma_desc_k128(smem_u32(bop));
     uint32_t st = 0, ph = 0;
@@ -397,20 +402,22 @@ __global__ void __launch_bounds__(S2_THREADS, 1) smpl_skin_tc2_kernel(const __gr
               umma_bf16(d, umma_desc_add(ad, ks * 2), umma_desc_add(bl, ks * 2), idesc, 1);
             }
             umma_commit(&r_empty[st]);
-          }
-          __syncwarp();
-          if (++st == S2_NST) { st = 0; ph ^= 1u; }
-          mbar_wait(&r_full[st], ph);
-          tc_fence_after();
-          if (umma_elect_one()) {
-            const uint64_t ad = umma_desc_add(rdesc0, st * (ST_CHUNK >> 4));
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma_bf16(d, umma_desc_add(ad, ks * 2), umma_desc_add(bh, ks * 2), idesc, 1);
-            umma_commit(&r_empty[st]);
             if (c == 2 && kc == 3) umma_commit(&acc_full);
           }
           __syncwarp();
           if (++st == S2_NST) { st = 0; ph ^= 1u; }
+          if (kc == 0) {
+            mbar_wait(&r_full[st], ph);
+            tc_fence_after();
+            if (umma_elect_one()) {
+              const uint64_t ad = umma_desc_add(rdesc0, st * (ST_CHUNK >> 4));
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) umma_bf16(d, umma_desc_add(ad, ks * 2), umma_desc_add(bh, ks * 2), idesc, 1);
+              umma_commit(&r_empty[st]);
+            }
+            __syncwarp();
+            if (++st == S2_NST) { st = 0; ph ^= 1u; }
+          }
         }
       }
     }
@@ -571,7 +578,10 @@ int smpl_skin_tc2(const void* bh, const void* bl, const float* coef, int ld_coef
     smpl_aop_pack_kernel<<<(unsigned)(((size_t)n_sub * 48 * 32 + 255) / 256), 256, 0, s>>>(A, F, reinterpret_cast<uint8_t*>(aopblob), n_sub);
     SEEME_LAUNCH_CHECK();
   }
-  SEEME_TRY(to_bf16_split(coef, ld_coef, F, n_coef, reinterpret_cast<__nv_bfloat16*>(ch), reinterpret_cast<__nv_bfloat16*>(cl), ST_KP, 0, s));
+  // coef [F, n_coef] fp32 -> fp16 (hi, lo) [F, 256]; the tensor maps only move 2-byte elements, so the bf16-typed maps serve
+  smpl_coef_split_f16_kernel<<<(unsigned)(((size_t)F * n_coef + 255) / 256), 256, 0, s>>>(coef, ld_coef, F, n_coef, reinterpret_cast<__half*>(ch),
+                                                                                       reinterpret_cast<__half*>(cl));
+  SEEME_LAUNCH_CHECK();
   StMaps maps;
   memset(&maps, 0, sizeof(maps));
   SEEME_TRY(umma_tensor_map_bf16(&maps.bh, bh, 3 * ST_VP, ST_KP, ST_KP, 128));
@@ -609,6 +619,35 @@ __global__ void smpl_basis_pack_kernel(const float* __restrict__ basis, int SK, 
   const __nv_bfloat16 h = __float2bfloat16_rn(x);
   bh[i] = h;
   bl[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+}
+
+// fp16 flavour for smpl_skin_tc2_kernel (same [3*VP][256] layout, IEEE half bits in the 2-byte buffers)
+__global__ void smpl_basis_pack_f16_kernel(const float* __restrict__ basis, int SK, __half* __restrict__ bh, __half* __restrict__ bl) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)3 * ST_VP * ST_KP) return;
+  const int k = (int)(i % ST_KP);
+  const size_t row = i / ST_KP;
+  const int c = (int)(row / ST_VP), v = (int)(row % ST_VP);
+  const float x = k < SK ? basis[((size_t)k * 3 + c) * ST_VP + v] : 0.f;
+  const __half h = __float2half_rn(x);
+  bh[i] = h;
+  bl[i] = __float2half_rn(x - __half2float(h));
+}
+__global__ void smpl_coef_split_f16_kernel(const float* __restrict__ coef, int ld, int F, int n, __half* __restrict__ ch, __half* __restrict__ cl) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)F * n) return;
+  const int f = (int)(i / n), k = (int)(i % n);
+  const float x = coef[(size_t)f * ld + k];
+  const __half h = __float2half_rn(x);
+  ch[(size_t)f * ST_KP + k] = h;
+  cl[(size_t)f * ST_KP + k] = __float2half_rn(x - __half2float(h));
+}
+
+int smpl_tc_pack_basis_f16(const float* basis, int SK, void* bh, void* bl) {
+  const size_t n = (size_t)3 * ST_VP * ST_KP;
+  smpl_basis_pack_f16_kernel<<<(unsigned)((n + 255) / 256), 256>>>(basis, SK, reinterpret_cast<__half*>(bh), reinterpret_cast<__half*>(bl));
+  SEEME_LAUNCH_CHECK();
+  return SEEME_OK;
 }
 
 size_t smpl_tc_basis_elems() { return (size_t)3 * ST_VP * ST_KP; }

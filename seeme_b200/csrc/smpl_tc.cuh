@@ -14,6 +14,7 @@ int smpl_skin_tc(const void* bh, const void* bl, const float* coef, int ld_coef,
 
 // version 2 (transform blend on the tensor cores as well; any number of skinning weights per vertex):
 // w24 [6912][24] dense fp32 -> wblob (smpl_tc_wblob_bytes()) at create; same call otherwise
+int smpl_tc_pack_basis_f16(const float* basis, int SK, void* bh, void* bl);   // version 2 streams an fp16 (hi, lo) basis
 size_t smpl_tc_wblob_bytes();
 size_t smpl_tc_aop_bytes(size_t frames);      // per-call scratch for the fp16 transform operands
 int smpl_tc_pack_wtiles(const float* w24, void* wblob);
