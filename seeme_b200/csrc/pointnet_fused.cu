@@ -1262,6 +1262,7 @@ __device__ __forceinline__ void pf_arrive_leader(uint64_t* bar, uint32_t rank) {
 // wait with cluster-scope acquire (the barrier receives arrivals from the peer CTA)
 __device__ __forceinline__ void pf_wait_cluster(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 24); ++it) {
     uint32_t ok;
     asm volatile(
@@ -1273,8 +1274,7 @@ __device__ __forceinline__ void pf_wait_cluster(uint64_t* bar, uint32_t parity) 
         : "memory");
     if (ok) return;
   }
-  printf("seeme_b200: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-  __trap();
+  pf_wait_timeout(addr);
 }
 __device__ __forceinline__ void umma2_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -1314,7 +1314,8 @@ constexpr int PF2_WSTEPS = 12;      // weight K-steps per tile: S 4, G1 4, G2 4 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PF_THREADS, 1)
     pointnet_block_pair_kernel(const __grid_constant__ PfMaps tm, const PfArgs a) {
   extern __shared__ __align__(1024) uint8_t pf_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pf_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = pf_smem_raw;                       // (the 1 KB of alignment slack holds the bias copy, as in pointnet_block_kernel)
+  if ((smem_u32(pf_smem_raw) & 1023u) != 0u) __trap();
   uint8_t* xbuf = smem;
   uint8_t* wring = smem + 2 * PF_XBUF;
   // local barriers (every CTA): w_full, x_full (TMA), w_empty, s_done, h_full, out_full (multicast commits)
@@ -1323,6 +1324,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PF_THREADS, 1)
       h_full[2], h_ready[2][4], out_full[2], out_drained[2];
   __shared__ uint32_t tmem_slot;
   __shared__ unsigned colmax_s[256];
+  __shared__ __align__(16) float bias_o_s[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -1370,7 +1372,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PF_THREADS, 1)
         for (int i = 0; i < PF2_WSTEPS; ++i) {
           const int phase = i >> 2, kc = i & 3;
           // blob chunk order: S (kc, nh), G1 (nh, kc), G2 (kc, nh)
-          const int chunk = phase == 1 ? 8 + (int)rank * 4 + kc : phase * 8 + kc * 2 + (int)rank;
+          const int kk = phase == 2 ? (((kc & 1) << 1) | (kc >> 1)) : kc;      // G2 runs its K-chunks in the order 0, 2, 1, 3
+          const int chunk = phase == 1 ? 8 + (int)rank * 4 + kc : phase * 8 + kk * 2 + (int)rank;
           mbar_wait(&w_empty[st], ph);
           mbar_arrive_expect_tx(&w_full[st], PF_CHUNK);
           bulk_load(wring + st * PF_CHUNK, a.wblob + (size_t)chunk * PF_CHUNK, PF_CHUNK, &w_full[st]);
@@ -1445,7 +1448,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PF_THREADS, 1)
         next_w();
       }
 #pragma unroll
-      for (int kc = 0; kc < 4; ++kc) {          // G2: OUT += H16 . W1^T, A operand from TMEM
+      for (int i4 = 0; i4 < 4; ++i4) {          // G2: OUT += H16 . W1^T, A operand from TMEM; K-chunk order 0, 2, 1, 3
+        const int kc = ((i4 & 1) << 1) | (i4 >> 1);
         pf_wait_cluster(&h_ready[b][kc], p2);
         wait_w();
         tc_fence_after();
@@ -1455,7 +1459,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PF_THREADS, 1)
           for (int ks = 0; ks < 4; ++ks)
             umma2_f16_ts(Ra, Rb + (uint32_t)((kc >> 1) * 128 + (kc & 1) * 32 + ks * 8), pf_desc_add(wd, ks * 2), idesc, 1);
           umma2_commit(&w_empty[st]);
-          if (kc == 3) umma2_commit(&out_full[b]);
+          if (i4 == 3) umma2_commit(&out_full[b]);
         }
         __syncwarp();
         next_w();
@@ -1486,40 +1490,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PF_THREADS, 1)
         asm volatile("fence.proxy.async;" ::: "memory");     // generic writes -> async proxy (the leader's MMA reads this tile)
         __syncwarp();
         if (lane == 0) pf_arrive_leader(&r_done[b][kc], rank);
-      }
-      const float* bh = a.bias_h + (size_t)sample * 256;
-      const uint32_t tbase = tmem_base + (uint32_t)(b ^ 1) * 256u + lane_off;
-      mbar_wait(&h_full[b], p2);
-      tc_fence_after();
-#pragma unroll 1
-      for (int hsel = 0; hsel < 2; ++hsel) {
-        const uint32_t thh = tbase + (uint32_t)hsel * 128u;
-        uint32_t raw[2][32];
-        tmem_ld32(thh, raw[0]);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float4 bv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bh + hsel * 128 + g * 32) + i);
-          tmem_ld_wait();
-          if (g < 3) tmem_ld32(thh + (g + 1) * 32, raw[(g + 1) & 1]);
-          const uint32_t* r = raw[g & 1];
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float f0 = fmaxf(__uint_as_float(r[4 * i]) + bv[i].x, 0.f), f1 = fmaxf(__uint_as_float(r[4 * i + 1]) + bv[i].y, 0.f);
-            const float f2 = fmaxf(__uint_as_float(r[4 * i + 2]) + bv[i].z, 0.f), f3 = fmaxf(__uint_as_float(r[4 * i + 3]) + bv[i].w, 0.f);
-            pk[2 * i] = pf_pack(f0, f1);
-            pk[2 * i + 1] = pf_pack(f2, f3);
-          }
-          tmem_st16(thh + g * 16, pk);
-          if (g & 1) {
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) pf_arrive_leader(&h_ready[b][hsel * 2 + (g >> 1)], rank);
-          }
-        }
       }
     }
   } else {
@@ -1556,49 +1526,84 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PF_THREADS, 1)
       tile_of(j, sample, n0);
       uint8_t* xb = xbuf + b * PF_XBUF;
       if (sample != cur_sample) {
-        if (cur_sample >= 0) flush_colmax(cur_sample);
+        if (cur_sample >= 0) flush_colmax(cur_sample);       // (ends with a group barrier: nobody reads the old bias any more)
+        bias_o_s[te] = __ldg(a.bias_o + (size_t)sample * 256 + te);
+        pf_epi_sync();
         cur_sample = sample;
       }
-      const float* bo = a.bias_o + (size_t)sample * 256 + hsel * 128;
+      // H epilogue of this CTA's tile (8 warps, both column halves in parallel); arrivals go to the leader's h_ready
+      {
+        const float* bh = a.bias_h + (size_t)sample * 256 + hsel * 128;
+        const uint32_t thh = tmem_base + (uint32_t)(b ^ 1) * 256u + lane_off + (uint32_t)hsel * 128u;
+        float4 bv0[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bv0[i] = __ldg(reinterpret_cast<const float4*>(bh) + i);
+        mbar_wait(&h_full[b], p2);
+        tc_fence_after();
+        uint32_t raw[2][32];
+        tmem_ld32(thh, raw[0]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float4 bv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bv[i] = g == 0 ? bv0[i] : __ldg(reinterpret_cast<const float4*>(bh + g * 32) + i);
+          tmem_ld_wait();
+          if (g < 3) tmem_ld32(thh + (g + 1) * 32, raw[(g + 1) & 1]);
+          const uint32_t* r = raw[g & 1];
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            pk[2 * i] = pf_relu_pack(__float_as_uint(__uint_as_float(r[4 * i]) + bv[i].x), __float_as_uint(__uint_as_float(r[4 * i + 1]) + bv[i].y));
+            pk[2 * i + 1] = pf_relu_pack(__float_as_uint(__uint_as_float(r[4 * i + 2]) + bv[i].z), __float_as_uint(__uint_as_float(r[4 * i + 3]) + bv[i].w));
+          }
+          tmem_st16(thh + g * 16, pk);
+          if (g & 1) {
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) pf_arrive_leader(&h_ready[b][hsel * 2 + (g >> 1)], rank);
+          }
+        }
+      }
       const uint32_t to = tmem_base + (uint32_t)b * 256u + (uint32_t)hsel * 128u + lane_off;
       const bool valid = n0 + row < a.n_points;
       mbar_wait(&out_full[b], p2);
       tc_fence_after();
-      uint32_t raw[2][32];
-      tmem_ld32(to, raw[0]);
+      // drain first (the region is the next tile's H accumulator), then stage and pool on the packed values
+      uint32_t pk[4][16];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
+        uint32_t raw[32];
+        tmem_ld32(to + g * 32, raw);
         float4 bv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bo + g * 32) + i);
+        for (int i = 0; i < 8; ++i) bv[i] = *(reinterpret_cast<const float4*>(bias_o_s + hsel * 128 + g * 32) + i);
         tmem_ld_wait();
-        if (g < 3) {
-          tmem_ld32(to + (g + 1) * 32, raw[(g + 1) & 1]);
-        } else {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) pf_arrive_leader(&out_drained[b], rank);
-        }
-        const uint32_t* r = raw[g & 1];
-        float f[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          f[4 * i] = __uint_as_float(r[4 * i]) + bv[i].x; f[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bv[i].y;
-          f[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bv[i].z; f[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bv[i].w;
+          pk[g][2 * i] = pf_pack(__uint_as_float(raw[4 * i]) + bv[i].x, __uint_as_float(raw[4 * i + 1]) + bv[i].y);
+          pk[g][2 * i + 1] = pf_pack(__uint_as_float(raw[4 * i + 2]) + bv[i].z, __uint_as_float(raw[4 * i + 3]) + bv[i].w);
         }
-        if (a.store_out) {
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) pf_arrive_leader(&out_drained[b], rank);
+      if (a.store_out) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
           uint8_t* ct = xb + (hsel * 2 + (g >> 1)) * PF_CHUNK;
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj)
-            *reinterpret_cast<uint4*>(ct + pf_sw128(row, (g & 1) * 4 + jj)) =
-                make_uint4(pf_pack(f[8 * jj], f[8 * jj + 1]), pf_pack(f[8 * jj + 2], f[8 * jj + 3]), pf_pack(f[8 * jj + 4], f[8 * jj + 5]),
-                           pf_pack(f[8 * jj + 6], f[8 * jj + 7]));
+            *reinterpret_cast<uint4*>(ct + pf_sw128(row, (g & 1) * 4 + jj)) = make_uint4(pk[g][4 * jj], pk[g][4 * jj + 1], pk[g][4 * jj + 2], pk[g][4 * jj + 3]);
         }
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
         if (!valid) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = -INFINITY;
+          for (int i = 0; i < 16; ++i) pk[g][i] = 0xfc00fc00u;      // -inf, -inf
         }
-        const float mine = __half2float(__float2half_rn(pf_colmax32(f, lane)));   // fp16(max) = max over the stored fp16 values, as pointnet_block_kernel pools
+        const float mine = pf_colmax32_h2(pk[g], lane);
         atomicMax(&colmax_s[hsel * 128 + g * 32 + lane], f2ord(mine));
       }
       if (a.store_out) fence_proxy_async();
@@ -1847,13 +1852,13 @@ int pf_block_forward(const void* x_in, void* x_out, const void* w_blob, const fl
   }
   static bool configured2 = false;
   if (!configured2) {
-    SEEME_CUDA(cudaFuncSetAttribute(pointnet_block_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    SEEME_CUDA(cudaFuncSetAttribute(pointnet_block_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BLK));
     configured2 = true;
   }
   ProfScope prof(prof_id - 1, s);
   if (h_in_tmem == 2) {            // CTA pairs (cta_group::2): 74 clusters of 2
     const int pairs = (a.n_tiles + 1) / 2 < NUM_SMS / 2 ? (a.n_tiles + 1) / 2 : NUM_SMS / 2;
-    pointnet_block_pair_kernel<<<2 * pairs, PF_THREADS, PF_SMEM, s>>>(maps, a);
+    pointnet_block_pair_kernel<<<2 * pairs, PF_THREADS, PF_SMEM_BLK, s>>>(maps, a);
     SEEME_LAUNCH_CHECK();
     return SEEME_OK;
   }
