@@ -366,7 +366,7 @@ def main():
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         ach = flops / (pn_ms / 1e3) / 1e12 if pn_ms > 0 else None
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_pointnet_kernels_s4_ncu.json")
+        tp = os.path.join(ROOT, "profiles", "r1_pointnet_kernels_final_ncu.json")
         if os.path.exists(tp):
             try:
                 k0 = [k for k in json.load(open(tp)) if "pointnet_block_kernel" in k["Kernel Name"]][0]
