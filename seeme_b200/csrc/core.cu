@@ -42,9 +42,10 @@ void prof_end(int id, cudaStream_t s) {
 // stay bit-level fp32 (small-K prologues, reference-precision mode) -- the tcgen05 path in
 // umma_gemm.cu takes the large dense contractions.
 // ------------------------------------------------------------------------------------------------
-constexpr int GK = 16;
-
-template <int BM, int BN, int TM, int TN>
+// GK: K depth of one shared-memory stage.  The few-row GEMMs (per-sample biases, cond-token projections, 256-row latent
+// maps) are bound by the latency of the K loop (one L2 round trip per stage), so they take small tiles and 64-deep stages:
+// same k order, hence bit-identical sums, in a quarter of the iterations and four times the CTAs.
+template <int BM, int BN, int TM, int TN, int GK = 16>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_f32_kernel(const GemmP p) {
   constexpr int NT = (BM / TM) * (BN / TN);
@@ -190,6 +191,9 @@ int gemm_f32(const GemmP& p, cudaStream_t s) {
   if (p.M >= 2048 && p.N >= 128) {
     dim3 grid((p.N + 127) / 128, (p.M + 127) / 128);
     gemm_f32_kernel<128, 128, 8, 8><<<grid, 256, 0, s>>>(p);
+  } else if ((long long)p.M * p.N <= 1024ll * 512 && p.K >= 128) {
+    dim3 grid((p.N + 31) / 32, (p.M + 31) / 32);
+    gemm_f32_kernel<32, 32, 2, 2, 64><<<grid, 256, 0, s>>>(p);
   } else {
     dim3 grid((p.N + 63) / 64, (p.M + 63) / 64);
     gemm_f32_kernel<64, 64, 4, 4><<<grid, 256, 0, s>>>(p);
