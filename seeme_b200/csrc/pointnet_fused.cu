@@ -1843,6 +1843,11 @@ int pf_block_forward(const void* x_in, void* x_out, const void* w_blob, const fl
   a.store_out = x_out != nullptr;
   a.wblob = reinterpret_cast<const uint8_t*>(w_blob);
   static const int dbg = getenv("SEEME_PF_DEBUG_SKIP") ? atoi(getenv("SEEME_PF_DEBUG_SKIP")) : 0;
+  static bool warned = false;
+  if (dbg && !warned) {
+    fprintf(stderr, "seeme_b200: SEEME_PF_DEBUG_SKIP=%d -- timing diagnostics only, the scene-encoder results are WRONG\n", dbg);
+    warned = true;
+  }
   a.debug_skip = dbg;
   static bool configured = false;
   if (!configured) {

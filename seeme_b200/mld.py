@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import os
 import time
+import weakref
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -337,13 +338,15 @@ class MLD(nn.Module):
         # would block the host until that slot's encoder has finished)
         length_t = batch[5 if "scene" in self.condition else 4]
         if torch.is_tensor(length_t) and length_t.is_cuda:
+            # keyed by the live tensor OBJECT (weak reference) and its version counter -- not by address: the caching allocator
+            # hands the address of a freed batch to the next one
             cache = self.__dict__.setdefault("_length_cache", {})
-            key = (length_t.data_ptr(), tuple(length_t.shape), length_t._version)
-            if key not in cache:
+            ent = cache.get(id(length_t))
+            if ent is None or ent[0]() is not length_t or ent[1] != length_t._version:
                 if len(cache) > 64:
                     cache.clear()
-                cache[key] = length_t.long().reshape(-1).tolist()
-            lengths_host = cache[key]
+                ent = cache[id(length_t)] = (weakref.ref(length_t), length_t._version, length_t.long().reshape(-1).tolist())
+            lengths_host = ent[2]
         else:
             lengths_host = torch.as_tensor(length_t).long().reshape(-1).tolist()
         pend = PendingEval(self, st, slot)
