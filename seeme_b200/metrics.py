@@ -126,3 +126,92 @@ class EgoMetric:
                 "ACCL": div(s["ACCL"], s["count_seq_accl"]),
                 "HEAD_ORIENTATION_ERROR": div(s["HEAD_ORIENTATION_ERROR"], s["count_seq_head_orientation"]),
                 "mpjpe_interactee": div(s["mpjpe_interactee"], s["count_seq_int"])}
+
+
+# ---- motion-reconstruction metrics (mld/models/metrics/mr.py, utils.py:267-407) and the per-vertex error ---------------------
+def similarity_transform(S1: torch.Tensor, S2: torch.Tensor) -> torch.Tensor:
+    """Batched orthogonal Procrustes (``batch_compute_similarity_transform_torch``, utils.py:267-318): every point set of
+    ``S1`` [N,J,3] is mapped by the similarity (s, R, t) that brings it closest to ``S2``.  One batched 3x3 SVD on the device."""
+    X1 = S1.transpose(1, 2)                                        # [N,3,J]
+    X2 = S2.transpose(1, 2)
+    mu1, mu2 = X1.mean(-1, keepdim=True), X2.mean(-1, keepdim=True)
+    X1c, X2c = X1 - mu1, X2 - mu2
+    var1 = (X1c ** 2).sum(dim=(1, 2))
+    K = X1c @ X2c.transpose(1, 2)
+    U, _, Vh = torch.linalg.svd(K)
+    V = Vh.transpose(1, 2)
+    Z = torch.eye(3, device=S1.device, dtype=S1.dtype).repeat(S1.shape[0], 1, 1)
+    Z[:, -1, -1] *= torch.sign(torch.det(U @ V.transpose(1, 2)))
+    R = V @ (Z @ U.transpose(1, 2))
+    scale = torch.diagonal(R @ K, dim1=1, dim2=2).sum(-1) / var1
+    t = mu2 - scale[:, None, None] * (R @ mu1)
+    return (scale[:, None, None] * (R @ X1) + t).transpose(1, 2)
+
+
+MR_STATE_KEYS = ["count", "count_seq", "MPJPE", "PAMPJPE", "ACCEL"]
+
+
+class MRMetric:
+    """``MRMetrics`` (mr.py:11-96) without the per-sequence Python loop and the host round trip: MPJPE (root-aligned),
+    PA-MPJPE and acceleration error summed over ALL frames of the padded sequences, as the reference does
+    (``rst[i]`` is the whole sequence; only ``count`` uses the lengths)."""
+
+    def __init__(self, njoints: int = 22, jointstype: str = "mmm", force_in_meter: bool = True, align_root: bool = True,
+                 dist_sync_on_step: bool = True, **kwargs):
+        if jointstype not in ["mmm", "humanml3d"]:
+            raise NotImplementedError("This jointstype is not implemented.")                 # mr.py:22-23
+        self.name = "Motion Reconstructions"
+        self.align_root, self.force_in_meter = align_root, force_in_meter
+        self.reset()
+
+    def reset(self):
+        self.state = {k: 0.0 for k in MR_STATE_KEYS}
+
+    def state_vector(self) -> torch.Tensor:
+        return torch.tensor([self.state[k] for k in MR_STATE_KEYS], dtype=torch.float64)
+
+    def load_state_vector(self, v: torch.Tensor):
+        for k, x in zip(MR_STATE_KEYS, v.tolist()):
+            self.state[k] = x
+
+    @torch.no_grad()
+    def update(self, joints_rst: torch.Tensor, joints_ref: torch.Tensor, lengths: List[int]):
+        assert joints_rst.shape == joints_ref.shape and joints_rst.dim() == 4
+        B, T, J, _ = joints_rst.shape
+        s = self.state
+        s["count"] += float(sum(lengths))
+        s["count_seq"] += len(lengths)
+        rst, ref = joints_rst.reshape(B * T, J, 3), joints_ref.reshape(B * T, J, 3)
+        valid = (ref[:, :, 0] != -2.0).to(rst.dtype)                                          # utils.py:356
+        pa, ta = (rst - rst[:, :1], ref - ref[:, :1]) if self.align_root else (rst, ref)
+        mpjpe = ((pa - ta).norm(dim=-1) * valid).sum(-1) / valid.sum(-1)
+        pampjpe = (similarity_transform(rst.float(), ref.float()) - ref.float()).norm(dim=-1).mean(-1)
+        if T >= 3:
+            acc = lambda x: x[:, :-2] - 2 * x[:, 1:-1] + x[:, 2:]
+            accel = (acc(joints_rst) - acc(joints_ref)).norm(dim=-1).mean(-1).sum()
+        else:
+            accel = torch.zeros((), device=rst.device)
+        a, b, c = torch.stack([mpjpe.sum().double(), pampjpe.sum().double(), accel.double()]).tolist()
+        s["MPJPE"] += a
+        s["PAMPJPE"] += b
+        s["ACCEL"] += c
+
+    def compute(self, sanity_flag=False) -> Dict[str, float]:
+        s = self.state
+        f = 1000.0 if self.force_in_meter else 1.0
+        div = lambda a, b: (a / b) if b else float("nan")
+        return {"MPJPE": div(s["MPJPE"], s["count"]) * f, "PAMPJPE": div(s["PAMPJPE"], s["count"]) * f,
+                "ACCEL": div(s["ACCEL"], s["count"] - 2 * s["count_seq"]) * f}
+
+
+def vertice_pve(pred_verts: torch.Tensor, target_verts: torch.Tensor, alignment: str = "none") -> torch.Tensor:
+    """Per-vertex error (``metrics_utils_egobody.py:144-171``) for [N,V,3] meshes, batched on the device."""
+    assert len(pred_verts) == len(target_verts)
+    if alignment == "procrustes":
+        pred_verts = similarity_transform(pred_verts, target_verts)
+    elif alignment == "scale":
+        sc = (pred_verts * target_verts).sum(dim=(1, 2)) / (pred_verts * pred_verts).sum(dim=(1, 2))
+        pred_verts = pred_verts * sc[:, None, None]
+    elif alignment != "none":
+        raise ValueError(f"Invalid value for alignment: {alignment}")
+    return (pred_verts - target_verts).norm(dim=-1).mean()

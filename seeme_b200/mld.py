@@ -173,12 +173,15 @@ class MLD(nn.Module):
     def configure_metrics(self, metrics=None):
         """base.py:160-173.  ``metrics`` may carry ready metric objects ({"EgoMetric": obj}); otherwise the
         in-repo batched EgoMetric is used (same state sums as mld/models/metrics/compute.py)."""
-        from .metrics import EgoMetric
+        from .metrics import EgoMetric, MRMetric
         for m in self.metrics_dict:
             if metrics and m in metrics:
                 obj = metrics[m]
             elif m == "EgoMetric":
                 obj = EgoMetric(njoints=self.njoints, dist_sync_on_step=self.cfg.METRIC.get("DIST_SYNC_ON_STEP", True))
+            elif m == "MRMetrics":                                              # base.py:180-185
+                obj = MRMetric(njoints=self.njoints, jointstype=self.cfg.get("DATASET", {}).get("JOINT_TYPE", "humanml3d"),
+                               dist_sync_on_step=self.cfg.METRIC.get("DIST_SYNC_ON_STEP", True))
             else:
                 raise NotImplementedError(f"Do not support Metric Type {m}")
             object.__setattr__(self, m, obj)     # metrics hold no persistent state (SURVEY App. A)
@@ -575,6 +578,9 @@ class MLD(nn.Module):
         def retire():
             rs_set = pending.popleft().result()
             for metric in self.metrics_dict:
+                if metric == "MRMetrics":
+                    getattr(self, metric).update(rs_set["joints_rst"], rs_set["joints_ref"], rs_set["lengths"])
+                    continue
                 getattr(self, metric).update(
                     split, rs_set["joints_rst"], rs_set["joints_ref"], rs_set["orientation_quat_rst"],
                     rs_set["orientation_quat_ref"], rs_set["root_interactee"], rs_set["joints_interactee"],
@@ -604,6 +610,8 @@ class MLD(nn.Module):
                     split, rs_set["joints_rst"], rs_set["joints_ref"], rs_set["orientation_quat_rst"],
                     rs_set["orientation_quat_ref"], rs_set["root_interactee"], rs_set["joints_interactee"],
                     rs_set["orientation_quat_int"], rs_set["joints_interactee_gt"], rs_set["lengths"], rs_set["list_names"])
+            elif metric == "MRMetrics":                                         # mld.py:2116-2119
+                getattr(self, metric).update(rs_set["joints_rst"], rs_set["joints_ref"], rs_set["lengths"])
             else:
                 raise TypeError(f"Not support this metric {metric}")
         if split == "test":

@@ -146,3 +146,33 @@ def test_metric_matches_reference_computemetrics():
             assert float(getattr(ref, k)) == pytest.approx(mine.state[k], rel=1e-5, abs=1e-6), (split, k)
         for k in ("count", "count_seq", "count_seq_root", "count_seq_accl", "count_seq_head_orientation"):
             assert float(getattr(ref, k)) == mine.state[k], (split, k)
+
+
+def test_mr_metric_and_pve_match_reference():
+    """batched MRMetric (MPJPE / PA-MPJPE / ACCEL) and vertice_pve vs the reference's per-sequence CPU code (build container only)"""
+    from oracle import ref_modules as R
+    if not R.available():
+        pytest.skip("/root/reference not present")
+    R.import_mld()
+    from mld.models.metrics.mr import MRMetrics
+    from mld.models.metrics import metrics_utils_egobody as U
+    from seeme_b200.metrics import MRMetric, vertice_pve
+    g = torch.Generator().manual_seed(5)
+    B, T_, J = 4, 60, 22
+    ref_j = torch.randn(B, T_, J, 3, generator=g) * 0.4
+    rst_j = 1.1 * ref_j @ torch.linalg.qr(torch.randn(3, 3, generator=g))[0] + 0.03 * torch.randn(B, T_, J, 3, generator=g) + 0.2
+    lengths = [60, 33, 60, 48]
+    a, b = MRMetrics(njoints=J, jointstype="humanml3d", dist_sync_on_step=False), MRMetric(njoints=J, jointstype="humanml3d")
+    for _ in range(2):
+        a.update(rst_j, ref_j, lengths)
+        b.update(rst_j, ref_j, lengths)
+    ra, rb = a.compute(sanity_flag=False), b.compute()
+    for k in ("MPJPE", "PAMPJPE", "ACCEL"):
+        assert float(ra[k]) == pytest.approx(rb[k], rel=2e-5), k
+    assert float(a.count) == b.state["count"] and float(a.count_seq) == b.state["count_seq"]
+    with pytest.raises(NotImplementedError):
+        MRMetric(njoints=J, jointstype="smpl")
+    pv = torch.randn(6, 500, 3, generator=g)
+    tv = 0.9 * pv @ torch.linalg.qr(torch.randn(3, 3, generator=g))[0] + 0.01 * torch.randn(6, 500, 3, generator=g)
+    for al in ("none", "scale", "procrustes"):
+        assert float(vertice_pve(pv, tv, al)) == pytest.approx(float(U.vertice_pve(pv.numpy(), tv.numpy(), alignment=al)), rel=1e-4), al

@@ -463,3 +463,26 @@ def test_error_conventions(den_op, vae_op):
         den_op.forward(torch.zeros(4, 256, device=DEV), 1, torch.zeros(5, 4, 256, device=DEV))
     with pytest.raises(RuntimeError, match="CUDA"):
         vae_op.decode(torch.zeros(1, 256), torch.tensor([4]), 4)
+
+
+def test_mr_metrics_on_device_through_the_model():
+    """MRMetrics (MPJPE / PA-MPJPE / ACCEL) selected like in the reference (METRIC.TYPE) and fed from rs_set on the device"""
+    import seeme_b200
+    from seeme_b200 import synthetic as S
+    B = 3
+    model = seeme_b200.build_model("config_mld_egobody.yaml", device=DEV, guidance_scale=7.5, max_batch=B, n_points=300)
+    model.metrics_dict = ["EgoMetric", "MRMetrics"]
+    model.configure_metrics()
+    batch = tuple(x.to(DEV) if torch.is_tensor(x) else x for x in S.make_batch(B, n_points=300, ragged=True))
+    out = model.test_step(batch, 0)
+    assert out.shape[0] == B
+    m = model.on_test_epoch_end()
+    assert {"Metrics/MPJPE", "Metrics/PAMPJPE", "Metrics/ACCEL"} <= set(m)
+    assert all(v == v and v >= 0 for k, v in m.items() if k in ("Metrics/PAMPJPE", "Metrics/ACCEL"))
+    # PA-MPJPE removes a similarity transform, so it cannot exceed the root-aligned MPJPE of the same frames
+    from seeme_b200.metrics import MRMetric
+    mr = MRMetric(njoints=23, jointstype="humanml3d")
+    rs = model.ego_eval(batch)
+    mr.update(rs["joints_rst"], rs["joints_ref"], rs["lengths"])
+    r = mr.compute()
+    assert r["PAMPJPE"] <= r["MPJPE"] + 1e-6
