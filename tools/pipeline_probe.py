@@ -56,10 +56,14 @@ if os.environ.get("PROBE_ASYNC"):      # the public async API (slots, sampler_gr
     model.pipeline_depth = D
     n = int(os.environ.get("PROBE_STEPS", "48"))
 
+    host_ms = []
+
     def run(n):
         pend = deque()
         for _ in range(n):
+            h0 = time.perf_counter()
             pend.append(model.ego_eval_async(batch, noise))
+            host_ms.append((time.perf_counter() - h0) * 1e3)
             if len(pend) >= D:
                 pend.popleft().synchronize()
         while pend:
@@ -71,7 +75,9 @@ if os.environ.get("PROBE_ASYNC"):      # the public async API (slots, sampler_gr
     run(n)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / n * 1e3
-    print(f"async depth {D} group {model.sampler_group}: {dt:.2f} ms per step -> {B / dt * 1e3:.0f} sequences/s")
+    hm = host_ms[-n:]
+    print(f"async depth {D} group {model.sampler_group}: {dt:.2f} ms per step -> {B / dt * 1e3:.0f} sequences/s | host submit ms: "
+          f"mean {sum(hm) / len(hm):.2f} max {max(hm):.2f} first8 {[round(x, 1) for x in hm[:8]]}")
     sys.exit(0)
 
 
