@@ -47,11 +47,26 @@ def reference_items(root_parent):
         os.chdir(cwd)
 
 
+def reference_gimo_items(root_parent):
+    """GimoData with condition ["text"]: the scene branch needs trimesh to read the scan and cannot run here"""
+    import mld.data.humanml.data.dataset as D
+    cwd = os.getcwd()
+    os.chdir(root_parent)
+    try:
+        ds = D.GimoData(None, None, "test.txt", "./datasets/GIMO/processed", condition=["text"], predict_transl=True,
+                        motion_length=60, data_type="angle", progress_bar=False)
+        return {ds.name_list[i]: ds[i] for i in range(len(ds))}
+    finally:
+        os.chdir(cwd)
+
+
 def main():
-    from seeme_b200.egobody_data import write_synthetic
+    from seeme_b200.egobody_data import write_synthetic, write_synthetic_gimo
     with tempfile.TemporaryDirectory() as tmp:
         write_synthetic(os.path.join(tmp, "datasets", "EgoBody"), "test", LENGTHS, SEED, N_POINTS)
+        write_synthetic_gimo(os.path.join(tmp, "datasets", "GIMO"), "test", 3, SEED)
         items = reference_items(tmp)
+        gimo = reference_gimo_items(tmp)
     out = {}
     for name, it in items.items():
         motion, transl, beta, utils_, scene, length, imgs = it
@@ -59,6 +74,10 @@ def main():
         for k, v in (("motion", motion), ("transl", transl), ("beta", beta), ("utils", utils_), ("scene", scene), ("length", length)):
             out[f"{key}/{k}"] = v.numpy()
         out[f"{key}/imgs"] = np.array(imgs)
+    for name, it in gimo.items():
+        motion, transl, beta, utils_, length = it
+        for k, v in (("motion", motion), ("transl", transl), ("beta", beta), ("utils", utils_), ("length", length)):
+            out[f"gimo/{name[:-4]}/{k}"] = v.numpy()
     path = os.path.join(ROOT, "tests", "golden", "egobody_items.npz")
     np.savez_compressed(path, **out)
     print(path, len(items), "items;", {k: (v.dtype, v.shape) for k, v in out.items() if k.startswith("seq_0002")})

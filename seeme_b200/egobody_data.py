@@ -36,12 +36,24 @@ _ADD_TRANS = np.array([[1.0, 0, 0, 0], [0, -1, 0, 0], [0, 0, -1, 0], [0, 0, 0, 1
 
 
 class EgoBodySequences(torch.utils.data.Dataset):
+    POSE_DIMS = 69                  # body-pose dims per frame; the statistics are [3 global orient | POSE_DIMS | 3 transl | ...]
+
     def __init__(self, root: str, split: str = "test", condition: Sequence[str] = ("text", "scene", "interactee"),
                  motion_length: int = 60, predict_transl: bool = True):
         self.root, self.split = root, split
         self.condition = list(condition)
         self.motion_length = int(motion_length)
         self.predict_transl = bool(predict_transl)
+        self._load(root, split)
+
+    def _transl_stats(self):
+        n = 3 + self.POSE_DIMS
+        return self.mean[0, n:n + 3], self.std[0, n:n + 3]
+
+    def _image_names(self, d) -> List[str]:
+        return [str(n) for n in d["recording_utils"]["original_imgname"]]
+
+    def _load(self, root: str, split: str) -> None:
         base = os.path.join(root, "our_process_smpl_split_NEW")
         self.mean = np.load(os.path.join(base, "mean.npy"))
         self.std = np.load(os.path.join(base, "std.npy"))
@@ -82,24 +94,26 @@ class EgoBodySequences(torch.utils.data.Dataset):
     def __getitem__(self, i: int):
         d = self.items[i]
         rec = d["recording_utils"]
-        names = [str(n) for n in rec["original_imgname"]]
+        names = self._image_names(d)
         T = len(d["video"])
         L = self.motion_length
         n_pad = L - T
         mean, std = self.mean, self.std
+        P = self.POSE_DIMS
+        t_mean, t_std = self._transl_stats()
 
         def person(p):
             pose = np.array(p["body_pose"])
             if n_pad:
-                pose = np.concatenate([pose, np.zeros((n_pad, 1, 69))], axis=0)
-            pose = (pose.reshape(L, -1) - mean[0, 3:72]) / std[0, 3:72]
+                pose = np.concatenate([pose, np.zeros((n_pad, 1, P))], axis=0)
+            pose = (pose.reshape(L, -1) - mean[0, 3:3 + P]) / std[0, 3:3 + P]
             pose = torch.tensor(pose, dtype=torch.float32).unsqueeze(1)                       # [L,1,69]
             go = self._pad(torch.tensor(np.array(p["global_orient"]), dtype=torch.float32), n_pad)
             # float32 tensor (-, /) float64 statistics: the reference mixes a tensor with an ndarray, which promotes to float64
             go = (go - torch.from_numpy(mean[0, :3])) / torch.from_numpy(std[0, :3])
             tr = self._pad(torch.tensor(np.array(p["transl"]), dtype=torch.float32), n_pad)
             if self.predict_transl:
-                tr = (tr - torch.from_numpy(mean[0, 72:75])) / torch.from_numpy(std[0, 72:75])
+                tr = (tr - torch.from_numpy(np.ascontiguousarray(t_mean))) / torch.from_numpy(np.ascontiguousarray(t_std))
             be = self._pad(torch.tensor(np.array(p["betas"]), dtype=torch.float32), n_pad)
             return pose, go, tr, be
 
@@ -114,8 +128,84 @@ class EgoBodySequences(torch.utils.data.Dataset):
             utils_ = torch.cat([utils_, torch.zeros((n_pad, 6))], dim=0)
         length = torch.tensor([T], dtype=torch.int32)
         if "scene" in self.condition:
-            return motion, transl, beta, utils_, self._scene(names[0]), length, names
+            return motion, transl, beta, utils_, self._scene(names[0] if names else ""), length, names
         return motion, transl, beta, utils_, length
+
+
+def read_ply_vertices(path: str) -> np.ndarray:
+    """x, y, z of the vertex element of an ASCII or binary-little-endian PLY file (what ``trimesh.load_mesh(...).vertices`` returns
+    for the GIMO scene scans; faces and extra vertex properties are skipped)."""
+    with open(path, "rb") as f:
+        fmt, n_vert, props, in_vertex = None, 0, [], False
+        while True:
+            line = f.readline().decode("ascii", "replace").strip()
+            if line.startswith("format"):
+                fmt = line.split()[1]
+            elif line.startswith("element"):
+                in_vertex = line.split()[1] == "vertex"
+                if in_vertex:
+                    n_vert = int(line.split()[2])
+            elif line.startswith("property") and in_vertex:
+                props.append((line.split()[-1], line.split()[1]))
+            elif line == "end_header":
+                break
+        names = [p[0] for p in props]
+        if fmt == "ascii":
+            rows = np.loadtxt(f, max_rows=n_vert, ndmin=2)
+            return np.asarray(rows[:, [names.index(c) for c in "xyz"]], dtype=np.float64)
+        if fmt != "binary_little_endian":
+            raise ValueError(f"{path}: unsupported PLY format {fmt}")
+        np_t = {"float": "<f4", "float32": "<f4", "double": "<f8", "float64": "<f8", "uchar": "u1", "uint8": "u1", "char": "i1",
+                "int": "<i4", "int32": "<i4", "uint": "<u4", "uint32": "<u4", "short": "<i2", "ushort": "<u2"}
+        rec = np.frombuffer(f.read(n_vert * sum(np.dtype(np_t[t]).itemsize for _, t in props)),
+                            dtype=np.dtype([(n, np_t[t]) for n, t in props]), count=n_vert)
+        return np.stack([rec["x"], rec["y"], rec["z"]], axis=1).astype(np.float64)
+
+
+class GimoSequences(EgoBodySequences):
+    """``GimoData`` (``dataset.py:1797-2509``): same per-sequence dicts, 21 body joints (63 pose dims; the statistics are
+    [3 | 63 | ... | 3 transl at the END]), image names taken from ``video``, and the scene cloud sampled (20 000 points with
+    replacement through NumPy's global RNG, like the reference) from ``<scene_root>/<scene>/scene_obj/scene_downsampled.ply``,
+    scaled by 1/1.03 and moved by ``transform_norm.txt``.  The motion / transl / beta / utils part is pinned against the
+    unmodified class (``tests/test_data.py``); the scene branch is NOT (the reference needs ``trimesh`` to read the scan,
+    which is not installable here), and the reference's zero-padding of short GIMO sequences is broken (it pads 69 pose
+    dims onto 63): full-length sequences only, as in the released data."""
+    POSE_DIMS = 63
+
+    def __init__(self, root: str, split: str = "test", condition: Sequence[str] = ("text", "scene"), motion_length: int = 60,
+                 predict_transl: bool = True, motion_dir: Optional[str] = None, scene_root: Optional[str] = None, n_points: int = 20000):
+        self.motion_dir = motion_dir if motion_dir is not None else os.path.join(root, "processed")
+        self.scene_root = scene_root if scene_root is not None else os.path.join(os.path.dirname(root.rstrip("/")), "gimo_raw", "group", "GIMO")
+        self.n_points = int(n_points)
+        super().__init__(root, split, condition, motion_length, predict_transl)
+
+    def _transl_stats(self):
+        return self.mean[0, -3:], self.std[0, -3:]
+
+    def _image_names(self, d) -> List[str]:
+        return [str(n) for n in d["video"]]
+
+    def _load(self, root: str, split: str) -> None:
+        self.mean = np.load(os.path.join(root, "processed", "mean.npy"))
+        self.std = np.load(os.path.join(root, "processed", "std.npy"))
+        seq_dir = os.path.join(self.motion_dir, "test" if split == "val" else split)       # GIMO has no val split (dataset.py:1841-1843)
+        self.names = sorted(n for n in os.listdir(seq_dir) if n.endswith(".npy"))
+        self.items = [np.load(os.path.join(seq_dir, n), allow_pickle=True).item() for n in self.names]
+        for n, d in zip(self.names, self.items):
+            if len(d["video"]) != self.motion_length:
+                raise ValueError(f"{n}: {len(d['video'])} frames; GIMO sequences must have motion_length = {self.motion_length} frames")
+
+    def _scene(self, first_image: str) -> torch.Tensor:
+        scene = first_image.split("/")[-4]
+        base = os.path.join(self.scene_root, scene, "scene_obj")
+        scale = 1.03
+        tn = np.loadtxt(os.path.join(base, "transform_norm.txt")).reshape((4, 4))
+        tn[:3, 3] /= scale
+        pts = read_ply_vertices(os.path.join(base, "scene_downsampled.ply"))
+        pts = pts[np.random.choice(range(len(pts)), self.n_points)]
+        pts = pts * (1 / scale)
+        pts = (tn[:3, :3] @ pts.T + tn[:3, 3:]).T
+        return torch.from_numpy(pts).float()
 
 
 def collate(items: List[tuple], pin: bool = False):
@@ -202,3 +292,40 @@ def write_synthetic(root: str, split: str = "test", lengths: Sequence[int] = (60
         pickle.dump(scene_verts, f)
     with open(os.path.join(root, "transf_matrices_all_seqs.pkl"), "wb") as f:
         pickle.dump(transf, f)
+
+
+def write_synthetic_gimo(root: str, split: str = "test", n_seq: int = 3, seed: int = 0, n_scene_points: int = 5000,
+                         scene_root: Optional[str] = None) -> None:
+    """GIMO-shaped recordings: ``<root>/processed/{mean,std}.npy`` ([1, 69]: 3 + 63 + 3), ``<root>/processed/<split>/*.npy`` and,
+    under ``scene_root``, one binary PLY scan + ``transform_norm.txt`` per scene."""
+    g = np.random.default_rng(seed)
+    os.makedirs(os.path.join(root, "processed", split), exist_ok=True)
+    np.save(os.path.join(root, "processed", "mean.npy"), g.normal(0, 0.1, (1, 69)))
+    np.save(os.path.join(root, "processed", "std.npy"), g.uniform(0.2, 0.6, (1, 69)))
+    scene_root = scene_root if scene_root is not None else os.path.join(os.path.dirname(root.rstrip("/")), "gimo_raw", "group", "GIMO")
+    T = 60
+    for s in range(n_seq):
+        scene = f"scene_{s % 2}"
+        video = [f"{scene}/2022-01-0{s}/eye_pc/{t}.ply" for t in range(T)]          # [-4] of the path is the scene
+
+        def person():
+            return {"global_orient": g.normal(0, 0.5, (T, 1, 3)), "body_pose": g.normal(0, 0.3, (T, 1, 63)),
+                    "betas": np.repeat(g.normal(0, 0.5, (1, 1, 10)), T, axis=0), "transl": g.normal(0, 1.0, (T, 1, 3))}
+
+        item = {"video": video,
+                "recording_utils": {"fx": list(g.uniform(600, 700, T)), "cx": list(g.uniform(300, 340, T)), "cy": list(g.uniform(160, 200, T)),
+                                    "center": g.uniform(100, 500, (T, 2)), "scale": list(g.uniform(0.5, 2.0, T))},
+                "wearer": person(), "interactee": person()}
+        np.save(os.path.join(root, "processed", split, f"seq_{s:04d}.npy"), item, allow_pickle=True)
+        obj = os.path.join(scene_root, scene, "scene_obj")
+        if not os.path.exists(os.path.join(obj, "scene_downsampled.ply")):
+            os.makedirs(obj, exist_ok=True)
+            pts = np.stack([g.uniform(-4, 4, n_scene_points), g.uniform(0, 3, n_scene_points), g.uniform(-4, 4, n_scene_points)], axis=1).astype("<f4")
+            with open(os.path.join(obj, "scene_downsampled.ply"), "wb") as f:
+                f.write(("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+                         "end_header\n" % n_scene_points).encode("ascii"))
+                f.write(pts.tobytes())
+            q, _ = np.linalg.qr(g.normal(size=(3, 3)))
+            m = np.eye(4)
+            m[:3, :3], m[:3, 3] = q, g.normal(0, 1.0, 3)
+            np.savetxt(os.path.join(obj, "transform_norm.txt"), m)

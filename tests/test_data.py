@@ -65,3 +65,52 @@ def test_pipeline_consumes_producer_batches(dataset):
     torch.manual_seed(0)
     rs = model.ego_eval(tuple(x.to(dev) if torch.is_tensor(x) else x for x in b))
     assert rs["lengths"] == [60, 60] and rs["joints_rst"].shape == (2, 60, 24, 3)
+
+
+def test_gimo_items_match_reference_dataset_and_scene_branch(tmp_path):
+    """GimoData (dataset.py:1797-2509): motion / transl / beta / utils bit-identical to the unmodified class (goldens made with
+    condition ["text"]: its scene branch needs trimesh); the scene branch -- own PLY reader, 1/1.03 rescale, transform_norm --
+    is checked against a direct NumPy evaluation with the same RNG state (unpinned against the reference)."""
+    root = str(tmp_path / "datasets" / "GIMO")
+    E.write_synthetic_gimo(root, "test", 3, SEED)
+    g = np.load(GOLDEN)
+    ds = E.GimoSequences(root, "test", condition=["text"])
+    assert len(ds) == 3
+    for i, name in enumerate(ds.names):
+        motion, transl, beta, utils_, length = ds[i]
+        for k, v in (("motion", motion), ("transl", transl), ("beta", beta), ("utils", utils_), ("length", length)):
+            ref = g[f"gimo/{name[:-4]}/{k}"]
+            assert v.numpy().dtype == ref.dtype and np.array_equal(v.numpy(), ref), (name, k)
+    assert motion.shape == (60, 2, 66)
+    # scene branch
+    dss = E.GimoSequences(root, "val", condition=["text", "scene"], n_points=777)           # "val" falls back to the test split
+    np.random.seed(5)
+    motion2, _, _, _, scene, length, imgs = dss[1]
+    assert torch.equal(motion2, ds[1][0]) and scene.shape == (777, 3) and scene.dtype == torch.float32 and len(imgs) == 60
+    obj = os.path.join(os.path.dirname(root), "gimo_raw", "group", "GIMO", imgs[0].split("/")[-4], "scene_obj")
+    pts = E.read_ply_vertices(os.path.join(obj, "scene_downsampled.ply"))
+    assert pts.shape == (5000, 3)
+    np.random.seed(5)
+    sel = pts[np.random.choice(range(len(pts)), 777)] / 1.03
+    tn = np.loadtxt(os.path.join(obj, "transform_norm.txt")).reshape(4, 4)
+    want = sel @ tn[:3, :3].T + tn[:3, 3] / 1.03
+    assert np.allclose(scene.numpy(), want, atol=1e-5)
+    # the model consumes GIMO batches with the 66-wide features
+    b = E.collate([dss[0], dss[1]])
+    assert b[0].shape == (2, 60, 2, 66) and b[4].shape == (2, 777, 3)
+    with pytest.raises(ValueError):
+        E.GimoSequences(root, "test", condition=["text"], motion_length=30)
+
+
+@pytest.mark.gpu
+def test_gimo_model_consumes_gimo_producer_batches(tmp_path):
+    """config_mld_gimo.yaml (scene-only conditioning, 66-wide rows) on pinned batches of the GIMO producer"""
+    import seeme_b200
+    root = str(tmp_path / "datasets" / "GIMO")
+    E.write_synthetic_gimo(root, "test", 3, SEED)
+    ds = E.GimoSequences(root, "test", condition=["text", "scene"], n_points=1500)
+    model = seeme_b200.build_model("config_mld_gimo.yaml", device="cuda:0", guidance_scale=7.5, max_batch=2, n_points=1500, pipeline_depth=2)
+    np.random.seed(0)
+    outs = list(model.run_test_batches(E.batches(ds, batch_size=2, pin=True)))
+    assert [tuple(o.shape) for o in outs] == [(2, 60, 24, 3), (1, 60, 24, 3)]
+    assert all(bool(torch.isfinite(o).all()) for o in outs)
