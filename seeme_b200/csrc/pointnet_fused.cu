@@ -222,11 +222,13 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
   //   s = 8..11  G2(kc)       step_full[s] also collects the 4 H-epilogue warps' arrivals
   // one phase per tile and barrier (parity = tile & 1); w_empty[s % 3] is committed once per step (4 ring rounds per tile, so
   // its parities are compile-time constants too)
-  __shared__ __align__(8) uint64_t step_full[12], w_empty[3], x_full[2], s_done[2][4], h_full[2][2], out_full[2], out_drained[2];
+  __shared__ __align__(8) uint64_t step_full[12], w_empty[3], x_full[2], s_done[2][4], h_full[2][2], out_full[2], out_drained[2], staged[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ unsigned colmax_s[256];
-  __shared__ __align__(16) float bias_o_s[256];     // cs[b] of the current sample: the L1 next to 225 KB of shared memory is tiny and the
-                                                   // output-epilogue drain waited ~800 cycles per 32 columns on __ldg of it
+  // c0[b] / cs[b] of the current sample: the L1 next to 225 KB of shared memory is tiny, and both epilogues waited ~800 cycles
+  // per 32 columns on __ldg of them.  (The pooled column maxima are kept in registers across the tiles of a sample instead of
+  // a shared-memory array, which is what makes room for the second vector.)
+  __shared__ __align__(16) float bias_h_s[256];
+  __shared__ __align__(16) float bias_o_s[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = a.n_tiles / (int)gridDim.x, rem = a.n_tiles % (int)gridDim.x;
@@ -243,6 +245,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       mbar_init(&x_full[b], 1);
       mbar_init(&out_full[b], 1);
       mbar_init(&out_drained[b], 8);
+      mbar_init(&staged[b], 8);
       for (int k = 0; k < 4; ++k) mbar_init(&s_done[b][k], 1);
       mbar_init(&h_full[b][0], 1);
       mbar_init(&h_full[b][1], 1);
@@ -250,7 +253,6 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_slot, 512);
-  if (threadIdx.x < 256) colmax_s[threadIdx.x] = 0u;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -355,6 +357,26 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
   } else if (warp < 6) {
     // ---- H group (4 warps): in-place relu of X, chunk by chunk behind the shortcut GEMM ------------------------
     const int th = (int)threadIdx.x - 64;           // 0..127
+    // Thread 0 of this group also writes the staged output tiles back and prefetches the X tiles: when the output group's
+    // elected thread did it, its wait for the TMA store to read the staging buffer delayed that warp's H epilogue of the
+    // NEXT tile, i.e. the first G2 step (event trace: ~700 cycles per tile)
+    auto store_and_prefetch = [&](int jp) {          // tile jp has been staged in X buffer jp & 1
+      const int bp = jp & 1;
+      const int t = t_begin + jp;
+      const int sample = t / a.tiles_per_sample, n0 = (t % a.tiles_per_sample) * 128;
+      mbar_wait(&staged[bp], (uint32_t)(jp >> 1) & 1u);
+      if (a.store_out) {
+        for (int kc = 0; kc < 4; ++kc) tma_store_3d(&tm.xout, xbuf + bp * PF_XBUF + kc * PF_CHUNK, kc * 64, n0, sample);
+        pf_store_commit();
+        pf_store_wait_read();
+      }
+      if (jp + 2 < nt) {
+        const int t2 = t_begin + jp + 2;
+        const int s2 = t2 / a.tiles_per_sample, m0 = (t2 % a.tiles_per_sample) * 128;
+        mbar_arrive_expect_tx(&x_full[bp], PF_XBUF);
+        for (int kc = 0; kc < 4; ++kc) tma_load_3d(xbuf + bp * PF_XBUF + kc * PF_CHUNK, &tm.xin, &x_full[bp], kc * 64, m0, s2);
+      }
+    };
     for (int j = 0; j < nt; ++j) {
       const int b = j & 1;
       const uint32_t p2 = (uint32_t)(j >> 1) & 1u;
@@ -377,7 +399,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
         if (lane == 0) pf_arrive(sf0 + (uint32_t)(4 + kc) * 8u);
         if (th == 0) PF_TR(j, 17 + 2 * kc);
       }
+      if (th == 0 && j > 0) store_and_prefetch(j - 1);
     }
+    if (th == 0 && nt > 0) store_and_prefetch(nt - 1);
   } else {
     // ---- O group (8 warps: lane quarter x column half): OUT epilogue, pooled column max, TMA stores, X-tile loads ---------
     const int te = (int)threadIdx.x - 192;         // 0..255
@@ -392,12 +416,14 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       mbar_arrive_expect_tx(&x_full[b], PF_XBUF);
       for (int kc = 0; kc < 4; ++kc) tma_load_3d(xbuf + b * PF_XBUF + kc * PF_CHUNK, &tm.xin, &x_full[b], kc * 64, n0, sample);
     };
+    // pooled column maxima of this warp's 32 rows, columns hsel * 128 + g * 32 + lane, accumulated over the tiles of a sample
+    float cmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     auto flush_colmax = [&](int sample) {
-      pf_epi_sync();
-      const unsigned v = colmax_s[te];
-      if (v) atomicMax(a.colmax + (size_t)sample * 256 + te, v);
-      colmax_s[te] = 0u;
-      pf_epi_sync();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (cmax[g] > -INFINITY) atomicMax(a.colmax + (size_t)sample * 256 + hsel * 128 + g * 32 + lane, f2ord(cmax[g]));
+        cmax[g] = -INFINITY;
+      }
     };
     if (elected) {
       if (nt > 0) load_x(0);
@@ -411,7 +437,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       const int sample = t / a.tiles_per_sample, n0 = (t % a.tiles_per_sample) * 128;
       uint8_t* xb = xbuf + b * PF_XBUF;
       if (sample != cur_sample) {
-        if (cur_sample >= 0) flush_colmax(cur_sample);       // (ends with a group barrier: nobody reads the old bias any more)
+        if (cur_sample >= 0) flush_colmax(cur_sample);
+        pf_epi_sync();                                       // nobody reads the previous sample's biases any more
+        bias_h_s[te] = __ldg(a.bias_h + (size_t)sample * 256 + te);
         bias_o_s[te] = __ldg(a.bias_o + (size_t)sample * 256 + te);
         pf_epi_sync();
         cur_sample = sample;
@@ -419,11 +447,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
       // H epilogue of THIS tile (both column halves in parallel on the 8 warps of this group; the 4 relu warps stay on the
       // relu pass): H16 = fp16(relu(H + c0[b])), in place in TMEM (or over relu(X) in shared memory)
       {
-        const float* bh = a.bias_h + (size_t)sample * 256 + hsel * 128;
+        const float* bh = bias_h_s + hsel * 128;
         const uint32_t thh = tmem_base + (uint32_t)(b ^ 1) * 256u + lane_off + (uint32_t)hsel * 128u;
-        float4 bv0[8];                                       // the first group's bias is fetched before the wait
-#pragma unroll
-        for (int i = 0; i < 8; ++i) bv0[i] = __ldg(reinterpret_cast<const float4*>(bh) + i);
         mbar_wait(&h_full[b][0], p2);
         if (elected) PF_TR(j, 24);
         tc_fence_after();
@@ -433,7 +458,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
         for (int g = 0; g < 4; ++g) {
           float4 bv[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) bv[i] = g == 0 ? bv0[i] : __ldg(reinterpret_cast<const float4*>(bh + g * 32) + i);
+          for (int i = 0; i < 8; ++i) bv[i] = *(reinterpret_cast<const float4*>(bh + g * 32) + i);
           tmem_ld_wait();
           if (g < 3) tmem_ld32(thh + (g + 1) * 32, raw[(g + 1) & 1]);
           const uint32_t* r = raw[g & 1];
@@ -503,22 +528,14 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[g][i] = 0xfc00fc00u;      // -inf, -inf
           }
-          const float mine = pf_colmax32_h2(pk[g], lane);
-          atomicMax(&colmax_s[hsel * 128 + g * 32 + lane], f2ord(mine));
+          cmax[g] = fmaxf(cmax[g], pf_colmax32_h2(pk[g], lane));
         }
       }
+      // the staged tile is complete for this warp: the relu group's thread 0 stores it and prefetches X tile j + 2
       if (a.store_out) fence_proxy_async();
-      pf_epi_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&staged[b]);
       if (elected) PF_TR(j, 30);
-      if (elected) {
-        if (a.store_out) {
-          for (int kc = 0; kc < 4; ++kc) tma_store_3d(&tm.xout, xb + kc * PF_CHUNK, kc * 64, n0, sample);
-          pf_store_commit();
-          pf_store_wait_read();
-        }
-        if (j + 2 < nt) load_x(j + 2);
-        PF_TR(j, 31);
-      }
     }
     if (cur_sample >= 0) flush_colmax(cur_sample);
   }
