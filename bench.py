@@ -39,10 +39,10 @@ def workload(batch):
                         "of the predicted body, joints for GT and interactee bodies",
             "batch_per_gpu": batch, "ddim_steps": 50, "guidance_scale": GUIDANCE, "scene_points": N_POINTS, "frames": 60,
             "l2_policy": "per-step inputs+activations (>= 1.3 GB per 128-cloud chunk) exceed the 126 MB L2; no flush needed",
-            "pipeline": "MLD.ego_eval_async with 8 batches in flight, each on its own CUDA stream and kernel-side handles; the 50-step "
-                        "sampler of 4 consecutive batches runs as ONE chain over their 2048 denoiser rows (sampler_group); the "
-                        "latency-bound 50-step sampler chain of batch k overlaps the scene encoder / VAE / SMPL kernels of "
-                        "batches k+1..; kernels.single_batch_* gives the unpipelined numbers"}
+            "pipeline": "MLD.ego_eval_async with up to pipeline_depth (default 8) batches in flight, each on its own CUDA stream "
+                        "and kernel-side handles (sampler_group 1: one 50-step chain per batch); the latency-bound sampler chain "
+                        "of batch k overlaps the scene encoder / VAE / SMPL kernels of batches k+1..; kernels.single_batch_* "
+                        "gives the unpipelined numbers"}
 
 
 class ClockSampler:
@@ -386,6 +386,7 @@ def main():
                                     "profiles/r1_pointnet_kernels_final_ncu.json; algorithmic 2.62 GB (fp16 tile in + out)",
                     "algorithmic_flop_per_launch": POINTNET_FLOP_PER_POINT * N_POINTS * min(B, 128) / 4,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
+                    "frac_of_burst_peak": (ach / peaks["bf16_tflops"]) if (ach and "bf16_tflops" in peaks) else None,
                     "launches": pn_n, "avg_launch_ms": pn_ms / pn_n if pn_n else None,
                     "share_of_step": (pn_ms / 1e3) / t_single if t_single else None,
                     "measured_in": "the single-batch (unpipelined) timed region, CUDA-event pairs on the launching stream"}
