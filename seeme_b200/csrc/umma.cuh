@@ -159,8 +159,9 @@ struct UmmaLinear {
   const float* pfold = nullptr;  // [N,4] rank-3 fold: + P[n][0..2] . xyz[m]  (scene encoder block 0)
   const float* xyz = nullptr;    // [M,3]
   int act = ACT_NONE;            // applied to acc + bias (+ pfold)
-  const float* R = nullptr;      // fp32 residual added after the activation
+  const float* R = nullptr;      // fp32 residual added after the activation (before it when act_after_residual)
   int ldr = 0;
+  int act_after_residual = 0;    // out = act(acc + bias + R): the bottleneck tail of the image backbone
   float* Y = nullptr;            // fp32 output (nullable)
   int ldy = 0;
   __nv_bfloat16 *Yh = nullptr, *Yl = nullptr;   // bf16 (hi, lo) of the output (nullable)

@@ -37,6 +37,7 @@ struct UmmaEpi {
   const float* pfold; const float* xyz;
   int act;
   int has_r, has_yf, has_yh, has_yl, has_zh, has_zl;
+  int act_post;                 // activation applied after the residual add
   unsigned* colmax; int colmax_group_rows;
   int fp16;
 };
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(192, MINB) umma_linear_kernel(const __grid_con
             f[i] += p.x * px + p.y * py + p.z * pz;
           }
         }
-        if (e.act != ACT_NONE) {
+        if (e.act != ACT_NONE && !e.act_post) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = apply_act(f[i], e.act);
         }
@@ -229,6 +230,10 @@ __global__ void __launch_bounds__(192, MINB) umma_linear_kernel(const __grid_con
             const float4 r = *reinterpret_cast<const float4*>(rt + sw128(row, j));
             f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
           }
+        }
+        if (e.act != ACT_NONE && e.act_post) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = apply_act(f[i], e.act);
         }
         if (e.has_yf) {                 // fp32 tile of 32 columns: slot 2 (half 0) / slot 3 (half 1)
           uint8_t* t = sbuf + (2 + half) * TILE_BYTES;
@@ -421,6 +426,7 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
   e.bias = g.bias; e.bias_group_rows = g.bias_group_rows; e.pfold = g.pfold; e.xyz = g.xyz; e.act = g.act;
   e.has_r = g.R != nullptr; e.has_yf = g.Y != nullptr; e.has_yh = g.Yh != nullptr; e.has_yl = g.Yl != nullptr;
   e.has_zh = g.Zh != nullptr; e.has_zl = g.Zl != nullptr;
+  e.act_post = g.act_after_residual;
   e.colmax = g.colmax; e.colmax_group_rows = g.colmax_group_rows;
   e.fp16 = g.fp16;
   // 64-wide tiles: the whole K = 256 of a latency-bound GEMM is in flight at once (4 stages), one CTA per SM.

@@ -247,20 +247,64 @@ class ResnetPointnet(_PackedModule):
         return feat
 
 
-class ProHMRScene(nn.Module):
-    """The slice of ``EgoHMR.models.prohmr.prohmr_scene.ProHMRScene`` on the path: ``scene_enc`` and
-    ``encode_scene`` (:51,102-104).  The ResNet-50 backbone / flow / discriminator sub-trees are never
-    run at SEE-ME test time and are not built (load reference checkpoints with ``strict=False``)."""
+class ResNet50Backbone(_PackedModule):
+    """``EgoHMR.models.resnet.resnet50`` (resnet.py:99-180, 211-224) at inference: same ``state_dict`` keys
+    (``conv1.weight``, ``bn1.*``, ``layer{1..4}.{i}.conv{1,2,3}.weight`` / ``bn{1,2,3}.*`` / ``downsample.{0,1}.*``),
+    eval-mode BatchNorm folded into the packed convolution weights by the kernel-side handle."""
 
-    def __init__(self, cfg=None, max_batch: int = 512, max_points: int = 20000, precision: int = -1, **kwargs):
+    def __init__(self, max_batch: int = 512):
+        super().__init__()
+        self.max_batch = max_batch
+        for conv, bn, cout, cin, k in synthetic.resnet50_convs():
+            for key, shape, buf in ((conv + ".weight", (cout, cin, k, k), False), (bn + ".weight", (cout,), False),
+                                    (bn + ".bias", (cout,), False), (bn + ".running_mean", (cout,), True),
+                                    (bn + ".running_var", (cout,), True), (bn + ".num_batches_tracked", (), True)):
+                parts = key.split(".")
+                mod = self
+                for p in parts[:-1]:
+                    if p not in mod._modules:
+                        mod.add_module(p, nn.Module())
+                    mod = mod._modules[p]
+                if buf:
+                    dt = torch.long if parts[-1] == "num_batches_tracked" else torch.float32
+                    init = torch.ones(shape) if parts[-1] == "running_var" else torch.zeros(shape, dtype=dt)
+                    mod.register_buffer(parts[-1], init.to(dt))
+                else:
+                    mod.register_parameter(parts[-1], nn.Parameter(torch.zeros(shape), requires_grad=False))
+
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version, str(p.device)) for p in list(self.parameters()) + list(self.buffers()))
+
+    @property
+    def op(self) -> ops.ResNet50Op:
+        self._require_cuda()
+        return self._op("rn50", lambda: ops.ResNet50Op(self.state_dict(), self.max_batch))
+
+    def forward(self, x):
+        """[B,3,224,224] -> [B,2048]"""
+        return self.op(x)
+
+
+class ProHMRScene(nn.Module):
+    """The slice of ``EgoHMR.models.prohmr.prohmr_scene.ProHMRScene`` on the path: ``scene_enc`` / ``encode_scene``
+    (:51,102-104) and, with ``with_backbone=True`` (the image-conditioned variants), ``backbone`` /
+    ``encode_image`` (:33-34,99-100).  The flow / discriminator sub-trees are never run at SEE-ME test time and are
+    not built (load reference checkpoints with ``strict=False``)."""
+
+    def __init__(self, cfg=None, max_batch: int = 512, max_points: int = 20000, precision: int = -1,
+                 with_backbone: bool = False, **kwargs):
         super().__init__()
         self.scene_enc = ResnetPointnet(512, 256, max_batch, max_points, precision=precision)
+        if with_backbone:
+            self.backbone = ResNet50Backbone(max_batch)
 
     def encode_scene(self, scene_pcd_verts):
         return self.scene_enc(scene_pcd_verts)
 
     def encode_image(self, x):
-        raise NotImplementedError("image conditioning (ResNet-50 backbone) is a 'next' row (SURVEY 8f-4)")
+        if "backbone" not in self._modules:
+            raise NotImplementedError("this ProHMRScene was built without the image backbone (with_backbone=True builds it)")
+        return self.backbone(x)
 
 
 SMPL_EXTRA_VERTEX_IDS = [332, 6260, 2800, 4071, 583,                     # nose, reye, leye, rear, lear

@@ -130,6 +130,38 @@ class PointNetOp(_Handle):
         return (emb, feat) if want_feat else emb
 
 
+def resnet50_keys() -> List[str]:
+    """``backbone.*`` keys in the tensor order of ``seeme_resnet50_create`` (include/seeme_b200.h)"""
+    from . import synthetic
+    k: List[str] = []
+    for conv, bn, _, _, _ in synthetic.resnet50_convs():
+        k += [conv + ".weight"] + [f"{bn}.{f}" for f in ("weight", "bias", "running_mean", "running_var")]
+    return k
+
+
+class ResNet50Op(_Handle):
+    """``proscene.encode_image(images)`` -- prohmr_scene.py:99-100, EgoHMR/models/resnet.py:168-180"""
+    _destroy = "seeme_resnet50_destroy"
+
+    def __init__(self, backbone_sd: Dict[str, torch.Tensor], max_batch: int):
+        super().__init__()
+        ts = [_dev_f32(backbone_sd[k], k) for k in resnet50_keys()]
+        self.device = ts[0].device
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().seeme_resnet50_create(C.byref(self.h), _ptr_array(ts), len(ts), max_batch), "seeme_resnet50_create")
+        self.max_batch = max_batch
+
+    def __call__(self, images: torch.Tensor) -> torch.Tensor:
+        images = _dev_f32(images, "images")
+        if images.dim() != 4 or tuple(images.shape[1:]) != (3, 224, 224):
+            raise ValueError(f"images must be [B,3,224,224], got {tuple(images.shape)}")
+        B = images.shape[0]
+        feat = torch.empty(B, 2048, device=images.device, dtype=torch.float32)
+        with torch.cuda.device(images.device):
+            _lib.check(_lib.lib().seeme_resnet50_forward(self.h, images.data_ptr(), B, feat.data_ptr(), _stream()), "seeme_resnet50_forward")
+        return feat
+
+
 class VaeOp(_Handle):
     """``MldVae.encode`` / ``MldVae.decode`` -- mld_vae.py:128-256"""
     _destroy = "seeme_vae_destroy"

@@ -176,6 +176,59 @@ def output_scene_state(seed: int = 0):
 
 
 # --------------------------------------------------------------------------------------------
+# image backbone: ResNet-50 state_dict keys of EgoHMR/models/resnet.py:99-150
+# --------------------------------------------------------------------------------------------
+RESNET50_LAYERS = (3, 4, 6, 3)
+_BN_FIELDS = ("weight", "bias", "running_mean", "running_var")
+
+
+def resnet50_convs() -> List[Tuple[str, str, int, int, int]]:
+    """(conv key prefix, bn key prefix, Cout, Cin, kernel) in the tensor order of ``seeme_resnet50_create``"""
+    out = [("conv1", "bn1", 64, 3, 7)]
+    cin = 64
+    for L, n in enumerate(RESNET50_LAYERS):
+        planes = 64 << L
+        for b in range(n):
+            p = f"layer{L + 1}.{b}."
+            out += [(p + "conv1", p + "bn1", planes, cin, 1), (p + "conv2", p + "bn2", planes, planes, 3),
+                    (p + "conv3", p + "bn3", planes * 4, planes, 1)]
+            if b == 0:
+                out.append((p + "downsample.0", p + "downsample.1", planes * 4, cin, 1))
+            cin = planes * 4
+    return out
+
+
+def resnet50_state(seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """Convolutions as the reference initialises them (N(0, sqrt(2 / (k*k*Cout))), resnet.py:115-118); BatchNorm
+    affine terms and running statistics get non-trivial values (a trained checkpoint has them; the reference's
+    1/0/0/1 init would make the BatchNorm fold untestable)."""
+    g = torch.Generator().manual_seed(5000 + seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for conv, bn, cout, cin, k in resnet50_convs():
+        sd[conv + ".weight"] = torch.randn((cout, cin, k, k), generator=g) * math.sqrt(2.0 / (k * k * cout))
+        last = conv.endswith("conv3")
+        lo, hi = (0.2, 0.5) if last else (0.7, 1.1)
+        sd[bn + ".weight"] = lo + (hi - lo) * torch.rand((cout,), generator=g)
+        sd[bn + ".bias"] = 0.1 * torch.randn((cout,), generator=g)
+        sd[bn + ".running_mean"] = 0.1 * torch.randn((cout,), generator=g)
+        sd[bn + ".running_var"] = 0.5 + torch.rand((cout,), generator=g)
+        sd[bn + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+    return sd
+
+
+def output_images_state(seed: int = 0):
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    _lin(s, "1", D, 2048)
+    return _fill(s, 6000 + seed, "default")
+
+
+def images(batch: int, seed: int = 0) -> torch.Tensor:
+    """[B,3,224,224] normalised crops (the reference feeds ImageNet-normalised 224x224 crops)"""
+    g = torch.Generator().manual_seed(7000 + seed)
+    return torch.randn((batch, 3, 224, 224), generator=g)
+
+
+# --------------------------------------------------------------------------------------------
 # SMPL-shaped body model buffers (smplx==0.1.28 buffer names; SURVEY App. C)
 # --------------------------------------------------------------------------------------------
 _REST_JOINTS = np.array([

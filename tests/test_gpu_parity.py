@@ -486,3 +486,49 @@ def test_mr_metrics_on_device_through_the_model():
     mr.update(rs["joints_rst"], rs["joints_ref"], rs["lengths"])
     r = mr.compute()
     assert r["PAMPJPE"] <= r["MPJPE"] + 1e-6
+
+
+# ---- image backbone ---------------------------------------------------------------------
+def test_image_backbone_vs_reference_golden_and_oracle():
+    """seeme_resnet50_forward through the C ABI against the golden of the UNMODIFIED reference ResNet-50 and against
+    the oracle on a fresh batch that spans two workspace chunks (SEEME_RESNET_CHUNK=2, B=3: ragged last chunk).
+    Tolerance: split-bf16 x3 operands with fp32 accumulation and BatchNorm folded into the weights: 2e-4 absolute +
+    2e-4 relative on features of magnitude <= ~2.5 (measured ~1e-5)."""
+    from seeme_b200 import ops, synthetic as S
+    from oracle import restate as O
+    g = np.load(os.path.join(GOLDEN, "resnet50_image.npz"))
+    sd = S.resnet50_state(int(g["seed"]))
+    os.environ["SEEME_RESNET_CHUNK"] = "2"
+    try:
+        op = ops.ResNet50Op(cu(sd), max_batch=3)
+    finally:
+        del os.environ["SEEME_RESNET_CHUNK"]
+    got = op(S.images(int(g["batch"]), int(g["seed"])).to(DEV)).cpu()
+    ref = T(g["feat"])
+    assert torch.allclose(got, ref, atol=2e-4, rtol=2e-4), float((got - ref).abs().max())
+    x = S.images(3, 11)
+    with torch.no_grad():
+        want = O.image_backbone_forward(sd, x)
+    got = op(x.to(DEV)).cpu()
+    assert torch.allclose(got, want, atol=2e-4, rtol=2e-4), float((got - want).abs().max())
+    with pytest.raises(RuntimeError):
+        op(S.images(4, 1).to(DEV))                      # beyond the handle's capacity: loud error, no fallback
+    with pytest.raises(ValueError):
+        op(torch.zeros(1, 3, 200, 200, device=DEV))
+
+
+def test_image_backbone_module_surface_and_state_dict_keys():
+    """ProHMRScene(with_backbone=True).encode_image has the reference module's state_dict keys (strict load of a
+    reference-shaped checkpoint) and returns [B,2048]"""
+    from seeme_b200 import modules, synthetic as S
+    sd = S.resnet50_state(0)
+    pro = modules.ProHMRScene(max_batch=2, with_backbone=True)
+    missing = pro.backbone.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    pro.to(DEV)
+    out = pro.encode_image(S.images(2, 0).to(DEV))
+    g = np.load(os.path.join(GOLDEN, "resnet50_image.npz"))
+    assert out.shape == (2, 2048)
+    assert torch.allclose(out.cpu(), T(g["feat"]), atol=2e-4, rtol=2e-4)
+    with pytest.raises(NotImplementedError):
+        modules.ProHMRScene(max_batch=2).encode_image(S.images(1, 0))

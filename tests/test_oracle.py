@@ -153,3 +153,15 @@ def test_smpl_kats(smpl_buffers):
     expect = torch.einsum("fab,fjb->fja", Rm, jrest - jrest[:, :1]) + jrest[:, :1]
     assert torch.allclose(j2, expect, atol=1e-5)
     assert float((b["lbs_weights"] > 0).sum(1).max()) <= 4
+
+
+def test_image_backbone_restatement_vs_reference_golden():
+    """oracle/restate.image_backbone_forward against the UNMODIFIED reference ResNet-50 (EgoHMR/models/resnet.py),
+    golden written by oracle/make_golden_image.py from the same seeded state_dict / crops"""
+    from seeme_b200 import synthetic as S
+    g = np.load(os.path.join(GOLDEN, "resnet50_image.npz"))
+    sd = S.resnet50_state(int(g["seed"]))
+    x = S.images(int(g["batch"]), int(g["seed"]))
+    with torch.no_grad():
+        got = O.image_backbone_forward(sd, x)
+    assert torch.allclose(got, torch.from_numpy(g["feat"]), atol=1e-5, rtol=1e-5)
