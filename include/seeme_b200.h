@@ -93,18 +93,20 @@ int seeme_pointnet_destroy(seeme_pointnet_t h);
 /* ------------------------------------------------------------------------------------------------
  * Image backbone.  Replaces `ProHMRScene.encode_image` -> `ResNet.forward`
  * (EgoHMR/models/prohmr/prohmr_scene.py:99-100, EgoHMR/models/resnet.py:60-180: ResNet-50, Bottleneck
- * [3,4,6,3], eval-mode BatchNorm, mean over the final 7x7 map).  `MLD.output_images` =
- * Sequential(ReLU, Linear(2048,256)) (mld/models/modeltype/mld.py:251-255) stays a host-side module.
- * Weight order (265 tensors, `backbone.*` state_dict names): conv1.weight, bn1.{weight,bias,running_mean,
+ * [3,4,6,3], eval-mode BatchNorm, mean over the final 7x7 map) and `MLD.output_images` =
+ * Sequential(ReLU, Linear(2048,256)) (mld/models/modeltype/mld.py:251-255).
+ * Weight order (267 tensors; 265 `backbone.*` state_dict names, then output_images.1.{weight,bias}): conv1.weight, bn1.{weight,bias,running_mean,
  * running_var}; then for every block layer{1..4}.{0..}: conv1.weight, bn1.{4}, conv2.weight, bn2.{4},
  * conv3.weight, bn3.{4} and, for block 0 of each layer, downsample.0.weight, downsample.1.{4}.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct seeme_resnet50* seeme_resnet50_t;
-#define SEEME_RESNET50_NUM_TENSORS 265
+#define SEEME_RESNET50_NUM_TENSORS 267
 int seeme_resnet50_create(seeme_resnet50_t* out, const float* const* weights /*HOST array of device ptrs*/,
                           int n_weights, int max_batch);
-/* images [B,3,224,224] fp32 (NCHW, as the reference feeds them) -> feat2048 [B,2048] */
-int seeme_resnet50_forward(seeme_resnet50_t h, const float* images, int B, float* feat2048, void* stream);
+/* images [B,3,224,224] fp32 (NCHW, as the reference feeds them) -> feat2048 [B,2048] (= encode_image, may be NULL)
+ * and emb256 [B,256] (= output_images(encode_image), may be NULL) */
+int seeme_resnet50_forward(seeme_resnet50_t h, const float* images, int B, float* feat2048, float* emb256,
+                           void* stream);
 int seeme_resnet50_destroy(seeme_resnet50_t h);
 
 /* ------------------------------------------------------------------------------------------------

@@ -48,6 +48,9 @@ def build_model(config: str = "config_mld_egobody.yaml", device="cuda", guidance
     if "scene" in model.condition:
         sd.update({"proscene.scene_enc." + k: v for k, v in synthetic.pointnet_state(seed).items()})
         sd.update({"output_scene." + k: v for k, v in synthetic.output_scene_state(seed).items()})
+    if "image" in model.condition:
+        sd.update({"proscene.backbone." + k: v for k, v in synthetic.resnet50_state(seed).items()})
+        sd.update({"output_images." + k: v for k, v in synthetic.output_images_state(seed).items()})
     missing, unexpected = model.load_state_dict(sd, strict=False)
     missing = [m for m in missing if not m.startswith("smpl_model.")]
     if missing or unexpected:

@@ -31,7 +31,7 @@ SIGNATURES = {
     "seeme_pointnet_forward": (C.c_int, [c_handle, c_float_p, C.c_int, C.c_int, c_float_p, c_float_p, C.c_void_p]),
     "seeme_pointnet_destroy": (C.c_int, [c_handle]),
     "seeme_resnet50_create": (C.c_int, [C.POINTER(c_handle), C.POINTER(C.c_void_p), C.c_int, C.c_int]),
-    "seeme_resnet50_forward": (C.c_int, [c_handle, c_float_p, C.c_int, c_float_p, C.c_void_p]),
+    "seeme_resnet50_forward": (C.c_int, [c_handle, c_float_p, C.c_int, c_float_p, c_float_p, C.c_void_p]),
     "seeme_resnet50_destroy": (C.c_int, [c_handle]),
     "seeme_vae_create": (C.c_int, [C.POINTER(c_handle), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]),
     "seeme_vae_encode": (C.c_int, [c_handle, c_float_p, C.c_void_p, c_float_p, C.c_int, C.c_int, c_float_p, c_float_p,

@@ -146,6 +146,10 @@ struct seeme_resnet50 {
   ActBuf x[2];                                              // block input / output (fp32 + hi/lo), <= 3136 x 256 per image
   ActBuf t1, t2;                                            // bottleneck intermediates (hi/lo)
   float* res = nullptr;                                     // downsample shortcut (fp32)
+  // output_images tail (mld.py:251-255): relu -> Linear(2048, 256)
+  PackedLinear tail;
+  float* feat = nullptr;                                    // [max_batch, 2048]
+  __nv_bfloat16 *feat_h = nullptr, *feat_l = nullptr;       // relu(feat) as bf16 (hi, lo)
 };
 
 static void rn_destroy(seeme_resnet50* h) {
@@ -182,11 +186,12 @@ extern "C" int seeme_resnet50_create(seeme_resnet50_t* out, const float* const* 
   h->chunk = max_batch < cap ? max_batch : (cap > 0 ? cap : 32);
   const size_t C = (size_t)h->chunk;
   // packed weights: 23.5 M folded parameters as bf16 (hi, lo) + biases + the fp32 fold scratch (largest conv: 512 x 4608)
-  const size_t wbytes = (size_t)26 * 1000 * 1000 * 4 + pad256((size_t)2048 * 1024 * 4 > (size_t)512 * 4608 * 4 ? (size_t)2048 * 1024 * 4
+  const size_t wbytes = (size_t)26 * 1000 * 1000 * 4 + 4096 + pad256((size_t)2048 * 1024 * 4 > (size_t)512 * 4608 * 4 ? (size_t)2048 * 1024 * 4
                                                                                                              : (size_t)512 * 4608 * 4) +
                         (size_t)60 * 4 * 256 * 16;
   const size_t rows1 = C * 3136;
-  const size_t ws = 2 * pad256(C * 12544 * 192 * 2) + pad256(C * 12544 * 64 * 4) + 2 * (pad256(rows1 * 256 * 4) + 2 * pad256(rows1 * 256 * 2)) +
+  const size_t tailb = 2 * pad256((size_t)256 * 2048 * 2) + pad256((size_t)max_batch * 2048 * 4) + 2 * pad256((size_t)max_batch * 2048 * 2);
+  const size_t ws = tailb + 2 * pad256(C * 12544 * 192 * 2) + pad256(C * 12544 * 64 * 4) + 2 * (pad256(rows1 * 256 * 4) + 2 * pad256(rows1 * 256 * 2)) +
                     2 * 2 * pad256(rows1 * 128 * 2) + pad256(rows1 * 256 * 4);
   int rc = h->arena.init(wbytes + ws + 65536);
   if (rc != SEEME_OK) { delete h; return rc; }
@@ -210,6 +215,13 @@ extern "C" int seeme_resnet50_create(seeme_resnet50_t* out, const float* const* 
       h->blocks.push_back(blk);
     }
   }
+  if (!rc) rc = pack_linear(h->arena, h->tail, w[k], 2048, 256, 2048, w[k + 1]);   // the bias pointer stays the caller's tensor
+  if (!rc) {
+    float* tb = h->arena.take<float>(256);
+    if (!tb) { set_error("seeme_resnet50_create: arena exhausted"); rc = SEEME_ENOMEM; }
+    else if (cudaMemcpy(tb, w[k + 1], 256 * 4, cudaMemcpyDeviceToDevice) != cudaSuccess) { set_error("seeme_resnet50_create: bias copy failed"); rc = SEEME_ECUDA; }
+    else h->tail.bias = tb;
+  }
   if (!rc) {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { set_error("seeme_resnet50_create: weight packing failed: %s", cudaGetErrorString(e)); rc = SEEME_ECUDA; }
@@ -228,7 +240,10 @@ extern "C" int seeme_resnet50_create(seeme_resnet50_t* out, const float* const* 
   h->t2.h = h->arena.take<__nv_bfloat16>(rows1 * 128);
   h->t2.l = h->arena.take<__nv_bfloat16>(rows1 * 128);
   h->res = h->arena.take<float>(rows1 * 256);
-  if (!h->res) { set_error("seeme_resnet50_create: arena exhausted (workspace)"); rn_destroy(h); return SEEME_ENOMEM; }
+  h->feat = h->arena.take<float>((size_t)max_batch * 2048);
+  h->feat_h = h->arena.take<__nv_bfloat16>((size_t)max_batch * 2048);
+  h->feat_l = h->arena.take<__nv_bfloat16>((size_t)max_batch * 2048);
+  if (!h->res || !h->feat_l) { set_error("seeme_resnet50_create: arena exhausted (workspace)"); rn_destroy(h); return SEEME_ENOMEM; }
   *out = h;
   return SEEME_OK;
 }
@@ -304,14 +319,21 @@ static int rn_chunk(seeme_resnet50* h, const float* img, int B, float* out, cuda
   return SEEME_OK;
 }
 
-extern "C" int seeme_resnet50_forward(seeme_resnet50_t h, const float* images, int B, float* feat2048, void* stream) {
-  SEEME_REQUIRE(h && images && feat2048, SEEME_EINVAL, "seeme_resnet50_forward: null argument");
+extern "C" int seeme_resnet50_forward(seeme_resnet50_t h, const float* images, int B, float* feat2048, float* emb256, void* stream) {
+  SEEME_REQUIRE(h && images && (feat2048 || emb256), SEEME_EINVAL, "seeme_resnet50_forward: null argument");
   SEEME_REQUIRE(B > 0, SEEME_EINVAL, "seeme_resnet50_forward: empty batch");
   SEEME_REQUIRE(B <= h->max_batch, SEEME_ECAP, "seeme_resnet50_forward: batch %d exceeds capacity %d", B, h->max_batch);
   cudaStream_t s = (cudaStream_t)stream;
   for (int b0 = 0; b0 < B; b0 += h->chunk) {
     const int nb = B - b0 < h->chunk ? B - b0 : h->chunk;
-    SEEME_TRY(rn_chunk(h, images + (size_t)b0 * 3 * 224 * 224, nb, feat2048 + (size_t)b0 * 2048, s));
+    SEEME_TRY(rn_chunk(h, images + (size_t)b0 * 3 * 224 * 224, nb, h->feat + (size_t)b0 * 2048, s));
+  }
+  if (feat2048) SEEME_CUDA(cudaMemcpyAsync(feat2048, h->feat, (size_t)B * 2048 * 4, cudaMemcpyDeviceToDevice, s));
+  if (emb256) {   // output_images: Sequential(ReLU, Linear(2048, 256))
+    SEEME_TRY(to_bf16_split(h->feat, 2048, B, 2048, h->feat_h, h->feat_l, 2048, 1, s));
+    ActBuf a; a.h = h->feat_h; a.l = h->feat_l; a.ld = 2048;
+    ActBuf o; o.f = emb256; o.ld = 256;
+    SEEME_TRY(run_linear(h->tail, a, nullptr, B, ACT_NONE, nullptr, 0, o, 3, s));
   }
   return SEEME_OK;
 }

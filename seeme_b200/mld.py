@@ -114,8 +114,10 @@ class MLD(nn.Module):
             unsupported.append("PREDICT_TRANSL must be True")
         if self.pred_betas or self.global_orient_egoego or self.transl_egoego or self.pose_estimation_task or self.see_future:
             unsupported.append("BETAS_PRED / *_EGOEGO / POSE_ESTIMATION_TASK / SEE_FUTURE variants are not built")
-        if "image" in self.condition:
-            unsupported.append("image conditioning is a 'next' row (SURVEY 8f-4)")
+        if "image" in self.condition and self.guidance_scale > 1.0:
+            # the image branches build no unconditional scene / image embedding (mld.py:1078-1099), so under CFG the
+            # reference's torch.cat of [1,2B,256] and [1,B,256] tokens fails (:1299); config_mld_interactee.yaml:120 runs 1.0
+            unsupported.append("image conditioning runs without classifier-free guidance (guidance_scale <= 1.0), as in the reference")
         if unsupported:
             raise NotImplementedError("MLD (sm_100a): " + "; ".join(unsupported))
 
@@ -135,8 +137,13 @@ class MLD(nn.Module):
             sp = kwargs.get("scene_precision", cfg.model.get("scene_precision", "fp16-fused"))
             sp = {"fp16-fused": 16, "fp16-fused-smem": 17, "split-bf16": 3, "bf16": 1, "fp32": 0}.get(sp, sp)
             self.scene_precision = int(sp)
-            self.proscene = ProHMRScene(cfg.get("PROSCENE"), max_batch=max_batch, max_points=n_points, precision=int(sp))
+            self.proscene = ProHMRScene(cfg.get("PROSCENE"), max_batch=max_batch, max_points=n_points, precision=int(sp),
+                                        with_backbone="image" in self.condition)
             self.output_scene = nn.Sequential(nn.ReLU(), nn.Linear(512, 256))                        # mld.py:257-261
+        elif "image" in self.condition:
+            self.proscene = ProHMRScene(cfg.get("PROSCENE"), max_batch=max_batch, max_points=128, with_backbone=True)
+        if "image" in self.condition:
+            self.output_images = nn.Sequential(nn.ReLU(), nn.Linear(2048, 256))                      # mld.py:251-255
         mv = cfg.model.motion_vae
         mv_params = dict(mv.get("params", {}))
         mv_params.setdefault("max_batch", max_batch)
@@ -225,6 +232,12 @@ class MLD(nn.Module):
         return z.view(bsz, 1, 256).permute(1, 0, 2)
 
     # ------------------------------------------------------------------------------------------
+    def _length_index(self) -> int:
+        """position of ``length`` in the dataset's item tuple (dataset.py:1778-1794)"""
+        if "image" in self.condition:
+            return 6 if "scene" in self.condition else 5
+        return 5 if "scene" in self.condition else 4
+
     def _encode_scene(self, scene):
         op = self.proscene.scene_enc.op(self.output_scene)
         emb = op(scene.float())                                           # output_scene(encode_scene(.)) fused
@@ -266,7 +279,7 @@ class MLD(nn.Module):
         from .dist import shard_range
         main = torch.cuda.current_stream(dev)
         # one device->host read of the lengths for the whole batch (mld.py:1264); every lane decodes to max(lengths)
-        lengths_all = batch[5 if "scene" in self.condition else 4].long().reshape(-1).tolist()
+        lengths_all = batch[self._length_index()].long().reshape(-1).tolist()
         t_max = int(max(lengths_all))
         streams = self.__dict__.setdefault("_lane_streams", {})
         outs = []
@@ -339,7 +352,7 @@ class MLD(nn.Module):
         # the Python list of lengths (mld.py:1264) is read BEFORE anything is enqueued: from the host tensor when the batch
         # is host-resident, else once per distinct device tensor (a .tolist() after the scene encoder has been enqueued
         # would block the host until that slot's encoder has finished)
-        length_t = batch[5 if "scene" in self.condition else 4]
+        length_t = batch[self._length_index()]
         if torch.is_tensor(length_t) and length_t.is_cuda:
             # keyed by the live tensor OBJECT (weak reference) and its version counter -- not by address: the caching allocator
             # hands the address of a freed batch to the next one
@@ -466,7 +479,18 @@ class MLD(nn.Module):
 
     def _stage_encode(self, batch, noise, lengths=None):
         """scene encoder + interactee VAE encode (cond and CFG-uncond) -> the denoiser's conditioning and the initial noise"""
-        if "scene" in self.condition:
+        image_emb = None
+        if "image" in self.condition:
+            # the tuple the dataset yields and train_diffusion_forward unpacks (dataset.py:1788-1792, mld.py:889-909);
+            # ego_eval's own unpacking drops `length` and then reads it (App. D4)
+            if "scene" in self.condition:
+                feats_ref, transl, beta, utils_, scene, images, length = batch
+                scene_emb = self._encode_scene(scene)
+            else:
+                feats_ref, transl, beta, utils_, images, length = batch
+                scene_emb = None
+            image_emb = self.proscene.backbone.op(self.output_images)(images.float())[None]   # mld.py:1083-1086
+        elif "scene" in self.condition:
             feats_ref, transl, beta, utils_, scene, length, dict_images = batch
             scene_emb = self._encode_scene(scene)                          # [1,B or 2B,256]
         else:
@@ -486,11 +510,13 @@ class MLD(nn.Module):
             if self.do_classifier_free_guidance:
                 unc = self._encode_uncond(B, T, f_ref_int.shape[-1], lengths, noise.get("eps_unc"), dev)
                 text_emb = torch.cat([unc, text_emb], dim=1)               # mld.py:1290 (UNCOND first)
-            cond_emb = torch.cat([text_emb, scene_emb], dim=0) if scene_emb is not None else text_emb
+            tokens = [text_emb, scene_emb, image_emb]                       # mld.py:1297-1313 (token order)
         else:
-            cond_emb = scene_emb
+            tokens = [scene_emb, image_emb]
+        tokens = [t for t in tokens if t is not None]
+        cond_emb = (tokens[0] if len(tokens) == 1 else torch.cat(tokens, dim=0)) if tokens else None
         if cond_emb is None:
-            raise NotImplementedError("MLD (sm_100a): at least one of scene / interactee conditioning is required")
+            raise NotImplementedError("MLD (sm_100a): at least one of scene / image / interactee conditioning is required")
         x_T = noise.get("x_T")
         if x_T is None:                                                    # drawn where the reference draws it (mld.py:449-453)
             x_T = torch.randn((feats_ref.shape[0], self.latent_dim[0], self.latent_dim[-1]), device=dev, dtype=torch.float)

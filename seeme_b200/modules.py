@@ -275,14 +275,35 @@ class ResNet50Backbone(_PackedModule):
     def _signature(self):
         return tuple((p.data_ptr(), p._version, str(p.device)) for p in list(self.parameters()) + list(self.buffers()))
 
-    @property
-    def op(self) -> ops.ResNet50Op:
-        self._require_cuda()
-        return self._op("rn50", lambda: ops.ResNet50Op(self.state_dict(), self.max_batch))
+    def op(self, output_images: Optional[nn.Module] = None) -> ops.ResNet50Op:
+        """One handle serves ``encode_image`` (2048-d) and the fused ``output_images`` tail (256-d); rebuilt when either
+        module's tensors change."""
+        dev = self._require_cuda()
+        if output_images is None:
+            output_images = self.__dict__.get("_out_images")
+            if output_images is None:   # standalone use: a zero tail, only the 2048-d code is read
+                output_images = nn.Sequential(nn.ReLU(), nn.Linear(2048, 256))
+                for p in output_images.parameters():
+                    p.requires_grad_(False).zero_()
+                self.__dict__["_out_images"] = output_images
+            output_images.to(dev)
+        else:
+            self.__dict__["_out_images"] = output_images
+        lin = output_images[1]
+        sig = (self._signature(), (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version))
+        cache = self.__dict__.setdefault("_op_cache", {})
+        key = ("rn50", _LANE[0])
+        ent = cache.get(key)
+        if ent is None or ent[0] != sig:
+            if ent is not None:
+                ent[1].close()
+            cache[key] = (sig, ops.ResNet50Op(self.state_dict(), {"1.weight": lin.weight, "1.bias": lin.bias}, self.max_batch))
+        return cache[key][1]
 
     def forward(self, x):
         """[B,3,224,224] -> [B,2048]"""
-        return self.op(x)
+        _, feat = self.op()(x, want_feat=True)
+        return feat
 
 
 class ProHMRScene(nn.Module):

@@ -140,26 +140,30 @@ def resnet50_keys() -> List[str]:
 
 
 class ResNet50Op(_Handle):
-    """``proscene.encode_image(images)`` -- prohmr_scene.py:99-100, EgoHMR/models/resnet.py:168-180"""
+    """``output_images(proscene.encode_image(images))`` -- prohmr_scene.py:99-100, EgoHMR/models/resnet.py:168-180,
+    mld.py:251-255,1083-1086"""
     _destroy = "seeme_resnet50_destroy"
 
-    def __init__(self, backbone_sd: Dict[str, torch.Tensor], max_batch: int):
+    def __init__(self, backbone_sd: Dict[str, torch.Tensor], output_images_sd: Dict[str, torch.Tensor], max_batch: int):
         super().__init__()
         ts = [_dev_f32(backbone_sd[k], k) for k in resnet50_keys()]
+        ts += [_dev_f32(output_images_sd["1.weight"], "output_images.1.weight"), _dev_f32(output_images_sd["1.bias"], "output_images.1.bias")]
         self.device = ts[0].device
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().seeme_resnet50_create(C.byref(self.h), _ptr_array(ts), len(ts), max_batch), "seeme_resnet50_create")
         self.max_batch = max_batch
 
-    def __call__(self, images: torch.Tensor) -> torch.Tensor:
+    def __call__(self, images: torch.Tensor, want_feat: bool = False):
         images = _dev_f32(images, "images")
         if images.dim() != 4 or tuple(images.shape[1:]) != (3, 224, 224):
             raise ValueError(f"images must be [B,3,224,224], got {tuple(images.shape)}")
         B = images.shape[0]
-        feat = torch.empty(B, 2048, device=images.device, dtype=torch.float32)
+        emb = torch.empty(B, 256, device=images.device, dtype=torch.float32)
+        feat = torch.empty(B, 2048, device=images.device, dtype=torch.float32) if want_feat else None
         with torch.cuda.device(images.device):
-            _lib.check(_lib.lib().seeme_resnet50_forward(self.h, images.data_ptr(), B, feat.data_ptr(), _stream()), "seeme_resnet50_forward")
-        return feat
+            _lib.check(_lib.lib().seeme_resnet50_forward(self.h, images.data_ptr(), B, feat.data_ptr() if want_feat else None,
+                                                         emb.data_ptr(), _stream()), "seeme_resnet50_forward")
+        return (emb, feat) if want_feat else emb
 
 
 class VaeOp(_Handle):

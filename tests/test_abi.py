@@ -91,8 +91,12 @@ def test_config_surface_and_model_builds_on_cpu():
 
 def test_unsupported_configs_raise():
     import seeme_b200
-    with pytest.raises(NotImplementedError):
-        seeme_b200.build_model(device="cpu", condition=["text", "scene", "image"])
+    with pytest.raises(NotImplementedError):     # the reference's image branches cannot run under CFG (mld.py:1299)
+        seeme_b200.build_model(device="cpu", condition=["text", "scene", "image"], guidance_scale=7.5)
+    m = seeme_b200.build_model(device="cpu", condition=["text", "scene", "image"], guidance_scale=1.0, max_batch=2, n_points=64)
+    keys = m.state_dict().keys()
+    assert "proscene.backbone.layer4.2.bn3.running_var" in keys and "output_images.1.weight" in keys
+    assert "proscene.backbone.layer1.0.downsample.1.num_batches_tracked" in keys
     from seeme_b200.modules import MldDenoiser
     abl = {"SKIP_CONNECT": True, "MD_TRANS": True, "DIFF_PE_TYPE": "mld", "VAE_TYPE": "actor"}
     with pytest.raises(TypeError):

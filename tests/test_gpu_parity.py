@@ -500,17 +500,19 @@ def test_image_backbone_vs_reference_golden_and_oracle():
     sd = S.resnet50_state(int(g["seed"]))
     os.environ["SEEME_RESNET_CHUNK"] = "2"
     try:
-        op = ops.ResNet50Op(cu(sd), max_batch=3)
+        op = ops.ResNet50Op(cu(sd), cu(S.output_images_state(0)), max_batch=3)
     finally:
         del os.environ["SEEME_RESNET_CHUNK"]
-    got = op(S.images(int(g["batch"]), int(g["seed"])).to(DEV)).cpu()
+    _, got = op(S.images(int(g["batch"]), int(g["seed"])).to(DEV), want_feat=True)
     ref = T(g["feat"])
-    assert torch.allclose(got, ref, atol=2e-4, rtol=2e-4), float((got - ref).abs().max())
+    assert torch.allclose(got.cpu(), ref, atol=2e-4, rtol=2e-4), float((got.cpu() - ref).abs().max())
     x = S.images(3, 11)
     with torch.no_grad():
         want = O.image_backbone_forward(sd, x)
-    got = op(x.to(DEV)).cpu()
-    assert torch.allclose(got, want, atol=2e-4, rtol=2e-4), float((got - want).abs().max())
+        want_emb = O.image_embed(sd, S.output_images_state(0), x)
+    emb, got = op(x.to(DEV), want_feat=True)
+    assert torch.allclose(got.cpu(), want, atol=2e-4, rtol=2e-4), float((got.cpu() - want).abs().max())
+    assert emb.shape == (3, 256) and torch.allclose(emb.cpu(), want_emb, atol=2e-4, rtol=2e-4), float((emb.cpu() - want_emb).abs().max())
     with pytest.raises(RuntimeError):
         op(S.images(4, 1).to(DEV))                      # beyond the handle's capacity: loud error, no fallback
     with pytest.raises(ValueError):
@@ -532,3 +534,34 @@ def test_image_backbone_module_surface_and_state_dict_keys():
     assert torch.allclose(out.cpu(), T(g["feat"]), atol=2e-4, rtol=2e-4)
     with pytest.raises(NotImplementedError):
         modules.ProHMRScene(max_batch=2).encode_image(S.images(1, 0))
+
+
+@pytest.mark.parametrize("cond", [("text", "image", "scene"), ("text", "image", "scene", "interactee")])
+def test_ego_eval_image_conditioned_vs_oracle(weights, smpl_buffers, cond):
+    """config_mld_interactee.yaml:113 conditioning (image + scene [+ interactee], guidance 1.0) through MLD.ego_eval on the
+    dataset's 7-tuple (motion, transl, beta, utils, scene, images, length), against the oracle's ego_eval with the image
+    token = output_images(encode_image(images)) appended after the scene token (mld.py:1297-1301).  Joints <= 1e-3 m."""
+    import seeme_b200
+    from seeme_b200 import synthetic as S
+    from oracle import restate as O
+    B = 2
+    model = seeme_b200.build_model("config_mld_egobody.yaml", device=DEV, guidance_scale=1.0, condition=cond, max_batch=B,
+                                   n_points=600, scene_precision="split-bf16")
+    feats_ref, transl, beta, utils_, scene, length, _ = S.make_batch(B, n_points=600, ragged=True)
+    batch = (feats_ref, transl, beta, utils_, scene, S.images(B, 3), length)
+    g = torch.Generator().manual_seed(5)
+    noise = {"eps_int": torch.randn(1, B, 256, generator=g), "x_T": torch.randn(B, 1, 256, generator=g)}
+    rs = model.ego_eval(tuple(x.to(DEV) for x in batch), {k: v.to(DEV) for k, v in noise.items()})
+    W = dict(weights, resnet50=S.resnet50_state(0), output_images=S.output_images_state(0))
+    with torch.no_grad():
+        ref = O.ego_eval(W, smpl_buffers, S.norm_stats(), batch, noise, condition=cond, guidance_scale=1.0)
+    assert rs["lengths"] == ref["lengths"]
+    ej = float((rs["joints_rst"].cpu() - ref["joints_rst"]).abs().max())
+    assert ej < 1e-3, ej
+    assert float((rs["joints_ref"].cpu() - ref["joints_ref"]).abs().max()) < 1e-5
+    # the image token matters: another crop changes the prediction
+    batch2 = batch[:5] + (S.images(B, 4),) + batch[6:]
+    rs2 = model.ego_eval(tuple(x.to(DEV) for x in batch2), {k: v.to(DEV) for k, v in noise.items()})
+    assert float((rs2["joints_rst"] - rs["joints_rst"]).abs().max()) > 1e-4
+    with pytest.raises(NotImplementedError):
+        seeme_b200.build_model("config_mld_egobody.yaml", device=DEV, guidance_scale=7.5, condition=cond, max_batch=B, n_points=600)
