@@ -344,6 +344,17 @@ def main():
         sub = {"scene_encoder_ms": t_scene, "chain_cached_scene_ms": t_cached,
                "sequences_per_s_cached_scene": world * B / (t_cached / 1e3), "smpl_only_ms": t_smpl,
                "smpl_only_frames_per_s": world * F / (t_smpl / 1e3)}
+        # image backbone (not part of the benchmarked conditioning): ResNet-50 on 64 crops of 224 x 224
+        from seeme_b200 import ops as _ops, synthetic as _S
+        rop = _ops.ResNet50Op({k: v.to(dev) for k, v in _S.resnet50_state(0).items()},
+                              {k: v.to(dev) for k, v in _S.output_images_state(0).items()}, max_batch=64)
+        crops = torch.randn(64, 3, 224, 224, device=dev)
+        rop(crops)
+        t_img = device_ms(lambda: rop(crops))
+        sub["image_backbone_ms_per_64_crops"] = t_img
+        sub["image_backbone_crops_per_s"] = world * 64 / (t_img / 1e3)
+        rop.close()
+        del rop, crops
     except Exception as e:      # noqa: BLE001
         sub = {"error": str(e)}
     finally:

@@ -17,6 +17,22 @@
 
 namespace seeme {
 
+// 16-bit copies of an fp32 value: bf16 (hi, lo) pair, or one IEEE fp16 stored in the bf16-typed `hi` buffer (f16 != 0)
+__device__ __forceinline__ void rn_store16(float v, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t i, int f16) {
+  if (f16) {
+    reinterpret_cast<__half*>(hi)[i] = __float2half_rn(v);
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+__global__ void rn_to_f16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) reinterpret_cast<__half*>(out)[i] = __float2half_rn(x[i]);
+}
+
 // W'[n, (ky,kx,c)] = W[n,c,ky,kx] * s[n] (zero-padded to Kp columns), b'[n] = beta[n] - mean[n] * s[n]
 __global__ void rn_fold_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ mean, const float* __restrict__ var, float* __restrict__ wf,
@@ -37,7 +53,7 @@ __global__ void rn_fold_kernel(const float* __restrict__ w, const float* __restr
 // stem patches: x [B,3,224,224] fp32 (NCHW, the reference's input) -> A [B*112*112, 192] bf16 (hi, lo),
 // k = (ky*7 + kx)*3 + c for the 7x7 stride-2 pad-3 convolution, columns 147..191 zero
 __global__ void rn_stem_patch_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                     int B) {
+                                     int B, int f16) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= (size_t)B * 12544 * 192) return;
   const int k = (int)(i % 192);
@@ -49,14 +65,12 @@ __global__ void rn_stem_patch_kernel(const float* __restrict__ x, __nv_bfloat16*
     const int iy = oy * 2 - 3 + ky, ix = ox * 2 - 3 + kx;
     if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224) v = x[(((size_t)b * 3 + c) * 224 + iy) * 224 + ix];
   }
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  hi[i] = h;
-  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  rn_store16(v, hi, lo, i, f16);
 }
 
 // 3x3 stride-2 pad-1 max pooling of the stem output y [B,112,112,64] fp32 -> [B,56,56,64] fp32 + bf16 (hi, lo)
 __global__ void rn_maxpool_kernel(const float* __restrict__ y, float* __restrict__ o, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo, int B) {
+                                  __nv_bfloat16* __restrict__ lo, int B, int f16) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;     // one thread per 4 channels
   if (i >= (size_t)B * 3136 * 16) return;
   const int c4 = (int)(i % 16);
@@ -75,11 +89,7 @@ __global__ void rn_maxpool_kernel(const float* __restrict__ y, float* __restrict
   }
   *reinterpret_cast<float4*>(o + pix * 64 + c4 * 4) = m;
   const float f[4] = {m.x, m.y, m.z, m.w};
-  for (int j = 0; j < 4; ++j) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(f[j]);
-    hi[pix * 64 + c4 * 4 + j] = h;
-    lo[pix * 64 + c4 * 4 + j] = __float2bfloat16_rn(f[j] - __bfloat162float(h));
-  }
+  for (int j = 0; j < 4; ++j) rn_store16(f[j], hi, lo, pix * 64 + c4 * 4 + j, f16);
 }
 
 // patch / subsample gather on the bf16 (hi, lo) NHWC activation: out[(b,oy,ox), tap*C + c] = in[b, oy*s - pad + ky,
@@ -101,11 +111,11 @@ __global__ void rn_gather_kernel(const __nv_bfloat16* __restrict__ ih, const __n
   if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
     const size_t src = (((size_t)b * H + iy) * W + ix) * C + c8 * 8;
     vh = *reinterpret_cast<const uint4*>(ih + src);
-    vl = *reinterpret_cast<const uint4*>(il + src);
+    if (il) vl = *reinterpret_cast<const uint4*>(il + src);
   }
   const size_t dst = r * ((size_t)ksz * ksz * C) + (size_t)tap * C + c8 * 8;
   *reinterpret_cast<uint4*>(oh + dst) = vh;
-  *reinterpret_cast<uint4*>(ol + dst) = vl;
+  if (il) *reinterpret_cast<uint4*>(ol + dst) = vl;
 }
 
 // x4.mean(dim=(2,3)) (resnet.py:180): [B,49,2048] fp32 -> [B,2048]
@@ -137,6 +147,7 @@ struct RnBlock {
 
 struct seeme_resnet50 {
   int device = 0, max_batch = 0, chunk = 0;
+  int f16 = 0;            // 1: IEEE fp16 operands, one MMA pass (SEEME_RESNET_PRECISION=16); 0: split-bf16 x3
   Arena arena;
   RnConv stem;
   std::vector<RnBlock> blocks;
@@ -169,7 +180,12 @@ static int rn_pack(seeme_resnet50* h, RnConv& c, const float* const* t, int Cin,
   const size_t n = (size_t)Cout * c.Kp;
   rn_fold_kernel<<<(unsigned)((n + 255) / 256), 256>>>(t[0], t[1], t[2], t[3], t[4], scratch, bias, Cout, Cin, ksz, ksz, c.Kp);
   SEEME_LAUNCH_CHECK();
-  return pack_linear(h->arena, c.w, scratch, c.Kp, Cout, c.Kp, bias);
+  SEEME_TRY(pack_linear(h->arena, c.w, scratch, c.Kp, Cout, c.Kp, bias));
+  if (h->f16) {
+    rn_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256>>>(scratch, c.w.hi, n);
+    SEEME_LAUNCH_CHECK();
+  }
+  return SEEME_OK;
 }
 
 extern "C" int seeme_resnet50_create(seeme_resnet50_t* out, const float* const* w, int n_w, int max_batch) {
@@ -181,9 +197,13 @@ extern "C" int seeme_resnet50_create(seeme_resnet50_t* out, const float* const* 
   seeme_resnet50* h = new seeme_resnet50();
   SEEME_CUDA(cudaGetDevice(&h->device));
   h->max_batch = max_batch;
+  const char* pe = getenv("SEEME_RESNET_PRECISION");
+  const int prec = pe ? atoi(pe) : 3;
+  if (prec != 3 && prec != 16) { set_error("SEEME_RESNET_PRECISION must be 3 (split-bf16) or 16 (fp16), got %d", prec); delete h; return SEEME_EINVAL; }
+  h->f16 = prec == 16;
   const char* ce = getenv("SEEME_RESNET_CHUNK");
-  const int cap = ce ? atoi(ce) : 32;
-  h->chunk = max_batch < cap ? max_batch : (cap > 0 ? cap : 32);
+  const int cap = ce ? atoi(ce) : 64;
+  h->chunk = max_batch < cap ? max_batch : (cap > 0 ? cap : 64);
   const size_t C = (size_t)h->chunk;
   // packed weights: 23.5 M folded parameters as bf16 (hi, lo) + biases + the fp32 fold scratch (largest conv: 512 x 4608)
   const size_t wbytes = (size_t)26 * 1000 * 1000 * 4 + 4096 + pad256((size_t)2048 * 1024 * 4 > (size_t)512 * 4608 * 4 ? (size_t)2048 * 1024 * 4
@@ -254,24 +274,28 @@ extern "C" int seeme_resnet50_destroy(seeme_resnet50_t h) {
 }
 
 // out = [relu](A . W'^T + b' [+ R]) with the requested copies
-static int rn_gemm(const RnConv& c, const __nv_bfloat16* ah, const __nv_bfloat16* al, int lda, int M, bool relu, const float* R,
-                   float* yf, __nv_bfloat16* yh, __nv_bfloat16* yl, cudaStream_t s) {
+static int rn_gemm(const seeme_resnet50* h, const RnConv& c, const __nv_bfloat16* ah, const __nv_bfloat16* al, int lda, int M, bool relu,
+                   const float* R, float* yf, __nv_bfloat16* yh, __nv_bfloat16* yl, cudaStream_t s) {
   UmmaLinear g;
+  const bool f16 = h->f16 != 0;
+  g.fp16 = f16;
+  if (f16) { al = nullptr; yl = nullptr; }
   g.A1 = {const_cast<__nv_bfloat16*>(ah), const_cast<__nv_bfloat16*>(al), lda};
-  g.W = {c.w.hi, c.w.lo, c.Kp};
+  g.W = {c.w.hi, f16 ? nullptr : c.w.lo, c.Kp};
   g.M = M; g.N = c.Cout; g.K1 = c.Kp; g.K2 = 0;
   g.bias = c.w.bias;
   g.act = relu ? ACT_RELU : ACT_NONE;
   g.R = R; g.ldr = c.Cout; g.act_after_residual = R != nullptr;
   g.Y = yf; g.ldy = c.Cout;
   g.Yh = yh; g.Yl = yl; g.ldb = c.Cout;
-  return umma_linear(g, 3, s);
+  return umma_linear(g, f16 ? 1 : 3, s);
 }
 
-static int rn_gather(const ActBuf& in, __nv_bfloat16* oh, __nv_bfloat16* ol, int B, int H, int W, int C, int ksz, int stride, int pad,
-                     int Ho, int Wo, cudaStream_t s) {
+static int rn_gather(const seeme_resnet50* h, const ActBuf& in, __nv_bfloat16* oh, __nv_bfloat16* ol, int B, int H, int W, int C, int ksz,
+                     int stride, int pad, int Ho, int Wo, cudaStream_t s) {
   const size_t total = (size_t)B * Ho * Wo * ksz * ksz * (C / 8);
-  rn_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in.h, in.l, oh, ol, B, H, W, C, ksz, stride, pad, Ho, Wo);
+  rn_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in.h, h->f16 ? nullptr : in.l, oh, ol, B, H, W, C, ksz, stride, pad, Ho,
+                                                                      Wo);
   SEEME_LAUNCH_CHECK();
   return SEEME_OK;
 }
@@ -279,11 +303,11 @@ static int rn_gather(const ActBuf& in, __nv_bfloat16* oh, __nv_bfloat16* ol, int
 static int rn_chunk(seeme_resnet50* h, const float* img, int B, float* out, cudaStream_t s) {
   {  // stem: conv 7x7/2 + BN + ReLU, max-pool 3x3/2
     const size_t n = (size_t)B * 12544 * 192;
-    rn_stem_patch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(img, h->patch_h, h->patch_l, B);
+    rn_stem_patch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(img, h->patch_h, h->patch_l, B, h->f16);
     SEEME_LAUNCH_CHECK();
-    SEEME_TRY(rn_gemm(h->stem, h->patch_h, h->patch_l, 192, B * 12544, true, nullptr, h->stem_out, nullptr, nullptr, s));
+    SEEME_TRY(rn_gemm(h, h->stem, h->patch_h, h->patch_l, 192, B * 12544, true, nullptr, h->stem_out, nullptr, nullptr, s));
     const size_t m = (size_t)B * 3136 * 16;
-    rn_maxpool_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(h->stem_out, h->x[0].f, h->x[0].h, h->x[0].l, B);
+    rn_maxpool_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(h->stem_out, h->x[0].f, h->x[0].h, h->x[0].l, B, h->f16);
     SEEME_LAUNCH_CHECK();
   }
   int cur = 0, H = 56;
@@ -292,24 +316,24 @@ static int rn_chunk(seeme_resnet50* h, const float* img, int B, float* out, cuda
     const ActBuf& xo = h->x[cur ^ 1];
     const int Ho = H / b.stride, Min = B * H * H, Mout = B * Ho * Ho, P = b.planes;
     // conv1 1x1 + BN + ReLU
-    SEEME_TRY(rn_gemm(b.c1, xi.h, xi.l, b.cin, Min, true, nullptr, nullptr, h->t1.h, h->t1.l, s));
+    SEEME_TRY(rn_gemm(h, b.c1, xi.h, xi.l, b.cin, Min, true, nullptr, nullptr, h->t1.h, h->t1.l, s));
     // conv2 3x3 (stride) + BN + ReLU on the patch matrix
     ActBuf t1v = h->t1;
-    SEEME_TRY(rn_gather(t1v, h->patch_h, h->patch_l, B, H, H, P, 3, b.stride, 1, Ho, Ho, s));
-    SEEME_TRY(rn_gemm(b.c2, h->patch_h, h->patch_l, 9 * P, Mout, true, nullptr, nullptr, h->t2.h, h->t2.l, s));
+    SEEME_TRY(rn_gather(h, t1v, h->patch_h, h->patch_l, B, H, H, P, 3, b.stride, 1, Ho, Ho, s));
+    SEEME_TRY(rn_gemm(h, b.c2, h->patch_h, h->patch_l, 9 * P, Mout, true, nullptr, nullptr, h->t2.h, h->t2.l, s));
     // shortcut
     const float* R = xi.f;
     if (b.has_ds) {
       if (b.stride == 1) {
-        SEEME_TRY(rn_gemm(b.ds, xi.h, xi.l, b.cin, Min, false, nullptr, h->res, nullptr, nullptr, s));
+        SEEME_TRY(rn_gemm(h, b.ds, xi.h, xi.l, b.cin, Min, false, nullptr, h->res, nullptr, nullptr, s));
       } else {
-        SEEME_TRY(rn_gather(xi, h->patch_h, h->patch_l, B, H, H, b.cin, 1, b.stride, 0, Ho, Ho, s));
-        SEEME_TRY(rn_gemm(b.ds, h->patch_h, h->patch_l, b.cin, Mout, false, nullptr, h->res, nullptr, nullptr, s));
+        SEEME_TRY(rn_gather(h, xi, h->patch_h, h->patch_l, B, H, H, b.cin, 1, b.stride, 0, Ho, Ho, s));
+        SEEME_TRY(rn_gemm(h, b.ds, h->patch_h, h->patch_l, b.cin, Mout, false, nullptr, h->res, nullptr, nullptr, s));
       }
       R = h->res;
     }
     // conv3 1x1 + BN, + shortcut, ReLU: fp32 copy (next shortcut) and bf16 copies (next A operand)
-    SEEME_TRY(rn_gemm(b.c3, h->t2.h, h->t2.l, P, Mout, true, R, xo.f, xo.h, xo.l, s));
+    SEEME_TRY(rn_gemm(h, b.c3, h->t2.h, h->t2.l, P, Mout, true, R, xo.f, xo.h, xo.l, s));
     cur ^= 1;
     H = Ho;
   }

@@ -29,3 +29,11 @@ ms = e0.elapsed_time(e1) / iters
 flop = 2 * 4.089e9 * B
 print(f"resnet50 B={B}: {ms:.2f} ms per batch, {B / ms * 1e3:.0f} crops/s, {flop / ms / 1e9:.0f} TFLOP/s algorithmic "
       f"(x3 executed: split-bf16), {(_lib.launch_count() - n0) // iters} launches per batch")
+if os.environ.get("RN_CHECK", "1") == "1":     # feature error against the reference golden (tests/golden/resnet50_image.npz)
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "resnet50_image.npz"))
+    _, feat = op(S.images(int(g["batch"]), int(g["seed"])).to(dev), want_feat=True)
+    ref = torch.from_numpy(g["feat"])
+    d = (feat.cpu() - ref)
+    print(f"precision {os.environ.get('SEEME_RESNET_PRECISION', '3')}: max|feat - reference| = {d.abs().max():.3e}, "
+          f"rel l2 = {d.norm() / ref.norm():.3e} (|feat| max {ref.abs().max():.2f})")
