@@ -54,18 +54,32 @@ __global__ void rn_fold_kernel(const float* __restrict__ w, const float* __restr
 // k = (ky*7 + kx)*3 + c for the 7x7 stride-2 pad-3 convolution, columns 147..191 zero
 __global__ void rn_stem_patch_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                      int B, int f16) {
-  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * 12544 * 192) return;
-  const int k = (int)(i % 192);
-  const size_t pix = i / 192;
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;     // one thread per 8 consecutive k (16-byte stores)
+  if (i >= (size_t)B * 12544 * 24) return;
+  const int k0 = (int)(i % 24) * 8;
+  const size_t pix = i / 24;
   const int ox = (int)(pix % 112), oy = (int)((pix / 112) % 112), b = (int)(pix / 12544);
-  float v = 0.f;
-  if (k < 147) {
-    const int c = k % 3, kx = (k / 3) % 7, ky = k / 21;
-    const int iy = oy * 2 - 3 + ky, ix = ox * 2 - 3 + kx;
-    if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224) v = x[(((size_t)b * 3 + c) * 224 + iy) * 224 + ix];
+  __align__(16) unsigned short vh[8], vl[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = k0 + j;
+    float v = 0.f;
+    if (k < 147) {
+      const int c = k % 3, kx = (k / 3) % 7, ky = k / 21;
+      const int iy = oy * 2 - 3 + ky, ix = ox * 2 - 3 + kx;
+      if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224) v = __ldg(x + (((size_t)b * 3 + c) * 224 + iy) * 224 + ix);
+    }
+    if (f16) {
+      vh[j] = __half_as_ushort(__float2half_rn(v));
+      vl[j] = 0;
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      vh[j] = __bfloat16_as_ushort(h);
+      vl[j] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+    }
   }
-  rn_store16(v, hi, lo, i, f16);
+  *reinterpret_cast<uint4*>(hi + pix * 192 + k0) = *reinterpret_cast<const uint4*>(vh);
+  if (!f16) *reinterpret_cast<uint4*>(lo + pix * 192 + k0) = *reinterpret_cast<const uint4*>(vl);
 }
 
 // 3x3 stride-2 pad-1 max pooling of the stem output y [B,112,112,64] fp32 -> [B,56,56,64] fp32 + bf16 (hi, lo)
@@ -202,8 +216,8 @@ extern "C" int seeme_resnet50_create(seeme_resnet50_t* out, const float* const* 
   if (prec != 3 && prec != 16) { set_error("SEEME_RESNET_PRECISION must be 3 (split-bf16) or 16 (fp16), got %d", prec); delete h; return SEEME_EINVAL; }
   h->f16 = prec == 16;
   const char* ce = getenv("SEEME_RESNET_CHUNK");
-  const int cap = ce ? atoi(ce) : 64;
-  h->chunk = max_batch < cap ? max_batch : (cap > 0 ? cap : 64);
+  const int cap = ce ? atoi(ce) : 128;
+  h->chunk = max_batch < cap ? max_batch : (cap > 0 ? cap : 128);
   const size_t C = (size_t)h->chunk;
   // packed weights: 23.5 M folded parameters as bf16 (hi, lo) + biases + the fp32 fold scratch (largest conv: 512 x 4608)
   const size_t wbytes = (size_t)26 * 1000 * 1000 * 4 + 4096 + pad256((size_t)2048 * 1024 * 4 > (size_t)512 * 4608 * 4 ? (size_t)2048 * 1024 * 4
@@ -302,7 +316,7 @@ static int rn_gather(const seeme_resnet50* h, const ActBuf& in, __nv_bfloat16* o
 
 static int rn_chunk(seeme_resnet50* h, const float* img, int B, float* out, cudaStream_t s) {
   {  // stem: conv 7x7/2 + BN + ReLU, max-pool 3x3/2
-    const size_t n = (size_t)B * 12544 * 192;
+    const size_t n = (size_t)B * 12544 * 24;
     rn_stem_patch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(img, h->patch_h, h->patch_l, B, h->f16);
     SEEME_LAUNCH_CHECK();
     SEEME_TRY(rn_gemm(h, h->stem, h->patch_h, h->patch_l, 192, B * 12544, true, nullptr, h->stem_out, nullptr, nullptr, s));
