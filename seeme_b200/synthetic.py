@@ -336,10 +336,11 @@ def gimo_scene(B: int, n_points: int, g: torch.Generator) -> torch.Tensor:
 
 
 def make_batch(B: int, seed: int = 1234, n_points: int = N_POINTS, T: int = T_MAX,
-               ragged: bool = False, dataset: str = "egobody"):
+               ragged: bool = False, dataset: str = "egobody", with_images: bool = False):
     """The 7-tuple ``ego_eval`` unpacks at ``mld/models/modeltype/mld.py:1135-1137``:
     (feats_ref[B,T,2,72], transl[B,2,T,3], beta[B,2,T,10], utils_[B,T,6], scene[B,N,3],
-    length[B,1] int32, dict_images: T tuples of B strings)."""
+    length[B,1] int32, dict_images: T tuples of B strings); ``with_images``: the image-conditioned item tuple
+    (..., scene, images[B,3,224,224], length) of ``dataset.py:1788-1790``."""
     g = torch.Generator().manual_seed(seed)
     # GIMO rows carry 21 body joints: 3 + 63 = 66 pose dims (mld.py:1656, Gimo.py numdims 69 with transl)
     feats_ref = torch.randn(B, T, 2, 72 if dataset == "egobody" else 66, generator=g)
@@ -352,5 +353,7 @@ def make_batch(B: int, seed: int = 1234, n_points: int = N_POINTS, T: int = T_MA
         length[0, 0] = T   # the reference sizes the decode by max(lengths)
     else:
         length = torch.full((B, 1), T, dtype=torch.int32)
+    if with_images:
+        return feats_ref, transl, beta, utils_, scene, images(B, seed), length
     dict_images = [tuple(f"img_{t:03d}_{b:04d}.jpg" for b in range(B)) for t in range(T)]
     return feats_ref, transl, beta, utils_, scene, length, dict_images

@@ -565,3 +565,26 @@ def test_ego_eval_image_conditioned_vs_oracle(weights, smpl_buffers, cond):
     assert float((rs2["joints_rst"] - rs["joints_rst"]).abs().max()) > 1e-4
     with pytest.raises(NotImplementedError):
         seeme_b200.build_model("config_mld_egobody.yaml", device=DEV, guidance_scale=7.5, condition=cond, max_batch=B, n_points=600)
+
+
+def test_interactee_protocol_with_image_tokens(tmp_path):
+    """config_mld_interactee.yaml as shipped by the reference (condition text + image + scene, guidance 1.0, one frame,
+    ESTIMATE interactee): host batches with crops through the replication driver; the pipelined result of a batch equals
+    the synchronous ego_eval of the same batch and noise"""
+    import seeme_b200
+    from seeme_b200.driver import run_test_protocol
+    B = 3
+    model = seeme_b200.build_model("config_mld_interactee.yaml", device=DEV, condition=["text", "image", "scene"], max_batch=B,
+                                   n_points=300, pipeline_depth=2)
+    assert model.estimate == "interactee" and not model.do_classifier_free_guidance
+    dm = model.datamodule
+    host = [dm.batch(i) for i in range(2)]
+    assert len(host[0]) == 7 and host[0][5].shape == (B, 3, 224, 224)
+    summary = run_test_protocol(model, lambda: iter(host), replication_times=2, out_json=str(tmp_path / "m.json"))
+    assert len(summary["Metrics/MPJPE"]) == 2
+    dev_batch = tuple(x.to(DEV) for x in host[0])
+    g = torch.Generator(device=DEV).manual_seed(1)
+    noise = {"x_T": torch.randn(B, 1, 256, generator=g, device=DEV)}
+    a = model.ego_eval(dev_batch, noise)
+    b = model.ego_eval_async(dev_batch, noise).result()
+    assert torch.equal(a["joints_rst"], b["joints_rst"]) and a["joints_rst"].shape == (B, 1, 24, 3)
