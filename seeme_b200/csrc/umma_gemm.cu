@@ -437,12 +437,6 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
     if (npass == 1) return launch<64, 1, 4, 1, 1>(g, maps, e, s);
     return small ? launch<64, 3, 2, 1, 2>(g, maps, e, s) : launch<64, 3, 4, 1, 1>(g, maps, e, s);
   }
-  // deep K with few tiles (the image backbone's 3x3 convolutions of layers 2-4: K = 1152..4608 on 100-600 tiles): a
-  // one-stage ring serialises TMA and MMA per k-block and there are too few co-resident CTAs to hide it -> deeper ring
-  static const bool deepk = !(getenv("SEEME_UMMA_DEEPK") && getenv("SEEME_UMMA_DEEPK")[0] == '0');
-  const long tiles = (long)(g.N / BN) * ((g.M + 127) / 128);
-  if (deepk && K >= 512 && tiles <= 4 * NUM_SMS)
-    return npass == 1 ? launch<128, 1, 4, 1, 1>(g, maps, e, s) : launch<128, 3, 3, 1, 1>(g, maps, e, s);
   return npass == 1 ? launch<128, 1, 2, 1, 2>(g, maps, e, s) : launch<128, 3, 1, 1, 2>(g, maps, e, s);
 }
 
