@@ -300,6 +300,8 @@ static int rn_gemm(const seeme_resnet50* h, const RnConv& c, const __nv_bfloat16
   g.bias = c.w.bias;
   g.act = relu ? ACT_RELU : ACT_NONE;
   g.R = R; g.ldr = c.Cout; g.act_after_residual = R != nullptr;
+  static const bool dense = !(getenv("SEEME_RESNET_DENSE") && getenv("SEEME_RESNET_DENSE")[0] == '0');
+  g.dense_ctas = dense && M > 2048;
   g.Y = yf; g.ldy = c.Cout;
   g.Yh = yh; g.Yl = yl; g.ldb = c.Cout;
   return umma_linear(g, f16 ? 1 : 3, s);

@@ -162,6 +162,8 @@ struct UmmaLinear {
   const float* R = nullptr;      // fp32 residual added after the activation (before it when act_after_residual)
   int ldr = 0;
   int act_after_residual = 0;    // out = act(acc + bias + R): the bottleneck tail of the image backbone
+  int dense_ctas = 0;            // many-row, short-K, bandwidth-bound GEMMs (image backbone): 112-register build with a
+                                 // one-stage ring so that three CTAs share an SM (the default builds fit two)
   float* Y = nullptr;            // fp32 output (nullable)
   int ldy = 0;
   __nv_bfloat16 *Yh = nullptr, *Yl = nullptr;   // bf16 (hi, lo) of the output (nullable)

@@ -437,9 +437,10 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
     // SEEME_UMMA64_STAGES=1: experiment knob (one-stage ring, 65 KB: three CTAs per SM when several chains share the GPU)
     static const bool one = getenv("SEEME_UMMA64_STAGES") && getenv("SEEME_UMMA64_STAGES")[0] == '1';
     if (npass == 1) return launch<64, 1, 4, 1, 1>(g, maps, e, s);
-    if (one) return launch<64, 3, 1, 1, 3>(g, maps, e, s);
+    if (one || g.dense_ctas) return launch<64, 3, 1, 1, 3>(g, maps, e, s);
     return small ? launch<64, 3, 2, 1, 2>(g, maps, e, s) : launch<64, 3, 4, 1, 1>(g, maps, e, s);
   }
+  if (g.dense_ctas && npass == 3) return launch<128, 3, 1, 1, 3>(g, maps, e, s);
   return npass == 1 ? launch<128, 1, 2, 1, 2>(g, maps, e, s) : launch<128, 3, 1, 1, 2>(g, maps, e, s);
 }
 
