@@ -440,7 +440,9 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
     if (one || g.dense_ctas) return launch<64, 3, 1, 1, 3>(g, maps, e, s);
     return small ? launch<64, 3, 2, 1, 2>(g, maps, e, s) : launch<64, 3, 4, 1, 1>(g, maps, e, s);
   }
-  if (g.dense_ctas && npass == 3) return launch<128, 3, 1, 1, 3>(g, maps, e, s);
+  // SEEME_UMMA_DENSE_ALL=1: experiment knob -- the three-CTA build for every many-row split-bf16 GEMM (VAE stacks)
+  static const bool dense_all = getenv("SEEME_UMMA_DENSE_ALL") && getenv("SEEME_UMMA_DENSE_ALL")[0] == '1';
+  if ((g.dense_ctas || (dense_all && !g.colmax)) && npass == 3) return launch<128, 3, 1, 1, 3>(g, maps, e, s);
   return npass == 1 ? launch<128, 1, 2, 1, 2>(g, maps, e, s) : launch<128, 3, 1, 1, 2>(g, maps, e, s);
 }
 
