@@ -249,8 +249,8 @@ extern "C" int seeme_resnet50_create(seeme_resnet50_t* out, const float* const* 
       h->blocks.push_back(blk);
     }
   }
-  if (!rc) rc = pack_linear(h->arena, h->tail, w[k], 2048, 256, 2048, w[k + 1]);   // the bias pointer stays the caller's tensor
-  if (!rc) {
+  if (!rc) rc = pack_linear(h->arena, h->tail, w[k], 2048, 256, 2048, w[k + 1]);
+  if (!rc) {   // the handle keeps its own copy of the tail bias (the caller's tensors may be freed after create)
     float* tb = h->arena.take<float>(256);
     if (!tb) { set_error("seeme_resnet50_create: arena exhausted"); rc = SEEME_ENOMEM; }
     else if (cudaMemcpy(tb, w[k + 1], 256 * 4, cudaMemcpyDeviceToDevice) != cudaSuccess) { set_error("seeme_resnet50_create: bias copy failed"); rc = SEEME_ECUDA; }
@@ -334,8 +334,7 @@ static int rn_chunk(seeme_resnet50* h, const float* img, int B, float* out, cuda
     // conv1 1x1 + BN + ReLU
     SEEME_TRY(rn_gemm(h, b.c1, xi.h, xi.l, b.cin, Min, true, nullptr, nullptr, h->t1.h, h->t1.l, s));
     // conv2 3x3 (stride) + BN + ReLU on the patch matrix
-    ActBuf t1v = h->t1;
-    SEEME_TRY(rn_gather(h, t1v, h->patch_h, h->patch_l, B, H, H, P, 3, b.stride, 1, Ho, Ho, s));
+    SEEME_TRY(rn_gather(h, h->t1, h->patch_h, h->patch_l, B, H, H, P, 3, b.stride, 1, Ho, Ho, s));
     SEEME_TRY(rn_gemm(h, b.c2, h->patch_h, h->patch_l, 9 * P, Mout, true, nullptr, nullptr, h->t2.h, h->t2.l, s));
     // shortcut
     const float* R = xi.f;
