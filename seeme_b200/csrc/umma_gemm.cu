@@ -85,6 +85,21 @@ __device__ __forceinline__ uint32_t sw128(int r, int j) { return (uint32_t)(r * 
 // STAGES: depth of the operand ring; NBUF: store-staging (and residual) buffers; MINB: CTAs per SM the
 // register allocation must allow (small-footprint configurations co-reside so that one CTA's epilogue
 // overlaps another's main loop)
+// activation of 32 accumulator values; the (uniform) selector is tested once, not per element (a per-element switch
+// compiles to 64 indirect branches per thread and tile)
+__device__ __forceinline__ void epi_act32(float (&f)[32], int act) {
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+  } else if (act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+  } else if (act == ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = silu(f[i]);
+  }
+}
+
 template <int BN, int NPASS, int STAGES, int NBUF, int MINB>
 __global__ void __launch_bounds__(192, MINB) umma_linear_kernel(const __grid_constant__ UmmaMaps tm, const UmmaEpi e) {
   using Cfg = UmmaCfg<BN, NPASS>;
@@ -219,10 +234,7 @@ __global__ void __launch_bounds__(192, MINB) umma_linear_kernel(const __grid_con
             f[i] += p.x * px + p.y * py + p.z * pz;
           }
         }
-        if (e.act != ACT_NONE && !e.act_post) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = apply_act(f[i], e.act);
-        }
+        if (e.act != ACT_NONE && !e.act_post) epi_act32(f, e.act);
         if (e.has_r) {
           const uint8_t* rt = res_stage + buf * RES_BUF_BYTES + half * TILE_BYTES;
 #pragma unroll
@@ -231,10 +243,7 @@ __global__ void __launch_bounds__(192, MINB) umma_linear_kernel(const __grid_con
             f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
           }
         }
-        if (e.act != ACT_NONE && e.act_post) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = apply_act(f[i], e.act);
-        }
+        if (e.act != ACT_NONE && e.act_post) epi_act32(f, e.act);
         if (e.has_yf) {                 // fp32 tile of 32 columns: slot 2 (half 0) / slot 3 (half 1)
           uint8_t* t = sbuf + (2 + half) * TILE_BYTES;
 #pragma unroll
