@@ -1,0 +1,1147 @@
+// Persistent cluster sampler: the whole 50-step DDIM loop of MLD._diffusion_reverse (mld/models/modeltype/mld.py:432-511)
+// over the skip-connected denoiser (mld_denoiser.py:151-244, cross_attention.py:67-83, mdiff_transformer.py:286-304)
+// as ONE kernel launch.
+//
+// Decomposition.  A cluster of CL = 8 CTAs owns a tile of 128 denoiser rows (under CFG: 64 latents x {uncond, cond}) for
+// the whole run; clusters never talk to one another.  Inside a cluster every GEMM is split over its OUTPUT features: CTA c
+// computes columns [32c, 32c+32) of every 256-wide activation (its "slice") on tcgen05 (M = 128 rows, N = 16..64 per
+// instruction, fp32 accumulators in tensor memory, split-bf16 x3 operands).  TMEM, mbarriers, the tensor maps and the
+// per-row state (residual stream slice, latent slice) live across all ~3 350 GEMM units of a run.
+//
+//   warp 0      producer: streams this CTA's weight "tape" (pre-swizzled bf16 hi|lo blobs in consumption order, one
+//               cp.async.bulk per K-block, ring of 4 x 16 KB) and the A operand K-blocks (TMA boxes of the cluster's
+//               exchange matrix in L2, ring of 4 x (16 KB hi + 16 KB lo) = one full K = 256 activation)
+//   warp 1      one elected lane issues tcgen05.mma; tcgen05.commit releases ring slots and signals the epilogue
+//   warps 2-5   epilogue, thread = row: tcgen05.ld, bias / attention / LayerNorm / FiLM / CFG + DDIM on its 32-column
+//               slice, then publishes the slice (bf16 hi, lo) into the exchange matrix for the next GEMM's A operand
+//
+// Exchanges (all mbarrier based, double buffered; no barrier.cluster in the loop):
+//   * activation all-gather through L2: st.global of the slice -> fence -> remote mbarrier arrive on every CTA of the
+//     cluster -> the producers TMA-load the full [128 x 256] activation.  FFN 256 -> 1024 -> 256 is K-split instead:
+//     each CTA keeps its 128 hidden units private and the 8 partial [128 x 256] results are reduce-scattered through
+//     a fp32 scratch (one exchange instead of a 512 KB all-gather).
+//   * row statistics through distributed shared memory: every reduction over the 256 features of a row (the 4-key
+//     attention logits, softmax_d of the linear cross-attention, every LayerNorm as a (mean, M2) Chan combine) sends
+//     <= 4 floats per row to each peer with st.shared::cluster + one remote arrive per warp.
+//
+// Algebra: H1 token-0-only self-attention, H2 linear attention as dot products, H3 cond-token K/V once
+// per run (on tensor cores, see den_persist_run), H4 per-timestep tables; plus the out-projection of the self-attention
+// folded into the value projection (W_ov = W_o W_v, computed in fp64 at create): sa = sum_j p_j (W_ov t_j + W_o b_v) + b_o.
+#include "denoiser.cuh"
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+namespace seeme {
+
+constexpr int DP_CL = 8;               // CTAs per cluster
+constexpr int DP_NS = 256 / DP_CL;     // slice width of a 256-wide activation
+constexpr int DP_HS = 1024 / DP_CL;    // hidden units of the 1024-wide FFN per CTA
+constexpr int DP_GS = 128 / DP_CL;     // hidden units of the 128-wide FFN per CTA
+constexpr int DP_THREADS = 192;
+constexpr int DP_NA = 4, DP_NW = 4;
+constexpr int DP_A_SLOT = 32768, DP_W_SLOT = 16384;
+constexpr int DP_STAT_FLOATS = 2 * DP_CL * 4 * 128;
+constexpr int DP_SMEM = DP_NA * DP_A_SLOT + DP_NW * DP_W_SLOT + DP_STAT_FLOATS * 4 + 1024;
+static_assert(DP_NS == 32, "the epilogues are written for 32-column slices (CL = 8)");
+// columns of the per-cluster exchange matrix [128 rows x XC_COLS] (bf16 hi and lo copies)
+enum { XC_P0 = 0, XC_P1 = 256, XC_L0 = 512, XC_L1 = 768, XC_XA = 1024, XC_LN = 1280, XC_HB0 = 1536, XC_HB1 = 1792,
+       XC_X3 = 2048, XC_G = 2304, XC_FF = 2432, XC_COLS = 3456 };
+constexpr int TM_XRES = 256, TM_LAT = 256 + DP_NS;   // tensor-memory columns of the per-row state
+
+struct DpUnit {             // one GEMM unit: acc[:, acc_col : acc_col + n] = A[128, 64 nkb] . W_unit^T
+  int a_col, a_col2;        // exchange-matrix column of K-block 0 / of K-block nkb1 (torch.cat([x, skip]))
+  int a_rstride;            // + rank * a_rstride (CTA-private FFN hidden units)
+  int nkb1, nkb, n, acc_col;
+  int wait;                 // 0: A visible already, 1: cluster exchange, 2: CTA-local hand-over
+  int reuse_a, release_a;   // sub-units of one stage share the A ring contents
+  int last;                 // the stage's epilogue runs after this unit
+  unsigned w_off;           // byte offset of the unit's first blob in the CTA's tape (blob = n x 256 bytes)
+};
+constexpr int DP_MAX_UNITS = 80;
+
+struct DpLayerP {
+  const float *bqkv, *bo, *n1g, *n1b, *b1, *b2, *n2g, *n2b, *cng, *cnb, *bcaq, *cpg, *cpb, *bcaout, *bf1, *bf2, *fpg, *fpb, *bfout;
+  const float *kt, *film_ca, *film_ff;   // [steps][512]: (k | ov) of the time token, FiLM (scale | shift)
+  const float* ctab;                     // [4][Nc][256][rows_pad]: k, ov (self-attention), softmax_n(key), value (cross-attention)
+};
+struct DpParams {
+  CUtensorMap map_hi, map_lo;
+  DpLayerP L[5];
+  const float *skip_b[2], *fng, *fnb, *pe0;
+  const uint8_t* tape;
+  unsigned long long tape_cta_bytes;
+  const DpUnit* units;
+  int n_units;
+  __nv_bfloat16 *xh, *xl;
+  float* part;          // [tiles][CL][256][128]
+  const float* x_in;
+  float* out;
+  const float *coef, *gscale;
+  int B, R, cfg, n_steps, mode, rows_pad;
+};
+
+// ---- PTX helpers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t dp_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void dp_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void dp_st_remote(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+static __device__ __noinline__ void dp_wait_timeout(uint32_t addr, int what) {
+  printf("seeme_b200: den_persist wait timed out (block %d thread %d barrier 0x%x kind %d)\n", blockIdx.x, threadIdx.x, addr, what);
+  __trap();
+}
+// wait with cluster-scope acquire (arrivals come from peer CTAs)
+__device__ __forceinline__ void dp_wait_cluster(uint64_t* bar, uint32_t parity, int what) {
+  const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  dp_wait_timeout(addr, what);
+}
+__device__ __forceinline__ void dp_wait(uint64_t* bar, uint32_t parity, int what) {
+  const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  dp_wait_timeout(addr, what);
+}
+__device__ __forceinline__ void dp_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void dp_fence_proxy_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait_dp() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void dp_ld32(uint32_t taddr, float (&f)[32]) {
+  uint32_t raw[32];
+  tmem_ld32(taddr, raw);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(raw[i]);
+}
+__device__ __forceinline__ void dp_st32(uint32_t taddr, const float (&f)[32]) {
+  uint32_t raw[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(f[i]);
+  tmem_st32(taddr, raw);
+  tmem_st_wait_dp();
+}
+__device__ __forceinline__ void dp_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// publish N (16 or 32) consecutive columns of this thread's row into the exchange matrix (bf16 hi and lo copies)
+template <int N>
+__device__ __forceinline__ void dp_publish(__nv_bfloat16* xh, __nv_bfloat16* xl, size_t elem_off, const float* f) {
+  uint32_t hb[N / 2], lb[N / 2];
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) dp_split2(f[2 * i], f[2 * i + 1], hb[i], lb[i]);
+  uint4* ph = reinterpret_cast<uint4*>(xh + elem_off);
+  uint4* pl = reinterpret_cast<uint4*>(xl + elem_off);
+#pragma unroll
+  for (int j = 0; j < N / 8; ++j) {
+    ph[j] = make_uint4(hb[4 * j], hb[4 * j + 1], hb[4 * j + 2], hb[4 * j + 3]);
+    pl[j] = make_uint4(lb[4 * j], lb[4 * j + 1], lb[4 * j + 2], lb[4 * j + 3]);
+  }
+}
+// 32 consecutive floats of a vector shared by all rows (bias, LayerNorm affine, FiLM, time-token tables)
+__device__ __forceinline__ void dp_ldvec(const float* __restrict__ p, float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + j);
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+}
+
+// per-row statistics exchange over distributed shared memory
+struct DpStat {
+  float* stats;      // [2][CL][4][128]
+  uint64_t* bar;     // [2][4]
+  uint32_t cnt;
+  int q, lane, row, rank;
+  const float* cur;
+  template <int K>
+  __device__ __forceinline__ void send(const float (&v)[K]) {
+    static_assert(K <= 4, "at most 4 values per round");
+    const uint32_t par = cnt & 1u;
+    const uint32_t laddr = smem_u32(stats + ((par * DP_CL + rank) * 4) * 128 + row);
+#pragma unroll
+    for (int pr = 0; pr < DP_CL; ++pr) {
+      const uint32_t ra = dp_mapa(laddr, pr);
+#pragma unroll
+      for (int k = 0; k < K; ++k) dp_st_remote(ra + k * 512, v[k]);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t b = smem_u32(&bar[par * 4 + q]);
+#pragma unroll
+      for (int pr = 0; pr < DP_CL; ++pr) dp_arrive_remote(dp_mapa(b, pr));
+    }
+    dp_wait_cluster(&bar[par * 4 + q], (cnt >> 1) & 1u, 10);
+    cur = stats + (par * DP_CL * 4) * 128 + row;
+    ++cnt;
+  }
+  __device__ __forceinline__ float get(int s, int k) const { return cur[(s * 4 + k) * 128]; }
+  // v[k] <- sum over the cluster
+  template <int K>
+  __device__ __forceinline__ void sum(float (&v)[K]) {
+    constexpr int K0 = K > 4 ? 4 : K;
+    {
+      float a[K0];
+#pragma unroll
+      for (int k = 0; k < K0; ++k) a[k] = v[k];
+      send<K0>(a);
+#pragma unroll
+      for (int k = 0; k < K0; ++k) {
+        float t = 0.f;
+#pragma unroll
+        for (int s = 0; s < DP_CL; ++s) t += get(s, k);
+        v[k] = t;
+      }
+    }
+    if constexpr (K > 4) {
+      float a[K - 4];
+#pragma unroll
+      for (int k = 0; k < K - 4; ++k) a[k] = v[4 + k];
+      send<K - 4>(a);
+#pragma unroll
+      for (int k = 0; k < K - 4; ++k) {
+        float t = 0.f;
+#pragma unroll
+        for (int s = 0; s < DP_CL; ++s) t += get(s, k);
+        v[4 + k] = t;
+      }
+    }
+  }
+  // LayerNorm(256) of a row whose slice is t[32]: Chan combine of the per-slice (mean, M2); biased variance, eps 1e-5
+  __device__ __forceinline__ void layernorm(float (&t)[32], const float* __restrict__ g, const float* __restrict__ b) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += t[i];
+    const float mc = s * (1.0f / 32.0f);
+    float m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { const float d = t[i] - mc; m2 = fmaf(d, d, m2); }
+    const float a[2] = {mc, m2};
+    send<2>(a);
+    float mean = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < DP_CL; ++s2) mean += get(s2, 0);
+    mean *= (1.0f / DP_CL);
+    float M2 = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < DP_CL; ++s2) { const float d = get(s2, 0) - mean; M2 += get(s2, 1) + 32.0f * d * d; }
+    const float rstd = rsqrtf(M2 * (1.0f / 256.0f) + 1e-5f);
+    float gg[32], bb[32];
+    dp_ldvec(g, gg);
+    dp_ldvec(b, bb);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t[i] = (t[i] - mean) * rstd * gg[i] + bb[i];
+  }
+};
+
+template <int NC>
+__global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) den_persist_kernel(const __grid_constant__ DpParams p) {
+  extern __shared__ __align__(1024) uint8_t dp_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dp_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* w_ring = smem + DP_NA * DP_A_SLOT;
+  float* stats = reinterpret_cast<float*>(w_ring + DP_NW * DP_W_SLOT);
+  __shared__ __align__(8) uint64_t full_a[DP_NA], empty_a[DP_NA], full_w[DP_NW], empty_w[DP_NW], acc_full, xbar[2], lbar[2], sbar[8], rbar[8];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int tile = blockIdx.x / DP_CL;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.map_hi);
+    tma_prefetch_desc(&p.map_lo);
+    for (int i = 0; i < DP_NA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < DP_NW; ++i) { mbar_init(&full_w[i], 1); mbar_init(&empty_w[i], 1); }
+    mbar_init(&acc_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&xbar[i], 4 * DP_CL); mbar_init(&lbar[i], 4); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&sbar[i], DP_CL); mbar_init(&rbar[i], DP_CL); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();      // every CTA's barriers exist before the first remote arrive
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ---- producer -----------------------------------------------------------------------------------
+    if (lane == 0) {
+      uint32_t ia = 0, iw = 0, nx = 0, nl = 0;
+      const uint8_t* tape = p.tape + (size_t)rank * p.tape_cta_bytes;
+      const int row0 = tile * 128;
+      for (int step = 0; step < p.n_steps; ++step) {
+        for (int u = 0; u < p.n_units; ++u) {
+          const DpUnit un = p.units[u];
+          const uint32_t wbytes = (uint32_t)un.n * 256u;
+          const uint8_t* wsrc = tape + un.w_off;
+          int kw = 0;
+          // the weights do not depend on the exchange: up to NW K-blocks travel while the previous epilogue runs
+          for (; kw < un.nkb && kw < DP_NW; ++kw) {
+            const uint32_t sw = iw % DP_NW;
+            dp_wait(&empty_w[sw], ((iw / DP_NW) & 1u) ^ 1u, 1);
+            mbar_arrive_expect_tx(&full_w[sw], wbytes);
+            dp_bulk_load(w_ring + sw * DP_W_SLOT, wsrc + (size_t)kw * wbytes, wbytes, &full_w[sw]);
+            ++iw;
+          }
+          if (un.wait == 1) { dp_wait_cluster(&xbar[nx & 1u], (nx >> 1) & 1u, 2); ++nx; dp_fence_proxy_all(); }
+          else if (un.wait == 2) { dp_wait(&lbar[nl & 1u], (nl >> 1) & 1u, 3); ++nl; dp_fence_proxy_all(); }
+          const int acol = un.a_col + rank * un.a_rstride;
+          for (int kb = 0; kb < un.nkb; ++kb) {
+            if (!un.reuse_a) {
+              const uint32_t sa = ia % DP_NA;
+              dp_wait(&empty_a[sa], ((ia / DP_NA) & 1u) ^ 1u, 4);
+              mbar_arrive_expect_tx(&full_a[sa], DP_A_SLOT);
+              const int col = kb < un.nkb1 ? acol + kb * 64 : un.a_col2 + (kb - un.nkb1) * 64;
+              tma_load_2d(a_ring + sa * DP_A_SLOT, &p.map_hi, &full_a[sa], col, row0);
+              tma_load_2d(a_ring + sa * DP_A_SLOT + 16384, &p.map_lo, &full_a[sa], col, row0);
+              ++ia;
+            }
+            if (kb >= kw) {
+              const uint32_t sw = iw % DP_NW;
+              dp_wait(&empty_w[sw], ((iw / DP_NW) & 1u) ^ 1u, 5);
+              mbar_arrive_expect_tx(&full_w[sw], wbytes);
+              dp_bulk_load(w_ring + sw * DP_W_SLOT, wsrc + (size_t)kb * wbytes, wbytes, &full_w[sw]);
+              ++iw;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer -----------------------------------------------------------------------------------
+    uint32_t ia = 0, iw = 0, a0 = 0;
+    const uint64_t da_base = umma_desc_k128(smem_u32(a_ring));
+    const uint64_t dw_base = umma_desc_k128(smem_u32(w_ring));
+    for (int step = 0; step < p.n_steps; ++step) {
+      for (int u = 0; u < p.n_units; ++u) {
+        const DpUnit un = p.units[u];
+        if (!un.reuse_a) a0 = ia;
+        const uint32_t idesc = umma_idesc_bf16(un.n);
+        const uint32_t wl16 = (uint32_t)(un.n * 128) >> 4;      // lo tile follows the hi tile
+        for (int kb = 0; kb < un.nkb; ++kb) {
+          const uint32_t ai = a0 + (uint32_t)kb;
+          const uint32_t sa = ai % DP_NA;
+          if (!un.reuse_a) dp_wait(&full_a[sa], (ai / DP_NA) & 1u, 6);
+          const uint32_t sw = iw % DP_NW;
+          dp_wait(&full_w[sw], (iw / DP_NW) & 1u, 7);
+          tc_fence_after();
+          if (umma_elect_one()) {
+            const uint64_t da0 = umma_desc_add(da_base, sa * (DP_A_SLOT >> 4));
+            const uint64_t dw0 = umma_desc_add(dw_base, sw * (DP_W_SLOT >> 4));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = umma_desc_add(da0, k * 2), dw = umma_desc_add(dw0, k * 2);
+              umma_bf16(tmem_base + (uint32_t)un.acc_col, da, dw, idesc, (kb | k) != 0);
+              umma_bf16(tmem_base + (uint32_t)un.acc_col, umma_desc_add(da, 16384 >> 4), dw, idesc, 1);
+              umma_bf16(tmem_base + (uint32_t)un.acc_col, da, umma_desc_add(dw, wl16), idesc, 1);
+            }
+            umma_commit(&empty_w[sw]);
+            if (un.release_a) umma_commit(&empty_a[sa]);
+            if (un.last && kb == un.nkb - 1) umma_commit(&acc_full);
+          }
+          __syncwarp();
+          ++iw;
+        }
+        if (!un.reuse_a) ia += (uint32_t)un.nkb;
+      }
+    }
+  } else {
+    // ---- epilogue: thread = row ------------------------------------------------------------------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int S = rank * DP_NS;
+    const int prow = tile * 128 + row;
+    int latrow, grow;
+    bool valid;
+    if (p.cfg) {
+      latrow = tile * 64 + (row & 63);
+      valid = latrow < p.B;
+      grow = (row >> 6) * p.B + latrow;
+    } else {
+      latrow = prow;
+      grow = prow;
+      valid = prow < p.R;
+    }
+    const size_t xrow = (size_t)prow * XC_COLS;
+    const size_t rp = (size_t)p.rows_pad;
+    uint32_t nstage = 0, nx = 0, nl = 0, nr = 0;
+    DpStat ex;
+    ex.stats = stats; ex.bar = sbar; ex.cnt = 0; ex.q = q; ex.lane = lane; ex.row = row; ex.rank = rank; ex.cur = stats;
+
+    auto acc_wait = [&]() {
+      dp_wait(&acc_full, nstage & 1u, 8);
+      ++nstage;
+      tc_fence_after();
+    };
+    auto signal_x = [&]() {      // the slice just written is part of the next A operand of every CTA of the cluster
+      __threadfence();
+      dp_fence_proxy_all();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t b = smem_u32(&xbar[nx & 1u]);
+#pragma unroll
+        for (int pr = 0; pr < DP_CL; ++pr) dp_arrive_remote(dp_mapa(b, pr));
+      }
+      ++nx;
+    };
+    auto signal_l = [&]() {      // CTA-private hand-over (FFN hidden units)
+      __threadfence();
+      dp_fence_proxy_all();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&lbar[nl & 1u]);
+      ++nl;
+    };
+
+    {   // initial state: x = latents (or the given sample) + learned PE row 0 (mld_denoiser.py:210)
+      float x[32], pe[32];
+      dp_ldvec(p.pe0 + S, pe);
+      if (valid) {
+        const float* src = p.x_in + (size_t)(p.mode == 0 ? latrow : grow) * 256 + S;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(src) + j);
+          x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = 0.f;
+      }
+      dp_st32(tl + TM_LAT, x);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] += pe[i];
+      dp_st32(tl + TM_XRES, x);
+      dp_publish<32>(p.xh, p.xl, xrow + XC_P0 + S, x);
+      signal_x();
+    }
+
+    for (int step = 0; step < p.n_steps; ++step) {
+      const size_t toff = (size_t)step * 512;
+#pragma unroll 1
+      for (int l = 0; l < 5; ++l) {
+        const DpLayerP& L = p.L[l];
+        const int xout_col = l == 0 ? XC_L0 : l == 1 ? XC_L1 : XC_P1;
+        if (l >= 3) {
+          // x = Linear(cat[x, skip]) (cross_attention.py:77-80)
+          acc_wait();
+          float x[32], b[32];
+          dp_ld32(tl, x);
+          dp_ldvec(p.skip_b[l - 3] + S, b);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] += b[i];
+          dp_st32(tl + TM_XRES, x);
+          dp_publish<32>(p.xh, p.xl, xrow + XC_P0 + S, x);
+          signal_x();
+        }
+        // ---- self-attention over {x, cond tokens, time token}, query = token 0 (mdiff_transformer.py:291-297) ----
+        {
+          acc_wait();
+          float pr[NC + 2];
+          {
+            float qv[32], kv[32], v[32];
+            dp_ld32(tl, qv);
+            dp_ld32(tl + 32, kv);
+            dp_ldvec(L.bqkv + S, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) qv[i] += v[i];
+            dp_ldvec(L.bqkv + 256 + S, v);
+            float d = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) d = fmaf(qv[i], kv[i] + v[i], d);
+            pr[0] = d;
+#pragma unroll
+            for (int n = 0; n < NC; ++n) {
+              const float* kc = L.ctab + ((size_t)(0 * NC + n) * 256 + S) * rp + prow;
+              float dn = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) dn = fmaf(qv[i], __ldg(kc + (size_t)i * rp), dn);
+              pr[1 + n] = dn;
+            }
+            dp_ldvec(L.kt + toff + S, v);
+            d = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) d = fmaf(qv[i], v[i], d);
+            pr[NC + 1] = d;
+          }
+          ex.sum<NC + 2>(pr);
+          {
+            float m = pr[0];
+#pragma unroll
+            for (int j = 1; j < NC + 2; ++j) m = fmaxf(m, pr[j]);
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < NC + 2; ++j) { pr[j] = expf(pr[j] - m); sum += pr[j]; }
+            const float inv = 1.0f / sum;
+#pragma unroll
+            for (int j = 0; j < NC + 2; ++j) pr[j] *= inv;
+          }
+          float t0[32];
+          {
+            float xr[32], v[32], w[32];
+            dp_ld32(tl + 64, t0);
+            dp_ld32(tl + TM_XRES, xr);
+            dp_ldvec(L.bqkv + 512 + S, v);
+            dp_ldvec(L.bo + S, w);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t0[i] = xr[i] + w[i] + pr[0] * (t0[i] + v[i]);
+#pragma unroll
+            for (int n = 0; n < NC; ++n) {
+              const float* oc = L.ctab + ((size_t)(1 * NC + n) * 256 + S) * rp + prow;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) t0[i] = fmaf(pr[1 + n], __ldg(oc + (size_t)i * rp), t0[i]);
+            }
+            dp_ldvec(L.kt + toff + 256 + S, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t0[i] = fmaf(pr[NC + 1], v[i], t0[i]);
+          }
+          ex.layernorm(t0, L.n1g + S, L.n1b + S);      // x1 = norm1(x + sa)
+          dp_st32(tl + TM_XRES, t0);
+          dp_publish<32>(p.xh, p.xl, xrow + XC_XA + S, t0);
+          signal_x();
+        }
+        // ---- FFN 256 -> 1024 (ReLU) -> 256, K-split over the cluster ----
+        {
+          acc_wait();
+#pragma unroll 1
+          for (int ch = 0; ch < DP_HS / 32; ++ch) {
+            float f[32], b[32];
+            dp_ld32(tl + ch * 32, f);
+            dp_ldvec(L.b1 + rank * DP_HS + ch * 32, b);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i] + b[i], 0.f);
+            dp_publish<32>(p.xh, p.xl, xrow + XC_FF + rank * DP_HS + ch * 32, f);
+          }
+          signal_l();
+        }
+        {
+          acc_wait();
+          float* mine = p.part + ((size_t)(tile * DP_CL + rank) * 256) * 128 + row;
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float f[32];
+            dp_ld32(tl + ch * 32, f);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) __stcg(mine + (size_t)(ch * 32 + i) * 128, f[i]);
+          }
+          __threadfence();
+          tc_fence_before();
+          __syncwarp();
+          const uint32_t par = nr & 1u;
+          if (lane == 0) {
+            const uint32_t b = smem_u32(&rbar[par * 4 + q]);
+#pragma unroll
+            for (int pr2 = 0; pr2 < DP_CL; ++pr2) dp_arrive_remote(dp_mapa(b, pr2));
+          }
+          dp_wait_cluster(&rbar[par * 4 + q], (nr >> 1) & 1u, 9);
+          ++nr;
+          float t1[32], v[32];
+          dp_ld32(tl + TM_XRES, t1);
+          dp_ldvec(L.b2 + S, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t1[i] += v[i];
+#pragma unroll
+          for (int s = 0; s < DP_CL; ++s) {
+            const float* src = p.part + ((size_t)(tile * DP_CL + s) * 256 + S) * 128 + row;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t1[i] += __ldcg(src + (size_t)i * 128);
+          }
+          ex.layernorm(t1, L.n2g + S, L.n2b + S);      // x2 = norm2(x1 + ffn)
+          dp_st32(tl + TM_XRES, t1);
+          ex.layernorm(t1, L.cng + S, L.cnb + S);      // input norm of the cross-attention
+          dp_publish<32>(p.xh, p.xl, xrow + XC_LN + S, t1);
+          signal_x();
+        }
+        // ---- linear cross-attention to the cond tokens + FiLM (mdiff_transformer.py:219-239, 152-163) ----
+        {
+          acc_wait();
+          float y[32];
+          {
+            float qv[32], v[32];
+            dp_ld32(tl, qv);
+            dp_ldvec(L.bcaq + S, v);
+            float m = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { qv[i] += v[i]; m = fmaxf(m, qv[i]); }
+            float st[2 + NC];
+            st[0] = m;
+            float ssum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { qv[i] = expf(qv[i] - m); ssum += qv[i]; }
+            st[1] = ssum;
+#pragma unroll
+            for (int n = 0; n < NC; ++n) {
+              const float* ks = L.ctab + ((size_t)(2 * NC + n) * 256 + S) * rp + prow;
+              float dn = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) dn = fmaf(qv[i], __ldg(ks + (size_t)i * rp), dn);
+              st[2 + n] = dn;
+            }
+            // combine the per-slice softmax pieces: M = max m_s, s = sum s_s e^(m_s - M), w_n = sum dn_s e^(m_s - M) / s
+            float wn[NC];
+            {
+              constexpr int K0 = (2 + NC) > 4 ? 4 : (2 + NC);
+              float a[K0];
+#pragma unroll
+              for (int k = 0; k < K0; ++k) a[k] = st[k];
+              ex.send<K0>(a);
+              float M = ex.get(0, 0);
+#pragma unroll
+              for (int s = 1; s < DP_CL; ++s) M = fmaxf(M, ex.get(s, 0));
+              float sc[DP_CL];
+              float tot = 0.f;
+#pragma unroll
+              for (int s = 0; s < DP_CL; ++s) { sc[s] = expf(ex.get(s, 0) - M); tot = fmaf(ex.get(s, 1), sc[s], tot); }
+#pragma unroll
+              for (int n = 0; n < NC && n < 2; ++n) {
+                float t = 0.f;
+#pragma unroll
+                for (int s = 0; s < DP_CL; ++s) t = fmaf(ex.get(s, 2 + n), sc[s], t);
+                wn[n] = t;
+              }
+              if constexpr (NC > 2) {
+                float a2[NC - 2];
+#pragma unroll
+                for (int k = 0; k < NC - 2; ++k) a2[k] = st[4 + k];
+                ex.send<NC - 2>(a2);
+#pragma unroll
+                for (int n = 2; n < NC; ++n) {
+                  float t = 0.f;
+#pragma unroll
+                  for (int s = 0; s < DP_CL; ++s) t = fmaf(ex.get(s, n - 2), sc[s], t);
+                  wn[n] = t;
+                }
+              }
+              const float inv = 1.0f / tot;
+#pragma unroll
+              for (int n = 0; n < NC; ++n) wn[n] *= inv;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = 0.f;
+#pragma unroll
+            for (int n = 0; n < NC; ++n) {
+              const float* vv = L.ctab + ((size_t)(3 * NC + n) * 256 + S) * rp + prow;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) y[i] = fmaf(wn[n], __ldg(vv + (size_t)i * rp), y[i]);
+            }
+          }
+          ex.layernorm(y, L.cpg + S, L.cpb + S);
+          {
+            float sc[32], sh[32];
+            dp_ldvec(L.film_ca + toff + S, sc);
+            dp_ldvec(L.film_ca + toff + 256 + S, sh);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = silu(y[i] * (1.0f + sc[i]) + sh[i]);
+          }
+          dp_publish<32>(p.xh, p.xl, xrow + XC_HB0 + S, y);
+          signal_x();
+        }
+        {   // x3 = x2 + out(h)
+          acc_wait();
+          float x[32], xr[32], b[32];
+          dp_ld32(tl, x);
+          dp_ld32(tl + TM_XRES, xr);
+          dp_ldvec(L.bcaout + S, b);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] += b[i] + xr[i];
+          dp_st32(tl + TM_XRES, x);
+          dp_publish<32>(p.xh, p.xl, xrow + XC_X3 + S, x);
+          signal_x();
+        }
+        // ---- FFN 256 -> 128 (GELU) -> 256 + FiLM (mdiff_transformer.py:241-254) ----
+        {
+          acc_wait();
+          float f[32];
+          dp_ld32(tl, f);                 // columns [0, 16) are this CTA's hidden units
+          float g[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) g[i] = gelu_erf(f[i] + __ldg(L.bf1 + rank * DP_GS + i));
+          dp_publish<16>(p.xh, p.xl, xrow + XC_G + rank * DP_GS, g);
+          signal_x();
+        }
+        {
+          acc_wait();
+          float y[32], b[32];
+          dp_ld32(tl, y);
+          dp_ldvec(L.bf2 + S, b);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) y[i] += b[i];
+          ex.layernorm(y, L.fpg + S, L.fpb + S);
+          float sc[32], sh[32];
+          dp_ldvec(L.film_ff + toff + S, sc);
+          dp_ldvec(L.film_ff + toff + 256 + S, sh);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) y[i] = silu(y[i] * (1.0f + sc[i]) + sh[i]);
+          dp_publish<32>(p.xh, p.xl, xrow + XC_HB1 + S, y);
+          signal_x();
+        }
+        {   // block output = x3 + out(h)
+          acc_wait();
+          float x[32], xr[32], b[32];
+          dp_ld32(tl, x);
+          dp_ld32(tl + TM_XRES, xr);
+          dp_ldvec(L.bfout + S, b);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] += b[i] + xr[i];
+          if (l < 4) {
+            dp_st32(tl + TM_XRES, x);
+            dp_publish<32>(p.xh, p.xl, xrow + xout_col + S, x);
+            signal_x();
+          } else {
+            // final LayerNorm (cross_attention.py:82), then CFG combine + DDIM update (mld.py:488-497)
+            ex.layernorm(x, p.fng + S, p.fnb + S);
+            if (p.mode == 1) {
+              if (valid) {
+                float4* dst = reinterpret_cast<float4*>(p.out + (size_t)grow * 256 + S);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+              }
+            } else {
+              if (p.cfg) {
+                // rows r (uncond) and r + 64 (cond) hold the two guidance branches of one latent; both halves apply the
+                // same update.  The statistics buffers are quiescent here: no peer can start the next exchange before
+                // this CTA has published the next step's input.
+                float* sw = stats;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sw[i * 128 + row] = x[i];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const float gs = __ldg(p.gscale);
+                const bool is_u = row < 64;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const float o = sw[i * 128 + (row ^ 64)];
+                  const float eu = is_u ? x[i] : o, ec = is_u ? o : x[i];
+                  x[i] = __fadd_rn(eu, __fmul_rn(gs, __fsub_rn(ec, eu)));
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+              }
+              const float c0 = __ldg(p.coef + step * 4), c1 = __ldg(p.coef + step * 4 + 1), c2 = __ldg(p.coef + step * 4 + 2),
+                          c3 = __ldg(p.coef + step * 4 + 3);
+              float lt[32];
+              dp_ld32(tl + TM_LAT, lt);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float x0 = __fdiv_rn(__fsub_rn(lt[i], __fmul_rn(c0, x[i])), c1);
+                lt[i] = __fadd_rn(__fmul_rn(c2, x0), __fmul_rn(c3, x[i]));
+              }
+              if (step == p.n_steps - 1) {
+                if (valid && (!p.cfg || row < 64)) {
+                  float4* dst = reinterpret_cast<float4*>(p.out + (size_t)latrow * 256 + S);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) dst[j] = make_float4(lt[4 * j], lt[4 * j + 1], lt[4 * j + 2], lt[4 * j + 3]);
+                }
+              } else {
+                dp_st32(tl + TM_LAT, lt);
+                float pe[32];
+                dp_ldvec(p.pe0 + S, pe);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) lt[i] += pe[i];
+                dp_st32(tl + TM_XRES, lt);
+                dp_publish<32>(p.xh, p.xl, xrow + XC_P0 + S, lt);
+                signal_x();
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // no CTA leaves while a peer may still arrive on its barriers / write its statistics buffers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// transposes the cond-token projections into the per-row tables the epilogue reads column by column:
+//   tab[which][n][col][prow], which = 0: k, 1: ov (self-attention; kov rows n R + grow: k | ov), 2: softmax over the
+//   tokens of the cross-attention key, 3: its value (kv2: key | value).  Rows beyond the batch are zero.
+__global__ void dp_ctab_kernel(const float* __restrict__ kov, const float* __restrict__ kv2, float* __restrict__ tab, int Nc, int B,
+                               int R, int cfg, int rows_pad) {
+  const int prow = blockIdx.x * 32 + threadIdx.x;
+  const int col = blockIdx.y * 8 + threadIdx.y;
+  if (prow >= rows_pad) return;
+  const int tile = prow >> 7, r = prow & 127;
+  int grow;
+  bool valid;
+  if (cfg) {
+    const int latrow = tile * 64 + (r & 63);
+    valid = latrow < B;
+    grow = (r >> 6) * B + latrow;
+  } else {
+    grow = prow;
+    valid = prow < R;
+  }
+  float k2[SEEME_MAX_COND_TOKENS];
+  float m = -INFINITY;
+  for (int n = 0; n < Nc; ++n) {
+    k2[n] = valid ? kv2[((size_t)n * R + grow) * 512 + col] : 0.f;
+    m = fmaxf(m, k2[n]);
+  }
+  float s = 0.f;
+  for (int n = 0; n < Nc; ++n) { k2[n] = expf(k2[n] - m); s += k2[n]; }
+  const float inv = 1.0f / s;
+  for (int n = 0; n < Nc; ++n) {
+    const size_t src = ((size_t)n * R + grow) * 512 + col;
+    const size_t rp = (size_t)rows_pad;
+    tab[((size_t)(0 * Nc + n) * 256 + col) * rp + prow] = valid ? kov[src] : 0.f;
+    tab[((size_t)(1 * Nc + n) * 256 + col) * rp + prow] = valid ? kov[src + 256] : 0.f;
+    tab[((size_t)(2 * Nc + n) * 256 + col) * rp + prow] = valid ? k2[n] * inv : 0.f;
+    tab[((size_t)(3 * Nc + n) * 256 + col) * rp + prow] = valid ? kv2[src + 256] : 0.f;
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+struct DenPersist {
+  Arena arena;
+  int max_tiles = 0, rows_pad_max = 0;
+  uint8_t* tape = nullptr;
+  size_t tape_cta_bytes = 0;
+  DpUnit* d_units = nullptr;
+  int n_units = 0;
+  __nv_bfloat16 *xh = nullptr, *xl = nullptr;
+  float* part = nullptr;
+  float* ctab[5] = {};
+  float* bqkv[5] = {};           // [768]: bq / 16 | bk | W_o b_v
+  float* wkov_f32[5] = {};       // [512,256]: W_k | W_o W_v  (time-token table GEMM)
+  float* bkov[5] = {};           // [512]
+  float* bk2v2[5] = {};          // [512]
+  float* tkov[5] = {};           // [MAX_STEPS,512]
+  PackedLinear Wkov[5], Wk2v2[5];
+  ActBuf condb, tnb;             // bf16 (hi, lo) of the cond tokens / of their text_norm
+  CUtensorMap map_hi, map_lo;
+};
+
+static inline uint16_t f2bf(float x) {    // round to nearest even, like __float2bfloat16_rn (finite inputs)
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline float bf2f(uint16_t h) {
+  const uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+namespace {
+struct HostW {      // host copy of one fp32 matrix [rows, ld]
+  std::vector<float> v;
+  int ld = 0;
+};
+// appends the blobs of one unit: rows `rowsel` (n of them) of W, K-blocks [k0, k0 + 64 nkb)
+void append_unit(std::vector<uint8_t>& tape, const HostW& W, const std::vector<int>& rowsel, int k0, int nkb) {
+  const int n = (int)rowsel.size();
+  for (int kb = 0; kb < nkb; ++kb) {
+    const size_t base = tape.size();
+    tape.resize(base + (size_t)n * 256);
+    uint8_t* hi = tape.data() + base;
+    uint8_t* lo = hi + (size_t)n * 128;
+    for (int r = 0; r < n; ++r)
+      for (int k = 0; k < 64; ++k) {
+        const float x = W.v[(size_t)rowsel[r] * W.ld + k0 + kb * 64 + k];
+        const uint16_t h = f2bf(x);
+        const uint16_t l = f2bf(x - bf2f(h));
+        const size_t off = (size_t)r * 128 + ((((k >> 3) ^ (r & 7)) << 4) | ((k & 7) << 1));   // SWIZZLE_128B image
+        memcpy(hi + off, &h, 2);
+        memcpy(lo + off, &l, 2);
+      }
+  }
+}
+std::vector<int> iota_rows(int first, int n) {
+  std::vector<int> r(n);
+  for (int i = 0; i < n; ++i) r[i] = first + i;
+  return r;
+}
+}  // namespace
+
+int den_persist_create(seeme_denoiser* h) {
+  DenPersist* P = new DenPersist();
+  h->persist = P;
+  P->max_tiles = (h->max_rows + 127) / 128;
+  P->rows_pad_max = P->max_tiles * 128;
+  // host copies of the GEMM weights (the q rows already carry the 1/16 attention scale)
+  auto fetch = [&](const float* d, size_t n, std::vector<float>& out) -> int {
+    out.resize(n);
+    SEEME_CUDA(cudaMemcpy(out.data(), d, n * 4, cudaMemcpyDeviceToHost));
+    return SEEME_OK;
+  };
+  std::vector<HostW> Wqkv(5), Wl1(5), Wl2(5), Wcaq(5), Wcaout(5), Wf1(5), Wf2(5), Wfout(5);
+  HostW Wskip[2];
+  std::vector<std::vector<float>> bqkv(5), bkov(5);
+  for (int l = 0; l < 5; ++l) {
+    std::vector<float> in_w, in_b, out_w;
+    SEEME_TRY(fetch(blkw(h, l, SA_IN_W), 768 * 256, in_w));
+    SEEME_TRY(fetch(blkw(h, l, SA_IN_B), 768, in_b));
+    SEEME_TRY(fetch(blkw(h, l, SA_OUT_W), 256 * 256, out_w));
+    Wqkv[l].v.assign(768 * 256, 0.f);
+    Wqkv[l].ld = 256;
+    memcpy(Wqkv[l].v.data(), in_w.data(), 512 * 256 * 4);          // q, k rows
+    // W_ov = W_o W_v and b_ov = W_o b_v in double precision
+    std::vector<double> acc(256);
+    std::vector<float> bov(256);
+    for (int n = 0; n < 256; ++n) {
+      for (int k = 0; k < 256; ++k) acc[k] = 0.0;
+      double bacc = 0.0;
+      for (int j = 0; j < 256; ++j) {
+        const double wo = out_w[(size_t)n * 256 + j];
+        const float* wv = &in_w[(size_t)(512 + j) * 256];
+        for (int k = 0; k < 256; ++k) acc[k] += wo * (double)wv[k];
+        bacc += wo * (double)in_b[512 + j];
+      }
+      for (int k = 0; k < 256; ++k) Wqkv[l].v[(size_t)(512 + n) * 256 + k] = (float)acc[k];
+      bov[n] = (float)bacc;
+    }
+    for (int n = 0; n < 256; ++n) in_b[512 + n] = bov[n];
+    bqkv[l] = in_b;
+    bkov[l].assign(in_b.begin() + 256, in_b.end());
+    SEEME_TRY(fetch(blkw(h, l, SA_L1_W), 1024 * 256, Wl1[l].v)); Wl1[l].ld = 256;
+    SEEME_TRY(fetch(blkw(h, l, SA_L2_W), 256 * 1024, Wl2[l].v)); Wl2[l].ld = 1024;
+    SEEME_TRY(fetch(blkw(h, l, CA_Q_W), 256 * 256, Wcaq[l].v)); Wcaq[l].ld = 256;
+    SEEME_TRY(fetch(blkw(h, l, CA_OUT_W), 256 * 256, Wcaout[l].v)); Wcaout[l].ld = 256;
+    SEEME_TRY(fetch(blkw(h, l, FF_L1_W), 128 * 256, Wf1[l].v)); Wf1[l].ld = 256;
+    SEEME_TRY(fetch(blkw(h, l, FF_L2_W), 256 * 128, Wf2[l].v)); Wf2[l].ld = 128;
+    SEEME_TRY(fetch(blkw(h, l, FF_OUT_W), 256 * 256, Wfout[l].v)); Wfout[l].ld = 256;
+  }
+  for (int i = 0; i < 2; ++i) { SEEME_TRY(fetch(h->w[DN_LB0_W + 2 * i], 256 * 512, Wskip[i].v)); Wskip[i].ld = 512; }
+
+  // unit list of one step and the tapes of the 8 CTAs (identical unit order, different rows)
+  std::vector<DpUnit> units;
+  std::vector<std::vector<uint8_t>> tapes(DP_CL);
+  for (int c = 0; c < DP_CL; ++c) {
+    std::vector<uint8_t>& T = tapes[c];
+    T.reserve(2700000);
+    const int S = c * DP_NS;
+    auto add = [&](const HostW& W, const std::vector<int>& rows, int k0, int nkb, DpUnit u) {
+      u.n = (int)rows.size();
+      u.nkb = nkb;
+      u.w_off = (unsigned)T.size();
+      if (c == 0) units.push_back(u);
+      append_unit(T, W, rows, k0, nkb);
+    };
+    auto U = [&](int a_col, int wait) {
+      DpUnit u;
+      memset(&u, 0, sizeof(u));
+      u.a_col = a_col; u.wait = wait; u.nkb1 = 1 << 20; u.release_a = 1; u.last = 1;
+      return u;
+    };
+    for (int l = 0; l < 5; ++l) {
+      const int xin = l == 0 ? XC_P0 : l == 1 ? XC_L0 : l == 2 ? XC_L1 : XC_P0;
+      if (l >= 3) {     // skip fusion: K = 512 = [current x (P1) | saved block output]
+        DpUnit u = U(XC_P1, 1);
+        u.nkb1 = 4;
+        u.a_col2 = l == 3 ? XC_L1 : XC_L0;
+        add(Wskip[l - 3], iota_rows(S, DP_NS), 0, 8, u);
+      }
+      {   // q | k slices (N = 64), then ov slice (N = 32) on the same A
+        std::vector<int> r = iota_rows(S, DP_NS), r2 = iota_rows(256 + S, DP_NS);
+        r.insert(r.end(), r2.begin(), r2.end());
+        DpUnit u = U(xin, 1);
+        u.release_a = 0; u.last = 0;
+        add(Wqkv[l], r, 0, 4, u);
+        DpUnit v = U(xin, 0);
+        v.reuse_a = 1; v.acc_col = 64;
+        add(Wqkv[l], iota_rows(512 + S, DP_NS), 0, 4, v);
+      }
+      for (int j = 0; j < DP_HS / 64; ++j) {   // hidden units [c HS + 64 j, +64)
+        DpUnit u = U(XC_XA, j == 0 ? 1 : 0);
+        u.reuse_a = j > 0; u.acc_col = 64 * j;
+        u.release_a = j == DP_HS / 64 - 1; u.last = u.release_a;
+        add(Wl1[l], iota_rows(c * DP_HS + 64 * j, 64), 0, 4, u);
+      }
+      for (int j = 0; j < 4; ++j) {            // partial result columns [64 j, +64) over this CTA's K slice
+        DpUnit u = U(XC_FF, j == 0 ? 2 : 0);
+        u.a_rstride = DP_HS;
+        u.reuse_a = j > 0; u.acc_col = 64 * j;
+        u.release_a = j == 3; u.last = j == 3;
+        add(Wl2[l], iota_rows(64 * j, 64), c * DP_HS, DP_HS / 64, u);
+      }
+      add(Wcaq[l], iota_rows(S, DP_NS), 0, 4, U(XC_LN, 1));
+      add(Wcaout[l], iota_rows(S, DP_NS), 0, 4, U(XC_HB0, 1));
+      add(Wf1[l], iota_rows(c * DP_GS, DP_GS), 0, 4, U(XC_X3, 1));
+      add(Wf2[l], iota_rows(S, DP_NS), 0, 2, U(XC_G, 1));
+      add(Wfout[l], iota_rows(S, DP_NS), 0, 4, U(XC_HB1, 1));
+    }
+  }
+  P->n_units = (int)units.size();
+  SEEME_REQUIRE(P->n_units <= DP_MAX_UNITS, SEEME_EINVAL, "den_persist: %d units", P->n_units);
+  P->tape_cta_bytes = tapes[0].size();
+  for (int c = 1; c < DP_CL; ++c)
+    SEEME_REQUIRE(tapes[c].size() == P->tape_cta_bytes, SEEME_EINVAL, "den_persist: tape size mismatch");
+
+  const size_t Rp = (size_t)P->rows_pad_max, NCM = SEEME_MAX_COND_TOKENS;
+  size_t bytes = pad256(P->tape_cta_bytes * DP_CL) + pad256(sizeof(DpUnit) * DP_MAX_UNITS) + 2 * pad256(Rp * XC_COLS * 2) +
+                 pad256((size_t)P->max_tiles * DP_CL * 256 * 128 * 4) + 5 * pad256(4 * NCM * 256 * Rp * 4) +
+                 5 * (pad256(768 * 4) + pad256(512 * 256 * 4) + 2 * pad256(512 * 4) + pad256((size_t)DEN_MAX_STEPS * 512 * 4)) +
+                 5 * 2 * 2 * pad256(512 * 256 * 2) + 5 * pad256(512 * 256 * 4) + 4 * pad256(NCM * (size_t)h->max_rows * 256 * 2) + 65536;
+  SEEME_TRY(P->arena.init(bytes));
+  P->tape = P->arena.take<uint8_t>(P->tape_cta_bytes * DP_CL);
+  P->d_units = P->arena.take<DpUnit>(DP_MAX_UNITS);
+  P->xh = P->arena.take<__nv_bfloat16>(Rp * XC_COLS);
+  P->xl = P->arena.take<__nv_bfloat16>(Rp * XC_COLS);
+  P->part = P->arena.take<float>((size_t)P->max_tiles * DP_CL * 256 * 128);
+  SEEME_REQUIRE(P->part, SEEME_ENOMEM, "den_persist: arena exhausted");
+  for (int c = 0; c < DP_CL; ++c)
+    SEEME_CUDA(cudaMemcpy(P->tape + (size_t)c * P->tape_cta_bytes, tapes[c].data(), P->tape_cta_bytes, cudaMemcpyHostToDevice));
+  SEEME_CUDA(cudaMemcpy(P->d_units, units.data(), sizeof(DpUnit) * units.size(), cudaMemcpyHostToDevice));
+  SEEME_CUDA(cudaMemset(P->xh, 0, Rp * XC_COLS * 2));
+  SEEME_CUDA(cudaMemset(P->xl, 0, Rp * XC_COLS * 2));
+  for (int l = 0; l < 5; ++l) {
+    P->ctab[l] = P->arena.take<float>(4 * NCM * 256 * Rp);
+    P->bqkv[l] = P->arena.take<float>(768);
+    P->wkov_f32[l] = P->arena.take<float>(512 * 256);
+    P->bkov[l] = P->arena.take<float>(512);
+    P->bk2v2[l] = P->arena.take<float>(512);
+    P->tkov[l] = P->arena.take<float>((size_t)DEN_MAX_STEPS * 512);
+    SEEME_REQUIRE(P->tkov[l], SEEME_ENOMEM, "den_persist: arena exhausted");
+    SEEME_CUDA(cudaMemcpy(P->bqkv[l], bqkv[l].data(), 768 * 4, cudaMemcpyHostToDevice));
+    SEEME_CUDA(cudaMemcpy(P->wkov_f32[l], Wqkv[l].v.data() + 256 * 256, 512 * 256 * 4, cudaMemcpyHostToDevice));
+    SEEME_CUDA(cudaMemcpy(P->bkov[l], bkov[l].data(), 512 * 4, cudaMemcpyHostToDevice));
+    SEEME_CUDA(cudaMemcpy(P->bk2v2[l], blkw(h, l, CA_K_B), 256 * 4, cudaMemcpyDeviceToDevice));
+    SEEME_CUDA(cudaMemcpy(P->bk2v2[l] + 256, blkw(h, l, CA_V_B), 256 * 4, cudaMemcpyDeviceToDevice));
+    float* k2v2 = P->arena.take<float>(512 * 256);
+    SEEME_REQUIRE(k2v2, SEEME_ENOMEM, "den_persist: arena exhausted");
+    SEEME_CUDA(cudaMemcpy(k2v2, blkw(h, l, CA_K_W), 256 * 256 * 4, cudaMemcpyDeviceToDevice));
+    SEEME_CUDA(cudaMemcpy(k2v2 + 256 * 256, blkw(h, l, CA_V_W), 256 * 256 * 4, cudaMemcpyDeviceToDevice));
+    SEEME_TRY(pack_linear(P->arena, P->Wkov[l], P->wkov_f32[l], 256, 512, 256, P->bkov[l]));
+    SEEME_TRY(pack_linear(P->arena, P->Wk2v2[l], k2v2, 256, 512, 256, P->bk2v2[l]));
+  }
+  auto mk = [&](ActBuf& a) {
+    a.ld = 256; a.f = nullptr;
+    a.h = P->arena.take<__nv_bfloat16>(NCM * (size_t)h->max_rows * 256);
+    a.l = P->arena.take<__nv_bfloat16>(NCM * (size_t)h->max_rows * 256);
+  };
+  mk(P->condb);
+  mk(P->tnb);
+  SEEME_REQUIRE(P->tnb.l, SEEME_ENOMEM, "den_persist: arena exhausted (cond buffers)");
+  SEEME_TRY(umma_tensor_map_bf16(&P->map_hi, P->xh, P->rows_pad_max, XC_COLS, XC_COLS, 128));
+  SEEME_TRY(umma_tensor_map_bf16(&P->map_lo, P->xl, P->rows_pad_max, XC_COLS, XC_COLS, 128));
+  SEEME_CUDA(cudaFuncSetAttribute(den_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM));
+  SEEME_CUDA(cudaFuncSetAttribute(den_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM));
+  SEEME_CUDA(cudaFuncSetAttribute(den_persist_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM));
+  SEEME_CUDA(cudaFuncSetAttribute(den_persist_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM));
+  SEEME_CUDA(cudaDeviceSynchronize());
+  return SEEME_OK;
+}
+
+void den_persist_destroy(seeme_denoiser* h) {
+  if (!h->persist) return;
+  h->persist->arena.release();
+  delete h->persist;
+  h->persist = nullptr;
+}
+
+int den_persist_build_tables(seeme_denoiser* h, int n, cudaStream_t s) {
+  DenPersist* P = h->persist;
+  for (int l = 0; l < 5; ++l)   // (k | ov) of the time token: rows of [W_k | W_o W_v]
+    SEEME_TRY(gemm_f32(gemm_params(h->temb, 256, P->wkov_f32[l], 256, P->bkov[l], P->tkov[l], 512, n, 512, 256), s));
+  return SEEME_OK;
+}
+
+int den_persist_run(seeme_denoiser* h, int mode, const float* x_in, int Nc, int B, int R, int cfg, int n_steps, float* out,
+                    cudaStream_t s) {
+  DenPersist* P = h->persist;
+  const int tiles = cfg ? (B + 63) / 64 : (R + 127) / 128;
+  SEEME_REQUIRE(tiles <= P->max_tiles, SEEME_ECAP, "den_persist: %d row tiles exceed capacity %d", tiles, P->max_tiles);
+  const int rows_pad = tiles * 128;
+  const int rows = Nc * R;
+  // cond-token projections, once per run, on tensor cores (H3): (k | ov) for the self-attention, (key | value) of
+  // text_norm(cond) for the cross-attention
+  SEEME_TRY(to_bf16_split(h->cond, 256, rows, 256, P->condb.h, P->condb.l, 256, 0, s));
+  for (int l = 0; l < 5; ++l) {
+    ActBuf o1; o1.f = h->kvc[l]; o1.ld = 512;
+    SEEME_TRY(run_linear(P->Wkov[l], P->condb, nullptr, rows, ACT_NONE, nullptr, 0, o1, 3, s));
+    SEEME_TRY(layernorm256(h->cond, nullptr, 0, blkw(h, l, CA_TN_W), blkw(h, l, CA_TN_B), h->tn, rows, s));
+    SEEME_TRY(to_bf16_split(h->tn, 256, rows, 256, P->tnb.h, P->tnb.l, 256, 0, s));
+    ActBuf o2; o2.f = h->kv2[l]; o2.ld = 512;
+    SEEME_TRY(run_linear(P->Wk2v2[l], P->tnb, nullptr, rows, ACT_NONE, nullptr, 0, o2, 3, s));
+    dp_ctab_kernel<<<dim3(rows_pad / 32, 32), dim3(32, 8), 0, s>>>(h->kvc[l], h->kv2[l], P->ctab[l], Nc, B, R, cfg, rows_pad);
+    SEEME_LAUNCH_CHECK();
+  }
+  DpParams p;
+  memset(&p, 0, sizeof(p));
+  p.map_hi = P->map_hi;
+  p.map_lo = P->map_lo;
+  for (int l = 0; l < 5; ++l) {
+    DpLayerP& L = p.L[l];
+    L.bqkv = P->bqkv[l]; L.bo = blkw(h, l, SA_OUT_B); L.n1g = blkw(h, l, SA_N1_W); L.n1b = blkw(h, l, SA_N1_B);
+    L.b1 = blkw(h, l, SA_L1_B); L.b2 = blkw(h, l, SA_L2_B); L.n2g = blkw(h, l, SA_N2_W); L.n2b = blkw(h, l, SA_N2_B);
+    L.cng = blkw(h, l, CA_N_W); L.cnb = blkw(h, l, CA_N_B); L.bcaq = blkw(h, l, CA_Q_B);
+    L.cpg = blkw(h, l, CA_PN_W); L.cpb = blkw(h, l, CA_PN_B); L.bcaout = blkw(h, l, CA_OUT_B);
+    L.bf1 = blkw(h, l, FF_L1_B); L.bf2 = blkw(h, l, FF_L2_B); L.fpg = blkw(h, l, FF_PN_W); L.fpb = blkw(h, l, FF_PN_B);
+    L.bfout = blkw(h, l, FF_OUT_B);
+    L.kt = P->tkov[l]; L.film_ca = h->film_ca[l]; L.film_ff = h->film_ff[l];
+    L.ctab = P->ctab[l];
+  }
+  p.skip_b[0] = h->w[DN_LB0_B]; p.skip_b[1] = h->w[DN_LB1_B];
+  p.fng = h->w[DN_NORM_W]; p.fnb = h->w[DN_NORM_B]; p.pe0 = h->w[DN_PE];
+  p.tape = P->tape; p.tape_cta_bytes = P->tape_cta_bytes;
+  p.units = P->d_units; p.n_units = P->n_units;
+  p.xh = P->xh; p.xl = P->xl; p.part = P->part;
+  p.x_in = x_in; p.out = out; p.coef = h->d_coef; p.gscale = h->d_gscale;
+  p.B = B; p.R = R; p.cfg = cfg; p.n_steps = n_steps; p.mode = mode; p.rows_pad = rows_pad;
+  {
+    ProfScope prof(PROF_SAMPLER_GRAPH, s);
+    const dim3 grid(tiles * DP_CL), block(DP_THREADS);
+    switch (Nc) {
+      case 1: den_persist_kernel<1><<<grid, block, DP_SMEM, s>>>(p); break;
+      case 2: den_persist_kernel<2><<<grid, block, DP_SMEM, s>>>(p); break;
+      case 3: den_persist_kernel<3><<<grid, block, DP_SMEM, s>>>(p); break;
+      default: den_persist_kernel<4><<<grid, block, DP_SMEM, s>>>(p); break;
+    }
+  }
+  SEEME_LAUNCH_CHECK();
+  return SEEME_OK;
+}
+
+}  // namespace seeme

@@ -37,10 +37,12 @@ class PendingEval:
     def __init__(self, model, stream, slot):
         self._model, self.stream, self.slot = model, stream, slot
         self._rs_set = self.last_vertices = self.last_latent = self.event = None
-        self._ctx = self._enc_event = None
+        self._ctx = self._enc_event = self._error = None
         self._callbacks = []
 
     def _ready(self):
+        if self._error is not None:
+            raise self._error
         if self._rs_set is None:
             self._model._flush_group()
         return self
@@ -223,10 +225,10 @@ class MLD(nn.Module):
             self.__dict__["_coef"] = self.scheduler.step_coefficients()
             self.__dict__["_sinus"] = time_sinusoid(self.scheduler.timesteps)
         op = self.denoiser.op if op is None else op
-        tables = self.__dict__.setdefault("_table_keys", {})          # per kernel-side handle (one per lane)
-        if tables.get(id(op)) != tuple(ts):
+        # the key lives on the kernel-side handle object (one per lane / slot), not in an id()-keyed dict: a rebuilt handle
+        # starts without it, and DenoiserOp.forward / set_time_table keep it in step with the C-side table
+        if getattr(op, "table_key", None) != tuple(ts):
             op.set_time_table(ts, self.__dict__["_sinus"])
-            tables[id(op)] = tuple(ts)
         cond = encoder_hidden_states.permute(1, 0, 2).contiguous()         # [Nc,B',256] as the denoiser receives it
         z = op.sample(latents.reshape(bsz, 256), cond, self.guidance_scale, ts, self.__dict__["_coef"])
         return z.view(bsz, 1, 256).permute(1, 0, 2)
@@ -370,6 +372,12 @@ class MLD(nn.Module):
             with torch.cuda.stream(st):
                 b = tuple((x.to(dev, non_blocking=True) if torch.is_tensor(x) and not x.is_cuda else x) for x in batch)
                 n = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and not v.is_cuda else v) for k, v in (noise or {}).items()}
+                # device-resident inputs were allocated on the caller's stream but are read here, on the slot's stream, up to
+                # tens of ms later (the decode stage reads feats / transl / beta after the sampler): tell the caching allocator,
+                # or a caller that drops the batch could see its memory handed out while the slot still reads it
+                for x in list(b) + list(n.values()):
+                    if torch.is_tensor(x) and x.is_cuda:
+                        x.record_stream(st)
                 pend._ctx = self._stage_encode(b, n, lengths_host)
                 pend._enc_event = torch.cuda.Event()
                 pend._enc_event.record(st)
@@ -392,6 +400,20 @@ class MLD(nn.Module):
         dev = members[0]._ctx["cond_emb"].device
         lane = _m._LANE[0]
         try:
+            self._flush_members(members, dev)
+        except BaseException as exc:
+            # members whose decode stage was never enqueued would otherwise fail later with an AttributeError on their
+            # missing event, hiding this error: they re-raise it from result() / synchronize()
+            for m in members:
+                if m._rs_set is None:
+                    m._error = exc
+            raise
+        finally:
+            _m._LANE[0] = lane
+
+    def _flush_members(self, members, dev):
+        from . import modules as _m
+        if True:
             if len(members) == 1:
                 m = members[0]
                 _m._LANE[0] = 1000 + m.slot
@@ -448,8 +470,6 @@ class MLD(nn.Module):
                     m.event = torch.cuda.Event()
                     m.event.record(m.stream)
                     m._rs_set, m._ctx = rs, None
-        finally:
-            _m._LANE[0] = lane
 
     def _encode_uncond(self, B: int, T: int, nfeats: int, lengths, eps, dev):
         """``vae.encode(zeros_like(feats), lengths)`` of the CFG branch (mld.py:1280-1290).  The input is all zeros, so the

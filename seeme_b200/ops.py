@@ -213,9 +213,11 @@ class DenoiserOp(_Handle):
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().seeme_denoiser_create(C.byref(self.h), _ptr_array(ts), len(ts), max_rows), "seeme_denoiser_create")
         self.max_rows = max_rows
+        self.table_key = None          # timesteps the C-side tables hold, when they were built from a host sinusoid
 
     def set_time_table(self, timesteps: Sequence[int], sinusoid: Optional[torch.Tensor] = None):
         n = len(timesteps)
+        self.table_key = tuple(int(t) for t in timesteps) if sinusoid is not None else None
         ts = (C.c_int32 * n)(*[int(t) for t in timesteps])
         sp = None
         if sinusoid is not None:
@@ -230,6 +232,8 @@ class DenoiserOp(_Handle):
         sample, cond = _dev_f32(sample, "sample"), _dev_f32(cond, "cond")
         R = sample.shape[0]
         Nc = cond.shape[0]
+        if self.table_key != (int(timestep),):
+            self.table_key = None      # the library rebuilds its table for [timestep] with its own sinusoid
         out = torch.empty_like(sample)
         with torch.cuda.device(sample.device):
             _lib.check(_lib.lib().seeme_denoiser_forward(self.h, sample.data_ptr(), int(timestep), cond.data_ptr(), Nc, R,
