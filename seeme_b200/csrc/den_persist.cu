@@ -46,6 +46,7 @@ static_assert(DP_NS == 32, "the epilogues are written for 32-column slices (CL =
 // columns of the per-cluster exchange matrix [128 rows x XC_COLS] (bf16 hi and lo copies)
 enum { XC_P0 = 0, XC_P1 = 256, XC_L0 = 512, XC_L1 = 768, XC_XA = 1024, XC_LN = 1280, XC_HB0 = 1536, XC_HB1 = 1792,
        XC_X3 = 2048, XC_G = 2304, XC_FF = 2432, XC_COLS = 3456 };
+constexpr int XC_KB = XC_COLS / 64;     // K-blocks (64 columns) per tile
 constexpr int TM_XRES = 256, TM_LAT = 256 + DP_NS;   // tensor-memory columns of the per-row state
 
 struct DpUnit {             // one GEMM unit: acc[:, acc_col : acc_col + n] = A[128, 64 nkb] . W_unit^T
@@ -61,24 +62,31 @@ constexpr int DP_MAX_UNITS = 80;
 
 struct DpLayerP {
   const float *bqkv, *bo, *n1g, *n1b, *b1, *b2, *n2g, *n2b, *cng, *cnb, *bcaq, *cpg, *cpb, *bcaout, *bf1, *bf2, *fpg, *fpb, *bfout;
-  const float *kt, *film_ca, *film_ff;   // [steps][512]: (k | ov) of the time token, FiLM (scale | shift)
-  const float* ctab;                     // [4][Nc][256][rows_pad]: k, ov (self-attention), softmax_n(key), value (cross-attention)
+  // [steps][512]: (k | ov) of the time token; FiLM folded into the LayerNorm affine: (g (1 + scale) | b (1 + scale) + shift)
+  const float *kt, *film_ca, *film_ff;
+  const float* ctab;                     // [tile][4][Nc][256][128 rows]: k, ov (self-attention), softmax_n(key), value (cross-attention)
 };
 struct DpParams {
-  CUtensorMap map_hi, map_lo;
   DpLayerP L[5];
   const float *skip_b[2], *fng, *fnb, *pe0;
   const uint8_t* tape;
   unsigned long long tape_cta_bytes;
   const DpUnit* units;
   int n_units;
-  __nv_bfloat16 *xh, *xl;
+  uint8_t* ximg;        // exchange matrix as shared-memory tile images: [tile][XC_KB K-blocks][hi 16 KB | lo 16 KB]
   float* part;          // [tiles][CL][256][128]
   const float* x_in;
   float* out;
   const float *coef, *gscale;
   int B, R, cfg, n_steps, mode, rows_pad;
+  unsigned long long* trace;   // diagnostics (SEEME_DP_TRACE): 3 roles x 4096 (clock64 << 8 | event) of cluster 0 / rank 0 at trace_step
+  int trace_step;
 };
+#define DP_TR(role, code)                                                                                       \
+  do {                                                                                                          \
+    if (p.trace && blockIdx.x == 0 && step == p.trace_step && tr_n < 4096)                                      \
+      p.trace[(role) * 4096 + tr_n++] = ((unsigned long long)clock64() << 8) | (unsigned long long)(code);      \
+  } while (0)
 
 // ---- PTX helpers ----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t dp_mapa(uint32_t addr, uint32_t rank) {
@@ -89,8 +97,17 @@ __device__ __forceinline__ uint32_t dp_mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void dp_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void dp_st_remote(uint32_t cluster_addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+// relaxed flavour: the caller has already ordered its writes with ONE release (every mbarrier.arrive.release.cluster costs a
+// MEMBAR.ALL.GPU -- eight of them per signal were ~5 000 cycles in the first trace)
+__device__ __forceinline__ void dp_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 16 bytes into a peer's shared memory, completing 16 tx bytes on the peer's mbarrier: data and signal travel together,
+// no fence on either side
+__device__ __forceinline__ void dp_st_async4(uint32_t cluster_addr, uint32_t cluster_bar, float a, float b, float c, float d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%2, %3, %4, %5}, [%1];" ::"r"(cluster_addr),
+               "r"(cluster_bar), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
+               : "memory");
 }
 static __device__ __noinline__ void dp_wait_timeout(uint32_t addr, int what) {
   printf("seeme_b200: den_persist wait timed out (block %d thread %d barrier 0x%x kind %d)\n", blockIdx.x, threadIdx.x, addr, what);
@@ -168,18 +185,21 @@ __device__ __forceinline__ void dp_split2(float a, float b, uint32_t& hi, uint32
   const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-// publish N (16 or 32) consecutive columns of this thread's row into the exchange matrix (bf16 hi and lo copies)
+// publish N (16 or 32) consecutive columns [col, col + N) of this thread's row into the tile's exchange images: the 16-byte
+// chunks go to their SWIZZLE_128B positions, so a K-block (hi image | lo image, 32 KB) is ONE contiguous bulk copy away
+// from being an A operand
 template <int N>
-__device__ __forceinline__ void dp_publish(__nv_bfloat16* xh, __nv_bfloat16* xl, size_t elem_off, const float* f) {
+__device__ __forceinline__ void dp_publish(uint8_t* ximg_tile, int col, int row, const float* f) {
   uint32_t hb[N / 2], lb[N / 2];
 #pragma unroll
   for (int i = 0; i < N / 2; ++i) dp_split2(f[2 * i], f[2 * i + 1], hb[i], lb[i]);
-  uint4* ph = reinterpret_cast<uint4*>(xh + elem_off);
-  uint4* pl = reinterpret_cast<uint4*>(xl + elem_off);
+  uint8_t* line = ximg_tile + (size_t)(col >> 6) * 32768 + row * 128;
+  const int j0 = (col & 63) >> 3, sw = row & 7;
 #pragma unroll
   for (int j = 0; j < N / 8; ++j) {
-    ph[j] = make_uint4(hb[4 * j], hb[4 * j + 1], hb[4 * j + 2], hb[4 * j + 3]);
-    pl[j] = make_uint4(lb[4 * j], lb[4 * j + 1], lb[4 * j + 2], lb[4 * j + 3]);
+    const int c = ((j0 + j) ^ sw) << 4;
+    *reinterpret_cast<uint4*>(line + c) = make_uint4(hb[4 * j], hb[4 * j + 1], hb[4 * j + 2], hb[4 * j + 3]);
+    *reinterpret_cast<uint4*>(line + 16384 + c) = make_uint4(lb[4 * j], lb[4 * j + 1], lb[4 * j + 2], lb[4 * j + 3]);
   }
 }
 // 32 consecutive floats of a vector shared by all rows (bias, LayerNorm affine, FiLM, time-token tables)
@@ -198,28 +218,26 @@ struct DpStat {
   uint32_t cnt;
   int q, lane, row, rank;
   const float* cur;
+  unsigned long long* tr;     // diagnostics: (clock64 << 8 | 7) before / 8 after each exchange
   template <int K>
   __device__ __forceinline__ void send(const float (&v)[K]) {
     static_assert(K <= 4, "at most 4 values per round");
+    if (tr) *tr++ = ((unsigned long long)clock64() << 8) | 7ull;
     const uint32_t par = cnt & 1u;
-    const uint32_t laddr = smem_u32(stats + ((par * DP_CL + rank) * 4) * 128 + row);
+    // stats[par][src][row][4]; this thread's 16 bytes land in every CTA of the cluster (its own included) and complete
+    // 16 tx bytes on that CTA's barrier of this warp's lane quarter: 32 rows x CL sources x 16 B per phase
+    const uint32_t laddr = smem_u32(stats + ((par * DP_CL + rank) * 128 + row) * 4);
+    const uint32_t lbar = smem_u32(&bar[par * 4 + q]);
+    if (lane == 0) mbar_arrive_expect_tx(&bar[par * 4 + q], 32 * DP_CL * 16);
+    const float v0 = v[0], v1 = K > 1 ? v[K > 1 ? 1 : 0] : 0.f, v2 = K > 2 ? v[K > 2 ? 2 : 0] : 0.f, v3 = K > 3 ? v[K > 3 ? 3 : 0] : 0.f;
 #pragma unroll
-    for (int pr = 0; pr < DP_CL; ++pr) {
-      const uint32_t ra = dp_mapa(laddr, pr);
-#pragma unroll
-      for (int k = 0; k < K; ++k) dp_st_remote(ra + k * 512, v[k]);
-    }
-    __syncwarp();
-    if (lane == 0) {
-      const uint32_t b = smem_u32(&bar[par * 4 + q]);
-#pragma unroll
-      for (int pr = 0; pr < DP_CL; ++pr) dp_arrive_remote(dp_mapa(b, pr));
-    }
-    dp_wait_cluster(&bar[par * 4 + q], (cnt >> 1) & 1u, 10);
-    cur = stats + (par * DP_CL * 4) * 128 + row;
+    for (int pr = 0; pr < DP_CL; ++pr) dp_st_async4(dp_mapa(laddr, pr), dp_mapa(lbar, pr), v0, v1, v2, v3);
+    dp_wait(&bar[par * 4 + q], (cnt >> 1) & 1u, 10);
+    cur = stats + ((par * DP_CL) * 128 + row) * 4;
     ++cnt;
+    if (tr) *tr++ = ((unsigned long long)clock64() << 8) | 8ull;
   }
-  __device__ __forceinline__ float get(int s, int k) const { return cur[(s * 4 + k) * 128]; }
+  __device__ __forceinline__ float get(int s, int k) const { return cur[s * 512 + k]; }
   // v[k] <- sum over the cluster
   template <int K>
   __device__ __forceinline__ void sum(float (&v)[K]) {
@@ -261,6 +279,9 @@ struct DpStat {
 #pragma unroll
     for (int i = 0; i < 32; ++i) { const float d = t[i] - mc; m2 = fmaf(d, d, m2); }
     const float a[2] = {mc, m2};
+    float gg[32], bb[32];          // requested before the exchange so that their L2 round trip overlaps it
+    dp_ldvec(g, gg);
+    dp_ldvec(b, bb);
     send<2>(a);
     float mean = 0.f;
 #pragma unroll
@@ -270,9 +291,6 @@ struct DpStat {
 #pragma unroll
     for (int s2 = 0; s2 < DP_CL; ++s2) { const float d = get(s2, 0) - mean; M2 += get(s2, 1) + 32.0f * d * d; }
     const float rstd = rsqrtf(M2 * (1.0f / 256.0f) + 1e-5f);
-    float gg[32], bb[32];
-    dp_ldvec(g, gg);
-    dp_ldvec(b, bb);
 #pragma unroll
     for (int i = 0; i < 32; ++i) t[i] = (t[i] - mean) * rstd * gg[i] + bb[i];
   }
@@ -293,13 +311,11 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
   const int tile = blockIdx.x / DP_CL;
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&p.map_hi);
-    tma_prefetch_desc(&p.map_lo);
     for (int i = 0; i < DP_NA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < DP_NW; ++i) { mbar_init(&full_w[i], 1); mbar_init(&empty_w[i], 1); }
     mbar_init(&acc_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&xbar[i], 4 * DP_CL); mbar_init(&lbar[i], 4); }
-    for (int i = 0; i < 8; ++i) { mbar_init(&sbar[i], DP_CL); mbar_init(&rbar[i], DP_CL); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&sbar[i], 1); mbar_init(&rbar[i], DP_CL); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_slot, 512);
@@ -313,14 +329,16 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
     // ---- producer -----------------------------------------------------------------------------------
     if (lane == 0) {
       uint32_t ia = 0, iw = 0, nx = 0, nl = 0;
+      int tr_n = 0;
       const uint8_t* tape = p.tape + (size_t)rank * p.tape_cta_bytes;
-      const int row0 = tile * 128;
+      const uint8_t* ximg_tile = p.ximg + (size_t)tile * XC_KB * 32768;
       for (int step = 0; step < p.n_steps; ++step) {
         for (int u = 0; u < p.n_units; ++u) {
           const DpUnit un = p.units[u];
           const uint32_t wbytes = (uint32_t)un.n * 256u;
           const uint8_t* wsrc = tape + un.w_off;
           int kw = 0;
+          DP_TR(0, 1);
           // the weights do not depend on the exchange: up to NW K-blocks travel while the previous epilogue runs
           for (; kw < un.nkb && kw < DP_NW; ++kw) {
             const uint32_t sw = iw % DP_NW;
@@ -329,17 +347,17 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
             dp_bulk_load(w_ring + sw * DP_W_SLOT, wsrc + (size_t)kw * wbytes, wbytes, &full_w[sw]);
             ++iw;
           }
-          if (un.wait == 1) { dp_wait_cluster(&xbar[nx & 1u], (nx >> 1) & 1u, 2); ++nx; dp_fence_proxy_all(); }
+          if (un.wait == 1) { dp_wait(&xbar[nx & 1u], (nx >> 1) & 1u, 2); ++nx; dp_fence_proxy_all(); }
           else if (un.wait == 2) { dp_wait(&lbar[nl & 1u], (nl >> 1) & 1u, 3); ++nl; dp_fence_proxy_all(); }
           const int acol = un.a_col + rank * un.a_rstride;
+          DP_TR(0, 2);
           for (int kb = 0; kb < un.nkb; ++kb) {
             if (!un.reuse_a) {
               const uint32_t sa = ia % DP_NA;
               dp_wait(&empty_a[sa], ((ia / DP_NA) & 1u) ^ 1u, 4);
               mbar_arrive_expect_tx(&full_a[sa], DP_A_SLOT);
               const int col = kb < un.nkb1 ? acol + kb * 64 : un.a_col2 + (kb - un.nkb1) * 64;
-              tma_load_2d(a_ring + sa * DP_A_SLOT, &p.map_hi, &full_a[sa], col, row0);
-              tma_load_2d(a_ring + sa * DP_A_SLOT + 16384, &p.map_lo, &full_a[sa], col, row0);
+              dp_bulk_load(a_ring + sa * DP_A_SLOT, ximg_tile + (size_t)(col >> 6) * 32768, DP_A_SLOT, &full_a[sa]);
               ++ia;
             }
             if (kb >= kw) {
@@ -350,12 +368,14 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
               ++iw;
             }
           }
+          DP_TR(0, 3);
         }
       }
     }
   } else if (warp == 1) {
     // ---- MMA issuer -----------------------------------------------------------------------------------
     uint32_t ia = 0, iw = 0, a0 = 0;
+    int tr_n = 0;
     const uint64_t da_base = umma_desc_k128(smem_u32(a_ring));
     const uint64_t dw_base = umma_desc_k128(smem_u32(w_ring));
     for (int step = 0; step < p.n_steps; ++step) {
@@ -371,6 +391,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
           const uint32_t sw = iw % DP_NW;
           dp_wait(&full_w[sw], (iw / DP_NW) & 1u, 7);
           tc_fence_after();
+          if (lane == 0 && kb == 0) DP_TR(1, 4);
           if (umma_elect_one()) {
             const uint64_t da0 = umma_desc_add(da_base, sa * (DP_A_SLOT >> 4));
             const uint64_t dw0 = umma_desc_add(dw_base, sw * (DP_W_SLOT >> 4));
@@ -388,6 +409,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
           __syncwarp();
           ++iw;
         }
+        if (lane == 0) DP_TR(1, 5);
         if (!un.reuse_a) ia += (uint32_t)un.nkb;
       }
     }
@@ -409,35 +431,42 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
       grow = prow;
       valid = prow < p.R;
     }
-    const size_t xrow = (size_t)prow * XC_COLS;
-    const size_t rp = (size_t)p.rows_pad;
+    uint8_t* const xt = p.ximg + (size_t)tile * XC_KB * 32768;
+    // per-row cond-token tables: ONE base pointer per layer, every (table, token, column) at a compile-time offset
+    const size_t ct_off = ((size_t)tile * 4 * NC * 256 + S) * 128 + row;
+#define DP_CT(w, n, i) (((w) * NC + (n)) * 256 + (i)) * 128
     uint32_t nstage = 0, nx = 0, nl = 0, nr = 0;
+    int tr_n = 0, step = 0;
+    const bool tr_me = warp == 2 && lane == 0;
     DpStat ex;
-    ex.stats = stats; ex.bar = sbar; ex.cnt = 0; ex.q = q; ex.lane = lane; ex.row = row; ex.rank = rank; ex.cur = stats;
+    ex.stats = stats; ex.bar = sbar; ex.cnt = 0; ex.q = q; ex.lane = lane; ex.row = row; ex.rank = rank; ex.cur = stats; ex.tr = nullptr;
 
     auto acc_wait = [&]() {
       dp_wait(&acc_full, nstage & 1u, 8);
       ++nstage;
       tc_fence_after();
+      if (tr_me) DP_TR(2, 6);
     };
     auto signal_x = [&]() {      // the slice just written is part of the next A operand of every CTA of the cluster
-      __threadfence();
+      if (tr_me) DP_TR(2, 9);
       dp_fence_proxy_all();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
+        // ONE release (MEMBAR.ALL.GPU: this warp's slice stores are performed at the L2) covers all eight arrives
         const uint32_t b = smem_u32(&xbar[nx & 1u]);
+        dp_arrive_remote(dp_mapa(b, 0));
 #pragma unroll
-        for (int pr = 0; pr < DP_CL; ++pr) dp_arrive_remote(dp_mapa(b, pr));
+        for (int pr = 1; pr < DP_CL; ++pr) dp_arrive_remote_relaxed(dp_mapa(b, pr));
       }
       ++nx;
+      if (tr_me) DP_TR(2, 10);
     };
     auto signal_l = [&]() {      // CTA-private hand-over (FFN hidden units)
-      __threadfence();
       dp_fence_proxy_all();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&lbar[nl & 1u]);
+      if (lane == 0) dp_arrive_remote(dp_mapa(smem_u32(&lbar[nl & 1u]), rank));   // release: the stores are at the L2
       ++nl;
     };
 
@@ -459,15 +488,17 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
 #pragma unroll
       for (int i = 0; i < 32; ++i) x[i] += pe[i];
       dp_st32(tl + TM_XRES, x);
-      dp_publish<32>(p.xh, p.xl, xrow + XC_P0 + S, x);
+      dp_publish<32>(xt, XC_P0 + S, row, x);
       signal_x();
     }
 
-    for (int step = 0; step < p.n_steps; ++step) {
+    for (step = 0; step < p.n_steps; ++step) {
       const size_t toff = (size_t)step * 512;
+      ex.tr = (p.trace && blockIdx.x == 0 && tr_me && step == p.trace_step) ? p.trace + 3 * 4096 : nullptr;
 #pragma unroll 1
       for (int l = 0; l < 5; ++l) {
         const DpLayerP& L = p.L[l];
+        const float* __restrict__ ct = L.ctab + ct_off;
         const int xout_col = l == 0 ? XC_L0 : l == 1 ? XC_L1 : XC_P1;
         if (l >= 3) {
           // x = Linear(cat[x, skip]) (cross_attention.py:77-80)
@@ -478,7 +509,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] += b[i];
           dp_st32(tl + TM_XRES, x);
-          dp_publish<32>(p.xh, p.xl, xrow + XC_P0 + S, x);
+          dp_publish<32>(xt, XC_P0 + S, row, x);
           signal_x();
         }
         // ---- self-attention over {x, cond tokens, time token}, query = token 0 (mdiff_transformer.py:291-297) ----
@@ -499,10 +530,9 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
             pr[0] = d;
 #pragma unroll
             for (int n = 0; n < NC; ++n) {
-              const float* kc = L.ctab + ((size_t)(0 * NC + n) * 256 + S) * rp + prow;
               float dn = 0.f;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) dn = fmaf(qv[i], __ldg(kc + (size_t)i * rp), dn);
+              for (int i = 0; i < 32; ++i) dn = fmaf(qv[i], __ldg(ct + DP_CT(0, n, i)), dn);
               pr[1 + n] = dn;
             }
             dp_ldvec(L.kt + toff + S, v);
@@ -511,6 +541,16 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
             for (int i = 0; i < 32; ++i) d = fmaf(qv[i], v[i], d);
             pr[NC + 1] = d;
           }
+          // operands of the second half, requested before the exchange (their L2 round trip overlaps it): merged bias
+          // b_o + W_o b_v (the softmax weights sum to 1), ov of the cond tokens and of the time token
+          float bs[32], ovc[NC][32], ovt[32];
+          dp_ldvec(L.bqkv + 512 + S, bs);
+#pragma unroll
+          for (int n = 0; n < NC; ++n) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ovc[n][i] = __ldg(ct + DP_CT(1, n, i));
+          }
+          dp_ldvec(L.kt + toff + 256 + S, ovt);
           ex.sum<NC + 2>(pr);
           {
             float m = pr[0];
@@ -518,33 +558,27 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
             for (int j = 1; j < NC + 2; ++j) m = fmaxf(m, pr[j]);
             float sum = 0.f;
 #pragma unroll
-            for (int j = 0; j < NC + 2; ++j) { pr[j] = expf(pr[j] - m); sum += pr[j]; }
+            for (int j = 0; j < NC + 2; ++j) { pr[j] = __expf(pr[j] - m); sum += pr[j]; }
             const float inv = 1.0f / sum;
 #pragma unroll
             for (int j = 0; j < NC + 2; ++j) pr[j] *= inv;
           }
           float t0[32];
           {
-            float xr[32], v[32], w[32];
+            float xr[32];
             dp_ld32(tl + 64, t0);
             dp_ld32(tl + TM_XRES, xr);
-            dp_ldvec(L.bqkv + 512 + S, v);
-            dp_ldvec(L.bo + S, w);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) t0[i] = xr[i] + w[i] + pr[0] * (t0[i] + v[i]);
+            for (int i = 0; i < 32; ++i) t0[i] = xr[i] + bs[i] + pr[0] * t0[i] + pr[NC + 1] * ovt[i];
 #pragma unroll
             for (int n = 0; n < NC; ++n) {
-              const float* oc = L.ctab + ((size_t)(1 * NC + n) * 256 + S) * rp + prow;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) t0[i] = fmaf(pr[1 + n], __ldg(oc + (size_t)i * rp), t0[i]);
+              for (int i = 0; i < 32; ++i) t0[i] = fmaf(pr[1 + n], ovc[n][i], t0[i]);
             }
-            dp_ldvec(L.kt + toff + 256 + S, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) t0[i] = fmaf(pr[NC + 1], v[i], t0[i]);
           }
           ex.layernorm(t0, L.n1g + S, L.n1b + S);      // x1 = norm1(x + sa)
           dp_st32(tl + TM_XRES, t0);
-          dp_publish<32>(p.xh, p.xl, xrow + XC_XA + S, t0);
+          dp_publish<32>(xt, XC_XA + S, row, t0);
           signal_x();
         }
         // ---- FFN 256 -> 1024 (ReLU) -> 256, K-split over the cluster ----
@@ -557,7 +591,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
             dp_ldvec(L.b1 + rank * DP_HS + ch * 32, b);
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i] + b[i], 0.f);
-            dp_publish<32>(p.xh, p.xl, xrow + XC_FF + rank * DP_HS + ch * 32, f);
+            dp_publish<32>(xt, XC_FF + rank * DP_HS + ch * 32, row, f);
           }
           signal_l();
         }
@@ -571,16 +605,16 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
 #pragma unroll
             for (int i = 0; i < 32; ++i) __stcg(mine + (size_t)(ch * 32 + i) * 128, f[i]);
           }
-          __threadfence();
           tc_fence_before();
           __syncwarp();
           const uint32_t par = nr & 1u;
           if (lane == 0) {
             const uint32_t b = smem_u32(&rbar[par * 4 + q]);
+            dp_arrive_remote(dp_mapa(b, 0));
 #pragma unroll
-            for (int pr2 = 0; pr2 < DP_CL; ++pr2) dp_arrive_remote(dp_mapa(b, pr2));
+            for (int pr2 = 1; pr2 < DP_CL; ++pr2) dp_arrive_remote_relaxed(dp_mapa(b, pr2));
           }
-          dp_wait_cluster(&rbar[par * 4 + q], (nr >> 1) & 1u, 9);
+          dp_wait(&rbar[par * 4 + q], (nr >> 1) & 1u, 9);
           ++nr;
           float t1[32], v[32];
           dp_ld32(tl + TM_XRES, t1);
@@ -596,7 +630,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
           ex.layernorm(t1, L.n2g + S, L.n2b + S);      // x2 = norm2(x1 + ffn)
           dp_st32(tl + TM_XRES, t1);
           ex.layernorm(t1, L.cng + S, L.cnb + S);      // input norm of the cross-attention
-          dp_publish<32>(p.xh, p.xl, xrow + XC_LN + S, t1);
+          dp_publish<32>(xt, XC_LN + S, row, t1);
           signal_x();
         }
         // ---- linear cross-attention to the cond tokens + FiLM (mdiff_transformer.py:219-239, 152-163) ----
@@ -614,15 +648,21 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
             st[0] = m;
             float ssum = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { qv[i] = expf(qv[i] - m); ssum += qv[i]; }
+            for (int i = 0; i < 32; ++i) { qv[i] = __expf(qv[i] - m); ssum += qv[i]; }
             st[1] = ssum;
 #pragma unroll
             for (int n = 0; n < NC; ++n) {
-              const float* ks = L.ctab + ((size_t)(2 * NC + n) * 256 + S) * rp + prow;
               float dn = 0.f;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) dn = fmaf(qv[i], __ldg(ks + (size_t)i * rp), dn);
+              for (int i = 0; i < 32; ++i) dn = fmaf(qv[i], __ldg(ct + DP_CT(2, n, i)), dn);
               st[2 + n] = dn;
+            }
+            // the value slices are requested before the exchange
+            float v2[NC][32];
+#pragma unroll
+            for (int n = 0; n < NC; ++n) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v2[n][i] = __ldg(ct + DP_CT(3, n, i));
             }
             // combine the per-slice softmax pieces: M = max m_s, s = sum s_s e^(m_s - M), w_n = sum dn_s e^(m_s - M) / s
             float wn[NC];
@@ -638,7 +678,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
               float sc[DP_CL];
               float tot = 0.f;
 #pragma unroll
-              for (int s = 0; s < DP_CL; ++s) { sc[s] = expf(ex.get(s, 0) - M); tot = fmaf(ex.get(s, 1), sc[s], tot); }
+              for (int s = 0; s < DP_CL; ++s) { sc[s] = __expf(ex.get(s, 0) - M); tot = fmaf(ex.get(s, 1), sc[s], tot); }
 #pragma unroll
               for (int n = 0; n < NC && n < 2; ++n) {
                 float t = 0.f;
@@ -667,20 +707,14 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
             for (int i = 0; i < 32; ++i) y[i] = 0.f;
 #pragma unroll
             for (int n = 0; n < NC; ++n) {
-              const float* vv = L.ctab + ((size_t)(3 * NC + n) * 256 + S) * rp + prow;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) y[i] = fmaf(wn[n], __ldg(vv + (size_t)i * rp), y[i]);
+              for (int i = 0; i < 32; ++i) y[i] = fmaf(wn[n], v2[n][i], y[i]);
             }
           }
-          ex.layernorm(y, L.cpg + S, L.cpb + S);
-          {
-            float sc[32], sh[32];
-            dp_ldvec(L.film_ca + toff + S, sc);
-            dp_ldvec(L.film_ca + toff + 256 + S, sh);
+          ex.layernorm(y, L.film_ca + toff + S, L.film_ca + toff + 256 + S);    // LN affine and FiLM folded (table)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) y[i] = silu(y[i] * (1.0f + sc[i]) + sh[i]);
-          }
-          dp_publish<32>(p.xh, p.xl, xrow + XC_HB0 + S, y);
+          for (int i = 0; i < 32; ++i) y[i] = __fdividef(y[i], 1.0f + __expf(-y[i]));            // SiLU
+          dp_publish<32>(xt, XC_HB0 + S, row, y);
           signal_x();
         }
         {   // x3 = x2 + out(h)
@@ -692,7 +726,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] += b[i] + xr[i];
           dp_st32(tl + TM_XRES, x);
-          dp_publish<32>(p.xh, p.xl, xrow + XC_X3 + S, x);
+          dp_publish<32>(xt, XC_X3 + S, row, x);
           signal_x();
         }
         // ---- FFN 256 -> 128 (GELU) -> 256 + FiLM (mdiff_transformer.py:241-254) ----
@@ -703,7 +737,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
           float g[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) g[i] = gelu_erf(f[i] + __ldg(L.bf1 + rank * DP_GS + i));
-          dp_publish<16>(p.xh, p.xl, xrow + XC_G + rank * DP_GS, g);
+          dp_publish<16>(xt, XC_G + rank * DP_GS, row, g);
           signal_x();
         }
         {
@@ -713,13 +747,10 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
           dp_ldvec(L.bf2 + S, b);
 #pragma unroll
           for (int i = 0; i < 32; ++i) y[i] += b[i];
-          ex.layernorm(y, L.fpg + S, L.fpb + S);
-          float sc[32], sh[32];
-          dp_ldvec(L.film_ff + toff + S, sc);
-          dp_ldvec(L.film_ff + toff + 256 + S, sh);
+          ex.layernorm(y, L.film_ff + toff + S, L.film_ff + toff + 256 + S);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) y[i] = silu(y[i] * (1.0f + sc[i]) + sh[i]);
-          dp_publish<32>(p.xh, p.xl, xrow + XC_HB1 + S, y);
+          for (int i = 0; i < 32; ++i) y[i] = __fdividef(y[i], 1.0f + __expf(-y[i]));
+          dp_publish<32>(xt, XC_HB1 + S, row, y);
           signal_x();
         }
         {   // block output = x3 + out(h)
@@ -732,7 +763,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
           for (int i = 0; i < 32; ++i) x[i] += b[i] + xr[i];
           if (l < 4) {
             dp_st32(tl + TM_XRES, x);
-            dp_publish<32>(p.xh, p.xl, xrow + xout_col + S, x);
+            dp_publish<32>(xt, xout_col + S, row, x);
             signal_x();
           } else {
             // final LayerNorm (cross_attention.py:82), then CFG combine + DDIM update (mld.py:488-497)
@@ -784,7 +815,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
 #pragma unroll
                 for (int i = 0; i < 32; ++i) lt[i] += pe[i];
                 dp_st32(tl + TM_XRES, lt);
-                dp_publish<32>(p.xh, p.xl, xrow + XC_P0 + S, lt);
+                dp_publish<32>(xt, XC_P0 + S, row, lt);
                 signal_x();
               }
             }
@@ -803,7 +834,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
 }
 
 // transposes the cond-token projections into the per-row tables the epilogue reads column by column:
-//   tab[which][n][col][prow], which = 0: k, 1: ov (self-attention; kov rows n R + grow: k | ov), 2: softmax over the
+//   tab[tile][which][n][col][row of the tile], which = 0: k, 1: ov (self-attention; kov rows n R + grow: k | ov), 2: softmax over the
 //   tokens of the cross-attention key, 3: its value (kv2: key | value).  Rows beyond the batch are zero.
 __global__ void dp_ctab_kernel(const float* __restrict__ kov, const float* __restrict__ kv2, float* __restrict__ tab, int Nc, int B,
                                int R, int cfg, int rows_pad) {
@@ -830,13 +861,13 @@ __global__ void dp_ctab_kernel(const float* __restrict__ kov, const float* __res
   float s = 0.f;
   for (int n = 0; n < Nc; ++n) { k2[n] = expf(k2[n] - m); s += k2[n]; }
   const float inv = 1.0f / s;
+  float* t = tab + (size_t)tile * 4 * Nc * 256 * 128 + r;
   for (int n = 0; n < Nc; ++n) {
     const size_t src = ((size_t)n * R + grow) * 512 + col;
-    const size_t rp = (size_t)rows_pad;
-    tab[((size_t)(0 * Nc + n) * 256 + col) * rp + prow] = valid ? kov[src] : 0.f;
-    tab[((size_t)(1 * Nc + n) * 256 + col) * rp + prow] = valid ? kov[src + 256] : 0.f;
-    tab[((size_t)(2 * Nc + n) * 256 + col) * rp + prow] = valid ? k2[n] * inv : 0.f;
-    tab[((size_t)(3 * Nc + n) * 256 + col) * rp + prow] = valid ? kv2[src + 256] : 0.f;
+    t[((size_t)(0 * Nc + n) * 256 + col) * 128] = valid ? kov[src] : 0.f;
+    t[((size_t)(1 * Nc + n) * 256 + col) * 128] = valid ? kov[src + 256] : 0.f;
+    t[((size_t)(2 * Nc + n) * 256 + col) * 128] = valid ? k2[n] * inv : 0.f;
+    t[((size_t)(3 * Nc + n) * 256 + col) * 128] = valid ? kv2[src + 256] : 0.f;
   }
 }
 
@@ -848,7 +879,7 @@ struct DenPersist {
   size_t tape_cta_bytes = 0;
   DpUnit* d_units = nullptr;
   int n_units = 0;
-  __nv_bfloat16 *xh = nullptr, *xl = nullptr;
+  uint8_t* ximg = nullptr;
   float* part = nullptr;
   float* ctab[5] = {};
   float* bqkv[5] = {};           // [768]: bq / 16 | bk | W_o b_v
@@ -856,9 +887,11 @@ struct DenPersist {
   float* bkov[5] = {};           // [512]
   float* bk2v2[5] = {};          // [512]
   float* tkov[5] = {};           // [MAX_STEPS,512]
+  float* film2_ca[5] = {};       // [MAX_STEPS,512]: g (1 + scale) | b (1 + scale) + shift
+  float* film2_ff[5] = {};
   PackedLinear Wkov[5], Wk2v2[5];
   ActBuf condb, tnb;             // bf16 (hi, lo) of the cond tokens / of their text_norm
-  CUtensorMap map_hi, map_lo;
+  unsigned long long* trace = nullptr;
 };
 
 static inline uint16_t f2bf(float x) {    // round to nearest even, like __float2bfloat16_rn (finite inputs)
@@ -942,9 +975,15 @@ int den_persist_create(seeme_denoiser* h) {
       for (int k = 0; k < 256; ++k) Wqkv[l].v[(size_t)(512 + n) * 256 + k] = (float)acc[k];
       bov[n] = (float)bacc;
     }
-    for (int n = 0; n < 256; ++n) in_b[512 + n] = bov[n];
+    {
+      std::vector<float> bo;
+      SEEME_TRY(fetch(blkw(h, l, SA_OUT_B), 256, bo));
+      // the softmax weights sum to 1: b_o + W_o b_v is added once; the (k | ov) tables of the cond / time tokens carry b_k only
+      for (int n = 0; n < 256; ++n) in_b[512 + n] = bo[n] + bov[n];
+    }
     bqkv[l] = in_b;
     bkov[l].assign(in_b.begin() + 256, in_b.end());
+    for (int n = 0; n < 256; ++n) bkov[l][256 + n] = 0.f;
     SEEME_TRY(fetch(blkw(h, l, SA_L1_W), 1024 * 256, Wl1[l].v)); Wl1[l].ld = 256;
     SEEME_TRY(fetch(blkw(h, l, SA_L2_W), 256 * 1024, Wl2[l].v)); Wl2[l].ld = 1024;
     SEEME_TRY(fetch(blkw(h, l, CA_Q_W), 256 * 256, Wcaq[l].v)); Wcaq[l].ld = 256;
@@ -1020,22 +1059,20 @@ int den_persist_create(seeme_denoiser* h) {
     SEEME_REQUIRE(tapes[c].size() == P->tape_cta_bytes, SEEME_EINVAL, "den_persist: tape size mismatch");
 
   const size_t Rp = (size_t)P->rows_pad_max, NCM = SEEME_MAX_COND_TOKENS;
-  size_t bytes = pad256(P->tape_cta_bytes * DP_CL) + pad256(sizeof(DpUnit) * DP_MAX_UNITS) + 2 * pad256(Rp * XC_COLS * 2) +
+  size_t bytes = pad256(P->tape_cta_bytes * DP_CL) + pad256(sizeof(DpUnit) * DP_MAX_UNITS) + pad256((size_t)P->max_tiles * XC_KB * 32768) +
                  pad256((size_t)P->max_tiles * DP_CL * 256 * 128 * 4) + 5 * pad256(4 * NCM * 256 * Rp * 4) +
-                 5 * (pad256(768 * 4) + pad256(512 * 256 * 4) + 2 * pad256(512 * 4) + pad256((size_t)DEN_MAX_STEPS * 512 * 4)) +
+                 5 * (pad256(768 * 4) + pad256(512 * 256 * 4) + 2 * pad256(512 * 4) + 3 * pad256((size_t)DEN_MAX_STEPS * 512 * 4)) +
                  5 * 2 * 2 * pad256(512 * 256 * 2) + 5 * pad256(512 * 256 * 4) + 4 * pad256(NCM * (size_t)h->max_rows * 256 * 2) + 65536;
   SEEME_TRY(P->arena.init(bytes));
   P->tape = P->arena.take<uint8_t>(P->tape_cta_bytes * DP_CL);
   P->d_units = P->arena.take<DpUnit>(DP_MAX_UNITS);
-  P->xh = P->arena.take<__nv_bfloat16>(Rp * XC_COLS);
-  P->xl = P->arena.take<__nv_bfloat16>(Rp * XC_COLS);
+  P->ximg = P->arena.take<uint8_t>((size_t)P->max_tiles * XC_KB * 32768);
   P->part = P->arena.take<float>((size_t)P->max_tiles * DP_CL * 256 * 128);
   SEEME_REQUIRE(P->part, SEEME_ENOMEM, "den_persist: arena exhausted");
   for (int c = 0; c < DP_CL; ++c)
     SEEME_CUDA(cudaMemcpy(P->tape + (size_t)c * P->tape_cta_bytes, tapes[c].data(), P->tape_cta_bytes, cudaMemcpyHostToDevice));
   SEEME_CUDA(cudaMemcpy(P->d_units, units.data(), sizeof(DpUnit) * units.size(), cudaMemcpyHostToDevice));
-  SEEME_CUDA(cudaMemset(P->xh, 0, Rp * XC_COLS * 2));
-  SEEME_CUDA(cudaMemset(P->xl, 0, Rp * XC_COLS * 2));
+  SEEME_CUDA(cudaMemset(P->ximg, 0, (size_t)P->max_tiles * XC_KB * 32768));
   for (int l = 0; l < 5; ++l) {
     P->ctab[l] = P->arena.take<float>(4 * NCM * 256 * Rp);
     P->bqkv[l] = P->arena.take<float>(768);
@@ -1043,7 +1080,9 @@ int den_persist_create(seeme_denoiser* h) {
     P->bkov[l] = P->arena.take<float>(512);
     P->bk2v2[l] = P->arena.take<float>(512);
     P->tkov[l] = P->arena.take<float>((size_t)DEN_MAX_STEPS * 512);
-    SEEME_REQUIRE(P->tkov[l], SEEME_ENOMEM, "den_persist: arena exhausted");
+    P->film2_ca[l] = P->arena.take<float>((size_t)DEN_MAX_STEPS * 512);
+    P->film2_ff[l] = P->arena.take<float>((size_t)DEN_MAX_STEPS * 512);
+    SEEME_REQUIRE(P->film2_ff[l], SEEME_ENOMEM, "den_persist: arena exhausted");
     SEEME_CUDA(cudaMemcpy(P->bqkv[l], bqkv[l].data(), 768 * 4, cudaMemcpyHostToDevice));
     SEEME_CUDA(cudaMemcpy(P->wkov_f32[l], Wqkv[l].v.data() + 256 * 256, 512 * 256 * 4, cudaMemcpyHostToDevice));
     SEEME_CUDA(cudaMemcpy(P->bkov[l], bkov[l].data(), 512 * 4, cudaMemcpyHostToDevice));
@@ -1064,8 +1103,6 @@ int den_persist_create(seeme_denoiser* h) {
   mk(P->condb);
   mk(P->tnb);
   SEEME_REQUIRE(P->tnb.l, SEEME_ENOMEM, "den_persist: arena exhausted (cond buffers)");
-  SEEME_TRY(umma_tensor_map_bf16(&P->map_hi, P->xh, P->rows_pad_max, XC_COLS, XC_COLS, 128));
-  SEEME_TRY(umma_tensor_map_bf16(&P->map_lo, P->xl, P->rows_pad_max, XC_COLS, XC_COLS, 128));
   SEEME_CUDA(cudaFuncSetAttribute(den_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM));
   SEEME_CUDA(cudaFuncSetAttribute(den_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM));
   SEEME_CUDA(cudaFuncSetAttribute(den_persist_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM));
@@ -1081,10 +1118,28 @@ void den_persist_destroy(seeme_denoiser* h) {
   h->persist = nullptr;
 }
 
+// FiLM (mdiff_transformer.py:152-163) folded into the affine of the LayerNorm it follows:
+//   LN(y) (1 + scale) + shift = n (g (1 + scale)) + (b (1 + scale) + shift),  n = the normalised row
+__global__ void dp_film_fold_kernel(const float* __restrict__ film, const float* __restrict__ g, const float* __restrict__ b,
+                                    float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 256) return;
+  const int t = i >> 8, c = i & 255;
+  const float sc = film[(size_t)t * 512 + c], sh = film[(size_t)t * 512 + 256 + c];
+  out[(size_t)t * 512 + c] = g[c] * (1.0f + sc);
+  out[(size_t)t * 512 + 256 + c] = b[c] * (1.0f + sc) + sh;
+}
+
 int den_persist_build_tables(seeme_denoiser* h, int n, cudaStream_t s) {
   DenPersist* P = h->persist;
-  for (int l = 0; l < 5; ++l)   // (k | ov) of the time token: rows of [W_k | W_o W_v]
+  for (int l = 0; l < 5; ++l) {
+    // (k | ov) of the time token: rows of [W_k | W_o W_v], bias (b_k | 0)
     SEEME_TRY(gemm_f32(gemm_params(h->temb, 256, P->wkov_f32[l], 256, P->bkov[l], P->tkov[l], 512, n, 512, 256), s));
+    dp_film_fold_kernel<<<(n * 256 + 255) / 256, 256, 0, s>>>(h->film_ca[l], blkw(h, l, CA_PN_W), blkw(h, l, CA_PN_B), P->film2_ca[l], n);
+    SEEME_LAUNCH_CHECK();
+    dp_film_fold_kernel<<<(n * 256 + 255) / 256, 256, 0, s>>>(h->film_ff[l], blkw(h, l, FF_PN_W), blkw(h, l, FF_PN_B), P->film2_ff[l], n);
+    SEEME_LAUNCH_CHECK();
+  }
   return SEEME_OK;
 }
 
@@ -1110,8 +1165,6 @@ int den_persist_run(seeme_denoiser* h, int mode, const float* x_in, int Nc, int 
   }
   DpParams p;
   memset(&p, 0, sizeof(p));
-  p.map_hi = P->map_hi;
-  p.map_lo = P->map_lo;
   for (int l = 0; l < 5; ++l) {
     DpLayerP& L = p.L[l];
     L.bqkv = P->bqkv[l]; L.bo = blkw(h, l, SA_OUT_B); L.n1g = blkw(h, l, SA_N1_W); L.n1b = blkw(h, l, SA_N1_B);
@@ -1120,16 +1173,23 @@ int den_persist_run(seeme_denoiser* h, int mode, const float* x_in, int Nc, int 
     L.cpg = blkw(h, l, CA_PN_W); L.cpb = blkw(h, l, CA_PN_B); L.bcaout = blkw(h, l, CA_OUT_B);
     L.bf1 = blkw(h, l, FF_L1_B); L.bf2 = blkw(h, l, FF_L2_B); L.fpg = blkw(h, l, FF_PN_W); L.fpb = blkw(h, l, FF_PN_B);
     L.bfout = blkw(h, l, FF_OUT_B);
-    L.kt = P->tkov[l]; L.film_ca = h->film_ca[l]; L.film_ff = h->film_ff[l];
+    L.kt = P->tkov[l]; L.film_ca = P->film2_ca[l]; L.film_ff = P->film2_ff[l];
     L.ctab = P->ctab[l];
   }
   p.skip_b[0] = h->w[DN_LB0_B]; p.skip_b[1] = h->w[DN_LB1_B];
   p.fng = h->w[DN_NORM_W]; p.fnb = h->w[DN_NORM_B]; p.pe0 = h->w[DN_PE];
   p.tape = P->tape; p.tape_cta_bytes = P->tape_cta_bytes;
   p.units = P->d_units; p.n_units = P->n_units;
-  p.xh = P->xh; p.xl = P->xl; p.part = P->part;
+  p.ximg = P->ximg; p.part = P->part;
   p.x_in = x_in; p.out = out; p.coef = h->d_coef; p.gscale = h->d_gscale;
   p.B = B; p.R = R; p.cfg = cfg; p.n_steps = n_steps; p.mode = mode; p.rows_pad = rows_pad;
+  const char* trace_path = getenv("SEEME_DP_TRACE");     // diagnostics: event trace of cluster 0 / rank 0 at step 1
+  if (trace_path && !P->trace) SEEME_CUDA(cudaMalloc(&P->trace, 4 * 4096 * 8));
+  if (trace_path) {
+    SEEME_CUDA(cudaMemsetAsync(P->trace, 0, 4 * 4096 * 8, s));
+    p.trace = P->trace;
+    p.trace_step = n_steps > 1 ? 1 : 0;
+  }
   {
     ProfScope prof(PROF_SAMPLER_GRAPH, s);
     const dim3 grid(tiles * DP_CL), block(DP_THREADS);
@@ -1141,6 +1201,18 @@ int den_persist_run(seeme_denoiser* h, int mode, const float* x_in, int Nc, int 
     }
   }
   SEEME_LAUNCH_CHECK();
+  if (trace_path) {
+    std::vector<unsigned long long> host(4 * 4096);
+    SEEME_CUDA(cudaStreamSynchronize(s));
+    SEEME_CUDA(cudaMemcpy(host.data(), P->trace, host.size() * 8, cudaMemcpyDeviceToHost));
+    FILE* f = fopen(trace_path, "w");
+    if (f) {
+      for (int role = 0; role < 4; ++role)
+        for (int i = 0; i < 4096 && host[role * 4096 + i]; ++i)
+          fprintf(f, "%d %llu %d\n", role, host[role * 4096 + i] >> 8, (int)(host[role * 4096 + i] & 255));
+      fclose(f);
+    }
+  }
   return SEEME_OK;
 }
 

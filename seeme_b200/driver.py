@@ -57,10 +57,11 @@ class _SceneEmbeddingCache:
     def __init__(self, model):
         self.model, self.orig, self.store, self.key = model, model._encode_scene, {}, None
         self.hits = self.misses = 0
+        self.fp = None
 
-    def __call__(self, scene, host_scene=None):
+    def __call__(self, scene):
         k = (self.key, tuple(scene.shape))
-        fp = _scene_fingerprint(host_scene if host_scene is not None else scene)
+        fp = self.fp if self.fp is not None else _scene_fingerprint(scene)   # the driver fingerprints the batch as yielded
         ent = self.store.get(k)
         if ent is not None and ent[0] == fp:
             self.hits += 1
@@ -70,7 +71,7 @@ class _SceneEmbeddingCache:
         emb = self.orig(scene)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(emb.device))
-        self.store[k] = (fp, emb, ev, scene if scene.is_cuda and host_scene is None else None)
+        self.store[k] = (fp, emb, ev, scene if self.fp is None else None)
         return emb
 
 
@@ -93,6 +94,7 @@ def run_test_protocol(model, batches: Callable[[], Iterable], replication_times:
                 for i, b in enumerate(batches()):
                     if cache is not None:
                         cache.key = i
+                        cache.fp = _scene_fingerprint(b[4]) if torch.is_tensor(b[4]) else None   # scene: item 4 of the tuple
                     yield b
             for _ in model.run_test_batches(keyed()):
                 pass
