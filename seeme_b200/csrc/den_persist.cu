@@ -56,6 +56,8 @@ struct DpUnit {             // one GEMM unit: acc[:, acc_col : acc_col + n] = A[
   int wait;                 // 0: A visible already, 1: cluster exchange, 2: CTA-local hand-over
   int reuse_a, release_a;   // sub-units of one stage share the A ring contents
   int last;                 // the stage's epilogue runs after this unit
+  int cat;                  // 1: hi.hi and hi.lo in ONE instruction (B = [W_hi; W_lo], N = 2n: the lo tile follows the hi tile in the
+                            //    blob); the hi.lo products land in columns [acc_col + n, acc_col + 2n) and the epilogue adds them
   unsigned w_off;           // byte offset of the unit's first blob in the CTA's tape (blob = n x 256 bytes)
 };
 constexpr int DP_MAX_UNITS = 80;
@@ -170,6 +172,18 @@ __device__ __forceinline__ void dp_ld32(uint32_t taddr, float (&f)[32]) {
   tmem_ld_wait();
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(raw[i]);
+}
+// accumulator of a `cat` unit: main columns + the hi.lo cross-term columns
+__device__ __forceinline__ void dp_ld32x2(uint32_t ta, uint32_t tb, float (&f)[32]) {
+  uint32_t r0[32];
+  tmem_ld32(ta, r0);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r0[i]);
+  tmem_ld32(tb, r0);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] += __uint_as_float(r0[i]);
 }
 __device__ __forceinline__ void dp_st32(uint32_t taddr, const float (&f)[32]) {
   uint32_t raw[32];
@@ -382,7 +396,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
       for (int u = 0; u < p.n_units; ++u) {
         const DpUnit un = p.units[u];
         if (!un.reuse_a) a0 = ia;
-        const uint32_t idesc = umma_idesc_bf16(un.n);
+        const uint32_t idesc = umma_idesc_bf16(un.n), idesc2 = umma_idesc_bf16(2 * un.n);
         const uint32_t wl16 = (uint32_t)(un.n * 128) >> 4;      // lo tile follows the hi tile
         for (int kb = 0; kb < un.nkb; ++kb) {
           const uint32_t ai = a0 + (uint32_t)kb;
@@ -398,9 +412,15 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t da = umma_desc_add(da0, k * 2), dw = umma_desc_add(dw0, k * 2);
-              umma_bf16(tmem_base + (uint32_t)un.acc_col, da, dw, idesc, (kb | k) != 0);
-              umma_bf16(tmem_base + (uint32_t)un.acc_col, umma_desc_add(da, 16384 >> 4), dw, idesc, 1);
-              umma_bf16(tmem_base + (uint32_t)un.acc_col, da, umma_desc_add(dw, wl16), idesc, 1);
+              // a tcgen05.mma with N <= 64 costs ~73 cycles whatever N is (A-operand read): two instructions instead of three
+              if (un.cat) {
+                umma_bf16(tmem_base + (uint32_t)un.acc_col, da, dw, idesc2, (kb | k) != 0);
+                umma_bf16(tmem_base + (uint32_t)un.acc_col, umma_desc_add(da, 16384 >> 4), dw, idesc, 1);
+              } else {
+                umma_bf16(tmem_base + (uint32_t)un.acc_col, da, dw, idesc, (kb | k) != 0);
+                umma_bf16(tmem_base + (uint32_t)un.acc_col, umma_desc_add(da, 16384 >> 4), dw, idesc, 1);
+                umma_bf16(tmem_base + (uint32_t)un.acc_col, da, umma_desc_add(dw, wl16), idesc, 1);
+              }
             }
             umma_commit(&empty_w[sw]);
             if (un.release_a) umma_commit(&empty_a[sa]);
@@ -502,10 +522,10 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
         const int xout_col = l == 0 ? XC_L0 : l == 1 ? XC_L1 : XC_P1;
         if (l >= 3) {
           // x = Linear(cat[x, skip]) (cross_attention.py:77-80)
-          acc_wait();
           float x[32], b[32];
-          dp_ld32(tl, x);
           dp_ldvec(p.skip_b[l - 3] + S, b);
+          acc_wait();
+          dp_ld32x2(tl, tl + 32, x);
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] += b[i];
           dp_st32(tl + TM_XRES, x);
@@ -514,33 +534,46 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
         }
         // ---- self-attention over {x, cond tokens, time token}, query = token 0 (mdiff_transformer.py:291-297) ----
         {
-          acc_wait();
           float pr[NC + 2];
           {
-            float qv[32], kv[32], v[32];
-            dp_ld32(tl, qv);
-            dp_ld32(tl + 32, kv);
-            dp_ldvec(L.bqkv + S, v);
+            // everything that does not depend on the accumulator is requested while the GEMM runs
+            float bq[32], bk[32], ktk[32], kc[NC < 2 ? NC : 2][32];
+            dp_ldvec(L.bqkv + S, bq);
+            dp_ldvec(L.bqkv + 256 + S, bk);
+            dp_ldvec(L.kt + toff + S, ktk);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) qv[i] += v[i];
-            dp_ldvec(L.bqkv + 256 + S, v);
-            float d = 0.f;
+            for (int n = 0; n < NC && n < 2; ++n) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) d = fmaf(qv[i], kv[i] + v[i], d);
+              for (int i = 0; i < 32; ++i) kc[n][i] = __ldg(ct + DP_CT(0, n, i));
+            }
+            acc_wait();
+            float qv[32];
+            dp_ld32x2(tl, tl + 64, qv);
+            float d = 0.f, dt = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { qv[i] += bq[i]; dt = fmaf(qv[i], ktk[i], dt); }
+            pr[NC + 1] = dt;
+            {
+              float kv[32];
+              dp_ld32x2(tl + 32, tl + 96, kv);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) d = fmaf(qv[i], kv[i] + bk[i], d);
+            }
             pr[0] = d;
 #pragma unroll
             for (int n = 0; n < NC; ++n) {
               float dn = 0.f;
+              if (n < 2) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) dn = fmaf(qv[i], __ldg(ct + DP_CT(0, n, i)), dn);
+                for (int i = 0; i < 32; ++i) dn = fmaf(qv[i], kc[n < 2 ? n : 0][i], dn);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) dn = fmaf(qv[i], __ldg(ct + DP_CT(0, n, i)), dn);
+              }
               pr[1 + n] = dn;
             }
-            dp_ldvec(L.kt + toff + S, v);
-            d = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) d = fmaf(qv[i], v[i], d);
-            pr[NC + 1] = d;
           }
+          asm volatile("" ::: "memory");   // keep the loads below from being hoisted into the first half (register pressure)
           // operands of the second half, requested before the exchange (their L2 round trip overlaps it): merged bias
           // b_o + W_o b_v (the softmax weights sum to 1), ov of the cond tokens and of the time token
           float bs[32], ovc[NC][32], ovt[32];
@@ -564,17 +597,20 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
             for (int j = 0; j < NC + 2; ++j) pr[j] *= inv;
           }
           float t0[32];
+          dp_ld32x2(tl + 128, tl + 160, t0);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t0[i] = bs[i] + pr[0] * t0[i] + pr[NC + 1] * ovt[i];
+#pragma unroll
+          for (int n = 0; n < NC; ++n) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t0[i] = fmaf(pr[1 + n], ovc[n][i], t0[i]);
+          }
+          asm volatile("" ::: "memory");
           {
             float xr[32];
-            dp_ld32(tl + 64, t0);
             dp_ld32(tl + TM_XRES, xr);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) t0[i] = xr[i] + bs[i] + pr[0] * t0[i] + pr[NC + 1] * ovt[i];
-#pragma unroll
-            for (int n = 0; n < NC; ++n) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) t0[i] = fmaf(pr[1 + n], ovc[n][i], t0[i]);
-            }
+            for (int i = 0; i < 32; ++i) t0[i] += xr[i];
           }
           ex.layernorm(t0, L.n1g + S, L.n1b + S);      // x1 = norm1(x + sa)
           dp_st32(tl + TM_XRES, t0);
@@ -587,8 +623,8 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
 #pragma unroll 1
           for (int ch = 0; ch < DP_HS / 32; ++ch) {
             float f[32], b[32];
-            dp_ld32(tl + ch * 32, f);
             dp_ldvec(L.b1 + rank * DP_HS + ch * 32, b);
+            dp_ld32x2(tl + (ch >> 1) * 128 + (ch & 1) * 32, tl + (ch >> 1) * 128 + (ch & 1) * 32 + 64, f);
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i] + b[i], 0.f);
             dp_publish<32>(xt, XC_FF + rank * DP_HS + ch * 32, row, f);
@@ -635,12 +671,12 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
         }
         // ---- linear cross-attention to the cond tokens + FiLM (mdiff_transformer.py:219-239, 152-163) ----
         {
-          acc_wait();
           float y[32];
           {
             float qv[32], v[32];
-            dp_ld32(tl, qv);
             dp_ldvec(L.bcaq + S, v);
+            acc_wait();
+            dp_ld32x2(tl, tl + 32, qv);
             float m = -INFINITY;
 #pragma unroll
             for (int i = 0; i < 32; ++i) { qv[i] += v[i]; m = fmaxf(m, qv[i]); }
@@ -718,11 +754,11 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
           signal_x();
         }
         {   // x3 = x2 + out(h)
-          acc_wait();
           float x[32], xr[32], b[32];
-          dp_ld32(tl, x);
-          dp_ld32(tl + TM_XRES, xr);
           dp_ldvec(L.bcaout + S, b);
+          dp_ld32(tl + TM_XRES, xr);
+          acc_wait();
+          dp_ld32x2(tl, tl + 32, x);
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] += b[i] + xr[i];
           dp_st32(tl + TM_XRES, x);
@@ -731,20 +767,22 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
         }
         // ---- FFN 256 -> 128 (GELU) -> 256 + FiLM (mdiff_transformer.py:241-254) ----
         {
+          float f[32], b[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) b[i] = __ldg(L.bf1 + rank * DP_GS + i);
           acc_wait();
-          float f[32];
-          dp_ld32(tl, f);                 // columns [0, 16) are this CTA's hidden units
+          dp_ld32(tl, f);                 // columns [0, 16): this CTA's hidden units, [16, 32): their hi.lo cross terms
           float g[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) g[i] = gelu_erf(f[i] + __ldg(L.bf1 + rank * DP_GS + i));
+          for (int i = 0; i < 16; ++i) g[i] = gelu_erf(f[i] + f[16 + i] + b[i]);
           dp_publish<16>(xt, XC_G + rank * DP_GS, row, g);
           signal_x();
         }
         {
-          acc_wait();
           float y[32], b[32];
-          dp_ld32(tl, y);
           dp_ldvec(L.bf2 + S, b);
+          acc_wait();
+          dp_ld32x2(tl, tl + 32, y);
 #pragma unroll
           for (int i = 0; i < 32; ++i) y[i] += b[i];
           ex.layernorm(y, L.film_ff + toff + S, L.film_ff + toff + 256 + S);
@@ -754,11 +792,11 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
           signal_x();
         }
         {   // block output = x3 + out(h)
-          acc_wait();
           float x[32], xr[32], b[32];
-          dp_ld32(tl, x);
-          dp_ld32(tl + TM_XRES, xr);
           dp_ldvec(L.bfout + S, b);
+          dp_ld32(tl + TM_XRES, xr);
+          acc_wait();
+          dp_ld32x2(tl, tl + 32, x);
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] += b[i] + xr[i];
           if (l < 4) {
@@ -1011,7 +1049,7 @@ int den_persist_create(seeme_denoiser* h) {
     auto U = [&](int a_col, int wait) {
       DpUnit u;
       memset(&u, 0, sizeof(u));
-      u.a_col = a_col; u.wait = wait; u.nkb1 = 1 << 20; u.release_a = 1; u.last = 1;
+      u.a_col = a_col; u.wait = wait; u.nkb1 = 1 << 20; u.release_a = 1; u.last = 1; u.cat = 1;
       return u;
     };
     for (int l = 0; l < 5; ++l) {
@@ -1029,18 +1067,19 @@ int den_persist_create(seeme_denoiser* h) {
         u.release_a = 0; u.last = 0;
         add(Wqkv[l], r, 0, 4, u);
         DpUnit v = U(xin, 0);
-        v.reuse_a = 1; v.acc_col = 64;
+        v.reuse_a = 1; v.acc_col = 128;
         add(Wqkv[l], iota_rows(512 + S, DP_NS), 0, 4, v);
       }
       for (int j = 0; j < DP_HS / 64; ++j) {   // hidden units [c HS + 64 j, +64)
         DpUnit u = U(XC_XA, j == 0 ? 1 : 0);
-        u.reuse_a = j > 0; u.acc_col = 64 * j;
+        u.reuse_a = j > 0; u.acc_col = 128 * j;
         u.release_a = j == DP_HS / 64 - 1; u.last = u.release_a;
         add(Wl1[l], iota_rows(c * DP_HS + 64 * j, 64), 0, 4, u);
       }
       for (int j = 0; j < 4; ++j) {            // partial result columns [64 j, +64) over this CTA's K slice
         DpUnit u = U(XC_FF, j == 0 ? 2 : 0);
         u.a_rstride = DP_HS;
+        u.cat = 0;                               // 256 result columns: no room for the cross-term columns
         u.reuse_a = j > 0; u.acc_col = 64 * j;
         u.release_a = j == 3; u.last = j == 3;
         add(Wl2[l], iota_rows(64 * j, 64), c * DP_HS, DP_HS / 64, u);
