@@ -177,6 +177,13 @@ int seeme_denoiser_forward(seeme_denoiser_t h, const float* sample, int timestep
 int seeme_sampler_run(seeme_denoiser_t h, const float* x_T, const float* cond, int Nc, int B,
                       float guidance_scale, int n_steps, const int32_t* timesteps, const float* coef,
                       float* z, void* stream);
+/* Sampler / denoiser back-end of this handle.  SEEME_SAMPLER_PERSISTENT (default): ONE launch of the persistent
+ * cluster kernel per run (8-CTA clusters per 128-row tile; lowest latency, 8 SMs per tile for the whole run).
+ * SEEME_SAMPLER_GRAPH: the CUDA graph of small kernels (less SM time per run: the choice when many chains share the
+ * GPU with the scene encoder, as in the batch pipeline).  Same results to fp32 rounding. */
+#define SEEME_SAMPLER_PERSISTENT 0
+#define SEEME_SAMPLER_GRAPH 1
+int seeme_denoiser_set_backend(seeme_denoiser_t h, int backend);
 int seeme_denoiser_destroy(seeme_denoiser_t h);
 /* standalone `DDIMScheduler.step` (eta = 0, epsilon prediction) for the scheduler duck type. */
 int seeme_ddim_step(const float* eps, const float* sample, float* prev, size_t n, float c0, float c1,

@@ -88,14 +88,21 @@ def main():
 
     # --- full ego_eval (mld.py:1076-1905) through the unmodified reference function -----------------
     smpl, stats = S.smpl_buffers(), S.norm_stats()
-    for name, dataset, cond, gs, B in (("egobody_cfg", "egobody", ("text", "scene", "interactee"), 7.5, 2),
-                                       ("egobody_nocfg", "egobody", ("text", "scene", "interactee"), 1.0, 2),
-                                       ("gimo_cfg", "gimo", ("text", "scene"), 7.5, 2)):
-        batch = S.make_batch(B, n_points=1000, ragged=True, dataset=dataset)
+    # name, dataset, condition, guidance, B, T (MOTION_LENGTH), ESTIMATE, TEST.GLOBAL_ORIENT_PRED.  The last three rows are the
+    # config_mld_interactee.yaml protocol (ESTIMATE: interactee, MOTION_LENGTH: 1, guidance 1.0; lines 18,20,73) through the
+    # working scene / scene+interactee branches, and the GLOBAL_ORIENT_PRED: False switch (mld.py:1501-1505)
+    for name, dataset, cond, gs, B, T, est, pgo in (
+            ("egobody_cfg", "egobody", ("text", "scene", "interactee"), 7.5, 2, 60, "wearer", True),
+            ("egobody_nocfg", "egobody", ("text", "scene", "interactee"), 1.0, 2, 60, "wearer", True),
+            ("gimo_cfg", "gimo", ("text", "scene"), 7.5, 2, 60, "wearer", True),
+            ("interactee_T1_scene", "egobody", ("text", "scene"), 1.0, 3, 1, "interactee", True),
+            ("interactee_T1_scene_int_cfg", "egobody", ("text", "scene", "interactee"), 7.5, 3, 1, "interactee", True),
+            ("egobody_gt_orient", "egobody", ("text", "scene", "interactee"), 7.5, 2, 60, "wearer", False)):
+        batch = S.make_batch(B, n_points=1000, T=T, ragged=T > 1, dataset=dataset)
         gg = torch.Generator().manual_seed(7)
         noise = {"eps_int": torch.randn(1, B, 256, generator=gg), "eps_unc": torch.randn(1, B, 256, generator=gg),
                  "x_T": torch.randn(B, 1, 256, generator=gg)}
-        c = R.make_carrier(W, smpl, stats, condition=cond, guidance_scale=gs, dataset=dataset)
+        c = R.make_carrier(W, smpl, stats, condition=cond, guidance_scale=gs, dataset=dataset, estimate=est, pred_global_orient=pgo)
         normal = []
         if "interactee" in cond:
             normal = [noise["eps_int"], noise["eps_unc"]] if gs > 1 else [noise["eps_int"]]
@@ -107,6 +114,7 @@ def main():
             keep.update({k: ref[k] for k in ("joints_interactee", "root_interactee", "orientation_quat_int")})
         keep["lengths"] = torch.tensor(ref["lengths"])
         keep.update({"noise_" + k: v for k, v in noise.items()})
+        keep.update({"cfg_T": np.int64(T), "cfg_estimate": np.str_(est), "cfg_pred_global_orient": np.bool_(pgo)})
         np.savez_compressed(os.path.join(OUT, f"ego_eval_{name}.npz"), **npify(keep))
         print(name, "joints_rst absmax", float(ref["joints_rst"].abs().max()))
     print("golden fixtures written to", OUT)

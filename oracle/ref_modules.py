@@ -182,7 +182,7 @@ class _SMPLOut:
 
 
 def make_carrier(weights, smpl_buffers, stats, condition=("text", "scene", "interactee"), guidance_scale=7.5,
-                 dataset="egobody", n_steps=50):
+                 dataset="egobody", n_steps=50, estimate="wearer", pred_global_orient=True):
     """An ``nn.Module`` carrying exactly the attributes the unmodified ``MLD.ego_eval`` /
     ``MLD._diffusion_reverse`` read, built WITHOUT ``MLD.__init__`` (which ``torch.load``s an absent
     EgoHMR checkpoint, mld.py:193-196, and constructs smplx).  Real reference networks; DDIM and SMPL
@@ -231,12 +231,12 @@ def make_carrier(weights, smpl_buffers, stats, condition=("text", "scene", "inte
     c.guidance_scale = guidance_scale
     c.do_classifier_free_guidance = guidance_scale > 1.0
     c.vae_type, c.stage, c.latent_dim = "mld", "diffusion", [1, 256]
-    c.estimate, c.predict_transl, c.data_type, c.name_dataset = "wearer", True, "angle", dataset
+    c.estimate, c.predict_transl, c.data_type, c.name_dataset = estimate, True, "angle", dataset   # cfg.ESTIMATE (mld.py:111)
     c.save_for_edo = False
     c.save_cnt = 0
     c.pred_betas = c.pose_estimation_task = c.see_future = False
     c.global_orient_egoego = c.transl_egoego = c.pred_transl_egohmr = False
-    c.pred_global_orient = True          # TEST.GLOBAL_ORIENT_PRED: True (config_mld_egobody.yaml:73)
+    c.pred_global_orient = pred_global_orient   # TEST.GLOBAL_ORIENT_PRED (config_mld_egobody.yaml:73: True; mld.py:112,1501-1505)
     c.times = []
     c.eval()
     c._ref_ego_eval = c.ego_eval

@@ -24,7 +24,8 @@ def __getattr__(name):
 
 
 def build_model(config: str = "config_mld_egobody.yaml", device="cuda", guidance_scale=None, condition=None,
-                max_batch: int = 8, n_points: int = 20000, seed: int = 0, datamodule=None, sparse_lbs: bool = True, **kw):
+                max_batch: int = 8, n_points: int = 20000, seed: int = 0, datamodule=None, sparse_lbs: bool = True,
+                overrides=None, **kw):
     """Synthetic-weights model of the named architecture (no checkpoints exist offline): the reference-keyed
     ``state_dict`` from ``seeme_b200.synthetic`` is loaded with ``load_state_dict`` exactly like ``test.py:111-113``."""
     import torch
@@ -38,6 +39,11 @@ def build_model(config: str = "config_mld_egobody.yaml", device="cuda", guidance
         over["model"]["guidance_scale"] = guidance_scale
     if condition is not None:
         over["model"]["condition"] = list(condition)
+    for k, v in (overrides or {}).items():          # e.g. {"TEST": {"GLOBAL_ORIENT_PRED": False}} (one level of nesting)
+        if isinstance(v, dict):
+            over.setdefault(k, {}).update(v)
+        else:
+            over[k] = v
     cfg = load_config(path, overrides=over)
     dm = datamodule or SyntheticDataModule(cfg, name=cfg.DATASET_NAME, batch_size=max_batch, n_points=n_points,
                                            T=int(cfg.MOTION_LENGTH))

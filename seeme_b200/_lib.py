@@ -43,6 +43,7 @@ SIGNATURES = {
     "seeme_denoiser_forward": (C.c_int, [c_handle, c_float_p, C.c_int, c_float_p, C.c_int, C.c_int, c_float_p, C.c_void_p]),
     "seeme_sampler_run": (C.c_int, [c_handle, c_float_p, c_float_p, C.c_int, C.c_int, C.c_float, C.c_int,
                                     C.POINTER(C.c_int32), C.POINTER(C.c_float), c_float_p, C.c_void_p]),
+    "seeme_denoiser_set_backend": (C.c_int, [c_handle, C.c_int]),
     "seeme_denoiser_destroy": (C.c_int, [c_handle]),
     "seeme_ddim_step": (C.c_int, [c_float_p, c_float_p, c_float_p, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_void_p]),

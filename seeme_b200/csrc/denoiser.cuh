@@ -41,6 +41,7 @@ struct seeme_denoiser {
   bool use_graph = true;
   // persistent cluster sampler (den_persist.cu); null when disabled (SEEME_SAMPLER=graph)
   seeme::DenPersist* persist = nullptr;
+  int backend = SEEME_SAMPLER_PERSISTENT;
 };
 
 static inline float* blkw(seeme_denoiser* h, int l, int k) { return h->w[seeme::DN_BLK + seeme::DN_BLK_STRIDE * l + k]; }

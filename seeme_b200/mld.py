@@ -173,6 +173,10 @@ class MLD(nn.Module):
         self.pipeline_depth = int(kwargs.get("pipeline_depth", cfg.model.get("pipeline_depth", os.environ.get("SEEME_PIPELINE_DEPTH", 8))))
         # ego_eval_async / run_test_batches: consecutive batches whose 50-step sampler runs as ONE chain over all their rows
         # (the chain is latency-bound: 3 750 dependent kernels take the same ~27 ms for 512 or 2 048 rows)
+        # sampler back-end (include/seeme_b200.h: seeme_denoiser_set_backend): "persistent" = one launch of the cluster kernel per
+        # run, "graph" = the CUDA graph of small kernels, "auto" = persistent for a single batch (ego_eval: lowest latency),
+        # graph inside the batch pipeline (ego_eval_async with several batches in flight: least SM time next to the scene encoder)
+        self.sampler_backend = str(kwargs.get("sampler_backend", cfg.model.get("sampler_backend", os.environ.get("SEEME_SAMPLER_BACKEND", "auto"))))
         self.sampler_group = int(kwargs.get("sampler_group", cfg.model.get("sampler_group", os.environ.get("SEEME_SAMPLER_GROUP", 1))))
         self.last_vertices: Dict[str, torch.Tensor] = {}
         self._uncond_scene = None
@@ -225,6 +229,11 @@ class MLD(nn.Module):
             self.__dict__["_coef"] = self.scheduler.step_coefficients()
             self.__dict__["_sinus"] = time_sinusoid(self.scheduler.timesteps)
         op = self.denoiser.op if op is None else op
+        backend = self.sampler_backend
+        if backend == "auto":
+            backend = "graph" if self.__dict__.get("_in_pipeline", False) and int(self.pipeline_depth) > 1 else "persistent"
+        if os.environ.get("SEEME_SAMPLER") != "graph":
+            op.set_backend(backend)
         # the key lives on the kernel-side handle object (one per lane / slot), not in an id()-keyed dict: a rebuilt handle
         # starts without it, and DenoiserOp.forward / set_time_table keep it in step with the C-side table
         if getattr(op, "table_key", None) != tuple(ts):
@@ -413,6 +422,14 @@ class MLD(nn.Module):
 
     def _flush_members(self, members, dev):
         from . import modules as _m
+        self.__dict__["_in_pipeline"] = True
+        try:
+            self._flush_members_inner(members, dev)
+        finally:
+            self.__dict__["_in_pipeline"] = False
+
+    def _flush_members_inner(self, members, dev):
+        from . import modules as _m
         if True:
             if len(members) == 1:
                 m = members[0]
@@ -564,10 +581,14 @@ class MLD(nn.Module):
         fr = feats_rst[:, :min_len]
         if self.name_dataset == "gimo":
             fr = torch.cat([fr[:, :, :66], fr[:, :, -3:]], dim=-1)          # mld.py:1692-1694
+        fr_pred = fr
         if not self.pred_global_orient:
             fr = torch.cat([f_ref[:, :, :3], fr[:, :, 3:]], dim=-1)         # mld.py:1501-1505 (same stats on both sides)
         m_rst, v_rst, joints_rst, quat_rst = self._body(fr.contiguous(), betas_w, mean, std, n_body,
                                                         self.compute_vertices in ("rst", "all"))
+        if not self.pred_global_orient:
+            # only the SMPL input takes the ground-truth orientation; rs_set["m_rst"] stays renorm(feats_rst) (mld.py:1490-1491)
+            m_rst[:, :, :3] = fr_pred[:, :, :3].double() * std[:3] + mean[:3]
         rs_set = {
             "m_ref": m_ref, "m_rst": m_rst, "joints_ref": joints_ref, "joints_rst": joints_rst,
             "orientation_quat_rst": quat_rst, "orientation_quat_ref": quat_ref,

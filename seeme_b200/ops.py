@@ -215,6 +215,14 @@ class DenoiserOp(_Handle):
         self.max_rows = max_rows
         self.table_key = None          # timesteps the C-side tables hold, when they were built from a host sinusoid
 
+    def set_backend(self, backend: str):
+        """"persistent": one launch of the cluster kernel per run (lowest latency); "graph": the CUDA graph of small
+        kernels (least SM time; for many concurrent chains next to the scene encoder)"""
+        code = {"persistent": 0, "graph": 1}[backend]
+        if getattr(self, "_backend", None) != code:
+            _lib.check(_lib.lib().seeme_denoiser_set_backend(self.h, code), "seeme_denoiser_set_backend")
+            self._backend = code
+
     def set_time_table(self, timesteps: Sequence[int], sinusoid: Optional[torch.Tensor] = None):
         n = len(timesteps)
         self.table_key = tuple(int(t) for t in timesteps) if sinusoid is not None else None

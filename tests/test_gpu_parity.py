@@ -325,20 +325,32 @@ def test_ego_eval_fp16_scene_encoder_bound(name, config, gs):
     assert (rs["joints_ref"].double().cpu() - T(g["joints_ref"]).double()).abs().max() < 1e-5
 
 
-@pytest.mark.parametrize("name,config,gs", [("egobody_cfg", "config_mld_egobody.yaml", 7.5),
-                                            ("egobody_nocfg", "config_mld_egobody.yaml", 1.0),
-                                            ("gimo_cfg", "config_mld_gimo.yaml", 7.5)])
-def test_ego_eval_vs_unmodified_reference_golden(name, config, gs):
+@pytest.mark.parametrize("name,config,gs,cond,over", [
+    ("egobody_cfg", "config_mld_egobody.yaml", 7.5, None, None),
+    ("egobody_nocfg", "config_mld_egobody.yaml", 1.0, None, None),
+    ("gimo_cfg", "config_mld_gimo.yaml", 7.5, None, None),
+    # BASELINE configs[3]: config_mld_interactee.yaml (ESTIMATE interactee -> idx_ref = 1, MOTION_LENGTH 1), scene-only and
+    # scene + interactee conditioning (the latter under CFG)
+    ("interactee_T1_scene", "config_mld_interactee.yaml", 1.0, ("text", "scene"), None),
+    ("interactee_T1_scene_int_cfg", "config_mld_interactee.yaml", 7.5, ("text", "scene", "interactee"), None),
+    # TEST.GLOBAL_ORIENT_PRED: False -> the predicted body is posed with the ground-truth global orientation (mld.py:1501-1505)
+    ("egobody_gt_orient", "config_mld_egobody.yaml", 7.5, None, {"TEST": {"GLOBAL_ORIENT_PRED": False}})])
+def test_ego_eval_vs_unmodified_reference_golden(name, config, gs, cond, over):
     """MLD.ego_eval (CUDA) vs the rs_set the UNMODIFIED reference ego_eval produced on the same weights,
     batch and noise (tests/golden/ego_eval_*.npz).  Joint tolerance 1e-3 m (north_star); observed ~1e-5."""
     import seeme_b200
     from seeme_b200 import synthetic as S
     g = dict(np.load(os.path.join(GOLDEN, f"ego_eval_{name}.npz")))
     B = g["joints_rst"].shape[0]
-    model = seeme_b200.build_model(config, device=DEV, guidance_scale=gs, max_batch=B, n_points=1000, scene_precision="split-bf16")
-    batch = S.make_batch(B, n_points=1000, ragged=True, dataset=model.name_dataset)
+    Tm = int(g["cfg_T"])
+    model = seeme_b200.build_model(config, device=DEV, guidance_scale=gs, condition=cond, max_batch=B, n_points=1000,
+                                   scene_precision="split-bf16", overrides=over)
+    assert model.estimate == str(g["cfg_estimate"]) and bool(model.pred_global_orient) == bool(g["cfg_pred_global_orient"])
+    assert int(model.cfg.MOTION_LENGTH) == Tm
+    batch = S.make_batch(B, n_points=1000, T=Tm, ragged=Tm > 1, dataset=model.name_dataset)
     batch = tuple(x.to(DEV) if torch.is_tensor(x) else x for x in batch)
     noise = {k[6:]: T(v).to(DEV) for k, v in g.items() if k.startswith("noise_")}
+    torch.manual_seed(5)
     rs = model.ego_eval(batch, noise)
     assert rs["lengths"] == g["lengths"].tolist() and rs["list_names"] == {}
     assert rs["m_rst"].dtype == torch.float64 and rs["m_ref"].dtype == torch.float64
@@ -351,6 +363,9 @@ def test_ego_eval_vs_unmodified_reference_golden(name, config, gs):
     if "interactee" in model.condition:
         for k in ("joints_interactee", "root_interactee", "orientation_quat_int"):
             assert (rs[k].cpu() - T(g[k])).abs().max() < 1e-5, k
+    if Tm == 1:
+        assert rs["joints_rst"].shape == (B, 1, 24, 3)
+        return
     v = model.last_vertices["rst"]
     assert v is not None and v.shape == (B, 60, 6890, 3) and bool(torch.isfinite(v).all())
     # test_step / metric surface
@@ -389,13 +404,16 @@ def test_ego_eval_lanes_match_single_lane():
     assert out.shape == (B, 60, 24, 3) and bool(torch.isfinite(out).all())
 
 
-def test_ego_eval_async_pipeline_matches_sync():
+@pytest.mark.parametrize("backend", ["graph", "persistent"])
+def test_ego_eval_async_pipeline_matches_sync(backend):
     """several batches in flight on the pipeline slots (own streams + handles, host-resident inputs copied on the slot's
-    stream) give exactly the results of the synchronous call"""
+    stream) give exactly the results of the synchronous call -- with either sampler back-end (the default, "auto", takes the
+    persistent cluster kernel for a single batch and the kernel graph inside the pipeline; the two agree to fp32 rounding)"""
     import seeme_b200
     from seeme_b200 import synthetic as S
     B = 6
-    model = seeme_b200.build_model("config_mld_egobody.yaml", device=DEV, guidance_scale=7.5, max_batch=B, n_points=500, pipeline_depth=2)
+    model = seeme_b200.build_model("config_mld_egobody.yaml", device=DEV, guidance_scale=7.5, max_batch=B, n_points=500, pipeline_depth=2,
+                                   sampler_backend=backend)
     batches, noises = [], []
     for i in range(5):
         b = S.make_batch(B, seed=100 + i, n_points=500, ragged=True)
@@ -423,6 +441,11 @@ def test_ego_eval_async_pipeline_matches_sync():
                 assert torch.equal(r2[k], r[k]), (G, k)
         assert seen == [(B, 60, 24, 3)]
     model.sampler_group = 1
+    # the other back-end: same rows, different kernels -> equal to fp32 rounding through 50 steps, VAE decode and SMPL
+    model.sampler_backend = "persistent" if backend == "graph" else "graph"
+    other = model.ego_eval(tuple(x.to(DEV) if torch.is_tensor(x) else x for x in batches[0]), {k: v.to(DEV) for k, v in noises[0].items()})
+    assert (other["joints_rst"] - got[0]["joints_rst"]).abs().max() < 1e-4
+    model.sampler_backend = backend
     # the pipelined test loop updates the metric for every batch, in order
     model.EgoMetric.reset()
     outs = list(model.run_test_batches(batches))

@@ -64,14 +64,21 @@ def test_aa_to_quat_vs_reference_golden(golden_stages):
 
 @pytest.mark.parametrize("name,dataset,cond,gs", [("egobody_cfg", "egobody", ("text", "scene", "interactee"), 7.5),
                                                   ("egobody_nocfg", "egobody", ("text", "scene", "interactee"), 1.0),
-                                                  ("gimo_cfg", "gimo", ("text", "scene"), 7.5)])
+                                                  ("gimo_cfg", "gimo", ("text", "scene"), 7.5),
+                                                  # config_mld_interactee.yaml protocol: ESTIMATE interactee, MOTION_LENGTH 1
+                                                  ("interactee_T1_scene", "egobody", ("text", "scene"), 1.0),
+                                                  ("interactee_T1_scene_int_cfg", "egobody", ("text", "scene", "interactee"), 7.5),
+                                                  # TEST.GLOBAL_ORIENT_PRED: False (mld.py:1501-1505)
+                                                  ("egobody_gt_orient", "egobody", ("text", "scene", "interactee"), 7.5)])
 def test_ego_eval_restatement_vs_reference_golden(weights, smpl_buffers, name, dataset, cond, gs):
     g = dict(np.load(os.path.join(GOLDEN, f"ego_eval_{name}.npz")))
     B = g["joints_rst"].shape[0]
-    batch = S.make_batch(B, n_points=1000, ragged=True, dataset=dataset)
+    Tm, est, pgo = int(g["cfg_T"]), str(g["cfg_estimate"]), bool(g["cfg_pred_global_orient"])
+    batch = S.make_batch(B, n_points=1000, T=Tm, ragged=Tm > 1, dataset=dataset)
     noise = {k[6:]: T(v) for k, v in g.items() if k.startswith("noise_")}
     with torch.no_grad():
-        rs = O.ego_eval(weights, smpl_buffers, S.norm_stats(), batch, noise, condition=cond, guidance_scale=gs, dataset=dataset)
+        rs = O.ego_eval(weights, smpl_buffers, S.norm_stats(), batch, noise, condition=cond, guidance_scale=gs, dataset=dataset,
+                        estimate=est, pred_global_orient=pgo)
     assert rs["lengths"] == g["lengths"].tolist()
     assert rs["m_rst"].dtype == torch.float64 and g["m_rst"].dtype == np.float64     # App. D7
     for k in ("m_ref", "m_rst", "joints_ref", "joints_rst", "orientation_quat_rst", "orientation_quat_ref"):
