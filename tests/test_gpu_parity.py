@@ -467,10 +467,23 @@ def test_replication_protocol_driver(config, tmp_path):
     host = [dm.batch(i) for i in range(3)]
     out = str(tmp_path / "metrics.json")
     torch.manual_seed(3)
-    summary = run_test_protocol(model, lambda: iter(host), replication_times=3, out_json=out)
+    summary = run_test_protocol(model, lambda: iter(host), replication_times=3, cache_scene_embeddings=True, out_json=out)
     assert len(summary["Metrics/MPJPE"]) == 3 and "Metrics/MPJPE/conf_interval" in summary
     if "scene" in model.condition:
         assert summary["_scene_embedding_cache"] == {"hits": 6, "misses": 3}
+        # a batch whose clouds changed between repetitions (GIMO re-draws its points per item, dataset.py:2018-2020) is
+        # re-encoded: the cache verifies a content fingerprint, and it is off unless the caller asks for it
+        host2 = [tuple(x.clone() if torch.is_tensor(x) else x for x in b) for b in host]
+        calls = [0]
+
+        def redrawn():
+            calls[0] += 1
+            for b in host2:
+                b[4].add_(0.01 * calls[0])
+                yield b
+        s2 = run_test_protocol(model, redrawn, replication_times=2, cache_scene_embeddings=True)
+        assert s2["_scene_embedding_cache"] == {"hits": 0, "misses": 6}
+        assert "_scene_embedding_cache" not in run_test_protocol(model, lambda: iter(host), replication_times=1)
     # (with random-init weights the reference's test-split gate -- head error < 0.9, root error < 300 mm -- can reject every
     # sequence, so MPJPE may be NaN; the bookkeeping is what is checked here)
     saved = json.load(open(out))
@@ -610,4 +623,6 @@ def test_interactee_protocol_with_image_tokens(tmp_path):
     noise = {"x_T": torch.randn(B, 1, 256, generator=g, device=DEV)}
     a = model.ego_eval(dev_batch, noise)
     b = model.ego_eval_async(dev_batch, noise).result()
-    assert torch.equal(a["joints_rst"], b["joints_rst"]) and a["joints_rst"].shape == (B, 1, 24, 3)
+    # default back-end policy: the synchronous call samples with the persistent cluster kernel, the pipeline with the
+    # kernel graph -- same rows, equal to fp32 rounding (bit-equality per back-end: test_ego_eval_async_pipeline_matches_sync)
+    assert (a["joints_rst"] - b["joints_rst"]).abs().max() < 1e-4 and a["joints_rst"].shape == (B, 1, 24, 3)
