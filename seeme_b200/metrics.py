@@ -2,8 +2,8 @@
 (``mld/models/metrics/compute.py:349-580`` update, ``:184-232`` compute).
 
 The reference loops over sequences and frames in Python/numpy (6.6 ms per sequence); here every
-sequence of the batch is reduced at once with masked tensor ops on the GPU and one small D2H copy
-per ``update``.  Semantics kept: start alignment on joint 15 of frame 0, per-frame root alignment,
+sequence of the batch is reduced at once with masked tensor ops on the GPU and the state sums stay
+on the device until ``compute`` (no host synchronisation per ``update``).  Semantics kept: start alignment on joint 15 of frame 0, per-frame root alignment,
 MPJPE / root error in mm, acceleration error (x1000), head-orientation error
 ``mean_t ||I - R_gt R_pred^-1||_F`` with ``quaternion_matrix`` normalisation, and the test-split
 gating ``head_err < 0.9 and root_err < 300 and accl > 0`` (``:545-562``).  States are plain sums
@@ -34,19 +34,42 @@ def quaternion_rotmat(q: torch.Tensor) -> torch.Tensor:
     return torch.where(small[:, :, None], eye, R)
 
 
+def _inv3(m: torch.Tensor) -> torch.Tensor:
+    """closed-form inverse of [...,3,3] matrices (adjugate / determinant): a handful of elementwise kernels, no LAPACK
+    call and no host-side status check (``torch.linalg.inv`` synchronises the host on CUDA)"""
+    a, b, c = m[..., 0, 0], m[..., 0, 1], m[..., 0, 2]
+    d, e, f = m[..., 1, 0], m[..., 1, 1], m[..., 1, 2]
+    g, h, i = m[..., 2, 0], m[..., 2, 1], m[..., 2, 2]
+    A, B, C = e * i - f * h, -(d * i - f * g), d * h - e * g
+    det = a * A + b * B + c * C
+    adj = torch.stack([A, -(b * i - c * h), b * f - c * e,
+                       B, a * i - c * g, -(a * f - c * d),
+                       C, -(a * h - b * g), a * e - b * d], dim=-1).view(*m.shape)
+    return adj / det[..., None, None]
+
+
+def _lengths_on(lengths: List[int], dev) -> torch.Tensor:
+    """the Python list of lengths as a device tensor WITHOUT blocking the host: a pageable host-to-device copy waits for the
+    work queued on the stream, a pinned one is just enqueued"""
+    t = torch.tensor(lengths, dtype=torch.int64)
+    if torch.device(dev).type == "cuda":
+        return t.pin_memory().to(dev, non_blocking=True)
+    return t
+
+
 def per_sequence_errors(jts_text, jts_ref, ori_quat_text, ori_quat_ref, lengths: List[int]) -> Dict[str, torch.Tensor]:
     """[B] vectors: mpjpe (mm), root_err (mm), accl (x1000), head_err."""
     B, T, NJ, _ = jts_text.shape
     dev = jts_text.device
-    ln = torch.as_tensor(lengths, device=dev)
+    ln = _lengths_on(lengths, dev)
     mask = (torch.arange(T, device=dev)[None, :] < ln[:, None])               # [B,T]
     fm = mask.double()
     jr = jts_ref.double() - jts_ref[:, 0:1, 15:16, :].double()                 # align_start (compute.py:367-372)
     jp = jts_text.double() - jts_text[:, 0:1, 15:16, :].double()
     pelvis_gt, pelvis_pred = jr[:, :, 0], jp[:, :, 0]
     root_err = ((pelvis_gt - pelvis_pred).norm(dim=-1) * fm).sum(1) / ln * 1000.0
-    jr = jr - jr[:, :, [0]]                                                    # align_root
-    jp = jp - jp[:, :, [0]]
+    jr = jr - jr[:, :, 0:1]                                                    # align_root
+    jp = jp - jp[:, :, 0:1]
     mpjpe = ((jp - jr).norm(dim=-1).mean(-1) * fm).sum(1) / ln * 1000.0
     # acceleration error over the valid prefix (compute.py:254-279): frames 0..len-3
     if T >= 3:
@@ -60,13 +83,20 @@ def per_sequence_errors(jts_text, jts_ref, ori_quat_text, ori_quat_ref, lengths:
     # head orientation (compute.py:335-346, 527)
     Rg = quaternion_rotmat(ori_quat_ref.double()).view(B, T, 3, 3)
     Rp = quaternion_rotmat(ori_quat_text.double()).view(B, T, 3, 3)
-    err = torch.eye(3, dtype=torch.float64, device=dev) - Rg @ torch.linalg.inv(Rp)
+    err = torch.eye(3, dtype=torch.float64, device=dev) - Rg @ _inv3(Rp)
     head = (err.flatten(-2).norm(dim=-1) * fm).sum(1) / ln
     return {"mpjpe": mpjpe, "root_err": root_err, "accl": accl, "head_err": head}
 
 
 class EgoMetric:
-    """Same call surface as the reference's ``ComputeMetrics``: ``update(split, ...)``, ``compute(sanity_flag)``, ``reset()``."""
+    """Same call surface as the reference's ``ComputeMetrics``: ``update(split, ...)``, ``compute(sanity_flag)``, ``reset()``.
+
+    The state sums that depend on the joints live in ONE float64 device vector that ``update`` adds to with device ops only
+    -- no host synchronisation per batch (the reference's ``.cpu().numpy()`` per sequence, and this class's former
+    ``.tolist()`` per batch, stalled the batch pipeline's retire loop); ``state`` / ``compute`` / ``state_vector`` read it."""
+
+    _DEV_KEYS = ["count_seq", "count_seq_root", "count_seq_accl", "count_seq_head_orientation", "MPJPE", "mpjpe_interactee",
+                 "ROOT_ERROR", "ACCL", "HEAD_ORIENTATION_ERROR"]
 
     def __init__(self, njoints: int = 23, jointstype: str = "humanml3d", force_in_meter: bool = True,
                  dist_sync_on_step: bool = True, **kwargs):
@@ -76,48 +106,62 @@ class EgoMetric:
         self.last_per_sequence: Optional[Dict[str, torch.Tensor]] = None
 
     def reset(self):
-        self.state = {k: 0.0 for k in STATE_KEYS}
+        self._host = {"count": 0.0, "n_batch": 0.0, "count_seq_int": 0.0}     # known on the host (lengths, batch count)
+        self._dev: Optional[torch.Tensor] = None                              # [len(_DEV_KEYS)] float64 on the joints' device
+
+    @property
+    def state(self) -> Dict[str, float]:
+        """all state sums as Python floats (one device-to-host read)"""
+        vals = self._dev.tolist() if self._dev is not None else [0.0] * len(self._DEV_KEYS)
+        d = dict(zip(self._DEV_KEYS, vals))
+        d.update(self._host)
+        return {k: d[k] for k in STATE_KEYS}
 
     def state_vector(self) -> torch.Tensor:
-        return torch.tensor([self.state[k] for k in STATE_KEYS], dtype=torch.float64)
+        s = self.state
+        return torch.tensor([s[k] for k in STATE_KEYS], dtype=torch.float64)
 
     def load_state_vector(self, v: torch.Tensor):
-        for k, x in zip(STATE_KEYS, v.tolist()):
-            self.state[k] = x
+        d = dict(zip(STATE_KEYS, v.tolist()))
+        self._host = {k: d[k] for k in self._host}
+        dev = self._dev.device if self._dev is not None else v.device
+        self._dev = torch.tensor([d[k] for k in self._DEV_KEYS], dtype=torch.float64, device=dev)
 
     @torch.no_grad()
     def update(self, split, jts_text, jts_ref, ori_quat_text, ori_quat_ref, root_interactee, joints_interactee,
                orientation_quat_int, joints_interactee_gt, lengths: Optional[List[int]] = None, list_names=None):
         if lengths is None:
             lengths = [jts_text.shape[1]] * jts_text.shape[0]
-        s = self.state
-        s["count"] += float(sum(lengths))
-        s["n_batch"] += 1
+        dev = jts_text.device
+        if self._dev is None or self._dev.device != dev:
+            old = self._dev
+            self._dev = torch.zeros(len(self._DEV_KEYS), dtype=torch.float64, device=dev)
+            if old is not None:
+                self._dev += old.to(dev)
+        self._host["count"] += float(sum(lengths))
+        self._host["n_batch"] += 1
         e = per_sequence_errors(jts_text, jts_ref, ori_quat_text, ori_quat_ref, lengths)
         self.last_per_sequence = e
+        zero = torch.zeros((), dtype=torch.float64, device=dev)
+        mi_sum = zero
         if joints_interactee_gt is not None:
-            ji = joints_interactee.double() - joints_interactee[:, :, [0]].double()
-            jg = joints_interactee_gt.double() - joints_interactee_gt[:, :, [0]].double()
-            ln = torch.as_tensor(lengths, device=ji.device)
-            fm = (torch.arange(ji.shape[1], device=ji.device)[None, :] < ln[:, None]).double()
-            mi = ((ji - jg).norm(dim=-1).mean(-1) * fm).sum(1) / ln * 1000.0
-            s["mpjpe_interactee"] += float(mi.sum())
-            s["count_seq_int"] += len(lengths)
+            ji = joints_interactee.double() - joints_interactee[:, :, 0:1].double()
+            jg = joints_interactee_gt.double() - joints_interactee_gt[:, :, 0:1].double()
+            ln = _lengths_on(lengths, dev)
+            fm = (torch.arange(ji.shape[1], device=dev)[None, :] < ln[:, None]).double()
+            mi_sum = (((ji - jg).norm(dim=-1).mean(-1) * fm).sum(1) / ln * 1000.0).sum()
+            self._host["count_seq_int"] += len(lengths)
         ok = e["accl"] > 0
         if split == "test":
             ok = ok & (e["head_err"] < 0.9) & (e["root_err"] < 300)
-        packed = torch.stack([ok.double(), torch.where(ok, e["mpjpe"], 0.0), torch.where(ok, e["root_err"], 0.0),
-                              torch.where(ok, e["accl"], 0.0), torch.where(ok, e["head_err"], 0.0)]).sum(1).cpu()
-        n, mp, rt, ac, hd = packed.tolist()
-        s["MPJPE"] += mp
-        s["count_seq"] += n
-        s["ROOT_ERROR"] += rt
-        s["count_seq_root"] += n
+        n = ok.double().sum()
+        mp, rt = torch.where(ok, e["mpjpe"], 0.0).sum(), torch.where(ok, e["root_err"], 0.0).sum()
         if split == "test":                                                   # compute.py:553-561
-            s["HEAD_ORIENTATION_ERROR"] += hd
-            s["count_seq_head_orientation"] += n
-            s["ACCL"] += ac
-            s["count_seq_accl"] += n
+            ac, hd, nt = torch.where(ok, e["accl"], 0.0).sum(), torch.where(ok, e["head_err"], 0.0).sum(), n
+        else:
+            ac = hd = nt = zero
+        # order of _DEV_KEYS
+        self._dev += torch.stack([n, n, nt, nt, mp, mi_sum, rt, ac, hd])
 
     def compute(self, sanity_flag=False) -> Dict[str, float]:
         s = self.state
@@ -154,7 +198,8 @@ MR_STATE_KEYS = ["count", "count_seq", "MPJPE", "PAMPJPE", "ACCEL"]
 class MRMetric:
     """``MRMetrics`` (mr.py:11-96) without the per-sequence Python loop and the host round trip: MPJPE (root-aligned),
     PA-MPJPE and acceleration error summed over ALL frames of the padded sequences, as the reference does
-    (``rst[i]`` is the whole sequence; only ``count`` uses the lengths)."""
+    (``rst[i]`` is the whole sequence; only ``count`` uses the lengths).  The sums stay on the device; the one host
+    synchronisation left in ``update`` is the cuSOLVER status check inside ``torch.linalg.svd``."""
 
     def __init__(self, njoints: int = 22, jointstype: str = "mmm", force_in_meter: bool = True, align_root: bool = True,
                  dist_sync_on_step: bool = True, **kwargs):
@@ -165,22 +210,36 @@ class MRMetric:
         self.reset()
 
     def reset(self):
-        self.state = {k: 0.0 for k in MR_STATE_KEYS}
+        self._host = {"count": 0.0, "count_seq": 0.0}
+        self._dev: Optional[torch.Tensor] = None          # [MPJPE, PAMPJPE, ACCEL] float64 sums on the joints' device
+
+    @property
+    def state(self) -> Dict[str, float]:
+        vals = self._dev.tolist() if self._dev is not None else [0.0, 0.0, 0.0]
+        return {"count": self._host["count"], "count_seq": self._host["count_seq"], "MPJPE": vals[0], "PAMPJPE": vals[1],
+                "ACCEL": vals[2]}
 
     def state_vector(self) -> torch.Tensor:
-        return torch.tensor([self.state[k] for k in MR_STATE_KEYS], dtype=torch.float64)
+        s = self.state
+        return torch.tensor([s[k] for k in MR_STATE_KEYS], dtype=torch.float64)
 
     def load_state_vector(self, v: torch.Tensor):
-        for k, x in zip(MR_STATE_KEYS, v.tolist()):
-            self.state[k] = x
+        d = dict(zip(MR_STATE_KEYS, v.tolist()))
+        self._host = {"count": d["count"], "count_seq": d["count_seq"]}
+        dev = self._dev.device if self._dev is not None else v.device
+        self._dev = torch.tensor([d["MPJPE"], d["PAMPJPE"], d["ACCEL"]], dtype=torch.float64, device=dev)
 
     @torch.no_grad()
     def update(self, joints_rst: torch.Tensor, joints_ref: torch.Tensor, lengths: List[int]):
         assert joints_rst.shape == joints_ref.shape and joints_rst.dim() == 4
         B, T, J, _ = joints_rst.shape
-        s = self.state
-        s["count"] += float(sum(lengths))
-        s["count_seq"] += len(lengths)
+        self._host["count"] += float(sum(lengths))
+        self._host["count_seq"] += len(lengths)
+        if self._dev is None or self._dev.device != joints_rst.device:
+            old = self._dev
+            self._dev = torch.zeros(3, dtype=torch.float64, device=joints_rst.device)
+            if old is not None:
+                self._dev += old.to(joints_rst.device)
         rst, ref = joints_rst.reshape(B * T, J, 3), joints_ref.reshape(B * T, J, 3)
         valid = (ref[:, :, 0] != -2.0).to(rst.dtype)                                          # utils.py:356
         pa, ta = (rst - rst[:, :1], ref - ref[:, :1]) if self.align_root else (rst, ref)
@@ -191,10 +250,7 @@ class MRMetric:
             accel = (acc(joints_rst) - acc(joints_ref)).norm(dim=-1).mean(-1).sum()
         else:
             accel = torch.zeros((), device=rst.device)
-        a, b, c = torch.stack([mpjpe.sum().double(), pampjpe.sum().double(), accel.double()]).tolist()
-        s["MPJPE"] += a
-        s["PAMPJPE"] += b
-        s["ACCEL"] += c
+        self._dev += torch.stack([mpjpe.sum().double(), pampjpe.sum().double(), accel.double()])     # no host round trip
 
     def compute(self, sanity_flag=False) -> Dict[str, float]:
         s = self.state

@@ -626,3 +626,47 @@ def test_interactee_protocol_with_image_tokens(tmp_path):
     # default back-end policy: the synchronous call samples with the persistent cluster kernel, the pipeline with the
     # kernel graph -- same rows, equal to fp32 rounding (bit-equality per back-end: test_ego_eval_async_pipeline_matches_sync)
     assert (a["joints_rst"] - b["joints_rst"]).abs().max() < 1e-4 and a["joints_rst"].shape == (B, 1, 24, 3)
+
+
+# ---- default product precision at the benchmarked size -------------------------------------------------------------------
+def _well_conditioned(sd, scale=0.25):
+    """SURVEY 8(d) 'well-conditioned' variant: the output-side Linear weights of every residual branch scaled down, so the
+    latent stays O(1) instead of growing to |z| ~ 300 under random init (App. G)"""
+    out = {}
+    for k, v in sd.items():
+        tail = k.endswith(("linear2.weight", "out_proj.weight", "out_layers.2.weight", "final_layer.weight")) or "linear_blocks" in k and k.endswith("weight")
+        out[k] = v * scale if tail else v
+    return out
+
+
+@pytest.mark.parametrize("variant", ["default_init", "well_conditioned"])
+def test_default_precision_drift_at_bench_size(variant):
+    """The DEFAULT configuration (fp16 scene-encoder operands, split-bf16 denoiser / VAE, persistent sampler) at the
+    benchmarked cloud size: B = 8, 20 000 points, CFG 7.5, 50 steps, ragged lengths, against the fp32 oracle.  north_star's
+    bound for reduced-precision GEMMs: MPJPE drift < 0.5 mm; the max-abs joint error is printed and bounded at 3 mm."""
+    import seeme_b200
+    from oracle import restate as O
+    from seeme_b200 import synthetic as S
+    B, N = 8, 20000
+    model = seeme_b200.build_model("config_mld_egobody.yaml", device=DEV, guidance_scale=7.5, max_batch=B, n_points=N)
+    assert model.scene_precision == 16
+    W = {"denoiser": S.denoiser_state(0), "vae": S.vae_state(0), "pointnet": S.pointnet_state(0), "output_scene": S.output_scene_state(0)}
+    if variant == "well_conditioned":
+        W["denoiser"], W["vae"] = _well_conditioned(W["denoiser"]), _well_conditioned(W["vae"])
+        sd = {"denoiser." + k: v for k, v in W["denoiser"].items()}
+        sd.update({"vae." + k: v for k, v in W["vae"].items()})
+        model.load_state_dict(sd, strict=False)
+    batch = S.make_batch(B, seed=77, n_points=N, ragged=True)
+    g = torch.Generator().manual_seed(13)
+    noise = {"eps_int": torch.randn(1, B, 256, generator=g), "eps_unc": torch.randn(1, B, 256, generator=g),
+             "x_T": torch.randn(B, 1, 256, generator=g)}
+    rs = model.ego_eval(tuple(x.to(DEV) if torch.is_tensor(x) else x for x in batch), {k: v.to(DEV) for k, v in noise.items()})
+    with torch.no_grad():
+        ref = O.ego_eval(W, S.smpl_buffers(), S.norm_stats(), batch, noise, guidance_scale=7.5)
+    d = rs["joints_rst"].double().cpu() - ref["joints_rst"].double()
+    drift_mm, max_mm = float(d.norm(dim=-1).mean()) * 1e3, float(d.abs().max()) * 1e3
+    zmax = float(ref["z"].abs().max())
+    print(f"{variant}: |z|max {zmax:.1f}, MPJPE drift {drift_mm:.4f} mm, max-abs {max_mm:.4f} mm (B={B}, N={N}, CFG 7.5)")
+    assert drift_mm < 0.5, drift_mm
+    assert max_mm < 3.0, max_mm
+    assert (rs["joints_ref"].double().cpu() - ref["joints_ref"].double()).abs().max() < 1e-5
