@@ -723,9 +723,10 @@ def main():
         # and would read 46 ms instead of 29 ms: let the clocks recover first
         torch.cuda.synchronize()
         time.sleep(1.0)
-        step_resident()
+        step_fixed = lambda: model.ego_eval(dev_batch, noise_d)     # ONE batch: every pass hits the cached embedding
+        step_fixed()
         torch.cuda.synchronize()
-        t_cached = device_ms(step_resident)
+        t_cached = device_ms(step_fixed)
         model._encode_scene = orig_encode
         F = B * 60
         bet = torch.zeros(F, 10, device=dev); pz = torch.zeros(F, 69, device=dev); gz = torch.zeros(F, 3, device=dev)
