@@ -183,6 +183,7 @@ int seeme_sampler_run(seeme_denoiser_t h, const float* x_T, const float* cond, i
  * GPU with the scene encoder, as in the batch pipeline).  Same results to fp32 rounding. */
 #define SEEME_SAMPLER_PERSISTENT 0
 #define SEEME_SAMPLER_GRAPH 1
+#define SEEME_SAMPLER_TILE 2   /* persistent kernel, ONE CTA per 128-row tile (no cluster): 1/8 of the SM time */
 int seeme_denoiser_set_backend(seeme_denoiser_t h, int backend);
 int seeme_denoiser_destroy(seeme_denoiser_t h);
 /* standalone `DDIMScheduler.step` (eta = 0, epsilon prediction) for the scheduler duck type. */

@@ -871,6 +871,658 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
   }
 }
 
+
+// =====================================================================================================================
+// Monolithic per-tile sampler ("tile" back-end): ONE CTA owns a tile of 128 denoiser rows for the whole run and computes
+// every GEMM in full -- no cluster, no exchange.  Same algebra and tables as the cluster kernel above, plus:
+//   * the self-attention logit of the latent token against itself, (W_q x + b_q).(W_k x + b_k), is evaluated as
+//     x.(M x + m) + c with M = W_q^T W_k (fp64 product at create): the q and k rows never have to exist at the same time
+//     (tensor memory holds ONE 256-column accumulator next to the fp32 residual stream);
+//   * the A operand [128 x 256] (bf16 hi | lo, SWIZZLE_128B K-blocks) lives in shared memory and is rewritten in place by
+//     the epilogue threads; only the weights stream (a tape of 16 KB tiles, 5-slot ring);
+//   * the FFN 256 -> 1024 -> 256 runs in 8 hidden chunks of 128: relu(h) goes back to tensor memory as packed bf16 (hi, lo)
+//     and is the A operand of the second GEMM straight from there (tcgen05.mma with A in TMEM); while it runs, the fp32
+//     residual is parked in an L2-resident scratch row.
+// SM time per run is ~1/8 of the cluster kernel's (4 CTAs instead of 32 for 512 rows) at about the same latency, which is
+// what the batch pipeline wants next to the scene encoder; with >= 148 tiles it is the saturating configuration.
+constexpr int DM_THREADS = 192;
+constexpr int DM_NW = 5;
+constexpr int DM_W_SLOT = 16384;             // one [128 n x 64 k] bf16 tile (hi or lo)
+constexpr int DM_A_BYTES = 4 * 32768;        // 4 K-blocks x (hi 16 KB | lo 16 KB)
+constexpr int DM_SWAP_BYTES = 128 * 32 * 4;  // CFG pair exchange, 32 columns at a time
+constexpr int DM_SMEM = DM_A_BYTES + DM_NW * DM_W_SLOT + DM_SWAP_BYTES + 1024;
+constexpr int DM_XR = 256;                   // tensor-memory columns: [0,256) accumulator, [256,512) fp32 residual stream;
+constexpr int DM_ACC1 = 256, DM_HHI = 384, DM_HLO = 448;   // during the FFN: chunk accumulator | relu(h) hi | lo
+
+struct DmUnit {       // one [128 rows x 128 outputs] GEMM unit; its weights are the next 2 nkb tiles of the tape
+  int nkb, acc_col, a_base, ts, first, commit, accum, swap;
+};
+constexpr int DM_MAX_UNITS = 400;
+
+struct DmParams {
+  DpLayerP L[5];
+  const float* mu[5];          // [257]: m = W_q^T b_k + W_k^T b_q, then c = b_q . b_k
+  const float *skip_b[2], *fng, *fnb, *pe0;
+  const uint8_t* tape;
+  const DmUnit* units;
+  int n_units, n_blobs;
+  float *lat, *xs1;            // [tiles][256][128] fp32 scratch: latents, residual parked during the FFN
+  uint8_t* skipimg;            // [tiles][2][4 K-blocks][32 KB]: outputs of blocks 0 / 1 as A-operand images
+  const float* x_in;
+  float* out;
+  const float *coef, *gscale;
+  int B, R, cfg, n_steps, mode;
+  unsigned long long* trace;   // diagnostics (SEEME_DP_TRACE): role 1 = MMA issuer (4 go received, 5 group committed), 2 = epilogue row 64
+  int trace_step;              // (6 accumulator ready, 10 go signalled), CTA 0 at trace_step
+};
+
+__device__ __forceinline__ void dm_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void dm_tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+// 32 consecutive columns [c0, c0 + 32) of this thread's row into the shared-memory A operand (bf16 hi | lo K-block tiles)
+__device__ __forceinline__ void dm_write_a(uint8_t* a_buf, int c0, int row, const float (&f)[32]) {
+  uint32_t hb[16], lb[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dp_split2(f[2 * i], f[2 * i + 1], hb[i], lb[i]);
+  uint8_t* line = a_buf + (c0 >> 6) * 32768 + row * 128;
+  const int j0 = (c0 & 63) >> 3, sw = row & 7;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = ((j0 + j) ^ sw) << 4;
+    *reinterpret_cast<uint4*>(line + c) = make_uint4(hb[4 * j], hb[4 * j + 1], hb[4 * j + 2], hb[4 * j + 3]);
+    *reinterpret_cast<uint4*>(line + 16384 + c) = make_uint4(lb[4 * j], lb[4 * j + 1], lb[4 * j + 2], lb[4 * j + 3]);
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_constant__ DmParams p) {
+  extern __shared__ __align__(1024) uint8_t dm_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dm_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_buf = smem;
+  uint8_t* w_ring = smem + DM_A_BYTES;
+  float* swapb = reinterpret_cast<float*>(w_ring + DM_NW * DM_W_SLOT);
+  __shared__ __align__(8) uint64_t full_w[DM_NW], empty_w[DM_NW], acc_full, go, a_free, a_full2;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < DM_NW; ++i) { mbar_init(&full_w[i], 1); mbar_init(&empty_w[i], 1); }
+    mbar_init(&acc_full, 1);
+    mbar_init(&go, 4);
+    mbar_init(&a_free, 1);
+    mbar_init(&a_full2, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ---- producer: the weight tape, in order; the saved block output for the second half of a skip fusion ----
+    if (lane == 0) {
+      uint32_t iw = 0, nsw = 0;
+      for (int step = 0; step < p.n_steps; ++step) {
+        const uint8_t* src = p.tape;
+        for (int u = 0; u < p.n_units; ++u) {
+          const DmUnit un = p.units[u];
+          if (un.swap) {
+            dp_wait(&a_free, nsw & 1u, 21);
+            ++nsw;
+            mbar_arrive_expect_tx(&a_full2, DM_A_BYTES);
+            const uint8_t* img = p.skipimg + ((size_t)(tile * 2 + (un.swap - 1)) * 4) * 32768;
+            dp_fence_proxy_all();
+            for (int kb = 0; kb < 4; ++kb) dp_bulk_load(a_buf + kb * 32768, img + (size_t)kb * 32768, 32768, &a_full2);
+          }
+          for (int t = 0; t < 2 * un.nkb; ++t) {
+            const uint32_t sw = iw % DM_NW;
+            dp_wait(&empty_w[sw], ((iw / DM_NW) & 1u) ^ 1u, 22);
+            mbar_arrive_expect_tx(&full_w[sw], DM_W_SLOT);
+            dp_bulk_load(w_ring + sw * DM_W_SLOT, src, DM_W_SLOT, &full_w[sw]);
+            src += DM_W_SLOT;
+            ++iw;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ----
+    uint32_t iw = 0, ngo = 0, nsw = 0;
+    int tr_n = 0;
+    const uint64_t da_base = umma_desc_k128(smem_u32(a_buf));
+    const uint64_t dw_base = umma_desc_k128(smem_u32(w_ring));
+    const uint32_t idesc = umma_idesc_bf16(128);
+    for (int step = 0; step < p.n_steps; ++step) {
+      for (int u = 0; u < p.n_units; ++u) {
+        const DmUnit un = p.units[u];
+        if (un.first) {
+          dp_wait(&go, ngo & 1u, 23);
+          ++ngo;
+          tc_fence_after();
+          if (lane == 0) DP_TR(1, 4);
+        }
+        if (un.swap) {
+          if (umma_elect_one()) umma_commit(&a_free);      // the MMAs of the first K half have read the A operand
+          __syncwarp();
+          dp_wait(&a_full2, nsw & 1u, 24);
+          ++nsw;
+        }
+        const uint32_t d_t = tmem_base + (uint32_t)un.acc_col;
+        for (int kb = 0; kb < un.nkb; ++kb) {
+          const uint32_t s0 = iw % DM_NW, s1 = (iw + 1) % DM_NW;
+          dp_wait(&full_w[s0], (iw / DM_NW) & 1u, 25);
+          dp_wait(&full_w[s1], ((iw + 1) / DM_NW) & 1u, 26);
+          tc_fence_after();
+          if (umma_elect_one()) {
+            const uint64_t dwh0 = umma_desc_add(dw_base, s0 * (DM_W_SLOT >> 4));
+            const uint64_t dwl0 = umma_desc_add(dw_base, s1 * (DM_W_SLOT >> 4));
+            if (!un.ts) {
+              const uint64_t da0 = umma_desc_add(da_base, (uint32_t)(un.a_base + kb) * (32768 >> 4));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = umma_desc_add(da0, k * 2), dwh = umma_desc_add(dwh0, k * 2), dwl = umma_desc_add(dwl0, k * 2);
+                umma_bf16(d_t, da, dwh, idesc, ((kb | k) != 0) || un.accum);
+                umma_bf16(d_t, umma_desc_add(da, 16384 >> 4), dwh, idesc, 1);
+                umma_bf16(d_t, da, dwl, idesc, 1);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t ta = tmem_base + (uint32_t)(un.a_base + kb * 32 + k * 8);
+                const uint64_t dwh = umma_desc_add(dwh0, k * 2), dwl = umma_desc_add(dwl0, k * 2);
+                dm_umma_ts(d_t, ta, dwh, idesc, ((kb | k) != 0) || un.accum);
+                dm_umma_ts(d_t, ta + (DM_HLO - DM_HHI), dwh, idesc, 1);
+                dm_umma_ts(d_t, ta, dwl, idesc, 1);
+              }
+            }
+            umma_commit(&empty_w[s0]);
+            umma_commit(&empty_w[s1]);
+            if (un.commit && kb == un.nkb - 1) umma_commit(&acc_full);
+          }
+          __syncwarp();
+          iw += 2;
+        }
+        if (un.commit && lane == 0) DP_TR(1, 5);
+      }
+    }
+  } else {
+    // ---- epilogue: thread = row, 256 columns in chunks of 32 ----
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const uint32_t tl = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const int prow = tile * 128 + row;
+    int latrow, grow;
+    bool valid;
+    if (p.cfg) {
+      latrow = tile * 64 + (row & 63);
+      valid = latrow < p.B;
+      grow = (row >> 6) * p.B + latrow;
+    } else {
+      latrow = prow;
+      grow = prow;
+      valid = prow < p.R;
+    }
+    float* const lat_g = p.lat + (size_t)tile * 256 * 128 + row;
+    float* const xs1_g = p.xs1 + (size_t)tile * 256 * 128 + row;
+    uint8_t* const skip_g = p.skipimg + (size_t)tile * 2 * 4 * 32768;
+    const size_t ct_off = (size_t)tile * 4 * NC * 256 * 128 + row;
+    uint32_t nacc = 0;
+    int tr_n = 0, step = 0;
+    const bool tr_me = warp == 2 && lane == 0;
+    auto acc_wait = [&]() {
+      dp_wait(&acc_full, nacc & 1u, 27);
+      ++nacc;
+      tc_fence_after();
+      if (tr_me) DP_TR(2, 6);
+    };
+    auto signal_go = [&]() {
+      dp_fence_proxy_all();        // shared-memory A operand written with st.shared -> read by the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&go);
+      if (tr_me) DP_TR(2, 10);
+    };
+    // LayerNorm over the 256 columns stored at TMEM columns [base, base + 256): returns (mean, rstd); biased variance, eps 1e-5
+    auto ln_stats = [&](uint32_t base, float sum, float& mean, float& rstd) {
+      mean = sum * (1.0f / 256.0f);
+      float m2 = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < 8; ++ch) {
+        float v[32];
+        dp_ld32(tl + base + ch * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; m2 = fmaf(d, d, m2); }
+      }
+      rstd = rsqrtf(m2 * (1.0f / 256.0f) + 1e-5f);
+    };
+
+    {   // initial state: x = latents (or the given sample) + learned PE row 0
+#pragma unroll 1
+      for (int ch = 0; ch < 8; ++ch) {
+        float x[32], pe[32];
+        dp_ldvec(p.pe0 + ch * 32, pe);
+        if (valid) {
+          const float* src = p.x_in + (size_t)(p.mode == 0 ? latrow : grow) * 256 + ch * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(src) + j);
+            x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { lat_g[(size_t)(ch * 32 + i) * 128] = x[i]; x[i] += pe[i]; }
+        dp_st32(tl + DM_XR + ch * 32, x);
+        dm_write_a(a_buf, ch * 32, row, x);
+      }
+      signal_go();
+    }
+
+    for (step = 0; step < p.n_steps; ++step) {
+      const size_t toff = (size_t)step * 512;
+#pragma unroll 1
+      for (int l = 0; l < 5; ++l) {
+        const DpLayerP& L = p.L[l];
+        const float* __restrict__ ct = L.ctab + ct_off;
+        if (l >= 3) {      // x = Linear(cat[x, skip])
+          acc_wait();
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float x[32], b[32];
+            dp_ldvec(p.skip_b[l - 3] + ch * 32, b);
+            dp_ld32(tl + ch * 32, x);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] += b[i];
+            dp_st32(tl + DM_XR + ch * 32, x);
+            dm_write_a(a_buf, ch * 32, row, x);
+          }
+          signal_go();
+        }
+        // ---- self-attention of the latent token over {x, cond tokens, time token} ----
+        float pr[NC + 2];
+        {   // u = M x: logit against itself = x . (u + m) + c
+          acc_wait();
+          float d = 0.f;
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float u[32], xr[32], m[32];
+            dp_ldvec(p.mu[l] + ch * 32, m);
+            dp_ld32(tl + ch * 32, u);
+            dp_ld32(tl + DM_XR + ch * 32, xr);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) d = fmaf(xr[i], u[i] + m[i], d);
+          }
+          pr[0] = d + __ldg(p.mu[l] + 256);
+          signal_go();
+        }
+        {   // q: logits against the cond tokens and the time token
+          acc_wait();
+          float dc[NC], dt = 0.f;
+#pragma unroll
+          for (int n = 0; n < NC; ++n) dc[n] = 0.f;
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float qv[32], v[32];
+            dp_ldvec(L.bqkv + ch * 32, v);
+            dp_ld32(tl + ch * 32, qv);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) qv[i] += v[i];
+            dp_ldvec(L.kt + toff + ch * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dt = fmaf(qv[i], v[i], dt);
+#pragma unroll
+            for (int n = 0; n < NC; ++n) {
+              const float* kc = ct + (size_t)DP_CT(0, n, 0) + (size_t)ch * 32 * 128;
+              float a = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) a = fmaf(qv[i], __ldg(kc + i * 128), a);
+              dc[n] += a;
+            }
+          }
+          signal_go();
+#pragma unroll
+          for (int n = 0; n < NC; ++n) pr[1 + n] = dc[n];
+          pr[NC + 1] = dt;
+          float m = pr[0];
+#pragma unroll
+          for (int j = 1; j < NC + 2; ++j) m = fmaxf(m, pr[j]);
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < NC + 2; ++j) { pr[j] = __expf(pr[j] - m); sum += pr[j]; }
+          const float inv = 1.0f / sum;
+#pragma unroll
+          for (int j = 0; j < NC + 2; ++j) pr[j] *= inv;
+        }
+        {   // ov: t0 = x + b + sum_j p_j ov_j; x1 = norm1(t0)
+          acc_wait();
+          float sum = 0.f;
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float t0[32], v[32];
+            dp_ld32(tl + ch * 32, t0);
+            dp_ldvec(L.bqkv + 512 + ch * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t0[i] = v[i] + pr[0] * t0[i];
+            dp_ldvec(L.kt + toff + 256 + ch * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t0[i] = fmaf(pr[NC + 1], v[i], t0[i]);
+#pragma unroll
+            for (int n = 0; n < NC; ++n) {
+              const float* oc = ct + (size_t)DP_CT(1, n, 0) + (size_t)ch * 32 * 128;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) t0[i] = fmaf(pr[1 + n], __ldg(oc + i * 128), t0[i]);
+            }
+            dp_ld32(tl + DM_XR + ch * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { t0[i] += v[i]; sum += t0[i]; }
+            dp_st32(tl + ch * 32, t0);
+          }
+          float mean, rstd;
+          ln_stats(0, sum, mean, rstd);
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float t0[32], g[32], b[32];
+            dp_ldvec(L.n1g + ch * 32, g);
+            dp_ldvec(L.n1b + ch * 32, b);
+            dp_ld32(tl + ch * 32, t0);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              t0[i] = (t0[i] - mean) * rstd * g[i] + b[i];
+              xs1_g[(size_t)(ch * 32 + i) * 128] = t0[i];       // the fp32 residual waits in L2 while the FFN uses its columns
+            }
+            dm_write_a(a_buf, ch * 32, row, t0);
+          }
+          signal_go();
+        }
+        // ---- FFN 256 -> 1024 (ReLU) -> 256 in 8 hidden chunks of 128; relu(h) returns to tensor memory as bf16 (hi, lo) ----
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+          acc_wait();
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            float f[32], b[32];
+            dp_ldvec(L.b1 + j * 128 + c4 * 32, b);
+            dp_ld32(tl + DM_ACC1 + c4 * 32, f);
+            uint32_t hb[16], lb[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dp_split2(fmaxf(f[2 * i] + b[2 * i], 0.f), fmaxf(f[2 * i + 1] + b[2 * i + 1], 0.f), hb[i], lb[i]);
+            dm_tmem_st16(tl + DM_HHI + c4 * 16, hb);
+            dm_tmem_st16(tl + DM_HLO + c4 * 16, lb);
+          }
+          tmem_st_wait_dp();
+          signal_go();
+        }
+        {   // x2 = norm2(x1 + ffn); then the input norm of the cross-attention
+          acc_wait();
+          float sum = 0.f;
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float t1[32], v[32];
+            dp_ldvec(L.b2 + ch * 32, v);
+            dp_ld32(tl + ch * 32, t1);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { t1[i] += v[i] + xs1_g[(size_t)(ch * 32 + i) * 128]; sum += t1[i]; }
+            dp_st32(tl + ch * 32, t1);
+          }
+          float mean, rstd;
+          ln_stats(0, sum, mean, rstd);
+          float sum2 = 0.f;
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float t1[32], g[32], b[32];
+            dp_ldvec(L.n2g + ch * 32, g);
+            dp_ldvec(L.n2b + ch * 32, b);
+            dp_ld32(tl + ch * 32, t1);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { t1[i] = (t1[i] - mean) * rstd * g[i] + b[i]; sum2 += t1[i]; }
+            dp_st32(tl + DM_XR + ch * 32, t1);      // the FFN is done with these columns: the residual stream is back
+          }
+          ln_stats(DM_XR, sum2, mean, rstd);
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float t1[32], g[32], b[32];
+            dp_ldvec(L.cng + ch * 32, g);
+            dp_ldvec(L.cnb + ch * 32, b);
+            dp_ld32(tl + DM_XR + ch * 32, t1);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t1[i] = (t1[i] - mean) * rstd * g[i] + b[i];
+            dm_write_a(a_buf, ch * 32, row, t1);
+          }
+          signal_go();
+        }
+        {   // linear cross-attention to the cond tokens + FiLM
+          acc_wait();
+          float m = -INFINITY;
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float qv[32], v[32];
+            dp_ldvec(L.bcaq + ch * 32, v);
+            dp_ld32(tl + ch * 32, qv);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { qv[i] += v[i]; m = fmaxf(m, qv[i]); }
+            dp_st32(tl + ch * 32, qv);
+          }
+          float ssum = 0.f, dn[NC];
+#pragma unroll
+          for (int n = 0; n < NC; ++n) dn[n] = 0.f;
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float qv[32];
+            dp_ld32(tl + ch * 32, qv);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { qv[i] = __expf(qv[i] - m); ssum += qv[i]; }
+#pragma unroll
+            for (int n = 0; n < NC; ++n) {
+              const float* ks = ct + (size_t)DP_CT(2, n, 0) + (size_t)ch * 32 * 128;
+              float a = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) a = fmaf(qv[i], __ldg(ks + i * 128), a);
+              dn[n] += a;
+            }
+          }
+          const float inv = 1.0f / ssum;
+#pragma unroll
+          for (int n = 0; n < NC; ++n) dn[n] *= inv;
+          float sum = 0.f;
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float y[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = 0.f;
+#pragma unroll
+            for (int n = 0; n < NC; ++n) {
+              const float* vv = ct + (size_t)DP_CT(3, n, 0) + (size_t)ch * 32 * 128;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) y[i] = fmaf(dn[n], __ldg(vv + i * 128), y[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sum += y[i];
+            dp_st32(tl + ch * 32, y);
+          }
+          float mean, rstd;
+          ln_stats(0, sum, mean, rstd);
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float y[32], g[32], b[32];
+            dp_ldvec(L.film_ca + toff + ch * 32, g);
+            dp_ldvec(L.film_ca + toff + 256 + ch * 32, b);
+            dp_ld32(tl + ch * 32, y);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float t = (y[i] - mean) * rstd * g[i] + b[i];
+              y[i] = __fdividef(t, 1.0f + __expf(-t));
+            }
+            dm_write_a(a_buf, ch * 32, row, y);
+          }
+          signal_go();
+        }
+        {   // x3 = x2 + out(h)
+          acc_wait();
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float x[32], xr[32], b[32];
+            dp_ldvec(L.bcaout + ch * 32, b);
+            dp_ld32(tl + ch * 32, x);
+            dp_ld32(tl + DM_XR + ch * 32, xr);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] += b[i] + xr[i];
+            dp_st32(tl + DM_XR + ch * 32, x);
+            dm_write_a(a_buf, ch * 32, row, x);
+          }
+          signal_go();
+        }
+        {   // FFN 256 -> 128 (GELU)
+          acc_wait();
+#pragma unroll 1
+          for (int c4 = 0; c4 < 4; ++c4) {
+            float f[32], b[32];
+            dp_ldvec(L.bf1 + c4 * 32, b);
+            dp_ld32(tl + c4 * 32, f);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i] + b[i]);
+            dm_write_a(a_buf, c4 * 32, row, f);
+          }
+          signal_go();
+        }
+        {   // -> 256, FiLM
+          acc_wait();
+          float sum = 0.f;
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float y[32], b[32];
+            dp_ldvec(L.bf2 + ch * 32, b);
+            dp_ld32(tl + ch * 32, y);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { y[i] += b[i]; sum += y[i]; }
+            dp_st32(tl + ch * 32, y);
+          }
+          float mean, rstd;
+          ln_stats(0, sum, mean, rstd);
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float y[32], g[32], b[32];
+            dp_ldvec(L.film_ff + toff + ch * 32, g);
+            dp_ldvec(L.film_ff + toff + 256 + ch * 32, b);
+            dp_ld32(tl + ch * 32, y);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float t = (y[i] - mean) * rstd * g[i] + b[i];
+              y[i] = __fdividef(t, 1.0f + __expf(-t));
+            }
+            dm_write_a(a_buf, ch * 32, row, y);
+          }
+          signal_go();
+        }
+        {   // block output = x3 + out(h)
+          acc_wait();
+          float sum = 0.f;
+#pragma unroll 1
+          for (int ch = 0; ch < 8; ++ch) {
+            float x[32], xr[32], b[32];
+            dp_ldvec(L.bfout + ch * 32, b);
+            dp_ld32(tl + ch * 32, x);
+            dp_ld32(tl + DM_XR + ch * 32, xr);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { x[i] += b[i] + xr[i]; sum += x[i]; }
+            if (l < 4) {
+              dp_st32(tl + DM_XR + ch * 32, x);
+              dm_write_a(a_buf, ch * 32, row, x);
+              if (l < 2) dp_publish<32>(skip_g + (size_t)l * 4 * 32768, ch * 32, row, x);    // saved for the skip fusion of block 4 - l
+            } else {
+              dp_st32(tl + ch * 32, x);
+            }
+          }
+          if (l < 4) {
+            if (l < 2) __threadfence();
+            signal_go();
+          } else {
+            // final LayerNorm, then CFG combine + DDIM update
+            float mean, rstd;
+            ln_stats(0, sum, mean, rstd);
+            const float c0 = __ldg(p.coef + step * 4), c1 = __ldg(p.coef + step * 4 + 1), c2 = __ldg(p.coef + step * 4 + 2),
+                        c3 = __ldg(p.coef + step * 4 + 3);
+            const float gs = __ldg(p.gscale);
+            const bool last = step == p.n_steps - 1;
+#pragma unroll 1
+            for (int ch = 0; ch < 8; ++ch) {
+              float e[32], g[32], b[32];
+              dp_ldvec(p.fng + ch * 32, g);
+              dp_ldvec(p.fnb + ch * 32, b);
+              dp_ld32(tl + ch * 32, e);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) e[i] = (e[i] - mean) * rstd * g[i] + b[i];
+              if (p.mode == 1) {
+                if (valid) {
+                  float4* dst = reinterpret_cast<float4*>(p.out + (size_t)grow * 256 + ch * 32);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) dst[j] = make_float4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+                }
+                continue;
+              }
+              if (p.cfg) {       // rows r (uncond) and r + 64 (cond) are the two guidance branches of one latent
+#pragma unroll
+                for (int i = 0; i < 32; ++i) swapb[i * 128 + row] = e[i];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const bool is_u = row < 64;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const float o = swapb[i * 128 + (row ^ 64)];
+                  const float eu = is_u ? e[i] : o, ec = is_u ? o : e[i];
+                  e[i] = __fadd_rn(eu, __fmul_rn(gs, __fsub_rn(ec, eu)));
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+              }
+              float lt[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float x0 = __fdiv_rn(__fsub_rn(lat_g[(size_t)(ch * 32 + i) * 128], __fmul_rn(c0, e[i])), c1);
+                lt[i] = __fadd_rn(__fmul_rn(c2, x0), __fmul_rn(c3, e[i]));
+              }
+              if (last) {
+                if (valid && (!p.cfg || row < 64)) {
+                  float4* dst = reinterpret_cast<float4*>(p.out + (size_t)latrow * 256 + ch * 32);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) dst[j] = make_float4(lt[4 * j], lt[4 * j + 1], lt[4 * j + 2], lt[4 * j + 3]);
+                }
+              } else {
+                float pe[32];
+                dp_ldvec(p.pe0 + ch * 32, pe);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { lat_g[(size_t)(ch * 32 + i) * 128] = lt[i]; lt[i] += pe[i]; }
+                dp_st32(tl + DM_XR + ch * 32, lt);
+                dm_write_a(a_buf, ch * 32, row, lt);
+              }
+            }
+            if (p.mode == 0 && !last) signal_go();
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // transposes the cond-token projections into the per-row tables the epilogue reads column by column:
 //   tab[tile][which][n][col][row of the tile], which = 0: k, 1: ov (self-attention; kov rows n R + grow: k | ov), 2: softmax over the
 //   tokens of the cross-attention key, 3: its value (kv2: key | value).  Rows beyond the batch are zero.
@@ -930,6 +1582,13 @@ struct DenPersist {
   PackedLinear Wkov[5], Wk2v2[5];
   ActBuf condb, tnb;             // bf16 (hi, lo) of the cond tokens / of their text_norm
   unsigned long long* trace = nullptr;
+  // monolithic per-tile kernel
+  uint8_t* tape_m = nullptr;
+  DmUnit* d_units_m = nullptr;
+  int n_units_m = 0, n_blobs_m = 0;
+  float* mu[5] = {};
+  float *lat_m = nullptr, *xs1_m = nullptr;
+  uint8_t* skipimg = nullptr;
 };
 
 static inline uint16_t f2bf(float x) {    // round to nearest even, like __float2bfloat16_rn (finite inputs)
@@ -1097,17 +1756,115 @@ int den_persist_create(seeme_denoiser* h) {
   for (int c = 1; c < DP_CL; ++c)
     SEEME_REQUIRE(tapes[c].size() == P->tape_cta_bytes, SEEME_EINVAL, "den_persist: tape size mismatch");
 
+  // ---- monolithic kernel: M = W_q^T W_k, m = W_q^T b_k + W_k^T b_q, c = b_q . b_k (fp64), its unit list and tape ----
+  std::vector<HostW> Wu(5);
+  std::vector<std::vector<float>> mu(5);
+  for (int l = 0; l < 5; ++l) {
+    const std::vector<float>& W = Wqkv[l].v;          // rows: q (scaled) | k | ov
+    Wu[l].v.assign(256 * 256, 0.f);
+    Wu[l].ld = 256;
+    std::vector<double> acc(256 * 256, 0.0);
+    for (int n = 0; n < 256; ++n) {
+      const float* wq = &W[(size_t)n * 256];
+      const float* wk = &W[(size_t)(256 + n) * 256];
+      for (int i = 0; i < 256; ++i) {
+        const double a = wq[i];
+        double* row = &acc[(size_t)i * 256];
+        for (int j = 0; j < 256; ++j) row[j] += a * (double)wk[j];
+      }
+    }
+    for (size_t i = 0; i < acc.size(); ++i) Wu[l].v[i] = (float)acc[i];
+    mu[l].assign(257, 0.f);
+    double c = 0.0;
+    for (int i = 0; i < 256; ++i) {
+      double m = 0.0;
+      for (int n = 0; n < 256; ++n) m += (double)W[(size_t)n * 256 + i] * (double)bqkv[l][256 + n] + (double)W[(size_t)(256 + n) * 256 + i] * (double)bqkv[l][n];
+      mu[l][i] = (float)m;
+    }
+    for (int n = 0; n < 256; ++n) c += (double)bqkv[l][n] * (double)bqkv[l][256 + n];
+    mu[l][256] = (float)c;
+  }
+  std::vector<DmUnit> munits;
+  std::vector<uint8_t> mtape;
+  mtape.reserve(21u << 20);
+  {
+    auto MU = [&](int nkb, int acc_col, int a_base, int ts, int first, int commit, int accum, int swap) {
+      DmUnit u;
+      u.nkb = nkb; u.acc_col = acc_col; u.a_base = a_base; u.ts = ts; u.first = first; u.commit = commit; u.accum = accum; u.swap = swap;
+      munits.push_back(u);
+    };
+    // a [256 outputs x K] linear on the shared-memory A operand: two 128-output units
+    auto linear = [&](const HostW& W, int row0, int k0, int nkb, int accum, int swap_first, bool first, bool commit) {
+      for (int half = 0; half < 2; ++half) {
+        MU(nkb, 128 * half, 0, 0, first && half == 0, commit && half == 1, accum, half == 0 ? swap_first : 0);
+        append_unit(mtape, W, iota_rows(row0 + 128 * half, 128), k0, nkb);
+      }
+    };
+    HostW Wq[5], Wov[5];
+    for (int l = 0; l < 5; ++l) {
+      Wq[l].ld = Wov[l].ld = 256;
+      Wq[l].v.assign(Wqkv[l].v.begin(), Wqkv[l].v.begin() + 256 * 256);
+      Wov[l].v.assign(Wqkv[l].v.begin() + 512 * 256, Wqkv[l].v.end());
+    }
+    for (int l = 0; l < 5; ++l) {
+      if (l >= 3) {     // K = 512: current x, then (after the A operand has been refilled) the saved output of block 4 - l
+        linear(Wskip[l - 3], 0, 0, 4, 0, 0, true, false);
+        linear(Wskip[l - 3], 0, 256, 4, 1, l == 3 ? 2 : 1, false, true);      // swap: 1 = block 0's output, 2 = block 1's
+      }
+      linear(Wu[l], 0, 0, 4, 0, 0, true, true);
+      linear(Wq[l], 0, 0, 4, 0, 0, true, true);
+      linear(Wov[l], 0, 0, 4, 0, 0, true, true);
+      // FFN: [G1_0] [G2_0 G1_1] ... [G2_6 G1_7] [G2_7]
+      auto g1 = [&](int j, bool first, bool commit) {
+        MU(4, DM_ACC1, 0, 0, first, commit, 0, 0);
+        append_unit(mtape, Wl1[l], iota_rows(128 * j, 128), 0, 4);
+      };
+      g1(0, true, true);
+      for (int j = 0; j < 8; ++j) {
+        for (int half = 0; half < 2; ++half) {
+          MU(2, 128 * half, DM_HHI, 1, half == 0, j == 7 && half == 1, j > 0, 0);
+          append_unit(mtape, Wl2[l], iota_rows(128 * half, 128), 128 * j, 2);
+        }
+        if (j < 7) g1(j + 1, false, true);
+      }
+      linear(Wcaq[l], 0, 0, 4, 0, 0, true, true);
+      linear(Wcaout[l], 0, 0, 4, 0, 0, true, true);
+      MU(4, 0, 0, 0, 1, 1, 0, 0);
+      append_unit(mtape, Wf1[l], iota_rows(0, 128), 0, 4);
+      linear(Wf2[l], 0, 0, 2, 0, 0, true, true);
+      linear(Wfout[l], 0, 0, 4, 0, 0, true, true);
+    }
+  }
+  P->n_units_m = (int)munits.size();
+  P->n_blobs_m = (int)(mtape.size() / DM_W_SLOT);
+  SEEME_REQUIRE(P->n_units_m <= DM_MAX_UNITS, SEEME_EINVAL, "den_persist: %d monolithic units", P->n_units_m);
+
   const size_t Rp = (size_t)P->rows_pad_max, NCM = SEEME_MAX_COND_TOKENS;
   size_t bytes = pad256(P->tape_cta_bytes * DP_CL) + pad256(sizeof(DpUnit) * DP_MAX_UNITS) + pad256((size_t)P->max_tiles * XC_KB * 32768) +
                  pad256((size_t)P->max_tiles * DP_CL * 256 * 128 * 4) + 5 * pad256(4 * NCM * 256 * Rp * 4) +
                  5 * (pad256(768 * 4) + pad256(512 * 256 * 4) + 2 * pad256(512 * 4) + 3 * pad256((size_t)DEN_MAX_STEPS * 512 * 4)) +
-                 5 * 2 * 2 * pad256(512 * 256 * 2) + 5 * pad256(512 * 256 * 4) + 4 * pad256(NCM * (size_t)h->max_rows * 256 * 2) + 65536;
+                 5 * 2 * 2 * pad256(512 * 256 * 2) + 5 * pad256(512 * 256 * 4) + 4 * pad256(NCM * (size_t)h->max_rows * 256 * 2) + 65536 +
+                 pad256(mtape.size()) + pad256(sizeof(DmUnit) * DM_MAX_UNITS) + 5 * pad256(257 * 4) +
+                 2 * pad256((size_t)P->max_tiles * 256 * 128 * 4) + pad256((size_t)P->max_tiles * 2 * 4 * 32768);
   SEEME_TRY(P->arena.init(bytes));
   P->tape = P->arena.take<uint8_t>(P->tape_cta_bytes * DP_CL);
   P->d_units = P->arena.take<DpUnit>(DP_MAX_UNITS);
   P->ximg = P->arena.take<uint8_t>((size_t)P->max_tiles * XC_KB * 32768);
   P->part = P->arena.take<float>((size_t)P->max_tiles * DP_CL * 256 * 128);
   SEEME_REQUIRE(P->part, SEEME_ENOMEM, "den_persist: arena exhausted");
+  P->tape_m = P->arena.take<uint8_t>(mtape.size());
+  P->d_units_m = P->arena.take<DmUnit>(DM_MAX_UNITS);
+  P->lat_m = P->arena.take<float>((size_t)P->max_tiles * 256 * 128);
+  P->xs1_m = P->arena.take<float>((size_t)P->max_tiles * 256 * 128);
+  P->skipimg = P->arena.take<uint8_t>((size_t)P->max_tiles * 2 * 4 * 32768);
+  SEEME_REQUIRE(P->skipimg, SEEME_ENOMEM, "den_persist: arena exhausted (monolithic kernel)");
+  SEEME_CUDA(cudaMemcpy(P->tape_m, mtape.data(), mtape.size(), cudaMemcpyHostToDevice));
+  SEEME_CUDA(cudaMemcpy(P->d_units_m, munits.data(), sizeof(DmUnit) * munits.size(), cudaMemcpyHostToDevice));
+  for (int l = 0; l < 5; ++l) {
+    P->mu[l] = P->arena.take<float>(257);
+    SEEME_REQUIRE(P->mu[l], SEEME_ENOMEM, "den_persist: arena exhausted");
+    SEEME_CUDA(cudaMemcpy(P->mu[l], mu[l].data(), 257 * 4, cudaMemcpyHostToDevice));
+  }
   for (int c = 0; c < DP_CL; ++c)
     SEEME_CUDA(cudaMemcpy(P->tape + (size_t)c * P->tape_cta_bytes, tapes[c].data(), P->tape_cta_bytes, cudaMemcpyHostToDevice));
   SEEME_CUDA(cudaMemcpy(P->d_units, units.data(), sizeof(DpUnit) * units.size(), cudaMemcpyHostToDevice));
@@ -1146,6 +1903,10 @@ int den_persist_create(seeme_denoiser* h) {
   SEEME_CUDA(cudaFuncSetAttribute(den_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM));
   SEEME_CUDA(cudaFuncSetAttribute(den_persist_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM));
   SEEME_CUDA(cudaFuncSetAttribute(den_persist_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM));
+  SEEME_CUDA(cudaFuncSetAttribute(den_mono_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM));
+  SEEME_CUDA(cudaFuncSetAttribute(den_mono_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM));
+  SEEME_CUDA(cudaFuncSetAttribute(den_mono_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM));
+  SEEME_CUDA(cudaFuncSetAttribute(den_mono_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM));
   SEEME_CUDA(cudaDeviceSynchronize());
   return SEEME_OK;
 }
@@ -1182,6 +1943,20 @@ int den_persist_build_tables(seeme_denoiser* h, int n, cudaStream_t s) {
   return SEEME_OK;
 }
 
+static int dp_dump_trace(unsigned long long* dtrace, const char* path, cudaStream_t s) {
+  std::vector<unsigned long long> host(4 * 4096);
+  SEEME_CUDA(cudaStreamSynchronize(s));
+  SEEME_CUDA(cudaMemcpy(host.data(), dtrace, host.size() * 8, cudaMemcpyDeviceToHost));
+  FILE* f = fopen(path, "w");
+  if (f) {
+    for (int role = 0; role < 4; ++role)
+      for (int i = 0; i < 4096 && host[role * 4096 + i]; ++i)
+        fprintf(f, "%d %llu %d\n", role, host[role * 4096 + i] >> 8, (int)(host[role * 4096 + i] & 255));
+    fclose(f);
+  }
+  return SEEME_OK;
+}
+
 int den_persist_run(seeme_denoiser* h, int mode, const float* x_in, int Nc, int B, int R, int cfg, int n_steps, float* out,
                     cudaStream_t s) {
   DenPersist* P = h->persist;
@@ -1201,6 +1976,45 @@ int den_persist_run(seeme_denoiser* h, int mode, const float* x_in, int Nc, int 
     SEEME_TRY(run_linear(P->Wk2v2[l], P->tnb, nullptr, rows, ACT_NONE, nullptr, 0, o2, 3, s));
     dp_ctab_kernel<<<dim3(rows_pad / 32, 32), dim3(32, 8), 0, s>>>(h->kvc[l], h->kv2[l], P->ctab[l], Nc, B, R, cfg, rows_pad);
     SEEME_LAUNCH_CHECK();
+  }
+  if (h->backend == SEEME_SAMPLER_TILE) {
+    DmParams m;
+    memset(&m, 0, sizeof(m));
+    for (int l = 0; l < 5; ++l) {
+      DpLayerP& L = m.L[l];
+      L.bqkv = P->bqkv[l]; L.n1g = blkw(h, l, SA_N1_W); L.n1b = blkw(h, l, SA_N1_B);
+      L.b1 = blkw(h, l, SA_L1_B); L.b2 = blkw(h, l, SA_L2_B); L.n2g = blkw(h, l, SA_N2_W); L.n2b = blkw(h, l, SA_N2_B);
+      L.cng = blkw(h, l, CA_N_W); L.cnb = blkw(h, l, CA_N_B); L.bcaq = blkw(h, l, CA_Q_B); L.bcaout = blkw(h, l, CA_OUT_B);
+      L.bf1 = blkw(h, l, FF_L1_B); L.bf2 = blkw(h, l, FF_L2_B); L.bfout = blkw(h, l, FF_OUT_B);
+      L.kt = P->tkov[l]; L.film_ca = P->film2_ca[l]; L.film_ff = P->film2_ff[l]; L.ctab = P->ctab[l];
+      m.mu[l] = P->mu[l];
+    }
+    m.skip_b[0] = h->w[DN_LB0_B]; m.skip_b[1] = h->w[DN_LB1_B];
+    m.fng = h->w[DN_NORM_W]; m.fnb = h->w[DN_NORM_B]; m.pe0 = h->w[DN_PE];
+    m.tape = P->tape_m; m.units = P->d_units_m; m.n_units = P->n_units_m; m.n_blobs = P->n_blobs_m;
+    m.lat = P->lat_m; m.xs1 = P->xs1_m; m.skipimg = P->skipimg;
+    m.x_in = x_in; m.out = out; m.coef = h->d_coef; m.gscale = h->d_gscale;
+    m.B = B; m.R = R; m.cfg = cfg; m.n_steps = n_steps; m.mode = mode;
+    const char* tpath = getenv("SEEME_DP_TRACE");
+    if (tpath && !P->trace) SEEME_CUDA(cudaMalloc(&P->trace, 4 * 4096 * 8));
+    if (tpath) {
+      SEEME_CUDA(cudaMemsetAsync(P->trace, 0, 4 * 4096 * 8, s));
+      m.trace = P->trace;
+      m.trace_step = n_steps > 1 ? 1 : 0;
+    }
+    {
+      ProfScope prof(PROF_SAMPLER_GRAPH, s);
+      const dim3 grid(tiles), block(DM_THREADS);
+      switch (Nc) {
+        case 1: den_mono_kernel<1><<<grid, block, DM_SMEM, s>>>(m); break;
+        case 2: den_mono_kernel<2><<<grid, block, DM_SMEM, s>>>(m); break;
+        case 3: den_mono_kernel<3><<<grid, block, DM_SMEM, s>>>(m); break;
+        default: den_mono_kernel<4><<<grid, block, DM_SMEM, s>>>(m); break;
+      }
+    }
+    SEEME_LAUNCH_CHECK();
+    if (tpath) SEEME_TRY(dp_dump_trace(P->trace, tpath, s));
+    return SEEME_OK;
   }
   DpParams p;
   memset(&p, 0, sizeof(p));
@@ -1240,18 +2054,7 @@ int den_persist_run(seeme_denoiser* h, int mode, const float* x_in, int Nc, int 
     }
   }
   SEEME_LAUNCH_CHECK();
-  if (trace_path) {
-    std::vector<unsigned long long> host(4 * 4096);
-    SEEME_CUDA(cudaStreamSynchronize(s));
-    SEEME_CUDA(cudaMemcpy(host.data(), P->trace, host.size() * 8, cudaMemcpyDeviceToHost));
-    FILE* f = fopen(trace_path, "w");
-    if (f) {
-      for (int role = 0; role < 4; ++role)
-        for (int i = 0; i < 4096 && host[role * 4096 + i]; ++i)
-          fprintf(f, "%d %llu %d\n", role, host[role * 4096 + i] >> 8, (int)(host[role * 4096 + i] & 255));
-      fclose(f);
-    }
-  }
+  if (trace_path) SEEME_TRY(dp_dump_trace(P->trace, trace_path, s));
   return SEEME_OK;
 }
 

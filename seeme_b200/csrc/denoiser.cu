@@ -462,7 +462,7 @@ extern "C" int seeme_denoiser_forward(seeme_denoiser_t h, const float* sample, i
   cudaStream_t s = (cudaStream_t)stream;
   if (!(h->table_ts.size() == 1 && h->table_ts[0] == timestep)) SEEME_TRY(den_build_tables(h, &timestep, 1, nullptr, s));
   SEEME_CUDA(cudaMemcpyAsync(h->cond, cond, (size_t)Nc * R * 256 * 4, cudaMemcpyDeviceToDevice, s));
-  if (h->persist && h->backend == SEEME_SAMPLER_PERSISTENT) return den_persist_run(h, 1, sample, Nc, R, R, 0, 1, out, s);
+  if (h->persist && h->backend != SEEME_SAMPLER_GRAPH) return den_persist_run(h, 1, sample, Nc, R, R, 0, 1, out, s);
   SEEME_TRY(den_cond_precompute(h, Nc, R, s));
   SEEME_CUDA(launch_pdl(den_prep_kernel, dim3((R + 7) / 8), dim3(256), 0, s, sample, h->w[DN_PE], h->x.f, h->x.h, h->x.l, R, R));
   SEEME_LAUNCH_CHECK();
@@ -513,7 +513,7 @@ extern "C" int seeme_sampler_run(seeme_denoiser_t h, const float* x_T, const flo
     h->gscale_host = guidance_scale;
   }
   SEEME_CUDA(cudaMemcpyAsync(h->cond, cond, (size_t)Nc * R * 256 * 4, cudaMemcpyDeviceToDevice, s));
-  if (h->persist && h->backend == SEEME_SAMPLER_PERSISTENT) return den_persist_run(h, 0, x_T, Nc, B, R, cfg, n_steps, z, s);
+  if (h->persist && h->backend != SEEME_SAMPLER_GRAPH) return den_persist_run(h, 0, x_T, Nc, B, R, cfg, n_steps, z, s);
   SEEME_CUDA(cudaMemcpyAsync(h->lat, x_T, (size_t)B * 256 * 4, cudaMemcpyDeviceToDevice, s));
   if (h->use_graph) {
     if (!(h->gexec && h->g_Nc == Nc && h->g_B == B && h->g_cfg == cfg && h->g_steps == n_steps)) {
@@ -546,7 +546,7 @@ extern "C" int seeme_sampler_run(seeme_denoiser_t h, const float* x_T, const flo
 
 extern "C" int seeme_denoiser_set_backend(seeme_denoiser_t h, int backend) {
   SEEME_REQUIRE(h, SEEME_EINVAL, "seeme_denoiser_set_backend: null handle");
-  SEEME_REQUIRE(backend == SEEME_SAMPLER_PERSISTENT || backend == SEEME_SAMPLER_GRAPH, SEEME_EINVAL,
+  SEEME_REQUIRE(backend == SEEME_SAMPLER_PERSISTENT || backend == SEEME_SAMPLER_GRAPH || backend == SEEME_SAMPLER_TILE, SEEME_EINVAL,
                 "seeme_denoiser_set_backend: unknown back-end %d", backend);
   SEEME_REQUIRE(backend == SEEME_SAMPLER_GRAPH || h->persist, SEEME_EINVAL,
                 "seeme_denoiser_set_backend: the persistent sampler was disabled at create (SEEME_SAMPLER=graph)");

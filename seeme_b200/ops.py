@@ -218,7 +218,7 @@ class DenoiserOp(_Handle):
     def set_backend(self, backend: str):
         """"persistent": one launch of the cluster kernel per run (lowest latency); "graph": the CUDA graph of small
         kernels (least SM time; for many concurrent chains next to the scene encoder)"""
-        code = {"persistent": 0, "graph": 1}[backend]
+        code = {"persistent": 0, "graph": 1, "tile": 2}[backend]
         if getattr(self, "_backend", None) != code:
             _lib.check(_lib.lib().seeme_denoiser_set_backend(self.h, code), "seeme_denoiser_set_backend")
             self._backend = code

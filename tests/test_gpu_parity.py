@@ -24,7 +24,7 @@ def cu(sd):
 @pytest.fixture(scope="module")
 def den_op(weights):
     from seeme_b200 import ops
-    return ops.DenoiserOp(cu(weights["denoiser"]), max_rows=64)
+    return ops.DenoiserOp(cu(weights["denoiser"]), max_rows=256)
 
 
 @pytest.fixture(scope="module")
@@ -46,11 +46,16 @@ def smpl_op(smpl_buffers):
 
 
 # ---- denoiser ---------------------------------------------------------------------------------------
+BACKENDS = ["persistent", "tile", "graph"]     # cluster kernel, one-CTA-per-tile kernel, CUDA graph of small kernels
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("key,t,enc", [("den_out_t481_nc2", 481, "den_enc2"), ("den_out_t1_nc2", 1, "den_enc2"),
                                        ("den_out_t981_nc1", 981, "den_enc1")])
-def test_denoiser_vs_reference_golden(den_op, golden_stages, key, t, enc):
+def test_denoiser_vs_reference_golden(den_op, golden_stages, key, t, enc, backend):
     from seeme_b200.modules import time_sinusoid
     g = golden_stages
+    den_op.set_backend(backend)
     den_op.set_time_table([t], time_sinusoid(torch.tensor([t])))
     out = den_op.forward(T(g["den_x"]).reshape(-1, 256).to(DEV), t, T(g[enc]).to(DEV)).cpu()
     ref = T(g[key]).reshape(-1, 256)
@@ -75,9 +80,11 @@ def test_denoiser_internal_sinusoid_and_module_surface(weights, golden_stages):
     assert (out2 - T(g["den_out_t481_nc2"]).reshape(-1, 256)).abs().max() < 2e-4
 
 
-@pytest.mark.parametrize("gs,B", [(7.5, 5), (1.0, 3)])
-def test_sampler_vs_oracle(den_op, weights, gs, B):
-    """50-step DDIM (+CFG) chain vs the restated _diffusion_reverse, with the per-step trajectory"""
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("gs,B", [(7.5, 5), (1.0, 3), (7.5, 70)])
+def test_sampler_vs_oracle(den_op, weights, gs, B, backend):
+    """50-step DDIM (+CFG) chain vs the restated _diffusion_reverse (B = 70 under CFG: two row tiles, the second ragged)"""
+    den_op.set_backend(backend)
     from oracle import restate as O
     from seeme_b200.modules import time_sinusoid
     from seeme_b200.scheduler import DDIMScheduler
@@ -494,7 +501,7 @@ def test_replication_protocol_driver(config, tmp_path):
 
 def test_error_conventions(den_op, vae_op):
     with pytest.raises(RuntimeError, match="capacity"):
-        den_op.forward(torch.zeros(65, 256, device=DEV), 1, torch.zeros(1, 65, 256, device=DEV))
+        den_op.forward(torch.zeros(257, 256, device=DEV), 1, torch.zeros(1, 257, 256, device=DEV))
     with pytest.raises(RuntimeError, match="Nc"):
         den_op.forward(torch.zeros(4, 256, device=DEV), 1, torch.zeros(5, 4, 256, device=DEV))
     with pytest.raises(RuntimeError, match="CUDA"):
