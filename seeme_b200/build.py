@@ -20,6 +20,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-O2",
          "-Xptxas", "-v"]
+if os.environ.get("SEEME_EXPERIMENTAL") == "1":      # retired kernel variants and experiment knobs (csrc/common.cuh: seeme_exp_env)
+    FLAGS.append("-DSEEME_EXPERIMENTAL")
 
 
 def sources():

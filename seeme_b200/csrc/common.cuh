@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <math.h>
 #include <string>
@@ -118,6 +119,18 @@ struct Arena {
   }
 };
 inline size_t pad256(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+
+// Experiment knobs (tile shapes, ring depths, retired kernel variants, PDL ...) are read in experimental builds only
+// (python -m seeme_b200.build with SEEME_EXPERIMENTAL=1 in the environment adds -DSEEME_EXPERIMENTAL); the product library
+// ignores them.  The knobs a user may set are listed in INTEGRATION.md.
+inline const char* seeme_exp_env(const char* name) {
+#ifdef SEEME_EXPERIMENTAL
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
 
 constexpr int D_MODEL = 256;
 constexpr int NUM_SMS = 148;

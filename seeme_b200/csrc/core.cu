@@ -15,7 +15,7 @@ void set_error(const char* fmt, ...) {
 }
 
 bool g_prof_on = false;
-bool g_pdl_on = getenv("SEEME_PDL") && getenv("SEEME_PDL")[0] == '1';   // measured: no gain inside the sampler graph
+bool g_pdl_on = seeme_exp_env("SEEME_PDL") && seeme_exp_env("SEEME_PDL")[0] == '1';   // measured: no gain inside the sampler graph
 namespace {
 struct ProfPair { cudaEvent_t a, b; };
 std::vector<ProfPair> g_prof_pairs[PROF_COUNT];

@@ -230,7 +230,7 @@ extern "C" int seeme_denoiser_create(seeme_denoiser_t* out, const float* const* 
   seeme_denoiser* h = new seeme_denoiser();
   SEEME_CUDA(cudaGetDevice(&h->device));
   h->max_rows = max_rows;
-  const char* ng = getenv("SEEME_NO_GRAPH");
+  const char* ng = seeme_exp_env("SEEME_NO_GRAPH");
   h->use_graph = !(ng && ng[0] == '1');
   size_t wbytes = 0;
   for (int i = 0; i < n_w; ++i) wbytes += pad256(den_tensor_elems(i) * 4);
@@ -318,7 +318,7 @@ extern "C" int seeme_denoiser_create(seeme_denoiser_t* out, const float* const* 
       h->backend = SEEME_SAMPLER_GRAPH;
     }
   }
-  if (!(getenv("SEEME_NO_CARVEOUT") && getenv("SEEME_NO_CARVEOUT")[0] == '1')) {
+  if (!(seeme_exp_env("SEEME_NO_CARVEOUT") && seeme_exp_env("SEEME_NO_CARVEOUT")[0] == '1')) {
     // the row-wise kernels use no shared memory; asking for the maximum carve-out anyway keeps the SMs in the
     // configuration of the 193 KB GEMM kernels they alternate with (no L1/shared re-partitioning between launches)
     cudaFuncSetAttribute(den_prep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -146,7 +146,7 @@ struct seeme_pointnet {
 
 // clouds per pass of the fused path (two fp16 [rows,256] activation buffers = 1 KB per point: 2.6 GB at 128 clouds x 20 000)
 static int pf_chunk_cap() {
-  const char* e = getenv("SEEME_PF_CHUNK");
+  const char* e = seeme_exp_env("SEEME_PF_CHUNK");
   const int v = e ? atoi(e) : 128;
   return v < 1 ? 128 : v;
 }

@@ -388,7 +388,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
         const __half2 z = __float2half2_rn(0.f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
+#ifdef SEEME_EXPERIMENTAL
           if (a.debug_skip & 1) break;
+#endif
           uint4 v = p[i * 128];
           __half2* h = reinterpret_cast<__half2*>(&v);
           h[0] = __hmax2(h[0], z); h[1] = __hmax2(h[1], z); h[2] = __hmax2(h[2], z); h[3] = __hmax2(h[3], z);
@@ -521,7 +523,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
             *reinterpret_cast<uint4*>(ct + pf_sw128(row, (g & 1) * 4 + jj)) = make_uint4(pk[g][4 * jj], pk[g][4 * jj + 1], pk[g][4 * jj + 2], pk[g][4 * jj + 3]);
         }
       }
-      if (!(a.debug_skip & 2)) {
+#ifdef SEEME_EXPERIMENTAL
+      if (!(a.debug_skip & 2))
+#endif
+      {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           if (!valid) {
@@ -547,6 +552,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block_kernel(const __g
   }
 }
 
+#ifdef SEEME_EXPERIMENTAL   // retired variant (CUDA-core generator of block 0): experimental builds only
 // ---------------------------------------------------------------------------------------------------------------------
 // Block 0 (+ fc_pos): the block's input relu(fc_pos(p)) [128, 512] is GENERATED on chip from the xyz coordinates (K = 3,
 // CUDA cores) chunk by chunk into a 4-slot shared-memory ring -- it never exists in HBM -- and its shortcut, an affine
@@ -837,6 +843,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pointnet_block0_kernel(const __
   }
 }
 
+#endif  // SEEME_EXPERIMENTAL
 // ---------------------------------------------------------------------------------------------------------------------
 // Block 0, tensor-core generator (default).  ncu on the kernel above showed the 4 generating warps (3 FMA + max + pack per
 // value, 2 400 instructions per thread and tile behind table loads) taking ~4x the tile's MMA time.  Here fc_pos itself, the
@@ -1256,6 +1263,7 @@ __global__ void __launch_bounds__(P0T_THREADS, 1) pointnet_block0_tc_kernel(cons
   }
 }
 
+#ifdef SEEME_EXPERIMENTAL   // retired variant (slower than the single-CTA kernel): experimental builds only
 // ---------------------------------------------------------------------------------------------------------------------
 // CTA-pair version of pointnet_block_kernel: tcgen05.mma.cta_group::2, M = 256 (two 128-point tiles, one per SM), N = 256.
 // Each CTA holds only ITS half of every weight K-chunk ([128 n x 64 k]: CTA 0 the output columns 0-127, CTA 1 128-255),
@@ -1645,6 +1653,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PF_THREADS, 1)
   }
 }
 
+#endif  // SEEME_EXPERIMENTAL
 // ---- host side ----------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 g_pf_encode = nullptr;
 static int pf_encoder() {
@@ -1779,12 +1788,16 @@ static int pf_grid_limit() {
 
 // SEEME_PF_BLOCK0=cuda selects the CUDA-core generator (pointnet_block0_kernel) for A/B measurements
 static bool pf_block0_use_tc() {
+#ifdef SEEME_EXPERIMENTAL
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SEEME_PF_BLOCK0");
     v = (e && strcmp(e, "cuda") == 0) ? 0 : 1;
   }
   return v == 1;
+#else
+  return true;
+#endif
 }
 
 int pf_block0_forward(const float* xyz, void* x_out, const void* w_blob, const void* wpb, const void* ctblob, const float* b0,
@@ -1800,7 +1813,9 @@ int pf_block0_forward(const float* xyz, void* x_out, const void* w_blob, const v
   const int grid = n_tiles < pf_grid_limit() ? n_tiles : pf_grid_limit();
   static bool configured = false;
   if (!configured) {
+#ifdef SEEME_EXPERIMENTAL
     SEEME_CUDA(cudaFuncSetAttribute(pointnet_block0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P0_SMEM));
+#endif
     SEEME_CUDA(cudaFuncSetAttribute(pointnet_block0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P0T_SMEM));
     configured = true;
   }
@@ -1814,6 +1829,7 @@ int pf_block0_forward(const float* xyz, void* x_out, const void* w_blob, const v
     a.ctblob = reinterpret_cast<const uint8_t*>(ctblob);
     pointnet_block0_tc_kernel<<<grid, P0T_THREADS, P0T_SMEM, s>>>(maps, a);
   } else {
+#ifdef SEEME_EXPERIMENTAL
     P0Args a;
     a.n_points = n_points; a.tiles_per_sample = tiles_per_sample; a.n_tiles = n_tiles;
     a.xyz = xyz;
@@ -1823,6 +1839,10 @@ int pf_block0_forward(const float* xyz, void* x_out, const void* w_blob, const v
     a.colmax = colmax;
     a.wblob = reinterpret_cast<const uint8_t*>(w_blob);
     pointnet_block0_kernel<<<grid, PF_THREADS, P0_SMEM, s>>>(maps, a);
+#else
+    (void)wpb; (void)b0; (void)cst0; (void)pfold;
+    SEEME_REQUIRE(false, SEEME_EINVAL, "the CUDA-core block-0 generator is compiled in experimental builds only (-DSEEME_EXPERIMENTAL)");
+#endif
   }
   SEEME_LAUNCH_CHECK();
   return SEEME_OK;
@@ -1859,6 +1879,7 @@ int pf_block_forward(const void* x_in, void* x_out, const void* w_blob, const fl
   a.bias_h = bias_h; a.bias_o = bias_o; a.colmax = colmax;
   a.store_out = x_out != nullptr;
   a.wblob = reinterpret_cast<const uint8_t*>(w_blob);
+#ifdef SEEME_EXPERIMENTAL
   static const int dbg = getenv("SEEME_PF_DEBUG_SKIP") ? atoi(getenv("SEEME_PF_DEBUG_SKIP")) : 0;
   static bool warned = false;
   if (dbg && !warned) {
@@ -1866,23 +1887,32 @@ int pf_block_forward(const void* x_in, void* x_out, const void* w_blob, const fl
     warned = true;
   }
   a.debug_skip = dbg;
+#else
+  a.debug_skip = 0;
+#endif
   static bool configured = false;
   if (!configured) {
     SEEME_CUDA(cudaFuncSetAttribute(pointnet_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BLK));
     SEEME_CUDA(cudaFuncSetAttribute(pointnet_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BLK));
     configured = true;
   }
+#ifdef SEEME_EXPERIMENTAL
   static bool configured2 = false;
   if (!configured2) {
     SEEME_CUDA(cudaFuncSetAttribute(pointnet_block_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BLK));
     configured2 = true;
   }
+#endif
   ProfScope prof(prof_id - 1, s);
   if (h_in_tmem == 2) {            // CTA pairs (cta_group::2): 74 clusters of 2
+#ifdef SEEME_EXPERIMENTAL
     const int pairs = (a.n_tiles + 1) / 2 < NUM_SMS / 2 ? (a.n_tiles + 1) / 2 : NUM_SMS / 2;
     pointnet_block_pair_kernel<<<2 * pairs, PF_THREADS, PF_SMEM_BLK, s>>>(maps, a);
     SEEME_LAUNCH_CHECK();
     return SEEME_OK;
+#else
+    SEEME_REQUIRE(false, SEEME_EINVAL, "the CTA-pair scene-encoder kernel (precision 18) is compiled in experimental builds only (-DSEEME_EXPERIMENTAL)");
+#endif
   }
   const int grid = a.n_tiles < pf_grid_limit() ? a.n_tiles : pf_grid_limit();
   if (h_in_tmem) pointnet_block_kernel<true><<<grid, PF_THREADS, PF_SMEM_BLK, s>>>(maps, a);

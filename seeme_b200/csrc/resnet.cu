@@ -215,7 +215,7 @@ extern "C" int seeme_resnet50_create(seeme_resnet50_t* out, const float* const* 
   const int prec = pe ? atoi(pe) : 3;
   if (prec != 3 && prec != 16) { set_error("SEEME_RESNET_PRECISION must be 3 (split-bf16) or 16 (fp16), got %d", prec); delete h; return SEEME_EINVAL; }
   h->f16 = prec == 16;
-  const char* ce = getenv("SEEME_RESNET_CHUNK");
+  const char* ce = seeme_exp_env("SEEME_RESNET_CHUNK");
   const int cap = ce ? atoi(ce) : 128;
   h->chunk = max_batch < cap ? max_batch : (cap > 0 ? cap : 128);
   const size_t C = (size_t)h->chunk;
@@ -300,7 +300,7 @@ static int rn_gemm(const seeme_resnet50* h, const RnConv& c, const __nv_bfloat16
   g.bias = c.w.bias;
   g.act = relu ? ACT_RELU : ACT_NONE;
   g.R = R; g.ldr = c.Cout; g.act_after_residual = R != nullptr;
-  static const bool dense = !(getenv("SEEME_RESNET_DENSE") && getenv("SEEME_RESNET_DENSE")[0] == '0');
+  static const bool dense = !(seeme_exp_env("SEEME_RESNET_DENSE") && seeme_exp_env("SEEME_RESNET_DENSE")[0] == '0');
   g.dense_ctas = dense && M > 2048;
   g.Y = yf; g.ldy = c.Cout;
   g.Yh = yh; g.Yl = yl; g.ldb = c.Cout;

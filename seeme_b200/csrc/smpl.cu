@@ -349,8 +349,12 @@ extern "C" int seeme_smpl_create(seeme_smpl_t* out, const float* v_template, con
   {
     const char* e = getenv("SEEME_SMPL_FP32");
     h->use_tc = !(e && e[0] == '1');
+#ifdef SEEME_EXPERIMENTAL
     const char* v = getenv("SEEME_SMPL_TC");
     h->tc_version = (v && v[0] == '1') ? 1 : 2;
+#else
+    h->tc_version = 2;
+#endif
   }
   int* d_nnz = h->arena.take<int>(1);
   if (!d_nnz) { set_error("seeme_smpl_create: arena exhausted"); h->arena.release(); delete h; return SEEME_ENOMEM; }

@@ -48,6 +48,7 @@ __device__ __forceinline__ void st_tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 
+#ifdef SEEME_EXPERIMENTAL   // retired variant (v1: sparse skinning from shared memory in the epilogue)
 // CL: thread-block cluster size along the frame-group axis.  The CTAs of a cluster work on different frame groups but the
 // SAME vertex tiles, so the basis chunk stream is identical: chunk n is fetched from L2 once, by CTA n % CL, and multicast
 // into the ring slot of every CTA of the cluster (the kernel is bound by this L2 -> SM stream, not by the MMAs).
@@ -221,6 +222,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) smpl_skin_tc_kernel(const __gri
     tmem_dealloc(tmem_base, 512);
   }
 }
+
+#endif  // SEEME_EXPERIMENTAL
 
 // ---- no-swizzle ("interleaved") K-major operand tiles with 64-byte rows (K = 32 fp16) -------------------------------------
 // canonical layout (cute: INTERLEAVE, ((8,m),(T,2)):((1T,SBO),(1,LBO)) in 16-byte units): core matrix = 8 rows x 16 bytes,
@@ -662,6 +665,11 @@ int smpl_tc_pack_basis(const float* basis, int SK, void* bh, void* bl) {
 
 int smpl_skin_tc(const void* bh, const void* bl, const float* coef, int ld_coef, int n_coef, void* ch, void* cl, const float* A,
                  const float* vt, const float* w4, const unsigned char* i4, int F, float* verts, int prof_id, cudaStream_t s) {
+#ifndef SEEME_EXPERIMENTAL
+  (void)bh; (void)bl; (void)coef; (void)ld_coef; (void)n_coef; (void)ch; (void)cl; (void)A; (void)vt; (void)w4; (void)i4; (void)F; (void)verts;
+  (void)prof_id; (void)s;
+  SEEME_REQUIRE(false, SEEME_EINVAL, "smpl_skin_tc_kernel (v1) is compiled in experimental builds only (-DSEEME_EXPERIMENTAL)");
+#else
   // coef [F, n_coef] fp32 -> bf16 (hi, lo) [F, 256]; columns [n_coef, 256) were zeroed at create
   SEEME_TRY(to_bf16_split(coef, ld_coef, F, n_coef, reinterpret_cast<__nv_bfloat16*>(ch), reinterpret_cast<__nv_bfloat16*>(cl), ST_KP, 0, s));
   StMaps maps;
@@ -672,7 +680,7 @@ int smpl_skin_tc(const void* bh, const void* bl, const float* coef, int ld_coef,
   SEEME_TRY(umma_tensor_map_bf16(&maps.cl, cl, F, ST_KP, ST_KP, ST_NF));
   static int csz = -1;
   if (csz < 0) {
-    const char* e = getenv("SEEME_SMPL_CLUSTER");
+    const char* e = seeme_exp_env("SEEME_SMPL_CLUSTER");
     csz = e ? atoi(e) : 1;   // measured on B200: multicast halves the L2 reads but not the time (the SM-inbound side bounds it)
     if (csz != 1 && csz != 2 && csz != 4) csz = 1;
   }
@@ -707,6 +715,7 @@ int smpl_skin_tc(const void* bh, const void* bl, const float* coef, int ld_coef,
   else SEEME_CUDA(cudaLaunchKernelEx(&cfg, smpl_skin_tc_kernel<4>, maps, a));
   SEEME_LAUNCH_CHECK();
   return SEEME_OK;
+#endif
 }
 
 }  // namespace seeme

@@ -409,7 +409,7 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
   // few rows (the latency-bound sampler / per-sample GEMMs): narrow tiles spread one GEMM over more SMs;
   // many rows: the widest tile that divides N (128 when a residual tile has to be staged as well)
   // SEEME_UMMA_SMALL_BN=128: experiment knob (fewer, fatter CTAs for the few-row GEMMs of the sampler chain)
-  static const int small_bn = getenv("SEEME_UMMA_SMALL_BN") ? atoi(getenv("SEEME_UMMA_SMALL_BN")) : 64;
+  static const int small_bn = seeme_exp_env("SEEME_UMMA_SMALL_BN") ? atoi(seeme_exp_env("SEEME_UMMA_SMALL_BN")) : 64;
   int BN = (g.M <= 2048 && !g.colmax) ? (small_bn == 128 ? 128 : 64) : 128;
   if (g.N % BN != 0) BN = 64;
   SEEME_REQUIRE(g.N % BN == 0, SEEME_EINVAL, "umma_linear: N=%d must be a multiple of 64", g.N);
@@ -442,15 +442,15 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
   // 128-wide tiles (many rows): a shallow ring (64 KB in split mode) and one staging buffer keep the footprint
   // small enough for 2-3 CTAs per SM, which is what overlaps TMA, MMA and epilogue phases across tiles.
   if (BN == 64) {
-    static const bool small = !(getenv("SEEME_UMMA64_STAGES4") && getenv("SEEME_UMMA64_STAGES4")[0] == '1');
+    static const bool small = !(seeme_exp_env("SEEME_UMMA64_STAGES4") && seeme_exp_env("SEEME_UMMA64_STAGES4")[0] == '1');
     // SEEME_UMMA64_STAGES=1: experiment knob (one-stage ring, 65 KB: three CTAs per SM when several chains share the GPU)
-    static const bool one = getenv("SEEME_UMMA64_STAGES") && getenv("SEEME_UMMA64_STAGES")[0] == '1';
+    static const bool one = seeme_exp_env("SEEME_UMMA64_STAGES") && seeme_exp_env("SEEME_UMMA64_STAGES")[0] == '1';
     if (npass == 1) return launch<64, 1, 4, 1, 1>(g, maps, e, s);
     if (one || g.dense_ctas) return launch<64, 3, 1, 1, 3>(g, maps, e, s);
     return small ? launch<64, 3, 2, 1, 2>(g, maps, e, s) : launch<64, 3, 4, 1, 1>(g, maps, e, s);
   }
   // SEEME_UMMA_DENSE_ALL=1: experiment knob -- the three-CTA build for every many-row split-bf16 GEMM (VAE stacks)
-  static const bool dense_all = getenv("SEEME_UMMA_DENSE_ALL") && getenv("SEEME_UMMA_DENSE_ALL")[0] == '1';
+  static const bool dense_all = seeme_exp_env("SEEME_UMMA_DENSE_ALL") && seeme_exp_env("SEEME_UMMA_DENSE_ALL")[0] == '1';
   if ((g.dense_ctas || (dense_all && !g.colmax)) && npass == 3) return launch<128, 3, 1, 1, 3>(g, maps, e, s);
   return npass == 1 ? launch<128, 1, 2, 1, 2>(g, maps, e, s) : launch<128, 3, 1, 1, 2>(g, maps, e, s);
 }

@@ -356,7 +356,7 @@ extern "C" int seeme_vae_create(seeme_vae_t* out, const float* const* w, int n_w
   SEEME_CUDA(cudaFuncSetAttribute(mha1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 256 * 4));
   SEEME_CUDA(cudaFuncSetAttribute(mha1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MH_SMEM));
   {
-    const char* e = getenv("SEEME_VAE_ATTN");
+    const char* e = seeme_exp_env("SEEME_VAE_ATTN");
     h->tiled_attn = !(e && e[0] == '0');
   }
   *out = h;

@@ -192,6 +192,12 @@ def test_pointnet_fused_fp16_vs_oracle(weights, precision):
     from oracle import restate as O
     from seeme_b200 import ops, synthetic as S
     op = ops.PointNetOp(cu(weights["pointnet"]), cu(weights["output_scene"]), max_batch=3, max_points=20000, precision=precision)
+    if precision == 18:      # the CTA-pair kernel is a retired variant: compiled with SEEME_EXPERIMENTAL=1 only, a loud error otherwise
+        try:
+            op(S.egobody_scene(1, 256, torch.Generator().manual_seed(1)).to(DEV))
+        except RuntimeError as e:
+            assert "experimental builds only" in str(e)
+            pytest.skip("product build: retired CTA-pair kernel not compiled")
     for B, N, seed in ((3, 777, 6), (2, 20000, 3), (1, 128, 9), (2, 50, 11)):
         p = S.egobody_scene(B, N, torch.Generator().manual_seed(seed))
         with torch.no_grad():
@@ -217,10 +223,13 @@ def test_pointnet_fused_variants_agree(weights):
     outs = []
     for precision in (16, 17, 18):
         op = ops.PointNetOp(cu(weights["pointnet"]), cu(weights["output_scene"]), max_batch=2, max_points=5000, precision=precision)
-        outs.append(op(p, want_feat=True)[1])
+        try:
+            outs.append(op(p, want_feat=True)[1])
+        except RuntimeError as e:          # precision 18 = retired CTA-pair kernel, experimental builds only
+            assert precision == 18 and "experimental builds only" in str(e)
     assert torch.equal(outs[0], outs[1])
-    # the CTA-pair kernel accumulates G1 / G2 in a different K order (fp32 re-association only)
-    assert (outs[0] - outs[2]).abs().max() <= 2e-3 * outs[0].abs().max()
+    if len(outs) == 3:   # the CTA-pair kernel accumulates G1 / G2 in a different K order (fp32 re-association only)
+        assert (outs[0] - outs[2]).abs().max() <= 2e-3 * outs[0].abs().max()
 
 
 # ---- SMPL -------------------------------------------------------------------------------------------------------
