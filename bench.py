@@ -325,7 +325,7 @@ def bench_gimo(args):
     import seeme_b200
     from seeme_b200 import synthetic as S
     scaling = args.scaling or "strong"
-    total = 512
+    total = int(args.total)
     B = total // world if scaling == "strong" else total
     model = seeme_b200.build_model("config_mld_gimo.yaml", device=dev, guidance_scale=GUIDANCE, max_batch=B, n_points=N_POINTS)
     depth = max(1, int(model.pipeline_depth))
@@ -539,6 +539,7 @@ def main():
                          "inside the timed epoch); smpl-sweep = configs[4] (standalone SMPL forward, 1k-64k frames)")
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"], help="default: strong for gimo, weak otherwise")
     ap.add_argument("--replications", type=int, default=10, help="interactee: TEST.REPLICATION_TIMES (line 71)")
+    ap.add_argument("--total", type=int, default=512, help="gimo: sequences per step over all ranks")
     ap.add_argument("--no-extras", action="store_true", help="egobody: skip the per-class roofline / stock-PyTorch sub-measurements")
     args = ap.parse_args()
     if args.impl == "reference":
