@@ -231,7 +231,12 @@ class MLD(nn.Module):
         op = self.denoiser.op if op is None else op
         backend = self.sampler_backend
         if backend == "auto":
-            backend = "graph" if self.__dict__.get("_in_pipeline", False) and int(self.pipeline_depth) > 1 else "persistent"
+            # measured on B200: inside the batch pipeline a 512-row chain costs least as the kernel graph (16.2k
+            # vs 14.9k sequences/s), a chain of <= 256 rows (<= 2 row tiles = 16 SMs) as the persistent cluster kernel (14.0k vs
+            # 10.2k sequences/s at 64 sequences per batch: the strong-scaling regime); a single batch always takes the cluster kernel
+            rows = encoder_hidden_states.shape[0]
+            in_pipe = self.__dict__.get("_in_pipeline", False) and int(self.pipeline_depth) > 1
+            backend = "graph" if in_pipe and rows > 256 else "persistent"
         if os.environ.get("SEEME_SAMPLER") != "graph":
             op.set_backend(backend)
         # the key lives on the kernel-side handle object (one per lane / slot), not in an id()-keyed dict: a rebuilt handle
