@@ -268,6 +268,8 @@ def class_rooflines(model, dev, dev_batch, B):
     out["sampler_rows_512_graph"] = sampler_entry(B, "graph", 3)
     out["sampler_rows_18944_persistent"] = sampler_entry(9472, "persistent", 2)     # 148 row tiles of 128: one per SM-octet wave
     out["sampler_rows_18944_graph"] = sampler_entry(9472, "graph", 2)
+    out["sampler_rows_18944_tile"] = sampler_entry(9472, "tile", 2)                 # one CTA per tile: 148 CTAs, one wave
+    out["sampler_rows_512_tile"] = sampler_entry(B, "tile", 3)
     # VAE stacks at the batch size of the step
     vae = model.vae
     lengths = [60] * B
