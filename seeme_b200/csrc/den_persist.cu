@@ -225,6 +225,38 @@ __device__ __forceinline__ void dp_ldvec(const float* __restrict__ p, float (&v)
   }
 }
 
+// 32-element reductions with four independent accumulators: the epilogue runs ONE warp per scheduler, so a serial chain of 32
+// dependent FMAs (4 cycles each) is pure latency
+__device__ __forceinline__ float dp_sum32(const float (&a)[32]) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) { s0 += a[i]; s1 += a[i + 1]; s2 += a[i + 2]; s3 += a[i + 3]; }
+  return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ float dp_dot32(const float (&a)[32], const float (&b)[32]) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    s0 = fmaf(a[i], b[i], s0); s1 = fmaf(a[i + 1], b[i + 1], s1); s2 = fmaf(a[i + 2], b[i + 2], s2); s3 = fmaf(a[i + 3], b[i + 3], s3);
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ float dp_sqdev32(const float (&a)[32], float mean) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float d0 = a[i] - mean, d1 = a[i + 1] - mean, d2 = a[i + 2] - mean, d3 = a[i + 3] - mean;
+    s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ float dp_max32(const float (&a)[32]) {
+  float m0 = a[0], m1 = a[1], m2 = a[2], m3 = a[3];
+#pragma unroll
+  for (int i = 4; i < 32; i += 4) { m0 = fmaxf(m0, a[i]); m1 = fmaxf(m1, a[i + 1]); m2 = fmaxf(m2, a[i + 2]); m3 = fmaxf(m3, a[i + 3]); }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
 // per-row statistics exchange over distributed shared memory
 struct DpStat {
   float* stats;      // [2][CL][4][128]
@@ -285,13 +317,8 @@ struct DpStat {
   }
   // LayerNorm(256) of a row whose slice is t[32]: Chan combine of the per-slice (mean, M2); biased variance, eps 1e-5
   __device__ __forceinline__ void layernorm(float (&t)[32], const float* __restrict__ g, const float* __restrict__ b) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) s += t[i];
-    const float mc = s * (1.0f / 32.0f);
-    float m2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) { const float d = t[i] - mc; m2 = fmaf(d, d, m2); }
+    const float mc = dp_sum32(t) * (1.0f / 32.0f);
+    const float m2 = dp_sqdev32(t, mc);
     const float a[2] = {mc, m2};
     float gg[32], bb[32];          // requested before the exchange so that their L2 round trip overlaps it
     dp_ldvec(g, gg);
@@ -549,28 +576,26 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
             acc_wait();
             float qv[32];
             dp_ld32x2(tl, tl + 64, qv);
-            float d = 0.f, dt = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { qv[i] += bq[i]; dt = fmaf(qv[i], ktk[i], dt); }
-            pr[NC + 1] = dt;
+            for (int i = 0; i < 32; ++i) qv[i] += bq[i];
+            pr[NC + 1] = dp_dot32(qv, ktk);
             {
               float kv[32];
               dp_ld32x2(tl + 32, tl + 96, kv);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) d = fmaf(qv[i], kv[i] + bk[i], d);
+              for (int i = 0; i < 32; ++i) kv[i] += bk[i];
+              pr[0] = dp_dot32(qv, kv);
             }
-            pr[0] = d;
 #pragma unroll
             for (int n = 0; n < NC; ++n) {
-              float dn = 0.f;
               if (n < 2) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) dn = fmaf(qv[i], kc[n < 2 ? n : 0][i], dn);
+                pr[1 + n] = dp_dot32(qv, kc[n < 2 ? n : 0]);
               } else {
+                float t[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) dn = fmaf(qv[i], __ldg(ct + DP_CT(0, n, i)), dn);
+                for (int i = 0; i < 32; ++i) t[i] = __ldg(ct + DP_CT(0, n, i));
+                pr[1 + n] = dp_dot32(qv, t);
               }
-              pr[1 + n] = dn;
             }
           }
           asm volatile("" ::: "memory");   // keep the loads below from being hoisted into the first half (register pressure)
@@ -677,21 +702,20 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
             dp_ldvec(L.bcaq + S, v);
             acc_wait();
             dp_ld32x2(tl, tl + 32, qv);
-            float m = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { qv[i] += v[i]; m = fmaxf(m, qv[i]); }
+            for (int i = 0; i < 32; ++i) qv[i] += v[i];
+            const float m = dp_max32(qv);
             float st[2 + NC];
             st[0] = m;
-            float ssum = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { qv[i] = __expf(qv[i] - m); ssum += qv[i]; }
-            st[1] = ssum;
+            for (int i = 0; i < 32; ++i) qv[i] = __expf(qv[i] - m);
+            st[1] = dp_sum32(qv);
 #pragma unroll
             for (int n = 0; n < NC; ++n) {
-              float dn = 0.f;
+              float t[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) dn = fmaf(qv[i], __ldg(ct + DP_CT(2, n, i)), dn);
-              st[2 + n] = dn;
+              for (int i = 0; i < 32; ++i) t[i] = __ldg(ct + DP_CT(2, n, i));
+              st[2 + n] = dp_dot32(qv, t);
             }
             // the value slices are requested before the exchange
             float v2[NC][32];
@@ -886,11 +910,10 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
 // SM time per run is ~1/8 of the cluster kernel's (4 CTAs instead of 32 for 512 rows) at about the same latency, which is
 // what the batch pipeline wants next to the scene encoder; with >= 148 tiles it is the saturating configuration.
 constexpr int DM_THREADS = 192;
-constexpr int DM_NW = 5;
+constexpr int DM_NW = 6;                     // 96 KB in flight: the weight stream is what bounds the MMA phases (trace: 26 B/clk with 5 slots)
 constexpr int DM_W_SLOT = 16384;             // one [128 n x 64 k] bf16 tile (hi or lo)
 constexpr int DM_A_BYTES = 4 * 32768;        // 4 K-blocks x (hi 16 KB | lo 16 KB)
-constexpr int DM_SWAP_BYTES = 128 * 32 * 4;  // CFG pair exchange, 32 columns at a time
-constexpr int DM_SMEM = DM_A_BYTES + DM_NW * DM_W_SLOT + DM_SWAP_BYTES + 1024;
+constexpr int DM_SMEM = DM_A_BYTES + DM_NW * DM_W_SLOT + 1024;    // the CFG pair exchange goes through the L2 scratch row
 constexpr int DM_XR = 256;                   // tensor-memory columns: [0,256) accumulator, [256,512) fp32 residual stream;
 constexpr int DM_ACC1 = 256, DM_HHI = 384, DM_HLO = 448;   // during the FFN: chunk accumulator | relu(h) hi | lo
 
@@ -946,13 +969,35 @@ __device__ __forceinline__ void dm_write_a(uint8_t* a_buf, int c0, int row, cons
   }
 }
 
+// A 256-float vector shared by all rows (bias, LayerNorm affine, FiLM, time-token table), distributed over the lanes of a
+// warp: lane l holds elements [8 l, 8 l + 8).  Loaded with two 16-byte loads per lane BEFORE the accumulator wait (the L2
+// round trip overlaps the GEMM) and read back with shuffles -- with 225 KB of shared memory the L1 is ~3 KB, so a per-chunk
+// __ldg of such a vector is an L2 round trip on the epilogue's critical path (55 % of a step in the first trace).
+struct RVec { float r[8]; };
+__device__ __forceinline__ RVec rv_load(const float* __restrict__ p, int lane) {
+  RVec v;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p) + 2 * lane), b = __ldg(reinterpret_cast<const float4*>(p) + 2 * lane + 1);
+  v.r[0] = a.x; v.r[1] = a.y; v.r[2] = a.z; v.r[3] = a.w; v.r[4] = b.x; v.r[5] = b.y; v.r[6] = b.z; v.r[7] = b.w;
+  return v;
+}
+// element ch * 32 + i (i compile-time)
+#define RV_GET(v, ch, i) __shfl_sync(0xffffffffu, (v).r[(i) & 7], (ch) * 4 + ((i) >> 3))
+// 128-float vector: lane l holds [4 l, 4 l + 4); element c4 * 32 + i
+struct RVec4 { float r[4]; };
+__device__ __forceinline__ RVec4 rv4_load(const float* __restrict__ p, int lane) {
+  RVec4 v;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p) + lane);
+  v.r[0] = a.x; v.r[1] = a.y; v.r[2] = a.z; v.r[3] = a.w;
+  return v;
+}
+#define RV4_GET(v, c4, i) __shfl_sync(0xffffffffu, (v).r[(i) & 3], (c4) * 8 + ((i) >> 2))
+
 template <int NC>
 __global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_constant__ DmParams p) {
   extern __shared__ __align__(1024) uint8_t dm_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dm_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_buf = smem;
   uint8_t* w_ring = smem + DM_A_BYTES;
-  float* swapb = reinterpret_cast<float*>(w_ring + DM_NW * DM_W_SLOT);
   __shared__ __align__(8) uint64_t full_w[DM_NW], empty_w[DM_NW], acc_full, go, a_free, a_full2;
   __shared__ uint32_t tmem_slot;
 
@@ -1104,17 +1149,22 @@ __global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_co
       for (int ch = 0; ch < 8; ++ch) {
         float v[32];
         dp_ld32(tl + base + ch * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; m2 = fmaf(d, d, m2); }
+        m2 += dp_sqdev32(v, mean);
       }
       rstd = rsqrtf(m2 * (1.0f / 256.0f) + 1e-5f);
     };
 
+    // per-row cond-token table chunk: 32 columns of token n, table w (0 k, 1 ov, 2 softmax_n(key), 3 value)
+    auto ct_load = [&](const float* __restrict__ ct, int w, int n, int ch, float (&v)[32]) {
+      const float* src = ct + (size_t)DP_CT(w, n, 0) + (size_t)ch * 32 * 128;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __ldg(src + i * 128);
+    };
     {   // initial state: x = latents (or the given sample) + learned PE row 0
+      const RVec pe = rv_load(p.pe0, lane);
 #pragma unroll 1
       for (int ch = 0; ch < 8; ++ch) {
-        float x[32], pe[32];
-        dp_ldvec(p.pe0 + ch * 32, pe);
+        float x[32];
         if (valid) {
           const float* src = p.x_in + (size_t)(p.mode == 0 ? latrow : grow) * 256 + ch * 32;
 #pragma unroll
@@ -1127,7 +1177,7 @@ __global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_co
           for (int i = 0; i < 32; ++i) x[i] = 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { lat_g[(size_t)(ch * 32 + i) * 128] = x[i]; x[i] += pe[i]; }
+        for (int i = 0; i < 32; ++i) { lat_g[(size_t)(ch * 32 + i) * 128] = x[i]; x[i] += RV_GET(pe, ch, i); }
         dp_st32(tl + DM_XR + ch * 32, x);
         dm_write_a(a_buf, ch * 32, row, x);
       }
@@ -1141,14 +1191,14 @@ __global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_co
         const DpLayerP& L = p.L[l];
         const float* __restrict__ ct = L.ctab + ct_off;
         if (l >= 3) {      // x = Linear(cat[x, skip])
+          const RVec b = rv_load(p.skip_b[l - 3], lane);
           acc_wait();
 #pragma unroll 1
           for (int ch = 0; ch < 8; ++ch) {
-            float x[32], b[32];
-            dp_ldvec(p.skip_b[l - 3] + ch * 32, b);
+            float x[32];
             dp_ld32(tl + ch * 32, x);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] += b[i];
+            for (int i = 0; i < 32; ++i) x[i] += RV_GET(b, ch, i);
             dp_st32(tl + DM_XR + ch * 32, x);
             dm_write_a(a_buf, ch * 32, row, x);
           }
@@ -1157,42 +1207,45 @@ __global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_co
         // ---- self-attention of the latent token over {x, cond tokens, time token} ----
         float pr[NC + 2];
         {   // u = M x: logit against itself = x . (u + m) + c
+          const RVec m = rv_load(p.mu[l], lane);
+          const float c0 = __ldg(p.mu[l] + 256);
           acc_wait();
           float d = 0.f;
 #pragma unroll 1
           for (int ch = 0; ch < 8; ++ch) {
-            float u[32], xr[32], m[32];
-            dp_ldvec(p.mu[l] + ch * 32, m);
+            float u[32], xr[32];
             dp_ld32(tl + ch * 32, u);
             dp_ld32(tl + DM_XR + ch * 32, xr);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) d = fmaf(xr[i], u[i] + m[i], d);
+            for (int i = 0; i < 32; ++i) u[i] += RV_GET(m, ch, i);
+            d += dp_dot32(xr, u);
           }
-          pr[0] = d + __ldg(p.mu[l] + 256);
+          pr[0] = d + c0;
           signal_go();
         }
         {   // q: logits against the cond tokens and the time token
+          const RVec bq = rv_load(L.bqkv, lane), ktk = rv_load(L.kt + toff, lane);
+          float kc[NC][32];
+#pragma unroll
+          for (int n = 0; n < NC; ++n) ct_load(ct, 0, n, 0, kc[n]);
           acc_wait();
           float dc[NC], dt = 0.f;
 #pragma unroll
           for (int n = 0; n < NC; ++n) dc[n] = 0.f;
 #pragma unroll 1
           for (int ch = 0; ch < 8; ++ch) {
-            float qv[32], v[32];
-            dp_ldvec(L.bqkv + ch * 32, v);
+            float qv[32];
             dp_ld32(tl + ch * 32, qv);
+            {
+              float kt32[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) qv[i] += v[i];
-            dp_ldvec(L.kt + toff + ch * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) dt = fmaf(qv[i], v[i], dt);
+              for (int i = 0; i < 32; ++i) { qv[i] += RV_GET(bq, ch, i); kt32[i] = RV_GET(ktk, ch, i); }
+              dt += dp_dot32(qv, kt32);
+            }
 #pragma unroll
             for (int n = 0; n < NC; ++n) {
-              const float* kc = ct + (size_t)DP_CT(0, n, 0) + (size_t)ch * 32 * 128;
-              float a = 0.f;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) a = fmaf(qv[i], __ldg(kc + i * 128), a);
-              dc[n] += a;
+              dc[n] += dp_dot32(qv, kc[n]);
+              if (ch < 7) ct_load(ct, 0, n, ch + 1, kc[n]);      // the next chunk's table values travel during this chunk's tail
             }
           }
           signal_go();
@@ -1210,40 +1263,43 @@ __global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_co
           for (int j = 0; j < NC + 2; ++j) pr[j] *= inv;
         }
         {   // ov: t0 = x + b + sum_j p_j ov_j; x1 = norm1(t0)
+          const RVec bs = rv_load(L.bqkv + 512, lane), ovt = rv_load(L.kt + toff + 256, lane);
+          const RVec g1 = rv_load(L.n1g, lane), b1n = rv_load(L.n1b, lane);
+          float oc[NC][32];
+#pragma unroll
+          for (int n = 0; n < NC; ++n) ct_load(ct, 1, n, 0, oc[n]);
           acc_wait();
           float sum = 0.f;
 #pragma unroll 1
           for (int ch = 0; ch < 8; ++ch) {
-            float t0[32], v[32];
+            float t0[32];
             dp_ld32(tl + ch * 32, t0);
-            dp_ldvec(L.bqkv + 512 + ch * 32, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) t0[i] = v[i] + pr[0] * t0[i];
-            dp_ldvec(L.kt + toff + 256 + ch * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) t0[i] = fmaf(pr[NC + 1], v[i], t0[i]);
+            for (int i = 0; i < 32; ++i) t0[i] = RV_GET(bs, ch, i) + pr[0] * t0[i] + pr[NC + 1] * RV_GET(ovt, ch, i);
 #pragma unroll
             for (int n = 0; n < NC; ++n) {
-              const float* oc = ct + (size_t)DP_CT(1, n, 0) + (size_t)ch * 32 * 128;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) t0[i] = fmaf(pr[1 + n], __ldg(oc + i * 128), t0[i]);
+              for (int i = 0; i < 32; ++i) t0[i] = fmaf(pr[1 + n], oc[n][i], t0[i]);
+              if (ch < 7) ct_load(ct, 1, n, ch + 1, oc[n]);
             }
-            dp_ld32(tl + DM_XR + ch * 32, v);
+            {
+              float xr[32];
+              dp_ld32(tl + DM_XR + ch * 32, xr);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { t0[i] += v[i]; sum += t0[i]; }
+              for (int i = 0; i < 32; ++i) t0[i] += xr[i];
+            }
+            sum += dp_sum32(t0);
             dp_st32(tl + ch * 32, t0);
           }
           float mean, rstd;
           ln_stats(0, sum, mean, rstd);
 #pragma unroll 1
           for (int ch = 0; ch < 8; ++ch) {
-            float t0[32], g[32], b[32];
-            dp_ldvec(L.n1g + ch * 32, g);
-            dp_ldvec(L.n1b + ch * 32, b);
+            float t0[32];
             dp_ld32(tl + ch * 32, t0);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              t0[i] = (t0[i] - mean) * rstd * g[i] + b[i];
+              t0[i] = (t0[i] - mean) * rstd * RV_GET(g1, ch, i) + RV_GET(b1n, ch, i);
               xs1_g[(size_t)(ch * 32 + i) * 128] = t0[i];       // the fp32 residual waits in L2 while the FFN uses its columns
             }
             dm_write_a(a_buf, ch * 32, row, t0);
@@ -1253,15 +1309,16 @@ __global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_co
         // ---- FFN 256 -> 1024 (ReLU) -> 256 in 8 hidden chunks of 128; relu(h) returns to tensor memory as bf16 (hi, lo) ----
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {
+          const RVec4 b = rv4_load(L.b1 + j * 128, lane);
           acc_wait();
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
-            float f[32], b[32];
-            dp_ldvec(L.b1 + j * 128 + c4 * 32, b);
+            float f[32];
             dp_ld32(tl + DM_ACC1 + c4 * 32, f);
             uint32_t hb[16], lb[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dp_split2(fmaxf(f[2 * i] + b[2 * i], 0.f), fmaxf(f[2 * i + 1] + b[2 * i + 1], 0.f), hb[i], lb[i]);
+            for (int i = 0; i < 16; ++i)
+              dp_split2(fmaxf(f[2 * i] + RV4_GET(b, c4, 2 * i), 0.f), fmaxf(f[2 * i + 1] + RV4_GET(b, c4, 2 * i + 1), 0.f), hb[i], lb[i]);
             dm_tmem_st16(tl + DM_HHI + c4 * 16, hb);
             dm_tmem_st16(tl + DM_HLO + c4 * 16, lb);
           }
@@ -1269,15 +1326,24 @@ __global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_co
           signal_go();
         }
         {   // x2 = norm2(x1 + ffn); then the input norm of the cross-attention
+          const RVec b2 = rv_load(L.b2, lane), g2 = rv_load(L.n2g, lane), b2n = rv_load(L.n2b, lane);
+          const RVec gc = rv_load(L.cng, lane), bc = rv_load(L.cnb, lane);
+          float xs[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) xs[i] = xs1_g[(size_t)i * 128];
           acc_wait();
           float sum = 0.f;
 #pragma unroll 1
           for (int ch = 0; ch < 8; ++ch) {
-            float t1[32], v[32];
-            dp_ldvec(L.b2 + ch * 32, v);
+            float t1[32];
             dp_ld32(tl + ch * 32, t1);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { t1[i] += v[i] + xs1_g[(size_t)(ch * 32 + i) * 128]; sum += t1[i]; }
+            for (int i = 0; i < 32; ++i) t1[i] += RV_GET(b2, ch, i) + xs[i];
+            sum += dp_sum32(t1);
+            if (ch < 7) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) xs[i] = xs1_g[(size_t)((ch + 1) * 32 + i) * 128];
+            }
             dp_st32(tl + ch * 32, t1);
           }
           float mean, rstd;
@@ -1285,37 +1351,38 @@ __global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_co
           float sum2 = 0.f;
 #pragma unroll 1
           for (int ch = 0; ch < 8; ++ch) {
-            float t1[32], g[32], b[32];
-            dp_ldvec(L.n2g + ch * 32, g);
-            dp_ldvec(L.n2b + ch * 32, b);
+            float t1[32];
             dp_ld32(tl + ch * 32, t1);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { t1[i] = (t1[i] - mean) * rstd * g[i] + b[i]; sum2 += t1[i]; }
+            for (int i = 0; i < 32; ++i) t1[i] = (t1[i] - mean) * rstd * RV_GET(g2, ch, i) + RV_GET(b2n, ch, i);
+            sum2 += dp_sum32(t1);
             dp_st32(tl + DM_XR + ch * 32, t1);      // the FFN is done with these columns: the residual stream is back
           }
           ln_stats(DM_XR, sum2, mean, rstd);
 #pragma unroll 1
           for (int ch = 0; ch < 8; ++ch) {
-            float t1[32], g[32], b[32];
-            dp_ldvec(L.cng + ch * 32, g);
-            dp_ldvec(L.cnb + ch * 32, b);
+            float t1[32];
             dp_ld32(tl + DM_XR + ch * 32, t1);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) t1[i] = (t1[i] - mean) * rstd * g[i] + b[i];
+            for (int i = 0; i < 32; ++i) t1[i] = (t1[i] - mean) * rstd * RV_GET(gc, ch, i) + RV_GET(bc, ch, i);
             dm_write_a(a_buf, ch * 32, row, t1);
           }
           signal_go();
         }
         {   // linear cross-attention to the cond tokens + FiLM
+          const RVec bq2 = rv_load(L.bcaq, lane), fg = rv_load(L.film_ca + toff, lane), fb = rv_load(L.film_ca + toff + 256, lane);
+          float tb[NC][32];
+#pragma unroll
+          for (int n = 0; n < NC; ++n) ct_load(ct, 2, n, 0, tb[n]);
           acc_wait();
           float m = -INFINITY;
 #pragma unroll 1
           for (int ch = 0; ch < 8; ++ch) {
-            float qv[32], v[32];
-            dp_ldvec(L.bcaq + ch * 32, v);
+            float qv[32];
             dp_ld32(tl + ch * 32, qv);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { qv[i] += v[i]; m = fmaxf(m, qv[i]); }
+            for (int i = 0; i < 32; ++i) qv[i] += RV_GET(bq2, ch, i);
+            m = fmaxf(m, dp_max32(qv));
             dp_st32(tl + ch * 32, qv);
           }
           float ssum = 0.f, dn[NC];
@@ -1326,14 +1393,13 @@ __global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_co
             float qv[32];
             dp_ld32(tl + ch * 32, qv);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { qv[i] = __expf(qv[i] - m); ssum += qv[i]; }
+            for (int i = 0; i < 32; ++i) qv[i] = __expf(qv[i] - m);
+            ssum += dp_sum32(qv);
 #pragma unroll
             for (int n = 0; n < NC; ++n) {
-              const float* ks = ct + (size_t)DP_CT(2, n, 0) + (size_t)ch * 32 * 128;
-              float a = 0.f;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) a = fmaf(qv[i], __ldg(ks + i * 128), a);
-              dn[n] += a;
+              dn[n] += dp_dot32(qv, tb[n]);
+              if (ch < 7) ct_load(ct, 2, n, ch + 1, tb[n]);
+              else ct_load(ct, 3, n, 0, tb[n]);                  // then the value table, chunk 0
             }
           }
           const float inv = 1.0f / ssum;
@@ -1347,25 +1413,22 @@ __global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_co
             for (int i = 0; i < 32; ++i) y[i] = 0.f;
 #pragma unroll
             for (int n = 0; n < NC; ++n) {
-              const float* vv = ct + (size_t)DP_CT(3, n, 0) + (size_t)ch * 32 * 128;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) y[i] = fmaf(dn[n], __ldg(vv + i * 128), y[i]);
+              for (int i = 0; i < 32; ++i) y[i] = fmaf(dn[n], tb[n][i], y[i]);
+              if (ch < 7) ct_load(ct, 3, n, ch + 1, tb[n]);
             }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sum += y[i];
+            sum += dp_sum32(y);
             dp_st32(tl + ch * 32, y);
           }
           float mean, rstd;
           ln_stats(0, sum, mean, rstd);
 #pragma unroll 1
           for (int ch = 0; ch < 8; ++ch) {
-            float y[32], g[32], b[32];
-            dp_ldvec(L.film_ca + toff + ch * 32, g);
-            dp_ldvec(L.film_ca + toff + 256 + ch * 32, b);
+            float y[32];
             dp_ld32(tl + ch * 32, y);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const float t = (y[i] - mean) * rstd * g[i] + b[i];
+              const float t = (y[i] - mean) * rstd * RV_GET(fg, ch, i) + RV_GET(fb, ch, i);
               y[i] = __fdividef(t, 1.0f + __expf(-t));
             }
             dm_write_a(a_buf, ch * 32, row, y);
@@ -1373,56 +1436,55 @@ __global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_co
           signal_go();
         }
         {   // x3 = x2 + out(h)
+          const RVec b = rv_load(L.bcaout, lane);
           acc_wait();
 #pragma unroll 1
           for (int ch = 0; ch < 8; ++ch) {
-            float x[32], xr[32], b[32];
-            dp_ldvec(L.bcaout + ch * 32, b);
+            float x[32], xr[32];
             dp_ld32(tl + ch * 32, x);
             dp_ld32(tl + DM_XR + ch * 32, xr);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] += b[i] + xr[i];
+            for (int i = 0; i < 32; ++i) x[i] += RV_GET(b, ch, i) + xr[i];
             dp_st32(tl + DM_XR + ch * 32, x);
             dm_write_a(a_buf, ch * 32, row, x);
           }
           signal_go();
         }
         {   // FFN 256 -> 128 (GELU)
+          const RVec4 b = rv4_load(L.bf1, lane);
           acc_wait();
 #pragma unroll 1
           for (int c4 = 0; c4 < 4; ++c4) {
-            float f[32], b[32];
-            dp_ldvec(L.bf1 + c4 * 32, b);
+            float f[32];
             dp_ld32(tl + c4 * 32, f);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i] + b[i]);
+            for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i] + RV4_GET(b, c4, i));
             dm_write_a(a_buf, c4 * 32, row, f);
           }
           signal_go();
         }
         {   // -> 256, FiLM
+          const RVec b = rv_load(L.bf2, lane), fg = rv_load(L.film_ff + toff, lane), fb = rv_load(L.film_ff + toff + 256, lane);
           acc_wait();
           float sum = 0.f;
 #pragma unroll 1
           for (int ch = 0; ch < 8; ++ch) {
-            float y[32], b[32];
-            dp_ldvec(L.bf2 + ch * 32, b);
+            float y[32];
             dp_ld32(tl + ch * 32, y);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { y[i] += b[i]; sum += y[i]; }
+            for (int i = 0; i < 32; ++i) y[i] += RV_GET(b, ch, i);
+            sum += dp_sum32(y);
             dp_st32(tl + ch * 32, y);
           }
           float mean, rstd;
           ln_stats(0, sum, mean, rstd);
 #pragma unroll 1
           for (int ch = 0; ch < 8; ++ch) {
-            float y[32], g[32], b[32];
-            dp_ldvec(L.film_ff + toff + ch * 32, g);
-            dp_ldvec(L.film_ff + toff + 256 + ch * 32, b);
+            float y[32];
             dp_ld32(tl + ch * 32, y);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const float t = (y[i] - mean) * rstd * g[i] + b[i];
+              const float t = (y[i] - mean) * rstd * RV_GET(fg, ch, i) + RV_GET(fb, ch, i);
               y[i] = __fdividef(t, 1.0f + __expf(-t));
             }
             dm_write_a(a_buf, ch * 32, row, y);
@@ -1430,16 +1492,17 @@ __global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_co
           signal_go();
         }
         {   // block output = x3 + out(h)
+          const RVec b = rv_load(L.bfout, lane);
           acc_wait();
           float sum = 0.f;
 #pragma unroll 1
           for (int ch = 0; ch < 8; ++ch) {
-            float x[32], xr[32], b[32];
-            dp_ldvec(L.bfout + ch * 32, b);
+            float x[32], xr[32];
             dp_ld32(tl + ch * 32, x);
             dp_ld32(tl + DM_XR + ch * 32, xr);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { x[i] += b[i] + xr[i]; sum += x[i]; }
+            for (int i = 0; i < 32; ++i) x[i] += RV_GET(b, ch, i) + xr[i];
+            sum += dp_sum32(x);
             if (l < 4) {
               dp_st32(tl + DM_XR + ch * 32, x);
               dm_write_a(a_buf, ch * 32, row, x);
@@ -1453,20 +1516,38 @@ __global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_co
             signal_go();
           } else {
             // final LayerNorm, then CFG combine + DDIM update
+            const RVec fg = rv_load(p.fng, lane), fb = rv_load(p.fnb, lane), pe = rv_load(p.pe0, lane);
             float mean, rstd;
             ln_stats(0, sum, mean, rstd);
             const float c0 = __ldg(p.coef + step * 4), c1 = __ldg(p.coef + step * 4 + 1), c2 = __ldg(p.coef + step * 4 + 2),
                         c3 = __ldg(p.coef + step * 4 + 3);
             const float gs = __ldg(p.gscale);
             const bool last = step == p.n_steps - 1;
+            if (p.mode == 0 && p.cfg) {
+              // rows r (uncond) and r + 64 (cond) are the two guidance branches of one latent: every row publishes its eps in the
+              // L2 scratch row (free between the FFN blocks), one CTA-wide epilogue barrier, then each row reads its partner's
+#pragma unroll 1
+              for (int ch = 0; ch < 8; ++ch) {
+                float e[32];
+                dp_ld32(tl + ch * 32, e);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  e[i] = (e[i] - mean) * rstd * RV_GET(fg, ch, i) + RV_GET(fb, ch, i);
+                  __stcg(xs1_g + (size_t)(ch * 32 + i) * 128, e[i]);
+                }
+                dp_st32(tl + ch * 32, e);
+              }
+              __threadfence_block();
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
 #pragma unroll 1
             for (int ch = 0; ch < 8; ++ch) {
-              float e[32], g[32], b[32];
-              dp_ldvec(p.fng + ch * 32, g);
-              dp_ldvec(p.fnb + ch * 32, b);
+              float e[32];
               dp_ld32(tl + ch * 32, e);
+              if (p.mode == 1 || !p.cfg) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) e[i] = (e[i] - mean) * rstd * g[i] + b[i];
+                for (int i = 0; i < 32; ++i) e[i] = (e[i] - mean) * rstd * RV_GET(fg, ch, i) + RV_GET(fb, ch, i);
+              }
               if (p.mode == 1) {
                 if (valid) {
                   float4* dst = reinterpret_cast<float4*>(p.out + (size_t)grow * 256 + ch * 32);
@@ -1475,18 +1556,15 @@ __global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_co
                 }
                 continue;
               }
-              if (p.cfg) {       // rows r (uncond) and r + 64 (cond) are the two guidance branches of one latent
-#pragma unroll
-                for (int i = 0; i < 32; ++i) swapb[i * 128 + row] = e[i];
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+              if (p.cfg) {
+                const float* partner = p.xs1 + (size_t)tile * 256 * 128 + (row ^ 64);
                 const bool is_u = row < 64;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                  const float o = swapb[i * 128 + (row ^ 64)];
+                  const float o = __ldcg(partner + (size_t)(ch * 32 + i) * 128);
                   const float eu = is_u ? e[i] : o, ec = is_u ? o : e[i];
                   e[i] = __fadd_rn(eu, __fmul_rn(gs, __fsub_rn(ec, eu)));
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
               }
               float lt[32];
 #pragma unroll
@@ -1501,15 +1579,16 @@ __global__ void __launch_bounds__(DM_THREADS, 1) den_mono_kernel(const __grid_co
                   for (int j = 0; j < 8; ++j) dst[j] = make_float4(lt[4 * j], lt[4 * j + 1], lt[4 * j + 2], lt[4 * j + 3]);
                 }
               } else {
-                float pe[32];
-                dp_ldvec(p.pe0 + ch * 32, pe);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { lat_g[(size_t)(ch * 32 + i) * 128] = lt[i]; lt[i] += pe[i]; }
+                for (int i = 0; i < 32; ++i) { lat_g[(size_t)(ch * 32 + i) * 128] = lt[i]; lt[i] += RV_GET(pe, ch, i); }
                 dp_st32(tl + DM_XR + ch * 32, lt);
                 dm_write_a(a_buf, ch * 32, row, lt);
               }
             }
-            if (p.mode == 0 && !last) signal_go();
+            if (p.mode == 0 && !last) {
+              if (p.cfg) asm volatile("bar.sync 1, 128;" ::: "memory");   // every partner read is done before the scratch row is reused
+              signal_go();
+            }
           }
         }
       }

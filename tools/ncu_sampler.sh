@@ -1,5 +1,6 @@
+# usage: tools/ncu_sampler.sh <backend> <kernel regex> <out name>
 set -x
-python tools/profile_sampler.py 256 7.5 persistent > gpurun_out/plain_sampler.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:den_persist_kernel -s 3 -c 1 -o gpurun_out/r2_den_persist python tools/profile_sampler.py 256 7.5 persistent > gpurun_out/ncu_sampler.log 2>&1
-tail -3 gpurun_out/ncu_sampler.log
-ls -la gpurun_out/*.ncu-rep
+BE=${1:-persistent}; RX=${2:-den_persist_kernel}; OUT=${3:-r2_den_persist}
+python tools/profile_sampler.py 256 7.5 $BE > gpurun_out/plain_sampler.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:$RX -s 3 -c 1 -o gpurun_out/$OUT python tools/profile_sampler.py 256 7.5 $BE > gpurun_out/ncu_sampler.log 2>&1
+ls -la gpurun_out/$OUT.ncu-rep
