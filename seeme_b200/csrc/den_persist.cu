@@ -216,6 +216,21 @@ __device__ __forceinline__ void dp_publish(uint8_t* ximg_tile, int col, int row,
     *reinterpret_cast<uint4*>(line + 16384 + c) = make_uint4(lb[4 * j], lb[4 * j + 1], lb[4 * j + 2], lb[4 * j + 3]);
   }
 }
+// 32 consecutive columns [c0, c0 + 32) of this thread's row into the shared-memory A operand (bf16 hi | lo K-block tiles)
+__device__ __forceinline__ void dm_write_a(uint8_t* a_buf, int c0, int row, const float (&f)[32]) {
+  uint32_t hb[16], lb[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dp_split2(f[2 * i], f[2 * i + 1], hb[i], lb[i]);
+  uint8_t* line = a_buf + (c0 >> 6) * 32768 + row * 128;
+  const int j0 = (c0 & 63) >> 3, sw = row & 7;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = ((j0 + j) ^ sw) << 4;
+    *reinterpret_cast<uint4*>(line + c) = make_uint4(hb[4 * j], hb[4 * j + 1], hb[4 * j + 2], hb[4 * j + 3]);
+    *reinterpret_cast<uint4*>(line + 16384 + c) = make_uint4(lb[4 * j], lb[4 * j + 1], lb[4 * j + 2], lb[4 * j + 3]);
+  }
+}
+
 // 32 consecutive floats of a vector shared by all rows (bias, LayerNorm affine, FiLM, time-token tables)
 __device__ __forceinline__ void dp_ldvec(const float* __restrict__ p, float (&v)[32]) {
 #pragma unroll
@@ -395,10 +410,17 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
           for (int kb = 0; kb < un.nkb; ++kb) {
             if (!un.reuse_a) {
               const uint32_t sa = ia % DP_NA;
-              dp_wait(&empty_a[sa], ((ia / DP_NA) & 1u) ^ 1u, 4);
-              mbar_arrive_expect_tx(&full_a[sa], DP_A_SLOT);
-              const int col = kb < un.nkb1 ? acol + kb * 64 : un.a_col2 + (kb - un.nkb1) * 64;
-              dp_bulk_load(a_ring + sa * DP_A_SLOT, ximg_tile + (size_t)(col >> 6) * 32768, DP_A_SLOT, &full_a[sa]);
+              if (un.wait == 2) {
+                // CTA-private operand (relu(h) of this CTA's FFN hidden units): the epilogue threads have written it straight
+                // into the ring slots (always slots 0, 1: the K-block count of a step is a multiple of the ring size up to
+                // here), so there is nothing to load -- only the slot's phase to complete
+                mbar_arrive(&full_a[sa]);
+              } else {
+                dp_wait(&empty_a[sa], ((ia / DP_NA) & 1u) ^ 1u, 4);
+                mbar_arrive_expect_tx(&full_a[sa], DP_A_SLOT);
+                const int col = kb < un.nkb1 ? acol + kb * 64 : un.a_col2 + (kb - un.nkb1) * 64;
+                dp_bulk_load(a_ring + sa * DP_A_SLOT, ximg_tile + (size_t)(col >> 6) * 32768, DP_A_SLOT, &full_a[sa]);
+              }
               ++ia;
             }
             if (kb >= kw) {
@@ -510,10 +532,10 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
       if (tr_me) DP_TR(2, 10);
     };
     auto signal_l = [&]() {      // CTA-private hand-over (FFN hidden units)
-      dp_fence_proxy_all();
+      dp_fence_proxy_all();        // st.shared (generic proxy) -> tcgen05.mma operand reads (async proxy)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) dp_arrive_remote(dp_mapa(smem_u32(&lbar[nl & 1u]), rank));   // release: the stores are at the L2
+      if (lane == 0) mbar_arrive(&lbar[nl & 1u]);
       ++nl;
     };
 
@@ -652,7 +674,7 @@ __global__ void __cluster_dims__(DP_CL, 1, 1) __launch_bounds__(DP_THREADS, 1) d
             dp_ld32x2(tl + (ch >> 1) * 128 + (ch & 1) * 32, tl + (ch >> 1) * 128 + (ch & 1) * 32 + 64, f);
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i] + b[i], 0.f);
-            dp_publish<32>(xt, XC_FF + rank * DP_HS + ch * 32, row, f);
+            dm_write_a(a_ring, ch * 32, row, f);      // K-blocks 0, 1 of the K-split second GEMM: ring slots 0, 1 (see the producer)
           }
           signal_l();
         }
@@ -953,20 +975,6 @@ __device__ __forceinline__ void dm_tmem_st16(uint32_t taddr, const uint32_t* v) 
       "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
       "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
-}
-// 32 consecutive columns [c0, c0 + 32) of this thread's row into the shared-memory A operand (bf16 hi | lo K-block tiles)
-__device__ __forceinline__ void dm_write_a(uint8_t* a_buf, int c0, int row, const float (&f)[32]) {
-  uint32_t hb[16], lb[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) dp_split2(f[2 * i], f[2 * i + 1], hb[i], lb[i]);
-  uint8_t* line = a_buf + (c0 >> 6) * 32768 + row * 128;
-  const int j0 = (c0 & 63) >> 3, sw = row & 7;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = ((j0 + j) ^ sw) << 4;
-    *reinterpret_cast<uint4*>(line + c) = make_uint4(hb[4 * j], hb[4 * j + 1], hb[4 * j + 2], hb[4 * j + 3]);
-    *reinterpret_cast<uint4*>(line + 16384 + c) = make_uint4(lb[4 * j], lb[4 * j + 1], lb[4 * j + 2], lb[4 * j + 3]);
-  }
 }
 
 // A 256-float vector shared by all rows (bias, LayerNorm affine, FiLM, time-token table), distributed over the lanes of a
