@@ -686,3 +686,31 @@ def test_default_precision_drift_at_bench_size(variant):
     assert drift_mm < 0.5, drift_mm
     assert max_mm < 3.0, max_mm
     assert (rs["joints_ref"].double().cpu() - ref["joints_ref"].double()).abs().max() < 1e-5
+
+
+def test_sampler_backends_agree_at_bench_size(weights):
+    """the benchmarked row count (256 sequences under CFG = 512 rows = 4 row tiles): the three sampler back-ends agree to fp32
+    rounding through 50 steps, and each persistent kernel is bit-reproducible run to run (its exchanges are fixed-order sums)"""
+    from seeme_b200 import ops
+    from seeme_b200.modules import time_sinusoid
+    from seeme_b200.scheduler import DDIMScheduler
+    B = 256
+    op = ops.DenoiserOp(cu(weights["denoiser"]), max_rows=2 * B)
+    s = DDIMScheduler(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                      clip_sample=False, set_alpha_to_one=False, steps_offset=1)
+    s.set_timesteps(50)
+    ts = s.timesteps.tolist()
+    op.set_time_table(ts, time_sinusoid(s.timesteps))
+    g = torch.Generator().manual_seed(31)
+    cond = torch.randn(2, 2 * B, 256, generator=g).to(DEV)
+    xT = torch.randn(B, 256, generator=g).to(DEV)
+    z = {}
+    for be in BACKENDS:
+        op.set_backend(be)
+        z[be] = op.sample(xT, cond, 7.5, ts, s.step_coefficients())
+        again = op.sample(xT, cond, 7.5, ts, s.step_coefficients())
+        assert torch.equal(z[be], again), be
+    scale = float(z["graph"].abs().max())
+    for be in ("persistent", "tile"):
+        err = float((z[be] - z["graph"]).abs().max())
+        assert err < 2e-4 * max(scale, 1.0), (be, err, scale)
