@@ -338,6 +338,194 @@ __global__ void __launch_bounds__(192, MINB) umma_linear_kernel(const __grid_con
   }
 }
 
+
+// ---- persistent variant for many-row GEMMs (VAE stacks, image backbone) ------------------------------------------------
+// One CTA per SM loops over [128 x 128] output tiles (n fastest: the CTAs that run at the same time share their A row tiles
+// in L2): a 2-stage operand ring, TWO 128-column accumulators in tensor memory so that the MMAs of tile i+1 run under the
+// epilogue of tile i, and an epilogue that keeps the TMA-staged stores / residual loads of the one-tile kernel above.
+// The one-tile-per-CTA kernel pays barrier init + TMEM allocation + a cold ring per tile and serialises load, MMA and
+// epilogue inside a CTA (2-3 co-resident CTAs hide part of it); here that cost is paid once per SM.
+// Split-bf16 (x3), bias per column, activation before the residual, fp32 and / or bf16 (hi, lo) outputs.
+constexpr int PL_STAGES = 2;
+constexpr int PL_STAGE_BYTES = UmmaCfg<128, 3>::STAGE_BYTES;                 // 64 KB
+constexpr int PL_SMEM = PL_STAGES * PL_STAGE_BYTES + STORE_BUF_BYTES + RES_BUF_BYTES + 1024;
+
+__global__ void __launch_bounds__(192, 1) umma_plinear_kernel(const __grid_constant__ UmmaMaps tm, const UmmaEpi e, int n_tiles_n, int n_tiles) {
+  using Cfg = UmmaCfg<128, 3>;
+  extern __shared__ __align__(1024) uint8_t pl_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pl_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sbuf = smem + PL_STAGES * PL_STAGE_BYTES;
+  uint8_t* res_stage = sbuf + STORE_BUF_BYTES;
+  __shared__ __align__(8) uint64_t full_bar[PL_STAGES], empty_bar[PL_STAGES], acc_full[2], acc_empty[2], res_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm.a1h); tma_prefetch_desc(&tm.a1l); tma_prefetch_desc(&tm.wh); tma_prefetch_desc(&tm.wl);
+    for (int i = 0; i < PL_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    mbar_init(&res_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  pdl_prologue();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles_n) * 128, n0 = (t % n_tiles_n) * 128;
+        for (int kb = 0; kb < e.nkb; ++kb, ++it) {
+          const uint32_t st = it % PL_STAGES;
+          mbar_wait(&empty_bar[st], ((it / PL_STAGES) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[st], PL_STAGE_BYTES);
+          uint8_t* sa = smem + (size_t)st * PL_STAGE_BYTES;
+          uint8_t* sw = sa + 2 * Cfg::A_BYTES;
+          const bool first = kb < e.nkb1;
+          const int kc = (first ? kb : kb - e.nkb1) * 64;
+          tma_load_2d(sa, first ? &tm.a1h : &tm.a2h, &full_bar[st], kc, m0);
+          tma_load_2d(sa + Cfg::A_BYTES, first ? &tm.a1l : &tm.a2l, &full_bar[st], kc, m0);
+          tma_load_2d(sw, &tm.wh, &full_bar[st], kb * 64, n0);
+          tma_load_2d(sw + Cfg::W_BYTES, &tm.wl, &full_bar[st], kb * 64, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_bf16(128);
+    const uint64_t d0 = umma_desc_k128(smem_u32(smem));
+    uint32_t it = 0, ti = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+      const uint32_t buf = ti & 1u;
+      mbar_wait(&acc_empty[buf], ((ti >> 1) & 1u) ^ 1u);       // the epilogue has drained this accumulator (tile ti - 2)
+      tc_fence_after();
+      const uint32_t d_t = tmem_base + buf * 128u;
+      for (int kb = 0; kb < e.nkb; ++kb, ++it) {
+        const uint32_t st = it % PL_STAGES;
+        mbar_wait(&full_bar[st], (it / PL_STAGES) & 1u);
+        tc_fence_after();
+        if (umma_elect_one()) {
+          const uint64_t da0 = umma_desc_add(d0, st * (PL_STAGE_BYTES >> 4));
+          const uint64_t dw0 = umma_desc_add(da0, (uint32_t)((2 * Cfg::A_BYTES) >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_desc_add(da0, k * 2), dw = umma_desc_add(dw0, k * 2);
+            umma_bf16(d_t, da, dw, idesc, (kb | k) != 0);
+            umma_bf16(d_t, umma_desc_add(da, Cfg::A_BYTES >> 4), dw, idesc, 1);
+            umma_bf16(d_t, da, umma_desc_add(dw, Cfg::W_BYTES >> 4), idesc, 1);
+          }
+          umma_commit(&empty_bar[st]);
+          if (kb == e.nkb - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool elected = (warp == 2 && lane == 0);
+    uint32_t ti = 0, ng = 0;        // ng: residual groups consumed so far (res_bar phase)
+    auto load_res = [&](int m0, int c) {      // fp32 residual of 64 columns [c, c + 64): two 32-column tiles
+      mbar_arrive_expect_tx(&res_bar, RES_BUF_BYTES);
+      tma_load_2d(res_stage, &tm.rf, &res_bar, c, m0);
+      tma_load_2d(res_stage + TILE_BYTES, &tm.rf, &res_bar, c + 32, m0);
+    };
+    if (e.has_r && elected && (int)blockIdx.x < n_tiles) load_res((blockIdx.x / n_tiles_n) * 128, (blockIdx.x % n_tiles_n) * 128);
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+      const uint32_t buf = ti & 1u;
+      const int m0 = (t / n_tiles_n) * 128, n0 = (t % n_tiles_n) * 128;
+      const int tn = t + gridDim.x;
+      mbar_wait(&acc_full[buf], (ti >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < 2; ++g) {
+        // the stores of the previous group must have read the staging buffer before it is rewritten
+        if (elected) tma_store_wait_read<0>();
+        epi_bar_sync();
+        if (e.has_r) { mbar_wait(&res_bar, ng & 1u); ++ng; }
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int c0 = g * 64 + half * 32;
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128u + (uint32_t)c0, raw);
+          tmem_ld_wait();
+          if (g == 1 && half == 1) {          // the whole accumulator is in registers / staged: the MMAs of tile ti + 2 may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
+          const int n = n0 + c0;
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(raw[i]);
+          if (e.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n + i));
+              f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+            }
+          }
+          if (e.act != ACT_NONE) epi_act32(f, e.act);
+          if (e.has_r) {
+            const uint8_t* rt = res_stage + half * TILE_BYTES;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 r = *reinterpret_cast<const float4*>(rt + sw128(row, j));
+              f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+            }
+          }
+          if (e.has_yf) {
+            uint8_t* tt = sbuf + (2 + half) * TILE_BYTES;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(tt + sw128(row, j)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
+          if (e.has_yh) {
+            uint32_t hb[16], lb[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) split_bf16x2(f[2 * i], f[2 * i + 1], hb[i], lb[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(sbuf + sw128(row, half * 4 + j)) = make_uint4(hb[4 * j], hb[4 * j + 1], hb[4 * j + 2], hb[4 * j + 3]);
+            if (e.has_yl) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(sbuf + TILE_BYTES + sw128(row, half * 4 + j)) =
+                    make_uint4(lb[4 * j], lb[4 * j + 1], lb[4 * j + 2], lb[4 * j + 3]);
+            }
+          }
+        }
+        fence_proxy_async();
+        epi_bar_sync();                 // staging complete; every thread is past its reads of the residual tiles
+        if (elected) {
+          const int c = n0 + g * 64;
+          if (e.has_yh) tma_store_2d(&tm.yh, sbuf, c, m0);
+          if (e.has_yl) tma_store_2d(&tm.yl, sbuf + TILE_BYTES, c, m0);
+          if (e.has_yf) {
+            tma_store_2d(&tm.yf, sbuf + 2 * TILE_BYTES, c, m0);
+            tma_store_2d(&tm.yf, sbuf + 3 * TILE_BYTES, c + 32, m0);
+          }
+          tma_store_commit();
+          if (e.has_r) {                // next residual group: the second half of this tile, or the first of this CTA's next tile
+            if (g == 0) load_res(m0, n0 + 64);
+            else if (tn < n_tiles) load_res((tn / n_tiles_n) * 128, (tn % n_tiles_n) * 128);
+          }
+        }
+      }
+    }
+    if (elected) tma_store_wait_read<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
@@ -438,6 +626,21 @@ int umma_linear(const UmmaLinear& g, int npass, cudaStream_t s) {
   e.act_post = g.act_after_residual;
   e.colmax = g.colmax; e.colmax_group_rows = g.colmax_group_rows;
   e.fp16 = g.fp16;
+  // many rows, split precision, plain epilogue: the persistent kernel (one CTA per SM, MMAs of the next tile under this tile's epilogue)
+  if (BN == 128 && npass == 3 && g.M >= 2048 && !g.fp16 && !g.pfold && !g.colmax && !g.Zh && !g.bias_group_rows && !g.act_after_residual &&
+      !g.dense_ctas && (!g.Yl || g.Yh)) {
+    static bool configured = false;
+    if (!configured) {
+      SEEME_CUDA(cudaFuncSetAttribute(umma_plinear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM));
+      configured = true;
+    }
+    const int tiles_n = g.N / 128, tiles = tiles_n * ((g.M + 127) / 128);
+    const int grid = tiles < NUM_SMS ? tiles : NUM_SMS;
+    ProfScope prof(g.prof_id - 1, s);
+    SEEME_CUDA(launch_pdl(umma_plinear_kernel, dim3(grid), dim3(192), (size_t)PL_SMEM, s, maps, e, tiles_n, tiles));
+    SEEME_LAUNCH_CHECK();
+    return SEEME_OK;
+  }
   // 64-wide tiles: the whole K = 256 of a latency-bound GEMM is in flight at once (4 stages), one CTA per SM.
   // 128-wide tiles (many rows): a shallow ring (64 KB in split mode) and one staging buffer keep the footprint
   // small enough for 2-3 CTAs per SM, which is what overlaps TMA, MMA and epilogue phases across tiles.
