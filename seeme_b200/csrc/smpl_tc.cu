@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) smpl_skin_tc2_kernel(const __gr
   uint8_t* ring = smem + ST_B_BYTES;
   uint8_t* wt = ring + S2_NST * ST_CHUNK;
   uint8_t* aop = wt + 2 * S2_WT;
-  __shared__ __align__(8) uint64_t r_full[S2_NST], r_empty[S2_NST], b_full, acc_full, acc_free, wt_full[2], wt_free[2], aop_full[4][2], t_free[4], t_full[4];
+  __shared__ __align__(8) uint64_t r_full[S2_NST], r_empty[S2_NST], b_full, acc_full, acc_free, wt_full[2], wt_free[2], aop_full[2], t_free, t_full;
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -344,7 +344,9 @@ __global__ void __launch_bounds__(S2_THREADS, 1) smpl_skin_tc2_kernel(const __gr
     mbar_init(&acc_full, 1);
     mbar_init(&acc_free, 16);
     for (int i = 0; i < 2; ++i) { mbar_init(&wt_full[i], 1); mbar_init(&wt_free[i], 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&aop_full[i][0], 1); mbar_init(&aop_full[i][1], 1); mbar_init(&t_free[i], 4); mbar_init(&t_full[i], 1); }
+    for (int i = 0; i < 2; ++i) mbar_init(&aop_full[i], 4);      // one arrive.expect_tx per frame quarter
+    mbar_init(&t_free, 16);
+    mbar_init(&t_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_slot, 512);
@@ -426,7 +428,10 @@ __global__ void __launch_bounds__(S2_THREADS, 1) smpl_skin_tc2_kernel(const __gr
     }
   } else if (warp == 18) {
     // ---- transform-blend GEMM issuer --------------------------------------------------------------------------------
-    constexpr uint32_t idesc = umma_idesc_f16(48);
+    // ONE N = 192 group per 4-frame sub-block round: the operand images of the four frame quarters sit next to each other in a
+    // buffer ([q0 | q1 | q2 | q3] hi, then lo), so 6 instructions serve all 16 frames (a tcgen05.mma with a small N costs
+    // ~70 cycles whatever N is: 24 instead of 96 instructions per tile)
+    constexpr uint32_t idesc = umma_idesc_f16(192);
     const uint64_t wdesc0 = st_desc_il(smem_u32(wt));
     const uint64_t adesc0 = st_desc_il(smem_u32(aop));
     for (int i = 0; i < nt; ++i) {
@@ -434,28 +439,24 @@ __global__ void __launch_bounds__(S2_THREADS, 1) smpl_skin_tc2_kernel(const __gr
       const uint64_t wh = umma_desc_add(wdesc0, (uint32_t)((i & 1) * (S2_WT >> 4))), wl = umma_desc_add(wh, 8192 >> 4);
 #pragma unroll 1
       for (int r = 0; r < 4; ++r) {
-#pragma unroll 1
-        for (int fq = 0; fq < 4; ++fq) {
-          // sub-block n = i * 4 + r of this frame quarter: its operand image has landed (buffer n & 1) and the quarter has
-          // finished reading T of sub-block n - 1
-          const uint32_t n = (uint32_t)(i * 4 + r);
-          mbar_wait(&aop_full[fq][n & 1u], (n >> 1) & 1u);
-          mbar_wait(&t_free[fq], (n & 1u) ^ 1u);
-          tc_fence_after();
-          if (umma_elect_one()) {
-            const uint64_t ah = umma_desc_add(adesc0, (uint32_t)((fq * 2 + (int)(n & 1u)) * (S2_AOP >> 4))), al = umma_desc_add(ah, 3072 >> 4);
-            const uint32_t d = tmem_base + S2_TCOL + (uint32_t)fq * 48u;
+        // round n = i * 4 + r: the four operand images have landed (buffer n & 1) and every frame quarter has read T of round n - 1
+        const uint32_t n = (uint32_t)(i * 4 + r);
+        mbar_wait(&aop_full[n & 1u], (n >> 1) & 1u);
+        mbar_wait(&t_free, (n & 1u) ^ 1u);
+        tc_fence_after();
+        if (umma_elect_one()) {
+          const uint64_t ah = umma_desc_add(adesc0, (uint32_t)((n & 1u) * ((4 * S2_AOP) >> 4))), al = umma_desc_add(ah, (4 * 3072) >> 4);
+          const uint32_t d = tmem_base + S2_TCOL;
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              umma_bf16(d, umma_desc_add(wh, ks * 16), umma_desc_add(ah, ks * 16), idesc, ks != 0);
-              umma_bf16(d, umma_desc_add(wl, ks * 16), umma_desc_add(ah, ks * 16), idesc, 1);
-              umma_bf16(d, umma_desc_add(wh, ks * 16), umma_desc_add(al, ks * 16), idesc, 1);
-            }
-            umma_commit(&t_full[fq]);
-            if (r == 3 && fq == 3) umma_commit(&wt_free[i & 1]);
+          for (int ks = 0; ks < 2; ++ks) {
+            umma_bf16(d, umma_desc_add(wh, ks * 16), umma_desc_add(ah, ks * 16), idesc, ks != 0);
+            umma_bf16(d, umma_desc_add(wl, ks * 16), umma_desc_add(ah, ks * 16), idesc, 1);
+            umma_bf16(d, umma_desc_add(wh, ks * 16), umma_desc_add(al, ks * 16), idesc, 1);
           }
-          __syncwarp();
+          umma_commit(&t_full);
+          if (r == 3) umma_commit(&wt_free[i & 1]);
         }
+        __syncwarp();
       }
     }
   } else {
@@ -469,8 +470,10 @@ __global__ void __launch_bounds__(S2_THREADS, 1) smpl_skin_tc2_kernel(const __gr
     const bool loader = tg == 0;
     auto load_aop = [&](uint32_t n) {        // n = i * 4 + r over the CTA's tiles (the 4 sub-blocks repeat every tile)
       const int sb = (f0 + fq * 16) / 4 + (int)(n & 3u);
-      mbar_arrive_expect_tx(&aop_full[fq][n & 1u], S2_AOP);
-      st_bulk_load(aop + (fq * 2 + (int)(n & 1u)) * S2_AOP, a.aopblob + (size_t)sb * S2_AOP, S2_AOP, &aop_full[fq][n & 1u]);
+      uint8_t* buf = aop + (size_t)(n & 1u) * (4 * S2_AOP);        // [4 quarters x 3 KB hi | 4 quarters x 3 KB lo]
+      mbar_arrive_expect_tx(&aop_full[n & 1u], S2_AOP);
+      st_bulk_load(buf + fq * 3072, a.aopblob + (size_t)sb * S2_AOP, 3072, &aop_full[n & 1u]);
+      st_bulk_load(buf + 4 * 3072 + fq * 3072, a.aopblob + (size_t)sb * S2_AOP + 3072, 3072, &aop_full[n & 1u]);
     };
     const uint32_t n_total = (uint32_t)nt * 4u;
     if (loader) { load_aop(0); if (n_total > 1) load_aop(1); }
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) smpl_skin_tc2_kernel(const __gr
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const uint32_t n = (uint32_t)(i * 4 + r);
-        mbar_wait(&t_full[fq], n & 1u);
+        mbar_wait(&t_full, n & 1u);
         tc_fence_after();
         // the MMAs of sub-block n are complete: its operand buffer is free for sub-block n + 2
         if (loader && n + 2 < n_total) load_aop(n + 2);
@@ -515,7 +518,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) smpl_skin_tc2_kernel(const __gr
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&t_free[fq]);          // T is in registers: the MMAs of sub-block n + 1 may overwrite the columns
+        if (lane == 0) mbar_arrive(&t_free);              // T is in registers: the MMAs of round n + 1 may overwrite the columns
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
           if (v < ST_V && f0 + fl + f < a.F) {
