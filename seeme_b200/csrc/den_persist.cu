@@ -1,28 +1,29 @@
-// Persistent cluster sampler: the whole 50-step DDIM loop of MLD._diffusion_reverse (mld/models/modeltype/mld.py:432-511)
+// Persistent samplers: the whole 50-step DDIM loop of MLD._diffusion_reverse (mld/models/modeltype/mld.py:432-511)
 // over the skip-connected denoiser (mld_denoiser.py:151-244, cross_attention.py:67-83, mdiff_transformer.py:286-304)
-// as ONE kernel launch.
+// as ONE kernel launch.  Two kernels: den_persist_kernel (an 8-CTA cluster per 128-row tile, described here; the default)
+// and den_mono_kernel (one CTA per tile, further down).  Measurements and what bounds each: DESIGN.md 4.2.
 //
 // Decomposition.  A cluster of CL = 8 CTAs owns a tile of 128 denoiser rows (under CFG: 64 latents x {uncond, cond}) for
 // the whole run; clusters never talk to one another.  Inside a cluster every GEMM is split over its OUTPUT features: CTA c
 // computes columns [32c, 32c+32) of every 256-wide activation (its "slice") on tcgen05 (M = 128 rows, N = 16..64 per
-// instruction, fp32 accumulators in tensor memory, split-bf16 x3 operands).  TMEM, mbarriers, the tensor maps and the
+// instruction, fp32 accumulators in tensor memory, split-bf16 x3 operands).  TMEM, mbarriers and the
 // per-row state (residual stream slice, latent slice) live across all ~3 350 GEMM units of a run.
 //
 //   warp 0      producer: streams this CTA's weight "tape" (pre-swizzled bf16 hi|lo blobs in consumption order, one
-//               cp.async.bulk per K-block, ring of 4 x 16 KB) and the A operand K-blocks (TMA boxes of the cluster's
-//               exchange matrix in L2, ring of 4 x (16 KB hi + 16 KB lo) = one full K = 256 activation)
+//               cp.async.bulk per K-block, ring of 4 x 16 KB) and the A operand K-blocks (one 32 KB bulk copy each from the
+//               cluster's exchange images in L2, ring of 4 x (16 KB hi + 16 KB lo) = one full K = 256 activation)
 //   warp 1      one elected lane issues tcgen05.mma; tcgen05.commit releases ring slots and signals the epilogue
 //   warps 2-5   epilogue, thread = row: tcgen05.ld, bias / attention / LayerNorm / FiLM / CFG + DDIM on its 32-column
 //               slice, then publishes the slice (bf16 hi, lo) into the exchange matrix for the next GEMM's A operand
 //
 // Exchanges (all mbarrier based, double buffered; no barrier.cluster in the loop):
 //   * activation all-gather through L2: st.global of the slice -> fence -> remote mbarrier arrive on every CTA of the
-//     cluster -> the producers TMA-load the full [128 x 256] activation.  FFN 256 -> 1024 -> 256 is K-split instead:
-//     each CTA keeps its 128 hidden units private and the 8 partial [128 x 256] results are reduce-scattered through
-//     a fp32 scratch (one exchange instead of a 512 KB all-gather).
+//     cluster -> the producers bulk-load the full [128 x 256] activation.  FFN 256 -> 1024 -> 256 is K-split instead:
+//     each CTA keeps its 128 hidden units private (its epilogue writes relu(h) straight into the A ring) and the 8
+//     partial [128 x 256] results are reduce-scattered through a fp32 scratch (one exchange instead of a 512 KB all-gather).
 //   * row statistics through distributed shared memory: every reduction over the 256 features of a row (the 4-key
 //     attention logits, softmax_d of the linear cross-attention, every LayerNorm as a (mean, M2) Chan combine) sends
-//     <= 4 floats per row to each peer with st.shared::cluster + one remote arrive per warp.
+//     <= 4 floats per row to each peer with st.async (...mbarrier::complete_tx): data and signal in one instruction.
 //
 // Algebra: H1 token-0-only self-attention, H2 linear attention as dot products, H3 cond-token K/V once
 // per run (on tensor cores, see den_persist_run), H4 per-timestep tables; plus the out-projection of the self-attention
@@ -63,7 +64,8 @@ struct DpUnit {             // one GEMM unit: acc[:, acc_col : acc_col + n] = A[
 constexpr int DP_MAX_UNITS = 80;
 
 struct DpLayerP {
-  const float *bqkv, *bo, *n1g, *n1b, *b1, *b2, *n2g, *n2b, *cng, *cnb, *bcaq, *cpg, *cpb, *bcaout, *bf1, *bf2, *fpg, *fpb, *bfout;
+  // bqkv [768]: b_q / 16 | b_k | b_o + W_o b_v (the softmax weights sum to 1); the FiLM LayerNorm affines live in the film tables
+  const float *bqkv, *n1g, *n1b, *b1, *b2, *n2g, *n2b, *cng, *cnb, *bcaq, *bcaout, *bf1, *bf2, *bfout;
   // [steps][512]: (k | ov) of the time token; FiLM folded into the LayerNorm affine: (g (1 + scale) | b (1 + scale) + shift)
   const float *kt, *film_ca, *film_ff;
   const float* ctab;                     // [tile][4][Nc][256][128 rows]: k, ov (self-attention), softmax_n(key), value (cross-attention)
@@ -950,7 +952,7 @@ struct DmParams {
   const float *skip_b[2], *fng, *fnb, *pe0;
   const uint8_t* tape;
   const DmUnit* units;
-  int n_units, n_blobs;
+  int n_units;
   float *lat, *xs1;            // [tiles][256][128] fp32 scratch: latents, residual parked during the FFN
   uint8_t* skipimg;            // [tiles][2][4 K-blocks][32 KB]: outputs of blocks 0 / 1 as A-operand images
   const float* x_in;
@@ -1672,7 +1674,7 @@ struct DenPersist {
   // monolithic per-tile kernel
   uint8_t* tape_m = nullptr;
   DmUnit* d_units_m = nullptr;
-  int n_units_m = 0, n_blobs_m = 0;
+  int n_units_m = 0;
   float* mu[5] = {};
   float *lat_m = nullptr, *xs1_m = nullptr;
   uint8_t* skipimg = nullptr;
@@ -1923,7 +1925,6 @@ int den_persist_create(seeme_denoiser* h) {
     }
   }
   P->n_units_m = (int)munits.size();
-  P->n_blobs_m = (int)(mtape.size() / DM_W_SLOT);
   SEEME_REQUIRE(P->n_units_m <= DM_MAX_UNITS, SEEME_EINVAL, "den_persist: %d monolithic units", P->n_units_m);
 
   const size_t Rp = (size_t)P->rows_pad_max, NCM = SEEME_MAX_COND_TOKENS;
@@ -2078,7 +2079,7 @@ int den_persist_run(seeme_denoiser* h, int mode, const float* x_in, int Nc, int 
     }
     m.skip_b[0] = h->w[DN_LB0_B]; m.skip_b[1] = h->w[DN_LB1_B];
     m.fng = h->w[DN_NORM_W]; m.fnb = h->w[DN_NORM_B]; m.pe0 = h->w[DN_PE];
-    m.tape = P->tape_m; m.units = P->d_units_m; m.n_units = P->n_units_m; m.n_blobs = P->n_blobs_m;
+    m.tape = P->tape_m; m.units = P->d_units_m; m.n_units = P->n_units_m;
     m.lat = P->lat_m; m.xs1 = P->xs1_m; m.skipimg = P->skipimg;
     m.x_in = x_in; m.out = out; m.coef = h->d_coef; m.gscale = h->d_gscale;
     m.B = B; m.R = R; m.cfg = cfg; m.n_steps = n_steps; m.mode = mode;
@@ -2107,11 +2108,11 @@ int den_persist_run(seeme_denoiser* h, int mode, const float* x_in, int Nc, int 
   memset(&p, 0, sizeof(p));
   for (int l = 0; l < 5; ++l) {
     DpLayerP& L = p.L[l];
-    L.bqkv = P->bqkv[l]; L.bo = blkw(h, l, SA_OUT_B); L.n1g = blkw(h, l, SA_N1_W); L.n1b = blkw(h, l, SA_N1_B);
+    L.bqkv = P->bqkv[l]; L.n1g = blkw(h, l, SA_N1_W); L.n1b = blkw(h, l, SA_N1_B);
     L.b1 = blkw(h, l, SA_L1_B); L.b2 = blkw(h, l, SA_L2_B); L.n2g = blkw(h, l, SA_N2_W); L.n2b = blkw(h, l, SA_N2_B);
     L.cng = blkw(h, l, CA_N_W); L.cnb = blkw(h, l, CA_N_B); L.bcaq = blkw(h, l, CA_Q_B);
-    L.cpg = blkw(h, l, CA_PN_W); L.cpb = blkw(h, l, CA_PN_B); L.bcaout = blkw(h, l, CA_OUT_B);
-    L.bf1 = blkw(h, l, FF_L1_B); L.bf2 = blkw(h, l, FF_L2_B); L.fpg = blkw(h, l, FF_PN_W); L.fpb = blkw(h, l, FF_PN_B);
+    L.bcaout = blkw(h, l, CA_OUT_B);
+    L.bf1 = blkw(h, l, FF_L1_B); L.bf2 = blkw(h, l, FF_L2_B);
     L.bfout = blkw(h, l, FF_OUT_B);
     L.kt = P->tkov[l]; L.film_ca = P->film2_ca[l]; L.film_ff = P->film2_ff[l];
     L.ctab = P->ctab[l];
