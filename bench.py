@@ -40,10 +40,11 @@ def workload(batch):
             "batch_per_gpu": batch, "ddim_steps": 50, "guidance_scale": GUIDANCE, "scene_points": N_POINTS, "frames": 60,
             "l2_policy": "per-step inputs+activations (>= 1.3 GB per 128-cloud chunk) exceed the 126 MB L2; no flush needed",
             "inputs": "8 distinct synthetic batches and noise draws per rank, rotated step by step",
-            "pipeline": "MLD.ego_eval_async with up to pipeline_depth (default 8) batches in flight, each on its own CUDA stream "
-                        "and kernel-side handles; sampler back-end 'auto': the kernel graph inside the pipeline (least SM time next "
-                        "to the scene encoder), the persistent cluster kernel for a single batch (kernels.single_batch_* and "
-                        "kernels.sampler_*: the unpipelined numbers)"}
+            "pipeline": "MLD.ego_eval_async with up to pipeline_depth (default 32) batches in flight, each on its own CUDA stream "
+                        "(CUDA_DEVICE_MAX_CONNECTIONS=32) and kernel-side handles, 4 shared scene-encoder handles; sampler back-end "
+                        "'auto': the one-CTA-per-tile kernel inside the pipeline (least SM time next to the scene encoder), the "
+                        "persistent cluster kernel for a single batch (kernels.single_batch_* and kernels.sampler_*: the unpipelined "
+                        "numbers)"}
 
 
 class ClockSampler:
@@ -527,7 +528,7 @@ def bench_smpl_sweep(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="seeme_b200", choices=["seeme_b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="sequences per GPU per step")

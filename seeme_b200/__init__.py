@@ -10,6 +10,11 @@ import os
 
 __all__ = ["MLD", "load_config", "build_model", "CONFIG_DIR"]
 
+# The batch pipeline (MLD.ego_eval_async) keeps up to 32 CUDA streams busy; with the driver's default of 8 hardware work queues
+# streams alias onto the same queue and one slot's scene encoder waits behind another slot's sampler (16.3 k ->
+# 20.2 k sequences/s).  The variable is read when the CUDA context is created, so it has to be set before the first CUDA call.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 CONFIG_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs")
 
 

@@ -170,14 +170,18 @@ class MLD(nn.Module):
         self.lanes = int(kwargs.get("lanes", cfg.model.get("lanes", 1)))
         self.min_lane_batch = int(kwargs.get("min_lane_batch", cfg.model.get("min_lane_batch", 32)))
         # batches in flight for ego_eval_async / run_test_batches
-        self.pipeline_depth = int(kwargs.get("pipeline_depth", cfg.model.get("pipeline_depth", os.environ.get("SEEME_PIPELINE_DEPTH", 8))))
+        self.pipeline_depth = int(kwargs.get("pipeline_depth", cfg.model.get("pipeline_depth", os.environ.get("SEEME_PIPELINE_DEPTH", 32))))
         # ego_eval_async / run_test_batches: consecutive batches whose 50-step sampler runs as ONE chain over all their rows
         # (the chain is latency-bound: 3 750 dependent kernels take the same ~27 ms for 512 or 2 048 rows)
-        # sampler back-end (include/seeme_b200.h: seeme_denoiser_set_backend): "persistent" = one launch of the cluster kernel per
-        # run, "graph" = the CUDA graph of small kernels, "auto" = persistent for a single batch (ego_eval: lowest latency),
-        # graph inside the batch pipeline (ego_eval_async with several batches in flight: least SM time next to the scene encoder)
+        # sampler back-end (include/seeme_b200.h: seeme_denoiser_set_backend): "persistent" = one launch of the 8-CTA-cluster kernel
+        # per run, "tile" = one launch of the one-CTA-per-128-rows kernel, "graph" = the CUDA graph of small kernels, "auto" =
+        # persistent for a single batch (ego_eval: lowest latency), tile inside the batch pipeline (ego_eval_async with several
+        # batches in flight: least SM time next to the scene encoder)
         self.sampler_backend = str(kwargs.get("sampler_backend", cfg.model.get("sampler_backend", os.environ.get("SEEME_SAMPLER_BACKEND", "auto"))))
         self.sampler_group = int(kwargs.get("sampler_group", cfg.model.get("sampler_group", os.environ.get("SEEME_SAMPLER_GROUP", 1))))
+        # pipeline slots share this many scene-encoder handles (2.6 GB of workspace each at 128 clouds x 20 000 points): an encoder
+        # fills every SM, so two of them never overlap anyway; 0 = one handle per slot
+        self.encoder_handles = int(kwargs.get("encoder_handles", cfg.model.get("encoder_handles", os.environ.get("SEEME_ENCODER_HANDLES", 4))))
         self.last_vertices: Dict[str, torch.Tensor] = {}
         self._uncond_scene = None
         self.eval()
@@ -231,12 +235,12 @@ class MLD(nn.Module):
         op = self.denoiser.op if op is None else op
         backend = self.sampler_backend
         if backend == "auto":
-            # measured on B200: inside the batch pipeline a 512-row chain costs least as the kernel graph (16.2k
-            # vs 14.9k sequences/s), a chain of <= 256 rows (<= 2 row tiles = 16 SMs) as the persistent cluster kernel (14.0k vs
-            # 10.2k sequences/s at 64 sequences per batch: the strong-scaling regime); a single batch always takes the cluster kernel
-            rows = encoder_hidden_states.shape[0]
+            # measured on B200: a single batch is fastest on the cluster kernel (16.8 ms per 512 rows on 32
+            # SMs); inside the batch pipeline the SM time counts, not the latency, and the one-CTA-per-tile kernel holds 4 SMs per
+            # 512 rows (20.2k sequences/s at depth 32 against 18.0k with the kernel graph and 16.0k with the cluster kernel; the
+            # same order at 128 and 64 sequences per batch)
             in_pipe = self.__dict__.get("_in_pipeline", False) and int(self.pipeline_depth) > 1
-            backend = "graph" if in_pipe and rows > 256 else "persistent"
+            backend = "tile" if in_pipe else "persistent"
         if os.environ.get("SEEME_SAMPLER") != "graph":
             op.set_backend(backend)
         # the key lives on the kernel-side handle object (one per lane / slot), not in an id()-keyed dict: a rebuilt handle
@@ -255,17 +259,39 @@ class MLD(nn.Module):
         return 5 if "scene" in self.condition else 4
 
     def _encode_scene(self, scene):
-        op = self.proscene.scene_enc.op(self.output_scene)
+        from . import modules as _m
+        lane = _m._LANE[0]
+        shared = 1000 <= lane < 2000 and int(self.encoder_handles) > 0      # a pipeline slot (ego_eval_async)
+        if shared:
+            # the handle's workspace is used inside the call only (the embedding is a fresh tensor), so slots k, k + E, ... take
+            # turns on handle k % E: the slot's stream waits for the previous user's encoder
+            k = (lane - 1000) % int(self.encoder_handles)
+            _m._LANE[0] = 3000 + k
+            try:
+                op = self.proscene.scene_enc.op(self.output_scene)
+            finally:
+                _m._LANE[0] = lane
+            events = self.__dict__.setdefault("_enc_events", {})
+            if k in events:
+                torch.cuda.current_stream(scene.device).wait_event(events[k])
+        else:
+            op = self.proscene.scene_enc.op(self.output_scene)
         emb = op(scene.float())                                           # output_scene(encode_scene(.)) fused
-        if not self.do_classifier_free_guidance:
+        unc = None
+        if self.do_classifier_free_guidance:
+            # encode_scene(zeros) is input independent (every point identical -> the max-pool is that point,
+            # SURVEY App. H8): computed once on a tiny all-zero cloud and cached per packed-weights handle
+            cache = self._uncond_scene if isinstance(self._uncond_scene, dict) else {}
+            self._uncond_scene = cache
+            if id(op) not in cache or cache[id(op)][0] is not op:
+                cache[id(op)] = (op, op(torch.zeros(1, 8, 3, device=scene.device)))
+            unc = cache[id(op)][1].expand(emb.shape[0], -1)
+        if shared:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(scene.device))
+            events[k] = ev
+        if unc is None:
             return emb[None]
-        # encode_scene(zeros) is input independent (every point identical -> the max-pool is that point,
-        # SURVEY App. H8): computed once on a tiny all-zero cloud and cached per packed-weights handle
-        cache = self._uncond_scene if isinstance(self._uncond_scene, dict) else {}
-        self._uncond_scene = cache
-        if id(op) not in cache or cache[id(op)][0] is not op:
-            cache[id(op)] = (op, op(torch.zeros(1, 8, 3, device=scene.device)))
-        unc = cache[id(op)][1].expand(emb.shape[0], -1)
         return torch.cat([emb, unc], dim=0)[None]                          # mld.py:1157-1158 (COND first)
 
     def ego_eval(self, batch, noise: Optional[Dict[str, torch.Tensor]] = None):

@@ -12,7 +12,7 @@ import seeme_b200  # noqa: E402
 from seeme_b200 import modules as M, synthetic as S  # noqa: E402
 
 D = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-B = 256
+B = int(os.environ.get("PROBE_B", "256"))
 dev = torch.device("cuda", 0)
 model = seeme_b200.build_model("config_mld_egobody.yaml", device=dev, guidance_scale=7.5, max_batch=B, n_points=20000, lanes=1)
 batch = tuple(x.to(dev) if torch.is_tensor(x) else x for x in S.make_batch(B, n_points=20000))
@@ -54,6 +54,10 @@ lengths = [60] * B
 if os.environ.get("PROBE_ASYNC"):      # the public async API (slots, sampler_group) instead of raw lanes
     from collections import deque
     model.pipeline_depth = D
+    if os.environ.get("PROBE_BACKEND"):
+        model.sampler_backend = os.environ["PROBE_BACKEND"]
+    if os.environ.get("PROBE_ENC_HANDLES"):
+        model.encoder_handles = int(os.environ["PROBE_ENC_HANDLES"])
     n = int(os.environ.get("PROBE_STEPS", "48"))
 
     host_ms = []
@@ -76,7 +80,7 @@ if os.environ.get("PROBE_ASYNC"):      # the public async API (slots, sampler_gr
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / n * 1e3
     hm = host_ms[-n:]
-    print(f"async depth {D} group {model.sampler_group}: {dt:.2f} ms per step -> {B / dt * 1e3:.0f} sequences/s | host submit ms: "
+    print(f"async depth {D} B {B} mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB alloc / {(torch.cuda.mem_get_info()[1] - torch.cuda.mem_get_info()[0]) / 2**30:.1f} GiB device: {dt:.2f} ms per step -> {B / dt * 1e3:.0f} sequences/s | host submit ms: "
           f"mean {sum(hm) / len(hm):.2f} max {max(hm):.2f} first8 {[round(x, 1) for x in hm[:8]]}")
     sys.exit(0)
 
