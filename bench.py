@@ -291,10 +291,12 @@ def class_rooflines(model, dev, dev_batch, B):
                      "frac": tf / tpeak}
     if attn_n:
         per = attn_ms / attn_n
-        fl = 2 * 2 * 64 * 64 * 256 * B                     # QK^T and PV over 62 (padded 64) tokens, one head of 256
-        out["vae_attention_kernel"] = {"bound": "fp32 FMA (mha1_tiled_kernel)", "launches": attn_n, "avg_launch_ms": per,
-                                       "achieved": fl / (per / 1e3) / 1e12, "unit": "TFLOP/s", "peak": tpeak,
-                                       "frac": fl / (per / 1e3) / 1e12 / tpeak}
+        # mha1_umma_kernel streams qkv (fp32, 62 x 768 per sequence) in and the split-bf16 context (62 x 256 x 2 x 2 B) out in
+        # lock-step phases: the L2 / HBM stream bounds it, not the two 64 x 64 x 256 contractions (1.07 GFLOP per launch)
+        by = (62 * 768 * 4 + 62 * 256 * 4) * B
+        out["vae_attention_kernel"] = {"bound": "hbm", "kernel": "mha1_umma_kernel (tcgen05, split fp16 x3)", "launches": attn_n,
+                                       "avg_launch_ms": per, "achieved": by / (per / 1e3) / 1e9, "unit": "GB/s",
+                                       "peak": peaks.get("hbm_gbs", 6650.0), "frac": by / (per / 1e3) / 1e9 / peaks.get("hbm_gbs", 6650.0)}
     return out
 
 

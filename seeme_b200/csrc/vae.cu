@@ -14,6 +14,7 @@
 
 namespace seeme {
 
+#ifdef SEEME_EXPERIMENTAL   // retired fp32 CUDA-core attention kernels (SEEME_VAE_ATTN=0 / 1 for A/B measurements)
 // Single-head attention over <= 64 tokens per sample.  One CTA per sample, K and V of the sample
 // staged in shared memory (2 x S x 1 KB), one warp per query row, fp32 softmax.
 // qkv [B*S, 768] = (q * 1/16 | k | v);  key j is valid iff j < n_prefix + lengths[b].
@@ -170,6 +171,291 @@ __global__ void __launch_bounds__(256) mha1_tiled_kernel(const float* __restrict
   }
 }
 
+#endif  // SEEME_EXPERIMENTAL
+
+// Single-head attention over <= 64 tokens per sample on the tensor cores: one CTA per PAIR of samples, both contractions on tcgen05.
+//     S = Q K^T : [128 x 256] x [256 x 128]   rows / keys = (sample 0 | sample 1) x 64 tokens; only the two diagonal 64 x 64
+//                                             blocks are used (the off-diagonal half is the price of M = 128)
+//     softmax   : thread = query row, 64 scores from tensor memory, key-padding mask, fp32
+//     O = P V   : [128 x 128] x [128 x 256]   P block-diagonal (zeros for the other sample's keys)
+// Operands are split fp16 (hi + lo, three products hi.hi + lo.hi + hi.lo, fp32 accumulation: ~2^-22 relative), written by
+// the threads straight into the 128-byte-swizzled K-major tile images the MMA reads: Q and K per 64-column chunk into a
+// double buffer (staging of chunk c+1 overlaps the MMAs of chunk c), V TRANSPOSED ([dim][key]: 8 consecutive keys of one
+// dim are one 16-byte chunk) into the same 128 KB once S is complete, P next to it.
+constexpr int MU_CH = 128 * 128;                       // [128 rows x 64 fp16] operand chunk
+constexpr int MU_R0 = 8 * MU_CH;                       // Q/K double buffer, later V^T hi | lo (2 x [2 K-blocks x 256 x 128 B])
+constexpr int MU_R1 = 4 * MU_CH;                       // P: hi (2 K-blocks) | lo (2 K-blocks)
+constexpr int MU_SMEM = MU_R0 + MU_R1 + 1024;
+constexpr int MU_THREADS = 256;
+
+
+__device__ __forceinline__ uint32_t mu_sw128(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+__device__ __forceinline__ void mu_split8(const float* x, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(MU_THREADS, 1) mha1_umma_kernel(const float* __restrict__ qkv, const int* __restrict__ lengths,
+                                                                    int n_prefix, int S, int B, __nv_bfloat16* __restrict__ oh,
+                                                                    __nv_bfloat16* __restrict__ ol) {
+  extern __shared__ __align__(1024) uint8_t mu_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mu_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* r0 = smem;
+  uint8_t* r1 = smem + MU_R0;
+  __shared__ __align__(8) uint64_t qk_done[2], o_full;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float sm_red[4][128];         // softmax: row max / row sum of the two key halves
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b0 = blockIdx.x * 2;
+
+  if (tid == 0) {
+    mbar_init(&qk_done[0], 1);
+    mbar_init(&qk_done[1], 1);
+    mbar_init(&o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t TS = tmem_base, TO = tmem_base + 128u;
+
+  // ---- S = Q K^T over four 64-column chunks ------------------------------------------------------------------------
+  // item = (matrix, row, 8-float chunk): 2 x 128 x 8 per K-chunk, 8 per thread; the loads of chunk c + 1 are in flight while
+  // chunk c is converted
+  auto load_qk = [&](int c, float4 (&x)[16]) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = it * MU_THREADS + tid;
+      const int mat = idx >> 10, row = (idx >> 3) & 127, ch = idx & 7;
+      const int sl = row >> 6, sq = row & 63;
+      if (sq < S && b0 + sl < B) {
+        const float4* src = reinterpret_cast<const float4*>(qkv + ((size_t)(b0 + sl) * S + sq) * 768 + mat * 256 + c * 64 + ch * 8);
+        x[2 * it] = __ldg(src);
+        x[2 * it + 1] = __ldg(src + 1);
+      } else {
+        x[2 * it] = x[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+  float4 cur[16];
+  load_qk(0, cur);
+  for (int c = 0; c < 4; ++c) {
+    uint8_t* buf = r0 + (c & 1) * (4 * MU_CH);                  // [Qh | Ql | Kh | Kl]
+    float4 nxt[16];
+    if (c < 3) load_qk(c + 1, nxt);
+    if (c >= 2) mbar_wait(&qk_done[c & 1], 0);                   // the MMAs of chunk c - 2 have read this buffer
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = it * MU_THREADS + tid;
+      const int mat = idx >> 10, row = (idx >> 3) & 127, ch = idx & 7;
+      const float x[8] = {cur[2 * it].x, cur[2 * it].y, cur[2 * it].z, cur[2 * it].w,
+                          cur[2 * it + 1].x, cur[2 * it + 1].y, cur[2 * it + 1].z, cur[2 * it + 1].w};
+      uint4 hi, lo;
+      mu_split8(x, hi, lo);
+      uint8_t* t = buf + mat * (2 * MU_CH) + mu_sw128(row, ch);
+      *reinterpret_cast<uint4*>(t) = hi;
+      *reinterpret_cast<uint4*>(t + MU_CH) = lo;
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (umma_elect_one()) {
+        constexpr uint32_t idesc = umma_idesc_f16(128);
+        const uint64_t qh = umma_desc_k128(smem_u32(buf)), ql = umma_desc_add(qh, MU_CH >> 4);
+        const uint64_t kh = umma_desc_add(qh, (2 * MU_CH) >> 4), kl = umma_desc_add(qh, (3 * MU_CH) >> 4);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          umma_bf16(TS, umma_desc_add(qh, ks * 2), umma_desc_add(kh, ks * 2), idesc, (c | ks) != 0);
+          umma_bf16(TS, umma_desc_add(ql, ks * 2), umma_desc_add(kh, ks * 2), idesc, 1);
+          umma_bf16(TS, umma_desc_add(qh, ks * 2), umma_desc_add(kl, ks * 2), idesc, 1);
+        }
+        umma_commit(&qk_done[c & 1]);
+      }
+      __syncwarp();
+    }
+    if (c < 3) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+    }
+  }
+  // V^T: task = (group of 8 keys, half of the dims); a lane owns dims lane + 32 i of the half: consecutive rows of the operand
+  // tile -> conflict-free 16-byte stores, 128-byte coalesced loads.  4 tasks per warp; the 32 loads of a task are issued together,
+  // those of the first task before the wait for the S MMAs (they are in flight under the softmax)
+  const int t_begin = warp * 4, t_end = t_begin + 4;
+  auto load_task = [&](int t, float (&x)[4][8]) {
+    const int kg = t >> 1, half = t & 1;
+    const int sl = kg >> 3, s0 = (kg & 7) * 8;
+    const bool sample_ok = b0 + sl < B;
+    const float* vb = qkv + ((size_t)(b0 + sl) * S + s0) * 768 + 512 + half * 128 + lane;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) x[i][jj] = (sample_ok && s0 + jj < S) ? __ldg(vb + (size_t)jj * 768 + i * 32) : 0.f;
+  };
+  auto store_task = [&](int t, float (&x)[4][8]) {
+    const int kg = t >> 1, half = t & 1, sl = kg >> 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 hi, lo;
+      mu_split8(x[i], hi, lo);
+      const int d = half * 128 + i * 32 + lane;
+      uint8_t* dst = r0 + sl * (2 * MU_CH) + mu_sw128(d, kg & 7);              // K-block sl: [256 dims x 64 keys]
+      *reinterpret_cast<uint4*>(dst) = hi;
+      *reinterpret_cast<uint4*>(dst + 4 * MU_CH) = lo;
+    }
+  };
+  float vx[4][8];
+  load_task(t_begin, vx);
+  mbar_wait(&qk_done[0], 1);
+  mbar_wait(&qk_done[1], 1);          // every MMA of S has completed: the score columns are final, the Q/K buffers are free
+  tc_fence_after();
+
+  // ---- softmax: two threads per query row (warps w and w + 4 share TMEM lane quarter w: 32 keys each) --------------------
+  {
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane, sl = row >> 6;
+    int nvalid = 0;
+    if (b0 + sl < B) {
+      nvalid = n_prefix + __ldg(lengths + b0 + sl);
+      nvalid = nvalid < S ? nvalid : S;
+    }
+    nvalid -= half * 32;                                       // valid keys among this thread's 32
+    uint32_t raw[32];
+    tmem_ld32(TS + ((uint32_t)(q * 32) << 16) + (uint32_t)(sl * 64 + half * 32), raw);
+    tmem_ld_wait();
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) m = (j < nvalid) ? fmaxf(m, __uint_as_float(raw[j])) : m;
+    sm_red[half][row] = m;
+    __syncthreads();
+    m = fmaxf(sm_red[0][row], sm_red[1][row]);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float e = (j < nvalid) ? exp2f((__uint_as_float(raw[j]) - m) * 1.4426950408889634f) : 0.f;
+      raw[j] = __float_as_uint(e);
+      sum += e;
+    }
+    sm_red[2 + half][row] = sum;
+    __syncthreads();
+    const float inv = 1.0f / (sm_red[2][row] + sm_red[3][row]);
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      float x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(raw[c4 * 8 + i]) * inv;
+      uint4 hi, lo;
+      mu_split8(x, hi, lo);
+      const uint32_t off = mu_sw128(row, half * 4 + c4);
+      *reinterpret_cast<uint4*>(r1 + sl * MU_CH + off) = hi;                       // own sample's keys: K-block sl
+      *reinterpret_cast<uint4*>(r1 + 2 * MU_CH + sl * MU_CH + off) = lo;
+      *reinterpret_cast<uint4*>(r1 + (1 - sl) * MU_CH + off) = z4;                 // the other sample's keys
+      *reinterpret_cast<uint4*>(r1 + 2 * MU_CH + (1 - sl) * MU_CH + off) = z4;
+    }
+  }
+  for (int t = t_begin; t < t_end; ++t) {
+    float nx[4][8];
+    if (t + 1 < t_end) load_task(t + 1, nx);
+    store_task(t, vx);
+    if (t + 1 < t_end) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) vx[i][jj] = nx[i][jj];
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+
+  // ---- O = P V ------------------------------------------------------------------------------------------------------
+  if (warp == 0) {
+    tc_fence_after();
+    if (umma_elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(256);
+      const uint64_t ph = umma_desc_k128(smem_u32(r1)), pl = umma_desc_add(ph, (2 * MU_CH) >> 4);
+      const uint64_t vh = umma_desc_k128(smem_u32(r0)), vl = umma_desc_add(vh, (4 * MU_CH) >> 4);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t ao = (uint32_t)(kb * (MU_CH >> 4) + ks * 2), bo = (uint32_t)(kb * ((2 * MU_CH) >> 4) + ks * 2);
+          umma_bf16(TO, umma_desc_add(ph, ao), umma_desc_add(vh, bo), idesc, (kb | ks) != 0);
+          umma_bf16(TO, umma_desc_add(pl, ao), umma_desc_add(vh, bo), idesc, 1);
+          umma_bf16(TO, umma_desc_add(ph, ao), umma_desc_add(vl, bo), idesc, 1);
+        }
+      umma_commit(&o_full);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&o_full, 0);
+  tc_fence_after();
+  {
+    // thread = (row, column half): 128 accumulator columns -> bf16 (hi, lo) into a [128 x 512 B] staging tile each (the operand
+    // buffers are free now), 16-byte chunks XOR-swizzled by the row so that both these row-per-lane stores and the
+    // row-per-warp reads below are conflict-free; then every warp copies 16 rows with 512-byte coalesced global stores
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t ta = TO + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
+    uint8_t* th = r0 + row * 512;
+    uint32_t rawb[2][32];
+    tmem_ld32(ta, rawb[0]);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      tmem_ld_wait();
+      if (g < 3) tmem_ld32(ta + (g + 1) * 32, rawb[(g + 1) & 1]);
+      const uint32_t* raw = rawb[g & 1];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float f0 = __uint_as_float(raw[jj * 8 + 2 * i]), f1 = __uint_as_float(raw[jj * 8 + 2 * i + 1]);
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(f0, f1);
+          const float2 hf = __bfloat1622float2(hh);
+          const __nv_bfloat162 ll = __floats2bfloat162_rn(f0 - hf.x, f1 - hf.y);
+          h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+          l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        const int ch = (half * 16 + g * 4 + jj) ^ (row & 7);
+        *reinterpret_cast<uint4*>(th + ch * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(th + 128 * 512 + ch * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int r = warp * 16 + i, sl = r >> 6, sq = r & 63;
+      if (sq < S && b0 + sl < B) {
+        const size_t o = ((size_t)(b0 + sl) * S + sq) * 256 + lane * 8;
+        const uint8_t* src = r0 + r * 512 + ((lane ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(oh + o) = *reinterpret_cast<const uint4*>(src);
+        *reinterpret_cast<uint4*>(ol + o) = *reinterpret_cast<const uint4*>(src + 128 * 512);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // xseq[b, s] = (s < 2 ? global_motion_token[s] : emb[b, s-2]) + pe[s]     (mld_vae.py:147-164)
 __global__ void vae_enc_assemble_kernel(const float* __restrict__ emb, const float* __restrict__ token,
                                         const float* __restrict__ pe, float* __restrict__ x,
@@ -256,7 +542,7 @@ struct seeme_vae {
   float* w[SEEME_VAE_NUM_TENSORS];
   float *emb, *qkv, *t0, *ca[5], *vtmp;
   int npass = 3;
-  bool tiled_attn = true;
+  int attn = 2;                 // 2 = tcgen05 (mha1_umma_kernel, default), 1 = register-tiled fp32, 0 = one warp per query row
   // per stack (0 encoder, 1 decoder) and block: packed (hi, lo) weights of the tcgen05 linears
   PackedLinear Wqkv[2][5], Wout[2][5], Wl1[2][5], Wl2[2][5], Wskip[2][2];
   ActBuf x0, x, L[5], att, x1, x2, ff;
@@ -353,11 +639,14 @@ extern "C" int seeme_vae_create(seeme_vae_t* out, const float* const* w, int n_w
   }
   if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_error("seeme_vae_create: weight packing failed"); rc = SEEME_ECUDA; }
   if (rc) { h->arena.release(); delete h; return rc; }
+#ifdef SEEME_EXPERIMENTAL
   SEEME_CUDA(cudaFuncSetAttribute(mha1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 256 * 4));
   SEEME_CUDA(cudaFuncSetAttribute(mha1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MH_SMEM));
+#endif
+  SEEME_CUDA(cudaFuncSetAttribute(mha1_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MU_SMEM));
   {
-    const char* e = seeme_exp_env("SEEME_VAE_ATTN");
-    h->tiled_attn = !(e && e[0] == '0');
+    const char* e = seeme_exp_env("SEEME_VAE_ATTN");      // A/B measurements: 0 / 1 select the fp32 CUDA-core kernels
+    h->attn = e ? atoi(e) : 2;
   }
   *out = h;
   return SEEME_OK;
@@ -376,8 +665,12 @@ static int vae_layer(seeme_vae* h, int st, int l, const ActBuf& xin, const ActBu
   SEEME_TRY(run_linear(h->Wqkv[st][l], xin, nullptr, rows, ACT_NONE, nullptr, 0, qkv, np, s));
   {
     ProfScope prof(PROF_VAE_ATTN, s);
-    if (h->tiled_attn) mha1_tiled_kernel<<<B, 256, MH_SMEM, s>>>(h->qkv, lengths, n_prefix, S, h->att.h, h->att.l);
-    else mha1_kernel<<<B, 256, (size_t)2 * S * 256 * 4, s>>>(h->qkv, lengths, n_prefix, S, h->att.h, h->att.l);
+#ifdef SEEME_EXPERIMENTAL
+    if (h->attn == 1) mha1_tiled_kernel<<<B, 256, MH_SMEM, s>>>(h->qkv, lengths, n_prefix, S, h->att.h, h->att.l);
+    else if (h->attn == 0) mha1_kernel<<<B, 256, (size_t)2 * S * 256 * 4, s>>>(h->qkv, lengths, n_prefix, S, h->att.h, h->att.l);
+    else
+#endif
+      mha1_umma_kernel<<<(B + 1) / 2, MU_THREADS, MU_SMEM, s>>>(h->qkv, lengths, n_prefix, S, B, h->att.h, h->att.l);
   }
   SEEME_LAUNCH_CHECK();
   SEEME_TRY(run_linear(h->Wout[st][l], h->att, nullptr, rows, ACT_NONE, xin.f, 256, t0, np, s));
