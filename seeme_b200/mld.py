@@ -179,6 +179,8 @@ class MLD(nn.Module):
         # batches in flight: least SM time next to the scene encoder)
         self.sampler_backend = str(kwargs.get("sampler_backend", cfg.model.get("sampler_backend", os.environ.get("SEEME_SAMPLER_BACKEND", "auto"))))
         self.sampler_group = int(kwargs.get("sampler_group", cfg.model.get("sampler_group", os.environ.get("SEEME_SAMPLER_GROUP", 1))))
+        # "auto" back-end: the cluster kernel while (batches in flight) x (8 SMs per 128-row tile) stays within this many SMs
+        self.persistent_sm_budget = int(kwargs.get("persistent_sm_budget", cfg.model.get("persistent_sm_budget", os.environ.get("SEEME_PERSISTENT_SM_BUDGET", 64))))
         # pipeline slots share this many scene-encoder handles (2.6 GB of workspace each at 128 clouds x 20 000 points): an encoder
         # fills every SM, so two of them never overlap anyway; 0 = one handle per slot
         self.encoder_handles = int(kwargs.get("encoder_handles", cfg.model.get("encoder_handles", os.environ.get("SEEME_ENCODER_HANDLES", 4))))
@@ -236,11 +238,15 @@ class MLD(nn.Module):
         backend = self.sampler_backend
         if backend == "auto":
             # measured on B200: a single batch is fastest on the cluster kernel (16.8 ms per 512 rows on 32
-            # SMs); inside the batch pipeline the SM time counts, not the latency, and the one-CTA-per-tile kernel holds 4 SMs per
+            # SMs); in a FULL batch pipeline the SM time counts, not the latency, and the one-CTA-per-tile kernel holds 4 SMs per
             # 512 rows (20.2k sequences/s at depth 32 against 18.0k with the kernel graph and 16.0k with the cluster kernel; the
-            # same order at 128 and 64 sequences per batch)
+            # same order at 128 and 64 sequences per batch).  While few batches are in flight (pipeline filling, or an epoch of
+            # a few small batches as in the interactee protocol) the clusters of all of them still fit next to each other
+            # (8 SMs per 128-row tile) and the lower latency wins.
             in_pipe = self.__dict__.get("_in_pipeline", False) and int(self.pipeline_depth) > 1
-            backend = "tile" if in_pipe else "persistent"
+            tiles = -(-encoder_hidden_states.shape[0] // 128)
+            crowded = (self.__dict__.get("_n_inflight", 0) + 1) * tiles * 8 > int(self.persistent_sm_budget)
+            backend = "tile" if in_pipe and crowded else "persistent"
         if os.environ.get("SEEME_SAMPLER") != "graph":
             op.set_backend(backend)
         # the key lives on the kernel-side handle object (one per lane / slot), not in an id()-keyed dict: a rebuilt handle
@@ -375,15 +381,30 @@ class MLD(nn.Module):
         own CUDA stream and its own kernel-side handles (workspaces, sampler graph) -- batch k+1's scene encoder runs
         under batch k's sampler.  CPU tensors in ``batch`` / ``noise`` (pinned host memory) are copied on the slot's
         stream, so the copies overlap other slots' compute as well.  ``PendingEval.result()`` makes the caller's current
-        stream wait for the slot and returns the ``rs_set``; slots are reused round-robin, so at most
-        ``pipeline_depth`` results should be outstanding."""
+        stream wait for the slot and returns the ``rs_set``; a batch takes the first idle slot (round robin when all are busy), so
+        at most ``pipeline_depth`` results should be outstanding."""
         from . import modules as _m
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("MLD (sm_100a): parameters are on the CPU; seeme_b200 runs on CUDA only")
         depth = max(1, int(self.pipeline_depth))
-        slot = self.__dict__.get("_next_slot", 0) % depth
-        self.__dict__["_next_slot"] = slot + 1
+        # slot choice: the lowest-numbered slot whose previous batch has finished (its handles and workspaces exist already: an
+        # epoch of a few batches keeps reusing the same warm slots), else a slot never used, else round robin
+        last = self.__dict__.setdefault("_slot_last", {})
+        slot = None
+        for k in range(depth):
+            ref = last.get(k)
+            if ref is None:
+                if slot is None:
+                    slot = k                                         # never used: taken unless a warm idle slot follows
+                continue
+            p = ref()
+            if p is None or p._error is not None or (p.event is not None and p.event.query()):
+                slot = k
+                break
+        if slot is None:
+            slot = self.__dict__.get("_next_slot", 0) % depth
+            self.__dict__["_next_slot"] = slot + 1
         streams = self.__dict__.setdefault("_slot_streams", {})
         st = streams.get((dev, slot))
         if st is None:
@@ -408,6 +429,16 @@ class MLD(nn.Module):
         else:
             lengths_host = torch.as_tensor(length_t).long().reshape(-1).tolist()
         pend = PendingEval(self, st, slot)
+        # batches submitted earlier and not yet finished on the device (the sampler back-end policy looks at it)
+        # (weak references: a result the caller has dropped must not be kept alive -- its vertices are 1.3 GB)
+        def _busy(ref):
+            p = ref()
+            return p is not None and p._error is None and (p.event is None or not p.event.query())
+        outstanding = [r for r in self.__dict__.get("_outstanding", []) if _busy(r)]
+        self.__dict__["_n_inflight"] = len(outstanding)
+        outstanding.append(weakref.ref(pend))
+        self.__dict__["_outstanding"] = outstanding
+        last[slot] = weakref.ref(pend)
         try:
             with torch.cuda.stream(st):
                 b = tuple((x.to(dev, non_blocking=True) if torch.is_tensor(x) and not x.is_cuda else x) for x in batch)
@@ -428,6 +459,37 @@ class MLD(nn.Module):
         if len(group) >= max(1, min(int(self.sampler_group), depth)):
             self._flush_group()
         return pend
+
+    def prepare_pipeline(self, n_slots: Optional[int] = None):
+        """Create the kernel-side handles (packed weights, workspaces, sampler tapes) of ``n_slots`` pipeline slots (default:
+        ``pipeline_depth``) up front.  A handle set costs ~150 ms of host time to build; without this call a slot is built
+        the first time a batch finds every existing slot busy, i.e. somewhere inside the first epochs."""
+        from . import modules as _m
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("MLD (sm_100a): parameters are on the CPU; seeme_b200 runs on CUDA only")
+        n = max(1, min(int(self.pipeline_depth), int(n_slots if n_slots is not None else self.pipeline_depth)))
+        lane = _m._LANE[0]
+        streams = self.__dict__.setdefault("_slot_streams", {})
+        last = self.__dict__.setdefault("_slot_last", {})
+        try:
+            with torch.cuda.device(dev):
+                for k in range(n):
+                    _m._LANE[0] = 1000 + k
+                    if (dev, k) not in streams:
+                        streams[(dev, k)] = torch.cuda.Stream(device=dev)
+                    self.vae.op, self.denoiser.op, self.smpl_model.op
+                    if "image" in self.condition:
+                        self.proscene.backbone.op(self.output_images)
+                    last.setdefault(k, lambda: None)                     # "used and idle" for the slot choice
+                if "scene" in self.condition:
+                    for k in range(min(n, max(1, int(self.encoder_handles))) if int(self.encoder_handles) > 0 else n):
+                        _m._LANE[0] = (3000 if int(self.encoder_handles) > 0 else 1000) + k
+                        self.proscene.scene_enc.op(self.output_scene)
+        finally:
+            _m._LANE[0] = lane
+        torch.cuda.synchronize(dev)
+        return self
 
     def _flush_group(self):
         """Launch the sampler of the open group -- ONE chain over the rows of all its batches, on a group stream with its

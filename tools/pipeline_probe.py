@@ -59,6 +59,7 @@ if os.environ.get("PROBE_ASYNC"):      # the public async API (slots, sampler_gr
     if os.environ.get("PROBE_ENC_HANDLES"):
         model.encoder_handles = int(os.environ["PROBE_ENC_HANDLES"])
     n = int(os.environ.get("PROBE_STEPS", "48"))
+    model.prepare_pipeline()
 
     host_ms = []
 
