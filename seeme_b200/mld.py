@@ -170,7 +170,10 @@ class MLD(nn.Module):
         self.lanes = int(kwargs.get("lanes", cfg.model.get("lanes", 1)))
         self.min_lane_batch = int(kwargs.get("min_lane_batch", cfg.model.get("min_lane_batch", 32)))
         # batches in flight for ego_eval_async / run_test_batches
-        self.pipeline_depth = int(kwargs.get("pipeline_depth", cfg.model.get("pipeline_depth", os.environ.get("SEEME_PIPELINE_DEPTH", 32))))
+        # (default: 32 slots, fewer for very large batches -- a slot's handles and its in-flight result, 6 890 x 60 vertices per
+        # sequence, take ~10 MB per sequence of capacity: 32 x 256 sequences = 76 GB of the 180 GB)
+        self.pipeline_depth = int(kwargs.get("pipeline_depth", cfg.model.get("pipeline_depth", os.environ.get(
+            "SEEME_PIPELINE_DEPTH", min(32, max(4, 8192 // max_batch))))))
         # ego_eval_async / run_test_batches: consecutive batches whose 50-step sampler runs as ONE chain over all their rows
         # (the chain is latency-bound: 3 750 dependent kernels take the same ~27 ms for 512 or 2 048 rows)
         # sampler back-end (include/seeme_b200.h: seeme_denoiser_set_backend): "persistent" = one launch of the 8-CTA-cluster kernel

@@ -39,7 +39,17 @@ class _PackedModule(nn.Module):
     """Tracks parameter versions/devices so the C-side packed weights are rebuilt when they change."""
 
     def _signature(self):
-        return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
+        # nn.Module.parameters() walks the module tree with de-duplication (~0.5 ms per call for the denoiser, three calls per
+        # batch): the (owning module, name) slots are cached instead and the CURRENT parameter object is read from each slot, so
+        # in-place updates (version counter), replaced parameter objects and moved devices all change the signature
+        slots = self.__dict__.get("_pslots")
+        if slots is None:
+            slots = self.__dict__["_pslots"] = [(m._parameters, n) for m in self.modules() for n in m._parameters]
+        sig = []
+        for d, n in slots:
+            p = d[n]
+            sig.append((p.data_ptr(), p._version, p.device.index) if p is not None else None)
+        return tuple(sig)
 
     def _op(self, key, factory):
         key = (key, _LANE[0])

@@ -420,6 +420,62 @@ def test_ego_eval_lanes_match_single_lane():
     assert out.shape == (B, 60, 24, 3) and bool(torch.isfinite(out).all())
 
 
+def test_pipeline_slots_shared_encoder_handles_and_auto_backend():
+    """The pipeline's resource policies do not change results: ONE scene-encoder handle shared by all slots (the slots take
+    turns through an event), slots prepared up front and reused lowest-idle-first, the "auto" sampler back-end choosing the
+    cluster kernel or the one-CTA-per-tile kernel by the number of batches in flight (every back-end agrees with the others
+    to fp32 rounding; here each batch is compared with the synchronous call on the SAME back-end family within 1e-4 m)."""
+    import seeme_b200
+    from seeme_b200 import ops as _ops, synthetic as S
+    B = 5
+    model = seeme_b200.build_model("config_mld_egobody.yaml", device=DEV, guidance_scale=7.5, max_batch=B, n_points=700, pipeline_depth=4,
+                                   encoder_handles=1, persistent_sm_budget=16)
+    model.prepare_pipeline()
+    assert len(model.__dict__["_slot_streams"]) == 4
+    created = []
+    orig_init = _ops._Handle.__init__
+
+    def counting_init(self, *a, **k):
+        created.append(type(self).__name__)
+        return orig_init(self, *a, **k)
+
+    batches, noises = [], []
+    for i in range(7):
+        b = S.make_batch(B, seed=300 + i, n_points=700, ragged=True)
+        g = torch.Generator().manual_seed(400 + i)
+        batches.append(tuple(x.pin_memory() if torch.is_tensor(x) else x for x in b))
+        noises.append({"eps_int": torch.randn(1, B, 256, generator=g).pin_memory(), "eps_unc": torch.randn(1, B, 256, generator=g).pin_memory(),
+                       "x_T": torch.randn(B, 1, 256, generator=g).pin_memory()})
+    chosen = []
+    orig_sb = _ops.DenoiserOp.set_backend
+
+    def recording_sb(self, name):
+        chosen.append(name)
+        return orig_sb(self, name)
+
+    _ops._Handle.__init__ = counting_init
+    _ops.DenoiserOp.set_backend = recording_sb
+    try:
+        pend = [model.ego_eval_async(b, n) for b, n in zip(batches, noises)]      # 7 submissions on 4 slots, 1 encoder handle
+        got = [p.synchronize() for p in pend]
+        in_pipe = list(chosen)
+        assert created == [], created                                             # prepare_pipeline had built everything
+        assert in_pipe[0] == "persistent" and "tile" in in_pipe, in_pipe          # budget 16 SMs: one 8-SM cluster, then tiles
+        # an idle pipeline reuses the lowest slot
+        p0 = model.ego_eval_async(batches[0], noises[0])
+        p0.synchronize()
+        assert p0.slot == 0
+    finally:
+        _ops._Handle.__init__ = orig_init
+        _ops.DenoiserOp.set_backend = orig_sb
+    for b, n, r in zip(batches, noises, got):
+        ref = model.ego_eval(tuple(x.to(DEV) if torch.is_tensor(x) else x for x in b), {k: v.to(DEV) for k, v in n.items()})
+        assert ref["lengths"] == r["lengths"]
+        assert torch.equal(ref["joints_ref"], r["joints_ref"])
+        assert (ref["joints_rst"] - r["joints_rst"]).abs().max() < 1e-4
+    assert (p0.rs_set["joints_rst"] - got[0]["joints_rst"]).abs().max() < 1e-4
+
+
 @pytest.mark.parametrize("backend", ["graph", "persistent"])
 def test_ego_eval_async_pipeline_matches_sync(backend):
     """several batches in flight on the pipeline slots (own streams + handles, host-resident inputs copied on the slot's
