@@ -170,10 +170,13 @@ class MLD(nn.Module):
         self.lanes = int(kwargs.get("lanes", cfg.model.get("lanes", 1)))
         self.min_lane_batch = int(kwargs.get("min_lane_batch", cfg.model.get("min_lane_batch", 32)))
         # batches in flight for ego_eval_async / run_test_batches
-        # (default: 32 slots, fewer for very large batches -- a slot's handles and its in-flight result, 6 890 x 60 vertices per
-        # sequence, take ~10 MB per sequence of capacity: 32 x 256 sequences = 76 GB of the 180 GB)
-        self.pipeline_depth = int(kwargs.get("pipeline_depth", cfg.model.get("pipeline_depth", os.environ.get(
-            "SEEME_PIPELINE_DEPTH", min(32, max(4, 8192 // max_batch))))))
+        # (default: 32 slots for batches of 256 sequences; fewer for larger ones -- a slot's handles and its in-flight result,
+        # 6 890 x 60 vertices per sequence, take ~10 MB per sequence of capacity: 32 x 256 sequences = 76 GB of the 180 GB -- and
+        # 8 for batches below 256, whose GPU time per batch is close to the host's submission time: measured at 64 sequences per
+        # batch, 8 slots with the cluster sampler give 4.0 ms per batch, 32 slots 4.4-6.3 ms with host stalls of up to 260 ms
+        # whenever a slot's stream pool misses in the caching allocator while 32 samplers are in flight)
+        default_depth = 8 if max_batch < 256 else min(32, max(4, 8192 // max_batch))
+        self.pipeline_depth = int(kwargs.get("pipeline_depth", cfg.model.get("pipeline_depth", os.environ.get("SEEME_PIPELINE_DEPTH", default_depth))))
         # ego_eval_async / run_test_batches: consecutive batches whose 50-step sampler runs as ONE chain over all their rows
         # (the chain is latency-bound: 3 750 dependent kernels take the same ~27 ms for 512 or 2 048 rows)
         # sampler back-end (include/seeme_b200.h: seeme_denoiser_set_backend): "persistent" = one launch of the 8-CTA-cluster kernel
@@ -245,10 +248,11 @@ class MLD(nn.Module):
             # 512 rows (20.2k sequences/s at depth 32 against 18.0k with the kernel graph and 16.0k with the cluster kernel; the
             # same order at 128 and 64 sequences per batch).  While few batches are in flight (pipeline filling, or an epoch of
             # a few small batches as in the interactee protocol) the clusters of all of them still fit next to each other
-            # (8 SMs per 128-row tile) and the lower latency wins.
+            # (8 SMs per 128-row tile) and the lower latency wins; a shallow pipeline (<= 8 slots: the small-batch default) always
+            # takes the cluster kernel.
             in_pipe = self.__dict__.get("_in_pipeline", False) and int(self.pipeline_depth) > 1
             tiles = -(-encoder_hidden_states.shape[0] // 128)
-            crowded = (self.__dict__.get("_n_inflight", 0) + 1) * tiles * 8 > int(self.persistent_sm_budget)
+            crowded = int(self.pipeline_depth) > 8 and (self.__dict__.get("_n_inflight", 0) + 1) * tiles * 8 > int(self.persistent_sm_budget)
             backend = "tile" if in_pipe and crowded else "persistent"
         if os.environ.get("SEEME_SAMPLER") != "graph":
             op.set_backend(backend)

@@ -428,10 +428,10 @@ def test_pipeline_slots_shared_encoder_handles_and_auto_backend():
     import seeme_b200
     from seeme_b200 import ops as _ops, synthetic as S
     B = 5
-    model = seeme_b200.build_model("config_mld_egobody.yaml", device=DEV, guidance_scale=7.5, max_batch=B, n_points=700, pipeline_depth=4,
+    model = seeme_b200.build_model("config_mld_egobody.yaml", device=DEV, guidance_scale=7.5, max_batch=B, n_points=700, pipeline_depth=10,
                                    encoder_handles=1, persistent_sm_budget=16)
     model.prepare_pipeline()
-    assert len(model.__dict__["_slot_streams"]) == 4
+    assert len(model.__dict__["_slot_streams"]) == 10
     created = []
     orig_init = _ops._Handle.__init__
 
@@ -456,11 +456,11 @@ def test_pipeline_slots_shared_encoder_handles_and_auto_backend():
     _ops._Handle.__init__ = counting_init
     _ops.DenoiserOp.set_backend = recording_sb
     try:
-        pend = [model.ego_eval_async(b, n) for b, n in zip(batches, noises)]      # 7 submissions on 4 slots, 1 encoder handle
+        pend = [model.ego_eval_async(b, n) for b, n in zip(batches, noises)]      # 7 batches in flight, 1 encoder handle
         got = [p.synchronize() for p in pend]
         in_pipe = list(chosen)
         assert created == [], created                                             # prepare_pipeline had built everything
-        assert in_pipe[0] == "persistent" and "tile" in in_pipe, in_pipe          # budget 16 SMs: one 8-SM cluster, then tiles
+        assert in_pipe[0] == "persistent" and "tile" in in_pipe, in_pipe          # budget 16 SMs: two 8-SM clusters, then tiles
         # an idle pipeline reuses the lowest slot
         p0 = model.ego_eval_async(batches[0], noises[0])
         p0.synchronize()

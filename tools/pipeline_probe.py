@@ -14,8 +14,9 @@ from seeme_b200 import modules as M, synthetic as S  # noqa: E402
 D = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 B = int(os.environ.get("PROBE_B", "256"))
 dev = torch.device("cuda", 0)
-model = seeme_b200.build_model("config_mld_egobody.yaml", device=dev, guidance_scale=7.5, max_batch=B, n_points=20000, lanes=1)
-batch = tuple(x.to(dev) if torch.is_tensor(x) else x for x in S.make_batch(B, n_points=20000))
+CFG = os.environ.get("PROBE_CONFIG", "config_mld_egobody.yaml")
+model = seeme_b200.build_model(CFG, device=dev, guidance_scale=7.5, max_batch=B, n_points=20000, lanes=1)
+batch = tuple(x.to(dev) if torch.is_tensor(x) else x for x in S.make_batch(B, n_points=20000, **({"dataset": "gimo"} if "gimo" in CFG else {})))
 noise = {k: v.to(dev) for k, v in bench.make_noise(B).items()}
 if os.environ.get("PROBE_CACHE_SCENE"):       # replication-protocol case: scene embeddings reused, no scene encoder in the loop
     _orig = model._encode_scene
