@@ -84,6 +84,7 @@ def run_test_protocol(model, batches: Callable[[], Iterable], replication_times:
     dict); GIMO re-draws its 20 000 points on every ``__getitem__`` (dataset.py:2018-2020), so its repetitions must
     re-encode -- the cache checks a content fingerprint and re-encodes on mismatch either way."""
     reps = int(replication_times if replication_times is not None else model.cfg.TEST.REPLICATION_TIMES)
+    model.prepare_pipeline()          # the slots' kernel-side handles: built once here instead of inside the first epochs
     cache = _SceneEmbeddingCache(model) if cache_scene_embeddings and "scene" in model.condition else None
     if cache is not None:
         model._encode_scene = cache
