@@ -105,6 +105,39 @@ def test_unsupported_configs_raise():
         MldDenoiser(abl, condition=["text"], latent_dim=[1, 256], num_layers=9, num_heads=4, text_encoded_dim=256)
 
 
+def test_pipeline_defaults_and_handle_signature():
+    """host logic of the batch pipeline that needs no GPU: the default depth by batch capacity, the work-queue variable, the
+    handle signature (detects in-place updates and replaced parameters without walking the module tree), and the loud
+    failure of the async entry points on the CPU"""
+    import torch
+    import seeme_b200
+    assert os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS") is not None      # set (if unset) by importing the package
+    for mb, depth in ((2, 8), (64, 8), (128, 8), (256, 32), (512, 16), (1024, 8), (4096, 4)):
+        m = seeme_b200.build_model(device="cpu", max_batch=mb, n_points=64)
+        assert m.pipeline_depth == depth, (mb, m.pipeline_depth)
+    assert seeme_b200.build_model(device="cpu", max_batch=256, n_points=64, pipeline_depth=5).pipeline_depth == 5
+    assert m.sampler_backend == "auto" and m.encoder_handles == 4 and m.persistent_sm_budget == 64
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.prepare_pipeline()
+    from seeme_b200 import synthetic as S
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.ego_eval_async(S.make_batch(2, n_points=64))
+    den = m.denoiser
+    s0 = den._signature()
+    assert s0 == den._signature() and len(s0) == len(list(den.parameters()))
+    p = next(den.parameters())
+    with torch.no_grad():
+        p.add_(1.0)                                                        # in-place update: version counter
+    s1 = den._signature()
+    assert s1 != s0
+    name, mod = None, None
+    for mod_ in den.modules():
+        for n_ in mod_._parameters:
+            name, mod = n_, mod_
+    setattr(mod, name, torch.nn.Parameter(mod._parameters[name].detach().clone(), requires_grad=False))   # replaced object
+    assert den._signature() != s1
+
+
 def test_no_cpu_fallback():
     """the product path must fail loudly when asked to run without CUDA"""
     import seeme_b200
