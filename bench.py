@@ -16,6 +16,11 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+# 32 hardware work queues for the pipeline's streams.  The CUDA context reads the variable when it is created,
+# which torch.cuda.set_device / the NCCL initialisation in _init_dist() do -- before `import seeme_b200` (which sets the same
+# default) in the gimo / interactee / smpl-sweep modes -- so it is set here, first thing.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import statistics
 import subprocess
 import sys
