@@ -456,15 +456,23 @@ def test_pipeline_slots_shared_encoder_handles_and_auto_backend():
     _ops._Handle.__init__ = counting_init
     _ops.DenoiserOp.set_backend = recording_sb
     try:
-        pend = [model.ego_eval_async(b, n) for b, n in zip(batches, noises)]      # 7 batches in flight, 1 encoder handle
+        pend = [model.ego_eval_async(b, n) for b, n in zip(batches, noises)]      # up to 7 batches in flight, 1 encoder handle
         got = [p.synchronize() for p in pend]
         in_pipe = list(chosen)
         assert created == [], created                                             # prepare_pipeline had built everything
-        assert in_pipe[0] == "persistent" and "tile" in in_pipe, in_pipe          # budget 16 SMs: two 8-SM clusters, then tiles
+        # the first batch finds an empty pipeline (one 8-SM cluster fits the 16-SM budget); how many of the later ones find it
+        # crowded depends on the host's pace
+        assert len(in_pipe) == 7 and in_pipe[0] == "persistent" and set(in_pipe) <= {"persistent", "tile"}, in_pipe
         # an idle pipeline reuses the lowest slot
         p0 = model.ego_eval_async(batches[0], noises[0])
         p0.synchronize()
         assert p0.slot == 0
+        # budget 0: every batch of this (deeper than 8) pipeline takes the one-CTA-per-tile kernel, whatever the timing
+        model.persistent_sm_budget = 0
+        del chosen[:]
+        pend_tile = [model.ego_eval_async(b, n) for b, n in zip(batches[:3], noises[:3])]
+        got_tile = [p.synchronize() for p in pend_tile]
+        assert chosen == ["tile"] * 3, chosen
     finally:
         _ops._Handle.__init__ = orig_init
         _ops.DenoiserOp.set_backend = orig_sb
@@ -474,6 +482,8 @@ def test_pipeline_slots_shared_encoder_handles_and_auto_backend():
         assert torch.equal(ref["joints_ref"], r["joints_ref"])
         assert (ref["joints_rst"] - r["joints_rst"]).abs().max() < 1e-4
     assert (p0.rs_set["joints_rst"] - got[0]["joints_rst"]).abs().max() < 1e-4
+    for r, t in zip(got, got_tile):
+        assert (r["joints_rst"] - t["joints_rst"]).abs().max() < 1e-4
 
 
 @pytest.mark.parametrize("backend", ["graph", "persistent"])
